@@ -1,0 +1,136 @@
+"""CPU: the oracle (oracle/) against the golden vectors produced by the reference's own code
+(tools/gen_golden.py) and against the reference's own seqscore.cpp built into oracle/_ref/."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pfann_oracle as orc
+from pfann_b200 import synth
+
+
+def _mel_inputs():
+    return np.concatenate([synth.synth_segments(3, seed=1), np.zeros((1, 8000), np.float32)])
+
+
+def test_mel_fbanks_structure():
+    fb = orc.mel_fbanks(synth.read_config('default'))
+    assert fb.shape == (513, 256)
+    assert (fb[:39] == 0).all()                      # rows < 39 are all zero
+    nnz = (fb > 0).sum(0)
+    assert nnz.min() >= 1 and nnz.max() <= 7
+
+
+def test_melspec_vs_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'mel_default.npz'))['mel']
+    y = orc.melspec(_mel_inputs(), synth.read_config('default'))
+    assert y.shape == g.shape == (4, 256, 32)
+    # all-zero row: log(0 + 1e-8) everywhere (melspec.py:41,46)
+    np.testing.assert_allclose(y[3], np.log(np.float32(1e-8)), rtol=0, atol=1e-6)
+    np.testing.assert_allclose(g[3], np.log(np.float32(1e-8)), rtol=0, atol=1e-6)
+    # tolerance: the reference computes in fp32 (cuFFT/pocketfft + sgemm); the oracle in double.
+    err = np.abs(y[:3] - g[:3])
+    assert err.max() < 2e-3, err.max()
+    assert err.mean() < 2e-5, err.mean()
+
+
+@pytest.mark.parametrize('name', ['tiny', 'n640d64', 'default'])
+def test_encoder_vs_reference_golden(golden_dir, name):
+    params = synth.read_config(name)
+    g = np.load(os.path.join(golden_dir, 'enc_%s.npz' % name))
+    mel = np.load(os.path.join(golden_dir, 'mel_default.npz'))['mel']
+    n = 4 if name == 'tiny' else 2                   # keep the CPU suite short
+    sd = synth.make_state_dict(params, seed=int(g['seed']))
+    z = orc.fpnetwork_forward(sd, mel[:n], params, norm=True)
+    zr, layers = orc.fpnetwork_forward(sd, mel[:n], params, norm=False, return_layers=True)
+    np.testing.assert_allclose(z, g['z'][:n], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(zr, g['z_raw'][:n], rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(layers[-1][1].reshape(n, -1), g['enc_out'][:n], rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(np.linalg.norm(z, axis=1), 1.0, atol=1e-6)
+
+
+def test_frame_pcm16_vs_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'musicdata.npz'))
+    for fsm in (1, 2):
+        for i, n in enumerate(g['lens']):
+            rows = orc.frame_pcm16(synth.synth_pcm(500 + i, int(n)), 8000, 4000 // fsm)
+            assert rows.shape[0] == int(g['nseg_f%d_c%d' % (fsm, i)])
+            if 'rows_f%d_c%d' % (fsm, i) in g:
+                np.testing.assert_allclose(rows, g['rows_f%d_c%d' % (fsm, i)], rtol=0, atol=2e-7)
+            else:
+                np.testing.assert_allclose(rows[0], g['row0_f%d_c%d' % (fsm, i)], rtol=0, atol=2e-7)
+                np.testing.assert_allclose(np.linalg.norm(rows.astype(np.float64), axis=1),
+                                           g['rownorm_f%d_c%d' % (fsm, i)], rtol=1e-6)
+
+
+def test_rerank_vs_reference_golden(golden_dir):
+    """database.py:117-166 run unmodified (golden) vs our numpy restatement and vs seq_score."""
+    g = np.load(os.path.join(golden_dir, 'db_small.npz'))
+    db, key = g['db'], g['key']
+    pos = synth.song_pos_from_key(key)
+    for c in range(int(g['n_cases'])):
+        q, labels, fsm = g['q%d' % c], g['labels%d' % c], int(g['fsm%d' % c])
+        sco, (sid, tim), ss = orc.query_embeddings_base(db, pos, q, labels, fsm, 0.5)
+        assert sid == int(g['song%d' % c]) and tim == float(g['time%d' % c])
+        assert abs(sco - float(g['score%d' % c])) < 1e-6
+        np.testing.assert_allclose(ss, g['ss%d' % c], rtol=0, atol=1e-6)
+        # the C restatement of cpp/seqscore.cpp gives the same answer through database.py:190-195
+        for use_ref in (False, True):
+            if use_ref and orc.ref_lib() is None:
+                continue
+            sco2, (sid2, tim2), ss2 = orc.query_embeddings_cpp(db, pos, q, labels, fsm, 0.5, use_ref=use_ref)
+            assert sid2 == sid and tim2 == tim
+            assert abs(sco2 - sco) < 1e-6
+            np.testing.assert_allclose(ss2, ss, rtol=0, atol=1e-6)
+
+
+def test_seq_score_restatement_bit_exact_vs_reference_build():
+    """Our C restatement == the reference's own seqscore.cpp (oracle/_ref), bit for bit."""
+    if orc.ref_lib() is None:
+        pytest.skip('oracle/_ref/seqscore.so not built (no /root/reference at build time)')
+    db, key = synth.synth_db(5000, d=32, seed=3, song_len=37)
+    pos = synth.song_pos_from_key(key)
+    qs, songs, offs = synth.synth_queries(db, key, 12, q_len=19, noise=1.0, seed=5)
+    for fsm in (1, 2, 3):
+        for alpha in (0.0, 4.0):
+            for i in range(qs.shape[0]):
+                q = qs[i]
+                _, labels = orc.flat_ip_search(db, q, 10)
+                if i == 3:
+                    labels[:, 5:] = -1                       # ragged: fewer than k hits
+                a, ssa = orc.seq_score(db, pos, q, labels, fsm, alpha)
+                b, ssb = orc.seq_score(db, pos, q, labels, fsm, alpha, use_ref=True)
+                assert a == b
+                assert np.array_equal(ssa.view(np.uint32), ssb.view(np.uint32))
+                if fsm == 1 and alpha == 0.0:
+                    assert a == songs[i] and ssa[a, 1] == offs[i]
+
+
+def test_seq_score_empty_labels():
+    db, key = synth.synth_db(100, d=8, seed=1, song_len=10)
+    pos = synth.song_pos_from_key(key)
+    q = db[:3].copy()
+    labels = np.full((3, 4), -1, np.int64)
+    best, ss = orc.seq_score(db, pos, q, labels)
+    assert best == -1 and not ss.any()
+    if orc.ref_lib() is not None:
+        best, ss = orc.seq_score(db, pos, q, labels, use_ref=True)
+        assert best == -1 and not ss.any()
+
+
+def test_flat_ip_search_contract():
+    db, _ = synth.synth_db(3000, d=24, seed=9)
+    q = db[[5, 77, 1234]] + 0.01
+    D, I = orc.flat_ip_search(db, q, 7)
+    s = (q.astype(np.float64) @ db.T.astype(np.float64))
+    ref = np.argsort(-s, axis=1, kind='stable')[:, :7]
+    assert np.array_equal(I, ref)
+    np.testing.assert_allclose(D, np.take_along_axis(s, ref, 1), rtol=0, atol=1e-6)
+    assert (np.diff(D, axis=1) <= 0).all()
+    # fewer rows than k -> -1 padded
+    D, I = orc.flat_ip_search(db[:4], q, 7)
+    assert (I[:, 4:] == -1).all() and (I[:, :4] >= 0).all()
+    # exact ties -> lower id first
+    dup = np.concatenate([db[:10], db[:10]])
+    D, I = orc.flat_ip_search(dup, db[:1], 4)
+    assert list(I[0, :2]) == [0, 10]
