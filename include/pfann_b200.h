@@ -1,0 +1,163 @@
+/*
+ * pfann_b200.h -- C-ABI of libpfann_b200.so: the B200 (sm_100a) implementation of pfann's hot path
+ *
+ *     8 kHz segments -> log-mel -> conv encoder + split head + L2 -> inner-product kNN -> sequence score
+ *
+ * This is the drop-in boundary.  Plain C: opaque handles, caller-owned buffers,
+ * plain pointers and sizes, int return codes (0 = ok, <0 = error, text via pfann_last_error()); no
+ * exception crosses the boundary and there is NO CPU fallback: without a Blackwell GPU
+ * pfann_ctx_create() fails.  Every data pointer may be a host pointer (staged through pinned/device
+ * scratch inside the call, results complete on return) or a device pointer of the context's device
+ * (work is enqueued on the context's stream, stream-ordered like any CUDA library).
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to stdio2016/pfann).
+ * Handles are thread-compatible, not thread-safe (the reference calls from one Python thread,
+ * database.py:178).
+ */
+#ifndef PFANN_B200_H
+#define PFANN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFANN_B200_VERSION 20261017001LL
+
+typedef struct pfann_ctx pfann_ctx;     /* one per (process, GPU): device ordinal, stream, scratch   */
+typedef struct pfann_mel pfann_mel;     /* stage 1 plan: windows, twiddles, sparse mel filter bank    */
+typedef struct pfann_model pfann_model; /* stage 2 weights in kernel layout                           */
+typedef struct pfann_db pfann_db;       /* stage 3 database shard resident in HBM                     */
+
+/* ---- library / context ---------------------------------------------------------------------- */
+
+/* ABI handshake, same idea as `version()` of cpp/seqscore.cpp:27-30 checked at database.py:29-32. */
+long long pfann_version(void);
+/* Message of the last failing call on this thread. */
+const char *pfann_last_error(void);
+
+int pfann_ctx_create(int device, pfann_ctx **out);
+void pfann_ctx_destroy(pfann_ctx *ctx);
+/* Enqueue all later work on `cuda_stream` (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream). */
+int pfann_ctx_set_stream(pfann_ctx *ctx, void *cuda_stream);
+int pfann_ctx_sync(pfann_ctx *ctx);
+/* Number of kernels of this library launched through the context so far (bench.py: gpu_launches). */
+long long pfann_ctx_launches(pfann_ctx *ctx);
+int pfann_ctx_sm_count(pfann_ctx *ctx);
+
+/* ---- stage 1: log-mel front end -------------------------------------------------------------- */
+
+/* Replaces datautil/melspec.py:52-63 build_mel_spec_layer(params) for the default option set
+ * (naf_mode=False, mel_log='log', spec_norm='l2').  n_fft must be 1024 (every shipped config). */
+int pfann_mel_create(pfann_ctx *ctx, int sample_rate, int n_fft, int hop, double f_min, double f_max,
+                     int n_mels, int seg_len, pfann_mel **out);
+void pfann_mel_destroy(pfann_mel *mel);
+/* Replaces MelSpec.forward (datautil/melspec.py:33-50): x[B][seg_len] fp32 -> out[B][n_mels][T] fp32,
+ * T = 1 + seg_len / hop.  L2-normalise, reflect-pad STFT power, HTK mel, log(. + 1e-8). */
+int pfann_mel_forward(pfann_mel *mel, const float *x, int64_t B, float *out);
+/* Same, but takes the segmenter's job too (datautil/musicdata.py:48,82-88): mono int16 PCM at the model
+ * rate; segment b covers pcm[seg_start[b] .. +seg_valid[b]) zero-padded to seg_len, scaled by 1/32768 and
+ * mean-removed before the mel.  seg_start/seg_valid are host or device arrays of length B. */
+int pfann_mel_forward_pcm16(pfann_mel *mel, const int16_t *pcm, int64_t n_samples, const int64_t *seg_start,
+                            const int32_t *seg_valid, int64_t B, float *out);
+int pfann_mel_n_frames(pfann_mel *mel);
+
+/* ---- stage 2: fingerprint network ------------------------------------------------------------- */
+
+#define PFANN_PRECISION_FP32 0 /* CUDA-core fp32 path (validation grade)                          */
+#define PFANN_PRECISION_BF16 1 /* tcgen05 tensor-core path: bf16 operands, fp32 accumulate + LN   */
+
+/* Replaces FpNetwork(d, h, u, F, T, params) (model.py:132-146).  Supported option set: k=3, stride 2,
+ * ReLU, relu_after_bn=True; `fuller` as in params['model'] (model.py:26-29). */
+int pfann_model_create(pfann_ctx *ctx, int d, int h, int u, int F, int T, int fuller, pfann_model **out);
+void pfann_model_destroy(pfann_model *m);
+/* Replaces load_state_dict (builder.py:56): `name` is the reference state_dict key
+ * ("f.convs.3.conv1.weight", "f.convs.0.ln2.bias", "g.linear1.weight", ...), `data` fp32 in the
+ * reference's own (PyTorch NCHW) element order, host or device. */
+int pfann_model_set_param(pfann_model *m, const char *name, const float *data, int64_t numel);
+/* Re-layout weights for the kernels; fails if any parameter is missing. */
+int pfann_model_finalize(pfann_model *m, int precision);
+/* Segments processed per internal pass (workspace is sized for it). */
+int pfann_model_set_chunk(pfann_model *m, int chunk);
+/* Replaces FpNetwork.forward(x, norm) (model.py:148-153): mel[B][F][T] fp32 -> z[B][d] fp32. */
+int pfann_model_forward(pfann_model *m, const float *mel, int64_t B, int norm, float *z);
+/* Debug/parity taps: pfann_model_set_tap(layer) before a forward of at most one chunk keeps the activation
+ * after SeparableConv2d `layer` (post ln2+ReLU, NCHW fp32, exactly the reference module's output,
+ * model.py:73); pfann_model_get_activation copies it out.  layer = -1 disables the tap. */
+int pfann_model_set_tap(pfann_model *m, int layer);
+int pfann_model_get_activation(pfann_model *m, int layer, float *out, int64_t numel);
+
+/* ---- stages 1+2 fused: the builder / matcher inner loop ---------------------------------------- */
+
+/* Replaces builder.py:88-99 / matcher.py:110-127 for already-framed rows: x[B][seg_len] -> z[B][d]. */
+int pfann_extract_segments(pfann_mel *mel, pfann_model *m, const float *x, int64_t B, int norm, float *z);
+/* Replaces musicdata.py:82-88 + builder.py:88-99 for a batch of clips stored back to back as mono int16
+ * PCM: clip c is pcm[clip_off[c] .. clip_off[c+1]); it yields max(len,seg)-seg)/hop+1 segments, written
+ * consecutively to z (song order, like the `embeddings` file builder.py:99).  seg_counts[n_clips] (host,
+ * may be NULL) receives the landmarkKey entries (builder.py:101).  clip_off is a HOST array [n_clips+1].
+ * z must hold pfann_count_segments(...) rows. */
+int pfann_extract_pcm16(pfann_mel *mel, pfann_model *m, const int16_t *pcm, const int64_t *clip_off,
+                        int n_clips, int hop_samples, int norm, float *z, int32_t *seg_counts);
+int64_t pfann_count_segments(const int64_t *clip_off, int n_clips, int seg_len, int hop_samples);
+
+/* ---- stage 3: database search + sequence score ------------------------------------------------- */
+
+/* Replaces Database.__init__ (database.py:74-99) for a Flat inner-product index: `emb` is the
+ * `embeddings` file (builder.py:99,122: fp32 [n][d], C order), `landmark_key` the `landmarkKey` file
+ * (int32 [n_songs], builder.py:138-139).  The rows are copied to HBM (fp32 for exact rescoring + bf16 for
+ * the tensor-core scan).  `id_base`/`song_base` are the global row / song index of this shard's first
+ * row / song when the database is row-sharded across GPUs at song boundaries (0 for a single GPU). */
+int pfann_db_open(pfann_ctx *ctx, const float *emb, int64_t n, int d, const int32_t *landmark_key,
+                  int n_songs, int64_t id_base, int64_t song_base, pfann_db **out);
+void pfann_db_close(pfann_db *db);
+int64_t pfann_db_ntotal(pfann_db *db);
+/* Testing hook: candidate slots per query (power of two <= 4096), rows of the threshold pre-pass, and
+ * whether the scan runs on tensor cores (1) or fp32 CUDA cores (0); <= 0 / < 0 keeps the current value. */
+int pfann_db_set_tuning(pfann_db *db, int cand_cap, int sample_rows, int use_tc);
+
+/* Replaces faiss IndexFlatIP.search as called at database.py:121,172: q[Q][d] fp32 -> dist[Q][k] fp32
+ * descending, labels[Q][k] int64 (global row ids), padded with -FLT_MAX / -1 when fewer than k rows.
+ * Scores are exact fp32 inner products (k-sequential fused multiply-add); ties -> lower id first. */
+int pfann_db_search(pfann_db *db, const float *q, int64_t Q, int k, float *dist, int64_t *labels);
+
+/* Replaces seq_score() of cpp/seqscore.cpp:32-43 with the faiss::Index* swapped for our handle; the
+ * remaining arguments, buffer ownership (song_scores[n_songs][2] in/out, caller zero-initialised,
+ * database.py:176), and the return value (best song id or -1) are identical.  song_pos is GLOBAL
+ * (int64 [n_songs+1]) and labels are global row ids; only candidates whose song lives in this shard are
+ * scored. */
+int pfann_db_seq_score(pfann_db *db, const int64_t *song_pos, int n_songs, const float *query,
+                       int query_len, const int64_t *labels, int top_k, float *song_scores,
+                       int frame_shift_mul, float score_alpha);
+
+/* Batched form of Database.query_embeddings (database.py:111-115,168-195) for many query files per
+ * call (the matchemb.py split, matchemb.py:59-80): queries[sum len][d] fp32, query_index[nq][2] int64
+ * (start, len) as in the `query_index` file (extractemb.py:85).  Outputs per query file:
+ * best_score[nq] fp32, best_song[nq] int32 (global id, -1 if none), best_time[nq] fp32 in FRAMES
+ * (t*fsm - shift, seqscore.cpp:113; seconds = frames*hop_size/fsm, database.py:191).
+ * If song_scores != NULL it is [nq][n_songs_total][2] fp32, zero-filled then raised like seq_score. */
+int pfann_db_query(pfann_db *db, const float *queries, const int64_t *query_index, int nq, int top_k,
+                   int frame_shift_mul, float score_alpha, float *best_score, int32_t *best_song,
+                   float *best_time, float *song_scores, int64_t n_songs_total);
+
+/* Multi-GPU pieces of the same path: local top-k (global ids) for an all-gather, then rerank given merged
+ * labels.  pfann_topk_merge merges G gathered lists [G][Q][k] into [Q][k] (score desc, id asc). */
+int pfann_topk_merge(pfann_ctx *ctx, const float *dist_g, const int64_t *labels_g, int G, int64_t Q, int k,
+                     float *dist, int64_t *labels);
+int pfann_db_rerank(pfann_db *db, const float *queries, const int64_t *query_index, int nq,
+                    const int64_t *labels, int top_k, int frame_shift_mul, float score_alpha,
+                    float *best_score, int32_t *best_song, float *best_time);
+
+/* ---- reference-compatible symbols ------------------------------------------------------------- */
+
+/* Bit-compatible with cpp/seqscore.cpp:27-43 so that database.py:15-32 can load this library in place of
+ * cpp/seqscore: version() returns 20220625002; seq_score()'s first argument is a pfann_db* instead of a
+ * faiss::Index*. */
+long long version(void);
+int seq_score(void *index, const int64_t *song_pos, int n_songs, const float *query, int query_len,
+              const int64_t *labels, int top_k, float *song_scores, int frame_shift_mul, float score_alpha);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFANN_B200_H */

@@ -1,0 +1,80 @@
+// db.cuh -- stage 3 state shared by knn.cu (search), knn_tc.cu (tensor-core scan) and seqscore.cu (rerank).
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+namespace pfann {
+
+struct Db {
+    Ctx *ctx;
+    int64_t n;          // rows in this shard
+    int d;
+    int n_songs;        // songs in this shard
+    int64_t id_base;    // global id of local row 0
+    int64_t song_base;  // global id of local song 0
+    float *emb32 = nullptr;          // [n][d] fp32, exact rescoring + rerank (database.py:155)
+    __nv_bfloat16 *emb16 = nullptr;  // [n][d] bf16, tensor-core scan operand
+    int64_t *song_pos = nullptr;     // device [n_songs+1]: GLOBAL start row of each local song
+    std::vector<int64_t> song_pos_host;
+    float max_norm = 0.f;            // max row L2 norm (error bound of the approximate scan)
+    // tuning (tests shrink these to force the overflow / backstop paths)
+    int cand_cap = 4096;             // candidate slots per query (power of two, <= 4096)
+    int sample_rows = 16384;         // rows scanned in the threshold pre-pass
+    int use_tc = 1;                  // tensor-core bf16 scan when available, else fp32 CUDA-core scan
+    // scratch
+    DevBuf qbuf, qnorm, thr, cnt, cand, sample, flags, dist, labels, rr_keys, rr_scores, rr_out, lab_stage;
+    void *tc_state = nullptr;
+};
+
+// exact canonical inner product shared with the oracle (oracle/pfann_oracle.c dot_fma_seq):
+// one fused multiply-add per element, k = 0..d-1 in order.
+#ifdef __CUDACC__
+__device__ __forceinline__ float dot_fma_seq(const float *__restrict__ a, const float *__restrict__ b, int d) {
+    float acc = 0.f;
+    for (int k = 0; k < d; k++) acc = __fmaf_rn(a[k], b[k], acc);
+    return acc;
+}
+// order-preserving float -> uint32 (larger float -> larger key)
+__device__ __forceinline__ uint32_t flipf(float f) {
+    uint32_t u = __float_as_uint(f);
+    return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float unflipf(uint32_t u) {
+    return __uint_as_float(u ^ ((u >> 31) ? 0x80000000u : 0xFFFFFFFFu));
+}
+// In-place bitonic sort of n (power of two) keys by one CTA; descending if DESC.
+template <typename K, bool DESC>
+__device__ void bitonic_sort(K *keys, int n) {
+    for (int size = 2; size <= n; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < (n >> 1); i += blockDim.x) {
+                const int lo = 2 * i - (i & (stride - 1));  // index with bit `stride` cleared
+                const int hi = lo + stride;
+                const bool up = ((lo & size) == 0);  // ascending block?
+                const K a = keys[lo], b = keys[hi];
+                const bool swap = DESC ? (up ? a < b : a > b) : (up ? a > b : a < b);
+                if (swap) {
+                    keys[lo] = b;
+                    keys[hi] = a;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+#endif
+
+// knn.cu: device-pointer search (q, dist, labels all on the device, stream-ordered except for the
+// overflow check which synchronises once per query group)
+int db_search_dev(Db *db, const float *q, int64_t Q, int k, float *dist, int64_t *labels);
+// knn_tc.cu
+int knn_tc_prepare(Db *db);
+void knn_tc_release(Db *db);
+// approximate scan of rows [r0, r1) against Qg <= 128 queries; mode 0: store all scores to
+// sample[q][row - r0] (ld = sample_ld); mode 1: push row ids with score >= thr[q] into cand/cnt
+int knn_tc_scan(Db *db, const float *q, int Qg, int64_t r0, int64_t r1, int mode, float *sample, int64_t sample_ld,
+                const float *thr, int *cnt, uint32_t *cand, int cap);
+
+}  // namespace pfann

@@ -1,0 +1,677 @@
+// encoder.cu -- stage 2: FpNetwork (model.py:14-153) layer pipeline, LayerNorm / head kernels and the
+// fp32 CUDA-core convolution path (PFANN_PRECISION_FP32, validation grade).  The tensor-core path
+// (PFANN_PRECISION_BF16) swaps the convolution GEMMs for encoder_tc.cu and keeps everything else.
+//
+// Per SeparableConv2d (model.py:54-73), activations channels-last X[b][f][t][c]:
+//     conv1 (1x3 along T, stride 2)  -> Y (raw, fp32)  -> per-sample LayerNorm statistics over (C,F,T)
+//     LN-apply: relu((Y - mean) * rstd * gamma[f][t][c] + beta[f][t][c])      (model.py:59-60)
+//     conv2 (3x1 along F, stride 2; dense if fuller else depthwise)  -> Y -> stats -> LN-apply
+// and after layer 7 the split head (model.py:122-130) fused with the last LN-apply and the L2 normalise.
+#include <math.h>
+#include <string.h>
+
+#include "encoder.cuh"
+#include "pfann_b200.h"
+
+using namespace pfann;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// fp32 CUDA-core implicit-GEMM convolution: 64x64 tile, BK = 16, 4x4 register micro-tile.
+// ------------------------------------------------------------------------------------------------
+template <typename InT>
+struct ConvArgs {
+    const InT *X;       // [nb][Fi][Ti][Ci]
+    const float *W;     // [K][Co]
+    const float *bias;  // [Co]
+    float *Y;           // [nb][Fo][To][Co]
+    long long M;        // nb * Fo * To
+    int Ci, Co, Fi, Ti, Fo, To, axis, ntaps, K;
+    int off[3];
+};
+
+constexpr int BM = 64, BN = 64, BK = 16;
+
+__device__ __forceinline__ float ld_act(const float *p) { return __ldg(p); }
+__device__ __forceinline__ float ld_act(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
+
+template <typename InT>
+__global__ void __launch_bounds__(256) conv_gemm_fp32_kernel(const ConvArgs<InT> a) {
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN];
+    const int tid = threadIdx.x;
+    const long long m0 = (long long)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+
+    // A-load role: row ar (0..63), 4 consecutive k starting at ak
+    const int ar = tid >> 2, ak = (tid & 3) * 4;
+    const long long am = m0 + ar;
+    const InT *rowp[3] = {nullptr, nullptr, nullptr};
+    if (am < a.M) {
+        const int to = (int)(am % a.To);
+        const long long r = am / a.To;
+        const int fo = (int)(r % a.Fo);
+        const long long b = r / a.Fo;
+        for (int j = 0; j < a.ntaps; j++) {
+            int fi = fo, ti = to;
+            if (a.axis == 0) ti = 2 * to + a.off[j]; else fi = 2 * fo + a.off[j];
+            if (fi >= 0 && fi < a.Fi && ti >= 0 && ti < a.Ti)
+                rowp[j] = a.X + ((b * a.Fi + fi) * a.Ti + ti) * (long long)a.Ci;
+        }
+    }
+    const bool vecA = (a.Ci & 3) == 0 && sizeof(InT) == 4;
+    // B-load role: k row bk (0..15), 4 consecutive n starting at bn
+    const int bk = tid >> 4, bn = (tid & 15) * 4;
+    const bool vecB = (a.Co & 3) == 0;
+
+    const int tx = tid & 15, ty = tid >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < a.K; k0 += BK) {
+        float av[4] = {0.f, 0.f, 0.f, 0.f};
+        const int kk = k0 + ak;
+        if (vecA) {
+            if (kk < a.K) {
+                const int tap = kk / a.Ci, c = kk - tap * a.Ci;
+                const InT *p = rowp[tap];
+                if (p) {
+                    const float4 v = __ldg(reinterpret_cast<const float4 *>(p + c));
+                    av[0] = v.x; av[1] = v.y; av[2] = v.z; av[3] = v.w;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int k = kk + e;
+                if (k < a.K) {
+                    const int tap = k / a.Ci, c = k - tap * a.Ci;
+                    const InT *p = rowp[tap];
+                    if (p) av[e] = ld_act(p + c);
+                }
+            }
+        }
+        float bv[4] = {0.f, 0.f, 0.f, 0.f};
+        const int kb = k0 + bk;
+        if (kb < a.K) {
+            const float *p = a.W + (long long)kb * a.Co + n0 + bn;
+            if (vecB && n0 + bn + 3 < a.Co) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
+                bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                    if (n0 + bn + e < a.Co) bv[e] = __ldg(p + e);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < 4; e++) As[ak + e][ar] = av[e];
+#pragma unroll
+        for (int e = 0; e < 4; e++) Bs[bk][bn + e] = bv[e];
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; k++) {
+            const float4 av4 = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
+            const float4 bv4 = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
+            const float aa[4] = {av4.x, av4.y, av4.z, av4.w};
+            const float bb[4] = {bv4.x, bv4.y, bv4.z, bv4.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const long long m = m0 + ty * 4 + i;
+        if (m >= a.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int n = n0 + tx * 4 + j;
+            if (n < a.Co) a.Y[m * a.Co + n] = acc[i][j] + __ldg(a.bias + n);
+        }
+    }
+}
+
+// Depthwise conv2 (fuller == false, model.py:29): a 3-tap FIR per channel along F.
+template <typename InT>
+__global__ void conv_dw_kernel(const InT *X, const float *W /*[Co][ntaps]*/, const float *bias, float *Y,
+                               long long total, int C, int Fi, int Ti, int Fo, int To, int ntaps, int off0, int off1,
+                               int off2) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const int to = (int)(r % To);
+    r /= To;
+    const int fo = (int)(r % Fo);
+    const long long b = r / Fo;
+    const int offs[3] = {off0, off1, off2};
+    float acc = __ldg(bias + c);
+    for (int j = 0; j < ntaps; j++) {
+        const int fi = 2 * fo + offs[j];
+        if (fi < 0 || fi >= Fi) continue;
+        acc = fmaf(__ldg(W + c * ntaps + j), (float)X[((b * Fi + fi) * Ti + to) * (long long)C + c], acc);
+    }
+    Y[i] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over the whole (C,F,T) volume of one sample (model.py:21,30; eps 1e-5, biased variance)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum_d(double v, double *red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int i = 0; i < nw; i++) t += red[i];
+    return t;
+}
+
+// two-pass statistics, one CTA per sample: stats[b] = (mean, 1/sqrt(var + eps))
+__global__ void __launch_bounds__(512) ln_stats_kernel(const float *Y, long long E, float2 *stats) {
+    __shared__ double red[16];
+    const float *y = Y + (long long)blockIdx.x * E;
+    double s = 0.0;
+    for (long long i = threadIdx.x; i < E; i += blockDim.x) s += (double)y[i];
+    const double mean = block_sum_d(s, red) / (double)E;
+    double q = 0.0;
+    for (long long i = threadIdx.x; i < E; i += blockDim.x) {
+        const double dlt = (double)y[i] - mean;
+        q += dlt * dlt;
+    }
+    const double var = block_sum_d(q, red) / (double)E;
+    if (threadIdx.x == 0) stats[blockIdx.x] = make_float2((float)mean, (float)(1.0 / sqrt(var + 1e-5)));
+}
+
+__device__ __forceinline__ void store_out(float *p, float v) { *p = v; }
+__device__ __forceinline__ void store_out(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
+
+// X[b][e] = relu((Y[b][e] - mean_b) * rstd_b * gamma[e] + beta[e]);  4 elements per thread
+template <typename OutT>
+__global__ void __launch_bounds__(256) ln_apply_kernel(const float *Y, const float2 *stats, const float *gamma,
+                                                       const float *beta, OutT *X, long long E) {
+    const long long b = blockIdx.y;
+    const float2 st = stats[b];
+    const long long e0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (e0 >= E) return;
+    const float *y = Y + b * E + e0;
+    OutT *x = X + b * E + e0;
+    if (e0 + 3 < E && (E & 3) == 0) {
+        const float4 v = *reinterpret_cast<const float4 *>(y);
+        const float4 g = __ldg(reinterpret_cast<const float4 *>(gamma + e0));
+        const float4 be = __ldg(reinterpret_cast<const float4 *>(beta + e0));
+        const float o0 = fmaxf(fmaf((v.x - st.x) * st.y, g.x, be.x), 0.f);
+        const float o1 = fmaxf(fmaf((v.y - st.x) * st.y, g.y, be.y), 0.f);
+        const float o2 = fmaxf(fmaf((v.z - st.x) * st.y, g.z, be.z), 0.f);
+        const float o3 = fmaxf(fmaf((v.w - st.x) * st.y, g.w, be.w), 0.f);
+        if (sizeof(OutT) == 4) {
+            *reinterpret_cast<float4 *>(x) = make_float4(o0, o1, o2, o3);
+        } else {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(o0, o1), p1 = __floats2bfloat162_rn(o2, o3);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t *>(&p0);
+            pk.y = *reinterpret_cast<uint32_t *>(&p1);
+            *reinterpret_cast<uint2 *>(x) = pk;
+        }
+    } else {
+        for (int i = 0; i < 4 && e0 + i < E; i++)
+            store_out(x + i, fmaxf(fmaf((y[i] - st.x) * st.y, __ldg(gamma + e0 + i), __ldg(beta + e0 + i)), 0.f));
+    }
+}
+
+// fp32 -> bf16 cast of the mel input for the tensor-core path is not needed (layer 0 conv1 has C_in = 1
+// and runs on CUDA cores in both paths).
+
+// channels-last [b][f][t][c] -> NCHW fp32 [b][c][f][t] (debug / parity taps only)
+template <typename InT>
+__global__ void to_nchw_kernel(const InT *X, float *out, long long total, int C, int F, int T) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int t = (int)(i % T);
+    long long r = i / T;
+    const int f = (int)(r % F);
+    r /= F;
+    const int c = (int)(r % C);
+    const long long b = r / C;
+    out[i] = (float)X[((b * F + f) * T + t) * (long long)C + c];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Head: last LN-apply + ReLU, grouped h -> d*u, ELU, grouped d*u -> d, optional L2 normalise
+// (model.py:122-130).  One CTA per sample, one thread per output dimension g.
+// ------------------------------------------------------------------------------------------------
+__global__ void head_kernel(const float *Y /*[nb][h]*/, const float2 *stats, const float *gamma, const float *beta,
+                            const float *w1, const float *b1, const float *w2, const float *b2, float *z, int d,
+                            int h, int u, int norm) {
+    extern __shared__ float hs[];  // [h] + [32]
+    float *red = hs + h;
+    const long long b = blockIdx.x;
+    const float2 st = stats[b];
+    for (int i = threadIdx.x; i < h; i += blockDim.x)
+        hs[i] = fmaxf(fmaf((Y[b * h + i] - st.x) * st.y, __ldg(gamma + i), __ldg(beta + i)), 0.f);
+    __syncthreads();
+    const int g = threadIdx.x, v = h / d;
+    float out = 0.f;
+    if (g < d) {
+        out = __ldg(b2 + g);
+        for (int j = 0; j < u; j++) {
+            float acc = __ldg(b1 + g * u + j);
+            const float *w = w1 + (long long)(g * u + j) * v;
+            for (int i = 0; i < v; i++) acc = fmaf(__ldg(w + i), hs[g * v + i], acc);
+            const float e = acc > 0.f ? acc : expm1f(acc);  // ELU(alpha = 1)
+            out = fmaf(__ldg(w2 + g * u + j), e, out);
+        }
+    }
+    if (norm) {
+        float s = g < d ? out * out : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+        __syncthreads();
+        float t = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += red[i];
+        out = out / fmaxf(sqrtf(t), 1e-12f);  // F.normalize(p=2, eps=1e-12)
+    }
+    if (g < d) z[b * d + g] = out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+int upload(const std::vector<float> &v, float **dst) {
+    PF_CUDA(cudaMalloc(dst, sizeof(float) * (v.size() ? v.size() : 1)));
+    PF_CUDA(cudaMemcpy(*dst, v.data(), sizeof(float) * v.size(), cudaMemcpyHostToDevice));
+    return PFANN_OK;
+}
+
+int upload_bf16(const std::vector<float> &v, __nv_bfloat16 **dst) {
+    std::vector<__nv_bfloat16> t(v.size());
+    for (size_t i = 0; i < v.size(); i++) t[i] = __float2bfloat16_rn(v[i]);
+    PF_CUDA(cudaMalloc(dst, sizeof(__nv_bfloat16) * (v.size() ? v.size() : 1)));
+    PF_CUDA(cudaMemcpy(*dst, t.data(), sizeof(__nv_bfloat16) * v.size(), cudaMemcpyHostToDevice));
+    return PFANN_OK;
+}
+
+void free_conv(ConvWeights &c) {
+    cudaFree(c.w_kn);
+    cudaFree(c.w_nk);
+    cudaFree(c.bias);
+    cudaFree(c.gamma);
+    cudaFree(c.beta);
+    c = ConvWeights();
+}
+
+// live taps of a k=3, stride-2 "same" convolution over an axis of length n (model.py:18-19)
+void live_taps(int n, int *ntaps, int *tap_k, int *tap_off) {
+    const int k = 3, s = 2;
+    const int no = (n - 1) / s + 1;
+    const int pad = (n - 1) / s * s + k - n, padl = pad / 2;
+    *ntaps = 0;
+    for (int j = 0; j < k; j++) {
+        bool live = false;
+        for (int o = 0; o < no && !live; o++) {
+            const int i = o * s + j - padl;
+            live = (i >= 0 && i < n);
+        }
+        if (live) {
+            tap_k[*ntaps] = j;
+            tap_off[*ntaps] = j - padl;
+            (*ntaps)++;
+        }
+    }
+}
+
+const std::vector<float> *find_param(Model *m, const std::string &key, size_t numel) {
+    auto it = m->host.find(key);
+    if (it == m->host.end()) {
+        set_error("pfann_model_finalize: parameter '%s' was never set", key.c_str());
+        return nullptr;
+    }
+    if (it->second.size() != numel) {
+        set_error("pfann_model_finalize: parameter '%s' has %zu elements, expected %zu", key.c_str(),
+                  it->second.size(), numel);
+        return nullptr;
+    }
+    return &it->second;
+}
+
+int finalize_conv(Model *m, int l, int which, const ConvGeom &g) {
+    ConvWeights &cw = m->conv[2 * l + which];
+    free_conv(cw);
+    cw.g = g;
+    char key[64];
+    const char *cn = which == 0 ? "conv1" : "conv2", *ln = which == 0 ? "ln1" : "ln2";
+    const int cin_w = g.depthwise ? 1 : g.Ci;
+    snprintf(key, sizeof key, "f.convs.%d.%s.weight", l, cn);
+    const std::vector<float> *w = find_param(m, key, (size_t)g.Co * cin_w * 3);
+    snprintf(key, sizeof key, "f.convs.%d.%s.bias", l, cn);
+    const std::vector<float> *b = find_param(m, key, (size_t)g.Co);
+    snprintf(key, sizeof key, "f.convs.%d.%s.weight", l, ln);
+    const std::vector<float> *ga = find_param(m, key, (size_t)g.Co * g.Fo * g.To);
+    snprintf(key, sizeof key, "f.convs.%d.%s.bias", l, ln);
+    const std::vector<float> *be = find_param(m, key, (size_t)g.Co * g.Fo * g.To);
+    if (!w || !b || !ga || !be) return PFANN_ERR_STATE;
+    // reference weight element order: [Co][Cin][kh][kw] with exactly one of kh/kw == 3 -> [Co][Cin][3]
+    if (g.depthwise) {
+        std::vector<float> t((size_t)g.Co * g.ntaps);
+        for (int o = 0; o < g.Co; o++)
+            for (int j = 0; j < g.ntaps; j++) t[(size_t)o * g.ntaps + j] = (*w)[(size_t)o * 3 + g.tap_k[j]];
+        PF_TRY(upload(t, &cw.w_kn));
+    } else {
+        const int K = g.K();
+        std::vector<float> kn((size_t)K * g.Co), nk((size_t)K * g.Co);
+        for (int o = 0; o < g.Co; o++)
+            for (int j = 0; j < g.ntaps; j++)
+                for (int c = 0; c < g.Ci; c++) {
+                    const float v = (*w)[((size_t)o * g.Ci + c) * 3 + g.tap_k[j]];
+                    kn[(size_t)(j * g.Ci + c) * g.Co + o] = v;
+                    nk[(size_t)o * K + j * g.Ci + c] = v;
+                }
+        PF_TRY(upload(kn, &cw.w_kn));
+        if (m->precision == PFANN_PRECISION_BF16) PF_TRY(upload_bf16(nk, &cw.w_nk));
+    }
+    PF_TRY(upload(*b, &cw.bias));
+    // LayerNorm affine [Co][Fo][To] -> channels-last [Fo][To][Co]
+    std::vector<float> gp(ga->size()), bp(be->size());
+    for (int o = 0; o < g.Co; o++)
+        for (int f = 0; f < g.Fo; f++)
+            for (int t = 0; t < g.To; t++) {
+                const size_t src = ((size_t)o * g.Fo + f) * g.To + t, dst = ((size_t)f * g.To + t) * g.Co + o;
+                gp[dst] = (*ga)[src];
+                bp[dst] = (*be)[src];
+            }
+    PF_TRY(upload(gp, &cw.gamma));
+    PF_TRY(upload(bp, &cw.beta));
+    return PFANN_OK;
+}
+
+template <typename InT>
+int launch_conv_fp32(Model *m, const ConvWeights &cw, const InT *X, float *Y, int nb) {
+    const ConvGeom &g = cw.g;
+    cudaStream_t st = m->ctx->stream;
+    if (g.depthwise) {
+        const long long total = (long long)nb * g.out_per_sample();
+        conv_dw_kernel<InT><<<cdiv(total, 256), 256, 0, st>>>(X, cw.w_kn, cw.bias, Y, total, g.Co, g.Fi, g.Ti, g.Fo,
+                                                                 g.To, g.ntaps, g.tap_off[0], g.tap_off[1],
+                                                                 g.tap_off[2]);
+    } else {
+        ConvArgs<InT> a;
+        a.X = X; a.W = cw.w_kn; a.bias = cw.bias; a.Y = Y;
+        a.M = (long long)nb * g.rows_per_sample();
+        a.Ci = g.Ci; a.Co = g.Co; a.Fi = g.Fi; a.Ti = g.Ti; a.Fo = g.Fo; a.To = g.To;
+        a.axis = g.axis; a.ntaps = g.ntaps; a.K = g.K();
+        for (int j = 0; j < 3; j++) a.off[j] = g.tap_off[j];
+        dim3 grid(cdiv(a.M, BM), cdiv(g.Co, BN));
+        conv_gemm_fp32_kernel<InT><<<grid, 256, 0, st>>>(a);
+    }
+    m->ctx->launches++;
+    PF_CUDA(cudaGetLastError());
+    return PFANN_OK;
+}
+
+template <typename OutT>
+int launch_ln_apply(Model *m, const ConvWeights &cw, const float *Y, OutT *X, int nb) {
+    const long long E = cw.g.out_per_sample();
+    dim3 grid(cdiv(E, 1024), nb);
+    ln_apply_kernel<OutT><<<grid, 256, 0, m->ctx->stream>>>(Y, m->stats.as<float2>(), cw.gamma, cw.beta, X, E);
+    m->ctx->launches++;
+    PF_CUDA(cudaGetLastError());
+    return PFANN_OK;
+}
+
+int launch_stats(Model *m, const ConvWeights &cw, const float *Y, int nb) {
+    ln_stats_kernel<<<nb, 512, 0, m->ctx->stream>>>(Y, cw.g.out_per_sample(), m->stats.as<float2>());
+    m->ctx->launches++;
+    PF_CUDA(cudaGetLastError());
+    return PFANN_OK;
+}
+
+template <typename ActT>
+int save_tap(Model *m, int l, const ActT *X, int nb) {
+    if (m->tap_layer != l) return PFANN_OK;
+    const ConvGeom &g = m->conv[2 * l + 1].g;
+    const long long total = (long long)nb * g.out_per_sample();
+    PF_TRY(m->tapbuf.ensure((size_t)total * 4));
+    to_nchw_kernel<ActT><<<cdiv(total, 256), 256, 0, m->ctx->stream>>>(X, m->tapbuf.as<float>(), total, g.Co, g.Fo,
+                                                                        g.To);
+    m->ctx->launches++;
+    PF_CUDA(cudaGetLastError());
+    m->tap_numel = total;
+    return PFANN_OK;
+}
+
+// one chunk of nb <= m->chunk samples through the 8 layers + head
+template <typename ActT>
+int forward_chunk(Model *m, const float *mel, int nb, int norm, float *z) {
+    const bool tc = (sizeof(ActT) == 2);
+    float *Y = m->ybuf.as<float>();
+    ActT *xa = m->xa.as<ActT>(), *xb = m->xb.as<ActT>();
+    for (int l = 0; l < 8; l++) {
+        for (int which = 0; which < 2; which++) {
+            const ConvWeights &cw = m->conv[2 * l + which];
+            const bool first = (l == 0 && which == 0);
+            bool stats_done = false;
+            if (first) {
+                // layer 0 conv1: C_in = 1, K = 3 -- CUDA cores in both paths, reads the fp32 mel directly
+                PF_TRY(launch_conv_fp32<float>(m, cw, mel, Y, nb));
+            } else {
+                const ActT *in = which == 0 ? xb : xa;
+                if (tc && tc_supported(cw.g)) {
+                    PF_TRY(tc_conv(m, 2 * l + which, reinterpret_cast<const __nv_bfloat16 *>(in), Y, nb));
+                    stats_done = true;  // statistics come out of the GEMM epilogue
+                } else {
+                    // depthwise conv2 (fuller == false) and geometries without a tensor-core mapping
+                    PF_TRY(launch_conv_fp32<ActT>(m, cw, in, Y, nb));
+                }
+            }
+            if (!stats_done) PF_TRY(launch_stats(m, cw, Y, nb));
+            if (l == 7 && which == 1) break;  // the head applies the last LayerNorm itself
+            PF_TRY(launch_ln_apply<ActT>(m, cw, Y, which == 0 ? xa : xb, nb));
+            if (which == 1) PF_TRY(save_tap<ActT>(m, l, xb, nb));
+        }
+    }
+    const ConvWeights &last = m->conv[15];
+    if (m->tap_layer == 7) {
+        // materialise the layer-7 output only when asked for
+        PF_TRY(launch_ln_apply<ActT>(m, last, Y, xb, nb));
+        PF_TRY(save_tap<ActT>(m, 7, xb, nb));
+    }
+    const int threads = ((m->d + 31) / 32) * 32;
+    head_kernel<<<nb, threads, (m->h + 32) * sizeof(float), m->ctx->stream>>>(
+        Y, m->stats.as<float2>(), last.gamma, last.beta, m->w1, m->b1, m->w2, m->b2, z, m->d, m->h, m->u, norm);
+    m->ctx->launches++;
+    PF_CUDA(cudaGetLastError());
+    return PFANN_OK;
+}
+
+int ensure_workspace(Model *m) {
+    long long maxY = 0, maxA = 0, maxB = 0;
+    for (int i = 0; i < 16; i++) {
+        const long long e = m->conv[i].g.out_per_sample();
+        if (e > maxY) maxY = e;
+        if ((i & 1) == 0 && e > maxA) maxA = e;
+        if ((i & 1) == 1 && e > maxB) maxB = e;
+    }
+    const size_t act = m->precision == PFANN_PRECISION_BF16 ? 2 : 4;
+    PF_TRY(m->ybuf.ensure((size_t)maxY * m->chunk * 4));
+    PF_TRY(m->xa.ensure((size_t)maxA * m->chunk * act));
+    PF_TRY(m->xb.ensure((size_t)maxB * m->chunk * act));
+    PF_TRY(m->stats.ensure((size_t)m->chunk * sizeof(float2)));
+    return PFANN_OK;
+}
+
+}  // namespace
+
+namespace pfann {
+
+// device-pointer forward used by the C-ABI wrappers and by extract.cu
+int model_forward_dev(Model *m, const float *mel, int64_t B, int norm, float *z) {
+    PF_CHECK(m->precision >= 0, PFANN_ERR_STATE, "pfann_model_forward: call pfann_model_finalize first");
+    PF_TRY(ensure_workspace(m));
+    const long long mel_per = (long long)m->F * m->T;
+    for (int64_t b0 = 0; b0 < B; b0 += m->chunk) {
+        const int nb = (int)((B - b0) < m->chunk ? (B - b0) : m->chunk);
+        if (m->precision == PFANN_PRECISION_BF16)
+            PF_TRY(forward_chunk<__nv_bfloat16>(m, mel + b0 * mel_per, nb, norm, z + b0 * m->d));
+        else
+            PF_TRY(forward_chunk<float>(m, mel + b0 * mel_per, nb, norm, z + b0 * m->d));
+    }
+    return PFANN_OK;
+}
+
+}  // namespace pfann
+
+extern "C" {
+
+int pfann_model_create(pfann_ctx *hctx, int d, int h, int u, int F, int T, int fuller, pfann_model **out) {
+    PF_CHECK(hctx && out, PFANN_ERR_ARG, "pfann_model_create: NULL argument");
+    PF_CHECK(d > 0 && h > 0 && u > 0 && F > 0 && T > 0, PFANN_ERR_ARG, "pfann_model_create: bad dimensions");
+    PF_CHECK(h % d == 0, PFANN_ERR_ARG, "h must be divisible by d");  // model.py:112
+    PF_CHECK(d <= 1024, PFANN_ERR_UNSUPPORTED, "pfann_model_create: d > 1024 unsupported");
+    int f = F, t = T;
+    for (int i = 0; i < 8; i++) {
+        f = (f - 1) / 2 + 1;
+        t = (t - 1) / 2 + 1;
+    }
+    PF_CHECK(f == 1 && t == 1, PFANN_ERR_ARG, "output must be 1x1");  // model.py:94
+    Model *m = new Model();
+    m->ctx = reinterpret_cast<Ctx *>(hctx);
+    m->d = d; m->h = h; m->u = u; m->F = F; m->T = T;
+    m->fuller = fuller != 0;
+    *out = reinterpret_cast<pfann_model *>(m);
+    return PFANN_OK;
+}
+
+void pfann_model_destroy(pfann_model *hm) {
+    Model *m = reinterpret_cast<Model *>(hm);
+    if (!m) return;
+    cudaSetDevice(m->ctx->device);
+    tc_release(m);
+    for (int i = 0; i < 16; i++) free_conv(m->conv[i]);
+    cudaFree(m->w1); cudaFree(m->b1); cudaFree(m->w2); cudaFree(m->b2);
+    m->ybuf.release(); m->xa.release(); m->xb.release(); m->stats.release(); m->partials.release();
+    m->tapbuf.release(); m->melbuf.release(); m->zbuf.release();
+    delete m;
+}
+
+int pfann_model_set_param(pfann_model *hm, const char *name, const float *data, int64_t numel) {
+    PF_CHECK(hm && name && data && numel >= 0, PFANN_ERR_ARG, "pfann_model_set_param: bad argument");
+    Model *m = reinterpret_cast<Model *>(hm);
+    std::vector<float> v((size_t)numel);
+    if (is_device_ptr(data)) {
+        PF_CUDA(cudaSetDevice(m->ctx->device));
+        PF_CUDA(cudaMemcpy(v.data(), data, sizeof(float) * numel, cudaMemcpyDeviceToHost));
+    } else {
+        memcpy(v.data(), data, sizeof(float) * numel);
+    }
+    m->host[name] = std::move(v);
+    m->precision = -1;  // needs (re)finalize
+    return PFANN_OK;
+}
+
+int pfann_model_finalize(pfann_model *hm, int precision) {
+    PF_CHECK(hm, PFANN_ERR_ARG, "pfann_model_finalize: NULL model");
+    PF_CHECK(precision == PFANN_PRECISION_FP32 || precision == PFANN_PRECISION_BF16, PFANN_ERR_ARG,
+             "pfann_model_finalize: unknown precision %d", precision);
+    Model *m = reinterpret_cast<Model *>(hm);
+    PF_CUDA(cudaSetDevice(m->ctx->device));
+    tc_release(m);
+    m->precision = precision;
+    const int ch[9] = {1, m->d, m->d, 2 * m->d, 2 * m->d, 4 * m->d, 4 * m->d, m->h, m->h};
+    int F = m->F, T = m->T;
+    for (int l = 0; l < 8; l++) {
+        const int F2 = (F - 1) / 2 + 1, T2 = (T - 1) / 2 + 1;
+        ConvGeom g1 = {};
+        g1.Ci = ch[l]; g1.Co = ch[l + 1]; g1.Fi = F; g1.Ti = T; g1.Fo = F; g1.To = T2; g1.axis = 0;
+        g1.depthwise = false;
+        live_taps(T, &g1.ntaps, g1.tap_k, g1.tap_off);
+        ConvGeom g2 = {};
+        g2.Ci = ch[l + 1]; g2.Co = ch[l + 1]; g2.Fi = F; g2.Ti = T2; g2.Fo = F2; g2.To = T2; g2.axis = 1;
+        g2.depthwise = !m->fuller;
+        live_taps(F, &g2.ntaps, g2.tap_k, g2.tap_off);
+        int rc = finalize_conv(m, l, 0, g1);
+        if (rc == PFANN_OK) rc = finalize_conv(m, l, 1, g2);
+        if (rc != PFANN_OK) {
+            m->precision = -1;
+            return rc;
+        }
+        F = F2; T = T2;
+    }
+    const int v = m->h / m->d;
+    const std::vector<float> *w1 = find_param(m, "g.linear1.weight", (size_t)m->d * m->u * v);
+    const std::vector<float> *b1 = find_param(m, "g.linear1.bias", (size_t)m->d * m->u);
+    const std::vector<float> *w2 = find_param(m, "g.linear2.weight", (size_t)m->d * m->u);
+    const std::vector<float> *b2 = find_param(m, "g.linear2.bias", (size_t)m->d);
+    if (!w1 || !b1 || !w2 || !b2) {
+        m->precision = -1;
+        return PFANN_ERR_STATE;
+    }
+    cudaFree(m->w1); cudaFree(m->b1); cudaFree(m->w2); cudaFree(m->b2);
+    PF_TRY(upload(*w1, &m->w1));
+    PF_TRY(upload(*b1, &m->b1));
+    PF_TRY(upload(*w2, &m->w2));
+    PF_TRY(upload(*b2, &m->b2));
+    if (precision == PFANN_PRECISION_BF16) {
+        int rc = tc_prepare(m);
+        if (rc != PFANN_OK) {
+            m->precision = -1;
+            return rc;
+        }
+    }
+    return PFANN_OK;
+}
+
+int pfann_model_set_chunk(pfann_model *hm, int chunk) {
+    PF_CHECK(hm && chunk > 0 && chunk <= 65535, PFANN_ERR_ARG, "pfann_model_set_chunk: chunk must be in 1..65535");
+    Model *m = reinterpret_cast<Model *>(hm);
+    m->chunk = chunk;
+    if (m->precision == PFANN_PRECISION_BF16) {
+        tc_release(m);
+        return tc_prepare(m);
+    }
+    return PFANN_OK;
+}
+
+int pfann_model_set_tap(pfann_model *hm, int layer) {
+    PF_CHECK(hm && layer >= -1 && layer < 8, PFANN_ERR_ARG, "pfann_model_set_tap: layer must be -1..7");
+    reinterpret_cast<Model *>(hm)->tap_layer = layer;
+    return PFANN_OK;
+}
+
+int pfann_model_forward(pfann_model *hm, const float *mel, int64_t B, int norm, float *z) {
+    PF_CHECK(hm && B >= 0 && (B == 0 || (mel && z)), PFANN_ERR_ARG, "pfann_model_forward: bad argument");
+    Model *m = reinterpret_cast<Model *>(hm);
+    if (B == 0) return PFANN_OK;
+    PF_CUDA(cudaSetDevice(m->ctx->device));
+    const size_t in_b = (size_t)B * m->F * m->T * 4, out_b = (size_t)B * m->d * 4;
+    const void *xd;
+    void *zd;
+    PF_TRY(stage_input(m->ctx, 0, mel, in_b, &xd));
+    PF_TRY(stage_output(m->ctx, 0, z, out_b, &zd));
+    PF_TRY(model_forward_dev(m, (const float *)xd, B, norm, (float *)zd));
+    return finish_output(m->ctx, 0, z, out_b);
+}
+
+int pfann_model_get_activation(pfann_model *hm, int layer, float *out, int64_t numel) {
+    PF_CHECK(hm && out, PFANN_ERR_ARG, "pfann_model_get_activation: NULL argument");
+    Model *m = reinterpret_cast<Model *>(hm);
+    PF_CHECK(layer == m->tap_layer && m->tap_numel > 0, PFANN_ERR_STATE,
+             "pfann_model_get_activation: layer %d was not tapped (pfann_model_set_tap before forward)", layer);
+    PF_CHECK(numel == m->tap_numel, PFANN_ERR_ARG, "pfann_model_get_activation: expected %lld elements, got %lld",
+             m->tap_numel, (long long)numel);
+    PF_CUDA(cudaSetDevice(m->ctx->device));
+    PF_CUDA(cudaMemcpyAsync(out, m->tapbuf.p, (size_t)numel * 4, cudaMemcpyDefault, m->ctx->stream));
+    PF_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    return PFANN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,65 @@
+// encoder.cuh -- stage 2 data structures shared by encoder.cu (pipeline + CUDA-core kernels) and
+// encoder_tc.cu (tcgen05 tensor-core convolution GEMMs).
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace pfann {
+
+// Activations are channels-last: X[b][f][t][c].  A convolution of the reference's SeparableConv2d
+// (model.py:54-73) is then a GEMM  Y[m][n] = sum_kk A[m][kk] W[kk][n] + bias[n]  with
+//   m  = (b, fo, to)  flattened output position,   n = output channel,
+//   kk = (live tap j, input channel c);  A[m][(j,c)] = X[b][fi][ti][c]  (zero outside the input)
+//   axis 0 (conv1, 1x3 along time, stride 2):  fi = fo,           ti = 2 to + off[j]
+//   axis 1 (conv2, 3x1 along freq, stride 2):  fi = 2 fo + off[j], ti = to
+// off[j] = k_j - pad_left for the TF-"same" padding of model.py:18-19,24-25.  Taps that only ever read
+// padding (e.g. two of three when the axis has length 1) are dropped at finalize time.
+struct ConvGeom {
+    int Ci, Co;          // input / output channels
+    int Fi, Ti, Fo, To;  // input / output spatial extent
+    int axis;            // 0 = along T, 1 = along F
+    int ntaps;           // live taps
+    int tap_k[3];        // original kernel index of live tap j
+    int tap_off[3];      // input offset of live tap j
+    bool depthwise;      // conv2 with fuller == false (groups = C, model.py:29)
+    long long rows_per_sample() const { return (long long)Fo * To; }
+    long long out_per_sample() const { return (long long)Fo * To * Co; }
+    int K() const { return ntaps * Ci; }
+};
+
+struct ConvWeights {
+    ConvGeom g;
+    float *w_kn = nullptr;           // fp32 [K][Co]   (CUDA-core path); depthwise: [Co][ntaps]
+    __nv_bfloat16 *w_nk = nullptr;   // bf16 [Co][K]   (tensor-core path, K-major)
+    float *bias = nullptr;           // [Co]
+    float *gamma = nullptr;          // LayerNorm affine permuted to channels-last [Fo][To][Co]
+    float *beta = nullptr;
+};
+
+struct Model {
+    Ctx *ctx;
+    int d, h, u, F, T;
+    bool fuller;
+    int precision = -1;
+    int chunk = 256;
+    std::map<std::string, std::vector<float>> host;  // reference-keyed fp32 parameters (as given)
+    ConvWeights conv[16];                            // conv[2l] = conv1 of layer l, conv[2l+1] = conv2
+    float *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;  // head (model.py:118-120)
+    DevBuf ybuf, xa, xb, stats, partials, tapbuf, melbuf, zbuf;
+    int tap_layer = -1;
+    long long tap_numel = 0;
+    void *tc_state = nullptr;  // tensor maps etc., owned by encoder_tc.cu
+};
+
+// encoder_tc.cu
+int tc_prepare(Model *m);                      // build per-layer state after weights are on the device
+void tc_release(Model *m);
+bool tc_supported(const ConvGeom &g);
+// Y[m][n] (fp32) = conv GEMM of X (bf16, channels-last) for `nb` samples; also writes per-sample
+// LayerNorm partial sums into m->partials and reduces them into m->stats (mean, rstd).
+int tc_conv(Model *m, int idx, const __nv_bfloat16 *X, float *Y, int nb);
+
+}  // namespace pfann

@@ -1,0 +1,503 @@
+// knn.cu -- stage 3a: brute-force inner-product top-k over the HBM-resident fingerprint database.
+//
+// Replaces faiss IndexFlatIP.search as called from database.py:121,172.  Structure (per group of queries):
+//   1. threshold pre-pass: scan a sample of rows, take the k-th best sample score per query.  That is a
+//      LOWER bound of the global k-th best score, so (minus the scan's error bound) it is a safe filter;
+//   2. one streaming scan of the whole shard (tcgen05 bf16 GEMM in knn_tc.cu, or the fp32 CUDA-core kernel
+//      below): rows whose approximate score passes the filter are appended to a per-query candidate list;
+//   3. select: every candidate is re-scored EXACTLY in fp32 with the canonical k-sequential fused
+//      multiply-add (bit-identical to the oracle), the list is bitonic-sorted by (score desc, id asc) and the
+//      first k are emitted.  Overflowing lists tighten the threshold from their own exact scores and rescan;
+//      a brute-force exact kernel is the backstop for degenerate inputs (all-equal rows etc.).
+// The result therefore does not depend on the precision of the scan: labels and distances are those of an
+// exact fp32 search.
+#include <float.h>
+#include <math.h>
+#include <string.h>
+
+#include "db.cuh"
+#include "pfann_b200.h"
+
+using namespace pfann;
+
+namespace {
+
+constexpr int QG = 32;        // queries per CUDA-core scan pass
+constexpr int SCAN_ROWS = 64; // rows per smem tile
+constexpr int SCAN_THREADS = 256;
+
+// ---- fp32 CUDA-core scan ---------------------------------------------------------------------------
+// grid.x = row tiles (grid-stride), 256 threads; thread -> (row r = tid % 64, query octet qs = tid / 64)
+__global__ void __launch_bounds__(SCAN_THREADS) knn_scan_fp32_kernel(
+    const float *__restrict__ db, int64_t r0, int64_t r1, int d, const float *__restrict__ q, int Qg, int mode,
+    float *sample, int64_t sample_ld, const float *__restrict__ thr, int *cnt, uint32_t *cand, int cap) {
+    extern __shared__ __align__(16) float sm[];
+    const int ldr = d + 4;                 // padded row stride (16-byte aligned, conflict-free for float4)
+    float *qs_ = sm;                       // [QG][d]
+    float *rows = sm + QG * d;             // [SCAN_ROWS][ldr]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < QG * d; i += SCAN_THREADS) qs_[i] = (i < Qg * d) ? q[i] : 0.f;
+    const int r = tid & (SCAN_ROWS - 1), qo = (tid >> 6) * 8;
+    const int64_t ntiles = (r1 - r0 + SCAN_ROWS - 1) / SCAN_ROWS;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t base = r0 + tile * SCAN_ROWS;
+        __syncthreads();
+        // coalesced tile load: SCAN_ROWS x d floats
+        const int nvec = SCAN_ROWS * d / 4;
+        for (int i = tid; i < nvec; i += SCAN_THREADS) {
+            const int rr = (i * 4) / d, cc = (i * 4) - rr * d;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (base + rr < r1) v = __ldg(reinterpret_cast<const float4 *>(db + (base + rr) * d + cc));
+            *reinterpret_cast<float4 *>(rows + rr * ldr + cc) = v;
+        }
+        __syncthreads();
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j] = 0.f;
+        const float *xr = rows + r * ldr;
+        for (int k = 0; k < d; k += 4) {
+            const float4 x = *reinterpret_cast<const float4 *>(xr + k);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float4 w = *reinterpret_cast<const float4 *>(qs_ + (qo + j) * d + k);
+                acc[j] = fmaf(x.x, w.x, acc[j]);
+                acc[j] = fmaf(x.y, w.y, acc[j]);
+                acc[j] = fmaf(x.z, w.z, acc[j]);
+                acc[j] = fmaf(x.w, w.w, acc[j]);
+            }
+        }
+        const int64_t row = base + r;
+        if (row < r1) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int qi = qo + j;
+                if (qi >= Qg) break;
+                if (mode == 0) {
+                    sample[qi * sample_ld + (row - r0)] = acc[j];
+                } else if (acc[j] >= thr[qi]) {
+                    const int pos = atomicAdd(cnt + qi, 1);
+                    if (pos < cap) cand[(int64_t)qi * cap + pos] = (uint32_t)row;
+                }
+            }
+        }
+    }
+}
+
+// ---- per-query threshold from the sample scores ---------------------------------------------------------
+// thr[q] = (k-th best sample score) - 2*eps*|q|*max_norm ; -inf when the sample has fewer than k rows.
+// Also writes qnorm[q].
+__global__ void __launch_bounds__(256) knn_kth_kernel(const float *sample, int64_t sample_ld, int S, int Spad,
+                                                      const float *q, int d, int k, float eps_rel, float max_norm,
+                                                      float *thr, float *qnorm) {
+    extern __shared__ uint32_t keys[];  // [Spad]
+    __shared__ float red[8];
+    const int qi = blockIdx.x;
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) ss = fmaf(q[qi * d + i], q[qi * d + i], ss);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    for (int i = threadIdx.x; i < Spad; i += blockDim.x) keys[i] = i < S ? flipf(sample[qi * sample_ld + i]) : 0u;
+    __syncthreads();
+    float tot = 0.f;
+    for (int i = 0; i < 8; i++) tot += red[i];
+    const float qn = sqrtf(tot);
+    bitonic_sort<uint32_t, true>(keys, Spad);
+    if (threadIdx.x == 0) {
+        qnorm[qi] = qn;
+        thr[qi] = (S >= k) ? unflipf(keys[k - 1]) - 2.f * eps_rel * qn * max_norm : -INFINITY;
+    }
+}
+
+// ---- select: exact rescoring + sort + emit --------------------------------------------------------------
+// flags[0] += 1 for every query whose candidate list overflowed (its threshold is tightened in place).
+__global__ void __launch_bounds__(256) knn_select_kernel(const float *__restrict__ db, int d, int64_t id_base,
+                                                         const float *__restrict__ q, const int *cnt,
+                                                         const uint32_t *cand, int cap, int k, float eps_rel,
+                                                         float max_norm, const float *qnorm, float *thr,
+                                                         float *dist, int64_t *labels, int *flags) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smraw);  // [cap]
+    float *qv = reinterpret_cast<float *>(keys + cap);                         // [d]
+    const int qi = blockIdx.x;
+    const int total = cnt[qi];
+    const int n = total < cap ? total : cap;
+    int P = 1;
+    while (P < n) P <<= 1;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) qv[i] = q[(int64_t)qi * d + i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        unsigned long long key = 0ull;
+        if (i < n) {
+            const uint32_t id = cand[(int64_t)qi * cap + i];
+            const float s = dot_fma_seq(db + (int64_t)id * d, qv, d);
+            key = ((unsigned long long)flipf(s) << 32) | (unsigned long long)(0xFFFFFFFFu - id);
+        }
+        keys[i] = key;
+    }
+    bitonic_sort<unsigned long long, true>(keys, P);
+    if (total > cap) {
+        // overflow: the stored subset still bounds the true k-th score from below (exact scores)
+        if (threadIdx.x == 0) {
+            atomicAdd(flags, 1);
+            if (n >= k) thr[qi] = fmaxf(thr[qi], unflipf((uint32_t)(keys[k - 1] >> 32)) - eps_rel * qnorm[qi] * max_norm);
+        }
+        return;
+    }
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        if (j < n) {
+            dist[(int64_t)qi * k + j] = unflipf((uint32_t)(keys[j] >> 32));
+            labels[(int64_t)qi * k + j] = id_base + (int64_t)(0xFFFFFFFFu - (uint32_t)(keys[j] & 0xFFFFFFFFull));
+        } else {
+            dist[(int64_t)qi * k + j] = -FLT_MAX;
+            labels[(int64_t)qi * k + j] = -1;
+        }
+    }
+}
+
+// ---- backstop: exact brute force, one CTA per query (degenerate inputs only) ------------------------------
+__global__ void __launch_bounds__(256) knn_exact_kernel(const float *__restrict__ db, int64_t n, int d,
+                                                        int64_t id_base, const float *__restrict__ q, int k,
+                                                        float *dist, int64_t *labels) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    unsigned long long *best = reinterpret_cast<unsigned long long *>(smraw);  // [k] sorted descending
+    unsigned long long *batch = best + k;                                      // [256]
+    float *qv = reinterpret_cast<float *>(batch + 256);                        // [d]
+    __shared__ int nbest;
+    const int qi = blockIdx.x;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) qv[i] = q[(int64_t)qi * d + i];
+    if (threadIdx.x == 0) nbest = 0;
+    __syncthreads();
+    for (int64_t r0 = 0; r0 < n; r0 += 256) {
+        const int64_t r = r0 + threadIdx.x;
+        unsigned long long key = 0ull;
+        if (r < n) {
+            const float s = dot_fma_seq(db + r * d, qv, d);
+            key = ((unsigned long long)flipf(s) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)r);
+        }
+        batch[threadIdx.x] = key;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int nb = nbest;
+            for (int i = 0; i < 256; i++) {
+                const unsigned long long kk = batch[i];
+                if (kk == 0ull) continue;
+                if (nb == k && kk <= best[k - 1]) continue;
+                int p = nb < k ? nb : k - 1;
+                while (p > 0 && best[p - 1] < kk) {
+                    best[p] = best[p - 1];
+                    p--;
+                }
+                best[p] = kk;
+                if (nb < k) nb++;
+            }
+            nbest = nb;
+        }
+        __syncthreads();
+    }
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        if (j < nbest) {
+            dist[(int64_t)qi * k + j] = unflipf((uint32_t)(best[j] >> 32));
+            labels[(int64_t)qi * k + j] = id_base + (int64_t)(0xFFFFFFFFu - (uint32_t)(best[j] & 0xFFFFFFFFull));
+        } else {
+            dist[(int64_t)qi * k + j] = -FLT_MAX;
+            labels[(int64_t)qi * k + j] = -1;
+        }
+    }
+}
+
+// ---- helpers ---------------------------------------------------------------------------------------------
+__global__ void row_norm_max_kernel(const float *db, int64_t n, int d, unsigned int *out) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float s = 0.f;
+    if (r < n)
+        for (int k = 0; k < d; k++) s = fmaf(db[r * d + k], db[r * d + k], s);
+    s = sqrtf(s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s = fmaxf(s, __shfl_xor_sync(0xffffffffu, s, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(s));  // non-negative floats order like uints
+}
+
+__global__ void to_bf16_kernel(const float *in, __nv_bfloat16 *out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __float2bfloat16_rn(in[i]);
+}
+
+__global__ void fill_empty_kernel(float *dist, int64_t *labels, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        dist[i] = -FLT_MAX;
+        labels[i] = -1;
+    }
+}
+
+// merge G gathered top-k lists: in [G][Q][k] -> out [Q][k]; (score desc, id asc); -1 labels sort last
+__global__ void topk_merge_kernel(const float *dist_g, const int64_t *labels_g, int G, int64_t Q, int k, int P,
+                                  float *dist, int64_t *labels) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    // 96-bit ordering (score, -id) does not fit a 64-bit key with int64 ids: sort indices by comparing pairs
+    float *s = reinterpret_cast<float *>(smraw);            // [P]
+    int64_t *id = reinterpret_cast<int64_t *>(s + P + (P & 1));  // [P]
+    const int64_t qi = blockIdx.x;
+    const int n = G * k;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        if (i < n) {
+            const int g = i / k, j = i - g * k;
+            s[i] = dist_g[((int64_t)g * Q + qi) * k + j];
+            id[i] = labels_g[((int64_t)g * Q + qi) * k + j];
+        } else {
+            s[i] = -FLT_MAX;
+            id[i] = -1;
+        }
+    }
+    // bitonic sort, descending by (valid, score, -id)
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < (P >> 1); i += blockDim.x) {
+                const int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+                const bool up = ((lo & size) == 0);
+                const float sa = s[lo], sb = s[hi];
+                const int64_t ia = id[lo], ib = id[hi];
+                // a_before_b: a should precede b in descending order
+                const bool a_valid = ia >= 0, b_valid = ib >= 0;
+                bool a_before_b;
+                if (a_valid != b_valid) a_before_b = a_valid;
+                else if (sa != sb) a_before_b = sa > sb;
+                else a_before_b = ia <= ib;
+                const bool swap = up ? !a_before_b : (a_before_b && !(sa == sb && ia == ib));
+                if (swap) {
+                    s[lo] = sb; s[hi] = sa;
+                    id[lo] = ib; id[hi] = ia;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        dist[qi * k + j] = s[j];
+        labels[qi * k + j] = id[j];
+    }
+}
+
+int scan(Db *db, bool tc, const float *q, int Qg, int64_t r0, int64_t r1, int mode, float *sample, int64_t sample_ld,
+         const float *thr, int *cnt, uint32_t *cand, int cap) {
+    if (tc) return knn_tc_scan(db, q, Qg, r0, r1, mode, sample, sample_ld, thr, cnt, cand, cap);
+    const int64_t ntiles = (r1 - r0 + SCAN_ROWS - 1) / SCAN_ROWS;
+    int64_t grid = (int64_t)db->ctx->sm_count * 4;
+    if (grid > ntiles) grid = ntiles;
+    const size_t smem = (size_t)(QG * db->d + SCAN_ROWS * (db->d + 4)) * 4;
+    for (int q0 = 0; q0 < Qg; q0 += QG) {
+        const int qn = (Qg - q0) < QG ? (Qg - q0) : QG;
+        knn_scan_fp32_kernel<<<(unsigned)grid, SCAN_THREADS, smem, db->ctx->stream>>>(
+            db->emb32, r0, r1, db->d, q + (int64_t)q0 * db->d, qn, mode, sample ? sample + q0 * sample_ld : nullptr,
+            sample_ld, thr ? thr + q0 : nullptr, cnt ? cnt + q0 : nullptr, cand ? cand + (int64_t)q0 * cap : nullptr,
+            cap);
+        db->ctx->launches++;
+    }
+    PF_CUDA(cudaGetLastError());
+    return PFANN_OK;
+}
+
+}  // namespace
+
+namespace pfann {
+
+int db_search_dev(Db *db, const float *q, int64_t Q, int k, float *dist, int64_t *labels) {
+    cudaStream_t st = db->ctx->stream;
+    if (Q == 0) return PFANN_OK;
+    if (db->n == 0) {
+        fill_empty_kernel<<<cdiv(Q * k, 256), 256, 0, st>>>(dist, labels, Q * k);
+        db->ctx->launches++;
+        PF_CUDA(cudaGetLastError());
+        return PFANN_OK;
+    }
+    const int d = db->d;
+    const bool tc = db->use_tc && db->tc_state != nullptr;
+    // |scan score - exact score| <= eps_rel * |q| * |x|: bf16 operand rounding 2^-8 (+ fp32 accumulation order)
+    const float eps_rel = (tc ? 4.0e-3f : 0.f) + fmaxf(1.0e-5f, 1.2e-7f * (float)d);
+    const int cap = db->cand_cap;
+    const int group = tc ? 128 : QG * 4;  // queries per database pass
+    int S = (int)(db->n < db->sample_rows ? db->n : db->sample_rows);
+    if (S > 8192) S = 8192;               // kth-select sorts the sample in shared memory
+    int Spad = 1;
+    while (Spad < S) Spad <<= 1;
+    PF_TRY(db->thr.ensure(sizeof(float) * group));
+    PF_TRY(db->qnorm.ensure(sizeof(float) * group));
+    PF_TRY(db->cnt.ensure(sizeof(int) * group));
+    PF_TRY(db->cand.ensure(sizeof(uint32_t) * (size_t)group * cap));
+    PF_TRY(db->sample.ensure(sizeof(float) * (size_t)group * S));
+    PF_TRY(db->flags.ensure(sizeof(int) * 4));
+    const size_t sel_smem = (size_t)cap * 8 + (size_t)d * 4;
+    PF_CUDA(cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
+    PF_CUDA(cudaFuncSetAttribute(knn_scan_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)((QG * d + SCAN_ROWS * (d + 4)) * 4)));
+    for (int64_t q0 = 0; q0 < Q; q0 += group) {
+        const int Qg = (int)((Q - q0) < group ? (Q - q0) : group);
+        const float *qg = q + q0 * d;
+        // 1. threshold pre-pass on the first S rows
+        PF_TRY(scan(db, tc, qg, Qg, 0, S, 0, db->sample.as<float>(), S, nullptr, nullptr, nullptr, 0));
+        knn_kth_kernel<<<Qg, 256, (size_t)Spad * 4, st>>>(db->sample.as<float>(), S, S, Spad, qg, d, k, eps_rel,
+                                                          db->max_norm, db->thr.as<float>(), db->qnorm.as<float>());
+        db->ctx->launches++;
+        PF_CUDA(cudaGetLastError());
+        bool done = false;
+        for (int iter = 0; iter < 4 && !done; iter++) {
+            PF_CUDA(cudaMemsetAsync(db->cnt.p, 0, sizeof(int) * Qg, st));
+            PF_CUDA(cudaMemsetAsync(db->flags.p, 0, sizeof(int) * 4, st));
+            // 2. filtered scan of the whole shard
+            PF_TRY(scan(db, tc, qg, Qg, 0, db->n, 1, nullptr, 0, db->thr.as<float>(), db->cnt.as<int>(),
+                        db->cand.as<uint32_t>(), cap));
+            // 3. exact rescoring + sort
+            knn_select_kernel<<<Qg, 256, sel_smem, st>>>(db->emb32, d, db->id_base, qg, db->cnt.as<int>(),
+                                                         db->cand.as<uint32_t>(), cap, k, eps_rel, db->max_norm,
+                                                         db->qnorm.as<float>(), db->thr.as<float>(), dist + q0 * k,
+                                                         labels + q0 * k, db->flags.as<int>());
+            db->ctx->launches++;
+            PF_CUDA(cudaGetLastError());
+            int overflow = 0;
+            PF_CUDA(cudaMemcpyAsync(&overflow, db->flags.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            PF_CUDA(cudaStreamSynchronize(st));
+            done = (overflow == 0);
+        }
+        if (!done) {
+            // degenerate score distribution (e.g. massive exact ties): exact brute force for this group
+            const size_t smem = (size_t)(k + 256) * 8 + (size_t)d * 4;
+            PF_CUDA(cudaFuncSetAttribute(knn_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            knn_exact_kernel<<<Qg, 256, smem, st>>>(db->emb32, db->n, d, db->id_base, qg, k, dist + q0 * k,
+                                                    labels + q0 * k);
+            db->ctx->launches++;
+            PF_CUDA(cudaGetLastError());
+        }
+    }
+    return PFANN_OK;
+}
+
+}  // namespace pfann
+
+extern "C" {
+
+int pfann_db_open(pfann_ctx *hctx, const float *emb, int64_t n, int d, const int32_t *landmark_key, int n_songs,
+                  int64_t id_base, int64_t song_base, pfann_db **out) {
+    PF_CHECK(hctx && out && n >= 0 && d > 0 && n_songs >= 0, PFANN_ERR_ARG, "pfann_db_open: bad argument");
+    PF_CHECK(n == 0 || emb, PFANN_ERR_ARG, "pfann_db_open: emb is NULL");
+    PF_CHECK(n_songs == 0 || landmark_key, PFANN_ERR_ARG, "pfann_db_open: landmark_key is NULL");
+    PF_CHECK(d % 4 == 0 && d <= 1024, PFANN_ERR_UNSUPPORTED, "pfann_db_open: d=%d must be a multiple of 4, <= 1024", d);
+    PF_CHECK(n < 0xFFFFFFF0LL, PFANN_ERR_UNSUPPORTED, "pfann_db_open: shard too large (%lld rows); shard it",
+             (long long)n);
+    Ctx *ctx = reinterpret_cast<Ctx *>(hctx);
+    PF_CUDA(cudaSetDevice(ctx->device));
+    Db *db = new Db();
+    db->ctx = ctx;
+    db->n = n; db->d = d; db->n_songs = n_songs; db->id_base = id_base; db->song_base = song_base;
+    db->song_pos_host.resize((size_t)n_songs + 1);
+    db->song_pos_host[0] = id_base;
+    for (int i = 0; i < n_songs; i++) {  // database.py:83-86: cumulative sum with a leading zero
+        PF_CHECK(landmark_key[i] >= 0, PFANN_ERR_ARG, "pfann_db_open: negative landmarkKey entry");
+        db->song_pos_host[i + 1] = db->song_pos_host[i] + landmark_key[i];
+    }
+    PF_CHECK(db->song_pos_host[n_songs] - id_base == n || n_songs == 0, PFANN_ERR_ARG,
+             "pfann_db_open: landmarkKey sums to %lld rows but %lld embeddings were given",
+             (long long)(db->song_pos_host[n_songs] - id_base), (long long)n);
+    PF_CUDA(cudaMalloc(&db->song_pos, sizeof(int64_t) * ((size_t)n_songs + 1)));
+    PF_CUDA(cudaMemcpy(db->song_pos, db->song_pos_host.data(), sizeof(int64_t) * ((size_t)n_songs + 1),
+                       cudaMemcpyHostToDevice));
+    const size_t ne = (size_t)n * d;
+    PF_CUDA(cudaMalloc(&db->emb32, sizeof(float) * (ne ? ne : 1)));
+    PF_CUDA(cudaMalloc(&db->emb16, sizeof(__nv_bfloat16) * (ne ? ne : 1)));
+    if (n > 0) {
+        PF_CUDA(cudaMemcpy(db->emb32, emb, sizeof(float) * ne, cudaMemcpyDefault));
+        to_bf16_kernel<<<cdiv((long long)ne, 256), 256, 0, ctx->stream>>>(db->emb32, db->emb16, (int64_t)ne);
+        unsigned int *dmax;
+        PF_CUDA(cudaMalloc(&dmax, sizeof(unsigned int)));
+        PF_CUDA(cudaMemsetAsync(dmax, 0, sizeof(unsigned int), ctx->stream));
+        row_norm_max_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(db->emb32, n, d, dmax);
+        ctx->launches += 2;
+        unsigned int hm = 0;
+        PF_CUDA(cudaMemcpyAsync(&hm, dmax, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+        PF_CUDA(cudaStreamSynchronize(ctx->stream));
+        PF_CUDA(cudaFree(dmax));
+        memcpy(&db->max_norm, &hm, sizeof(float));
+    }
+    int rc = knn_tc_prepare(db);
+    if (rc != PFANN_OK) {
+        pfann_db_close(reinterpret_cast<pfann_db *>(db));
+        return rc;
+    }
+    *out = reinterpret_cast<pfann_db *>(db);
+    return PFANN_OK;
+}
+
+void pfann_db_close(pfann_db *h) {
+    Db *db = reinterpret_cast<Db *>(h);
+    if (!db) return;
+    cudaSetDevice(db->ctx->device);
+    knn_tc_release(db);
+    cudaFree(db->emb32);
+    cudaFree(db->emb16);
+    cudaFree(db->song_pos);
+    DevBuf *bufs[] = {&db->qbuf, &db->qnorm, &db->thr, &db->cnt, &db->cand, &db->sample, &db->flags, &db->dist,
+                      &db->labels, &db->rr_keys, &db->rr_scores, &db->rr_out, &db->lab_stage};
+    for (DevBuf *b : bufs) b->release();
+    delete db;
+}
+
+int64_t pfann_db_ntotal(pfann_db *h) { return h ? reinterpret_cast<Db *>(h)->n : 0; }
+
+int pfann_db_set_tuning(pfann_db *h, int cand_cap, int sample_rows, int use_tc) {
+    PF_CHECK(h, PFANN_ERR_ARG, "pfann_db_set_tuning: NULL db");
+    Db *db = reinterpret_cast<Db *>(h);
+    if (cand_cap > 0) {
+        PF_CHECK((cand_cap & (cand_cap - 1)) == 0 && cand_cap <= 4096 && cand_cap >= 2, PFANN_ERR_ARG,
+                 "pfann_db_set_tuning: cand_cap must be a power of two in [2, 4096]");
+        db->cand_cap = cand_cap;
+    }
+    if (sample_rows > 0) db->sample_rows = sample_rows;
+    if (use_tc >= 0) db->use_tc = use_tc;
+    return PFANN_OK;
+}
+
+int pfann_db_search(pfann_db *h, const float *q, int64_t Q, int k, float *dist, int64_t *labels) {
+    PF_CHECK(h && Q >= 0 && k > 0 && (Q == 0 || (q && dist && labels)), PFANN_ERR_ARG, "pfann_db_search: bad argument");
+    Db *db = reinterpret_cast<Db *>(h);
+    PF_CHECK(k <= db->cand_cap && k <= 2048, PFANN_ERR_UNSUPPORTED, "pfann_db_search: k=%d too large (max %d)", k,
+             db->cand_cap < 2048 ? db->cand_cap : 2048);
+    if (Q == 0) return PFANN_OK;
+    PF_CUDA(cudaSetDevice(db->ctx->device));
+    const void *qd;
+    void *dd, *ld;
+    PF_TRY(stage_input(db->ctx, 0, q, (size_t)Q * db->d * 4, &qd));
+    PF_TRY(stage_output(db->ctx, 0, dist, (size_t)Q * k * 4, &dd));
+    PF_TRY(stage_output(db->ctx, 1, labels, (size_t)Q * k * 8, &ld));
+    PF_TRY(db_search_dev(db, (const float *)qd, Q, k, (float *)dd, (int64_t *)ld));
+    PF_TRY(finish_output(db->ctx, 0, dist, (size_t)Q * k * 4));
+    return finish_output(db->ctx, 1, labels, (size_t)Q * k * 8);
+}
+
+int pfann_topk_merge(pfann_ctx *hctx, const float *dist_g, const int64_t *labels_g, int G, int64_t Q, int k,
+                     float *dist, int64_t *labels) {
+    PF_CHECK(hctx && G > 0 && Q >= 0 && k > 0, PFANN_ERR_ARG, "pfann_topk_merge: bad argument");
+    Ctx *ctx = reinterpret_cast<Ctx *>(hctx);
+    if (Q == 0) return PFANN_OK;
+    PF_CUDA(cudaSetDevice(ctx->device));
+    int P = 1;
+    while (P < G * k) P <<= 1;
+    PF_CHECK(P <= 8192, PFANN_ERR_UNSUPPORTED, "pfann_topk_merge: G*k too large");
+    const size_t gb = (size_t)G * Q * k;
+    const void *dg, *lg;
+    void *dd, *ld;
+    PF_TRY(stage_input(ctx, 0, dist_g, gb * 4, &dg));
+    PF_TRY(stage_input(ctx, 1, labels_g, gb * 8, &lg));
+    PF_TRY(stage_output(ctx, 0, dist, (size_t)Q * k * 4, &dd));
+    PF_TRY(stage_output(ctx, 1, labels, (size_t)Q * k * 8, &ld));
+    const size_t smem = (size_t)(P + (P & 1)) * 4 + (size_t)P * 8;
+    PF_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    topk_merge_kernel<<<(unsigned)Q, 256, smem, ctx->stream>>>((const float *)dg, (const int64_t *)lg, G, Q, k, P,
+                                                                (float *)dd, (int64_t *)ld);
+    ctx->launches++;
+    PF_CUDA(cudaGetLastError());
+    PF_TRY(finish_output(ctx, 0, dist, (size_t)Q * k * 4));
+    return finish_output(ctx, 1, labels, (size_t)Q * k * 8);
+}
+
+}  // extern "C"

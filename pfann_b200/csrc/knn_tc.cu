@@ -1,0 +1,250 @@
+// knn_tc.cu -- stage 3a scan on tcgen05 tensor cores: scores = DB_tile[128 x d] (bf16) . Q^T[d x N] (bf16).
+//
+// Persistent, warp-specialised kernel, one CTA per SM:
+//   warp 0   TMA producer: streams 128-row database tiles (SWIZZLE_128B, K-major) through a 4-stage
+//            shared-memory ring -- the whole kernel is a single pass over the shard, i.e. HBM-bound when few
+//            queries are searched per pass (the per-query-file regime of matcher.py:136) and tensor-bound when
+//            hundreds are batched;
+//   warp 1   MMA issuer: d/16 tcgen05.mma per tile into one of two TMEM accumulator buffers (128 lanes = the
+//            tile's database rows, N columns = the queries, which stay resident in shared memory);
+//   warps 2-5 epilogue: tcgen05.ld their lane quarter, compare against the per-query threshold and append the
+//            few survivors to the candidate lists (mode 1), or dump the scores of the sample pre-pass (mode 0).
+// The bf16 scores only SELECT candidates; knn.cu re-scores them exactly in fp32.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "db.cuh"
+#include "pfann_b200.h"
+
+using namespace pfann;
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int STAGES = 4;
+constexpr int KNN_THREADS = 192;
+
+struct KnnTcState {
+    CUtensorMap mapA;  // [n][d] bf16, box (64, 128)
+};
+
+struct ScanArgs {
+    const float *q;      // [Qg][d] fp32
+    int Qg, d;
+    long long r0, r1;    // row range
+    int mode;
+    float *sample;       // mode 0: [Qg][sample_ld]
+    long long sample_ld;
+    const float *thr;    // mode 1
+    int *cnt;
+    uint32_t *cand;
+    int cap;
+};
+
+template <int N>
+__global__ void __launch_bounds__(KNN_THREADS, 1) knn_scan_tc_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                     const ScanArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *sbase = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int KBLK = a.d / BK;                         // K blocks per tile (d = 128 -> 2)
+    const uint32_t A_KB_BYTES = BM * BK * 2;           // 16 KB per K block
+    const uint32_t STAGE_BYTES = A_KB_BYTES * KBLK;
+    const uint32_t B_KB_BYTES = N * BK * 2;
+    unsigned char *sB = sbase;                         // [KBLK][N rows][128 B]
+    unsigned char *sA = sbase + (size_t)B_KB_BYTES * KBLK;  // [STAGES][KBLK][128 rows][128 B]
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float thr_s[N];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long ntiles = (a.r1 - a.r0 + BM - 1) / BM;
+
+    if (tid == 0) {
+        ptx::prefetch_tmap(&mapA);
+        for (int s = 0; s < STAGES; s++) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; s++) {
+            ptx::mbar_init(&tfull_bar[s], 1);
+            ptx::mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(&tmem_base_s, 2 * N < 32 ? 32 : 2 * N);
+        ptx::tmem_relinquish();
+    }
+    // queries -> bf16, K-major, 128-byte swizzle (the layout TMA SWIZZLE_128B would have produced)
+    for (int i = tid; i < N * (a.d / 8); i += KNN_THREADS) {
+        const int n = i / (a.d / 8), ch = i - n * (a.d / 8);  // 16-byte chunk = 8 consecutive k
+        const int kb = ch >> 3, c = ch & 7;
+        uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+        if (n < a.Qg) {
+            const float *src = a.q + (long long)n * a.d + ch * 8;
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(src[0], src[1]), p1 = __floats2bfloat162_rn(src[2], src[3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(src[4], src[5]), p3 = __floats2bfloat162_rn(src[6], src[7]);
+            pk.x = *reinterpret_cast<uint32_t *>(&p0);
+            pk.y = *reinterpret_cast<uint32_t *>(&p1);
+            pk.z = *reinterpret_cast<uint32_t *>(&p2);
+            pk.w = *reinterpret_cast<uint32_t *>(&p3);
+        }
+        *reinterpret_cast<uint4 *>(sB + (size_t)kb * B_KB_BYTES + (size_t)n * 128 + ((c ^ (n & 7)) << 4)) = pk;
+    }
+    for (int i = tid; i < N; i += KNN_THREADS) thr_s[i] = (a.mode == 1 && i < a.Qg) ? a.thr[i] : INFINITY;
+    ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            long long it = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+                const int s = (int)(it % STAGES);
+                if (it >= STAGES) ptx::mbar_wait(&empty_bar[s], (uint32_t)((it / STAGES) - 1) & 1);
+                ptx::mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                const int row0 = (int)(a.r0 + tile * BM);
+                for (int kb = 0; kb < KBLK; kb++)
+                    ptx::tma_load_2d(sA + (size_t)s * STAGE_BYTES + (size_t)kb * A_KB_BYTES, &mapA, &full_bar[s], kb * BK,
+                                     row0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, N);
+            long long it = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+                const int s = (int)(it % STAGES), buf = (int)(it & 1);
+                if (it >= 2) ptx::mbar_wait(&tempty_bar[buf], (uint32_t)((it >> 1) - 1) & 1);
+                ptx::mbar_wait(&full_bar[s], (uint32_t)(it / STAGES) & 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N);
+                for (int kb = 0; kb < KBLK; kb++) {
+                    const uint64_t da = ptx::umma_desc_k_sw128(ptx::smem_u32(sA + (size_t)s * STAGE_BYTES + (size_t)kb * A_KB_BYTES));
+                    const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(sB + (size_t)kb * B_KB_BYTES));
+#pragma unroll
+                    for (int k = 0; k < BK / 16; k++)
+                        ptx::umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                }
+                ptx::umma_commit(&empty_bar[s]);
+                ptx::umma_commit(&tfull_bar[buf]);
+            }
+        }
+    } else {
+        // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
+        const int quarter = warp & 3;
+        long long it = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+            const int buf = (int)(it & 1);
+            ptx::mbar_wait(&tfull_bar[buf], (uint32_t)(it >> 1) & 1);
+            ptx::tc_fence_after();
+            const long long row = a.r0 + tile * BM + quarter * 32 + lane;
+            const bool rvalid = row < a.r1;
+#pragma unroll 1
+            for (int c = 0; c < N; c += 32) {
+                uint32_t v[32];
+                ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * N + c), v);
+                ptx::tmem_ld_wait();
+                if (a.mode == 0) {
+                    if (rvalid) {
+#pragma unroll
+                        for (int i = 0; i < 32; i++)
+                            if (c + i < a.Qg) a.sample[(long long)(c + i) * a.sample_ld + (row - a.r0)] = __uint_as_float(v[i]);
+                    }
+                } else {
+                    bool any = false;
+#pragma unroll
+                    for (int i = 0; i < 32; i++) any |= (__uint_as_float(v[i]) >= thr_s[c + i]);
+                    if (any && rvalid) {
+#pragma unroll
+                        for (int i = 0; i < 32; i++) {
+                            if (__uint_as_float(v[i]) >= thr_s[c + i]) {
+                                const int pos = atomicAdd(a.cnt + c + i, 1);
+                                if (pos < a.cap) a.cand[(long long)(c + i) * a.cap + pos] = (uint32_t)row;
+                            }
+                        }
+                    }
+                }
+            }
+            // this warp is done reading the buffer: hand it back to the MMA issuer
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty_bar[buf]);
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 2 * N < 32 ? 32 : 2 * N);
+    }
+}
+
+template <int N>
+int launch_scan(Db *db, KnnTcState *st, const ScanArgs &a) {
+    const int KBLK = db->d / BK;
+    const size_t smem = 1024 + (size_t)N * BK * 2 * KBLK + (size_t)STAGES * BM * BK * 2 * KBLK;
+    PF_CUDA(cudaFuncSetAttribute(knn_scan_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long ntiles = (a.r1 - a.r0 + BM - 1) / BM;
+    long long grid = db->ctx->sm_count;
+    if (grid > ntiles) grid = ntiles;
+    if (grid < 1) return PFANN_OK;
+    knn_scan_tc_kernel<N><<<(unsigned)grid, KNN_THREADS, smem, db->ctx->stream>>>(st->mapA, a);
+    db->ctx->launches++;
+    PF_CUDA(cudaGetLastError());
+    return PFANN_OK;
+}
+
+}  // namespace
+
+namespace pfann {
+
+int knn_tc_prepare(Db *db) {
+    db->tc_state = nullptr;
+    if (db->n == 0 || db->d % BK != 0 || db->d > 256) return PFANN_OK;  // CUDA-core scan serves these
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    PF_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    PF_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess, PFANN_ERR_CUDA,
+             "cuTensorMapEncodeTiled is not available from the driver");
+    auto encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    KnnTcState *st = new KnnTcState();
+    cuuint64_t dims[2] = {(cuuint64_t)db->d, (cuuint64_t)db->n};
+    cuuint64_t str[1] = {(cuuint64_t)db->d * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&st->mapA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, db->emb16, dims, str, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        delete st;
+        set_error("knn_tc_prepare: cuTensorMapEncodeTiled failed (%d)", (int)r);
+        return PFANN_ERR_CUDA;
+    }
+    db->tc_state = st;
+    return PFANN_OK;
+}
+
+void knn_tc_release(Db *db) {
+    delete reinterpret_cast<KnnTcState *>(db->tc_state);
+    db->tc_state = nullptr;
+}
+
+int knn_tc_scan(Db *db, const float *q, int Qg, int64_t r0, int64_t r1, int mode, float *sample, int64_t sample_ld,
+                const float *thr, int *cnt, uint32_t *cand, int cap) {
+    KnnTcState *st = reinterpret_cast<KnnTcState *>(db->tc_state);
+    PF_CHECK(st != nullptr, PFANN_ERR_STATE, "knn_tc_scan: tensor-core state missing");
+    PF_CHECK(Qg >= 1 && Qg <= 128, PFANN_ERR_ARG, "knn_tc_scan: 1..128 queries per pass");
+    ScanArgs a;
+    a.q = q; a.Qg = Qg; a.d = db->d; a.r0 = r0; a.r1 = r1; a.mode = mode;
+    a.sample = sample; a.sample_ld = sample_ld; a.thr = thr; a.cnt = cnt; a.cand = cand; a.cap = cap;
+    if (Qg <= 32) return launch_scan<32>(db, st, a);
+    return launch_scan<128>(db, st, a);
+}
+
+}  // namespace pfann

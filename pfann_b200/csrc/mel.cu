@@ -1,0 +1,476 @@
+// mel.cu -- stage 1: framed STFT power + HTK mel filter bank + log, one fused kernel.
+//
+// Replaces datautil/melspec.py:33-50 (MelSpec.forward -> torchaudio MelSpectrogram -> torch.stft + matmul,
+// ~8 library launches and three HBM round trips of the [B,513,32] spectrum) and, on the PCM entry point,
+// the segmenter tail datautil/musicdata.py:48,82-88.
+//
+// One CTA (8 warps) per 1-second segment:
+//   * the segment (32 000 B fp32 or 16 000 B int16) is pulled into shared memory with ONE bulk async
+//     copy (cp.async.bulk, TMA engine) completing on an mbarrier; mean removal (PCM path), the L2 norm
+//     and the reflect padding are done in place in shared memory;
+//   * each warp transforms whole frames: the 1024-point real FFT is a 512-point complex FFT held in
+//     registers (16 complex points per lane): a 16-point in-lane DIF, a twiddle, then a 32-point radix-2
+//     DIF ACROSS lanes made of shfl_xor butterflies; only the finished spectrum touches shared memory
+//     (for the Z[k] / conj Z[512-k] real-FFT recombination);
+//   * the mel projection uses the filter bank's sparsity (<= 7 taps per mel bin for the default config,
+//     rows < 39 all zero) instead of the reference's dense [513 x 256] sgemm;
+//   * log(. + 1e-8) and the [n_mels][T] tile is written once, coalesced.
+// Algorithmic HBM bytes per segment: 32 000 in + 32 768 out (fp32 entry point).
+// tools/fft_dataflow_check.py holds a numpy emulation of exactly this dataflow.
+#include <math.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "pfann_b200.h"
+
+using namespace pfann;
+
+namespace {
+
+constexpr int NFFT = 1024;
+constexpr int NTHREADS = 256;
+constexpr int NWARPS = NTHREADS / 32;
+constexpr int ZSTRIDE = 17;                 // padded row of 16 complex values (bank-conflict free)
+constexpr int ZBUF_F2 = 32 * ZSTRIDE;       // float2 per warp
+
+struct MelPlan {
+    Ctx *ctx;
+    int sample_rate, n_fft, hop, n_mels, seg_len, T;
+    int fb_stride;
+    float2 *d_tw = nullptr;   // W_1024^k = exp(-2 pi i k / 1024), k in [0, 1024)
+    float *d_win = nullptr;   // periodic Hann, 1024
+    int *d_fb_start = nullptr, *d_fb_cnt = nullptr;
+    float *d_fb_w = nullptr;  // [n_mels][fb_stride]
+    DevBuf seg_start, seg_valid;
+    size_t smem_bytes;
+};
+
+struct MelArgs {
+    const float *x;          // fp32 rows [B][n]           (x != nullptr)
+    const int16_t *pcm;      // or int16 PCM + descriptors  (pcm != nullptr)
+    int64_t pcm_len;
+    const int64_t *seg_start;
+    const int32_t *seg_valid;
+    float *out;              // [B][n_mels][T]
+    int n, hop, T, n_mels, fb_stride;
+    const float2 *tw;
+    const float *win;
+    const int *fb_start, *fb_cnt;
+    const float *fb_w;
+};
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+__host__ __device__ constexpr int bitrev4(int i) {
+    return ((i & 1) << 3) | ((i & 2) << 1) | ((i & 4) >> 1) | ((i & 8) >> 3);
+}
+
+// 16-point radix-2 DIF in registers; output a[i] = X[bitrev4(i)].
+__device__ __forceinline__ void fft16_dif(float2 (&a)[16]) {
+    // W_16^j, j = 0..7
+    const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, r2 = 0.70710678118654752f;
+    const float2 W[8] = {{1.f, 0.f}, {c1, -s1}, {r2, -r2}, {s1, -c1}, {0.f, -1.f}, {-s1, -c1}, {-r2, -r2}, {-c1, -s1}};
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        const int half = 8 >> s;
+#pragma unroll
+        for (int base = 0; base < 16; base += 2 * half) {
+#pragma unroll
+            for (int j = 0; j < half; j++) {
+                float2 u = a[base + j], v = a[base + j + half];
+                a[base + j] = cadd(u, v);
+                float2 d = csub(u, v);
+                a[base + j + half] = (j == 0) ? d : cmul(d, W[j * (8 / half)]);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ float block_sum(float v, float *red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();  // protect red[] from a previous use
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < NWARPS; i++) t += red[i];  // same order in every thread: deterministic
+    return t;
+}
+
+template <bool PCM>
+__global__ void __launch_bounds__(NTHREADS, 2) mel_kernel(const MelArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int n = a.n, pad = NFFT / 2;
+    float *xs = reinterpret_cast<float *>(smem_raw);                        // [n + NFFT]
+    float2 *zbuf = reinterpret_cast<float2 *>(xs + ((n + NFFT + 3) & ~3));  // [NWARPS][ZBUF_F2]
+    float *tile = reinterpret_cast<float *>(zbuf + NWARPS * ZBUF_F2);       // [n_mels][T+1] (also int16 stage)
+    __shared__ float red[NWARPS];
+    __shared__ __align__(8) uint64_t bar;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t b = blockIdx.x;
+    float *x = xs + pad;
+
+    if (tid == 0) {
+        ptx::mbar_init(&bar, 1);
+        ptx::fence_mbar_init();
+    }
+    __syncthreads();
+
+    // ---- load the segment ------------------------------------------------------------------
+    if (!PCM) {
+        const float *src = a.x + b * (int64_t)n;
+        const bool bulk = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((n & 3) == 0);
+        if (bulk) {
+            if (tid == 0) {
+                ptx::mbar_expect_tx(&bar, (uint32_t)n * 4u);
+                ptx::bulk_g2s(x, src, (uint32_t)n * 4u, &bar);
+            }
+            ptx::mbar_wait(&bar, 0);
+        } else {
+            for (int i = tid; i < n; i += NTHREADS) x[i] = __ldg(src + i);
+            __syncthreads();
+        }
+    } else {
+        const int64_t start = a.seg_start[b];
+        const int valid = a.seg_valid[b];
+        const int16_t *src = a.pcm + start;
+        int16_t *stg = reinterpret_cast<int16_t *>(tile);
+        const bool bulk = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((valid & 7) == 0) && valid > 0;
+        if (bulk) {
+            if (tid == 0) {
+                ptx::mbar_expect_tx(&bar, (uint32_t)valid * 2u);
+                ptx::bulk_g2s(stg, src, (uint32_t)valid * 2u, &bar);
+            }
+            ptx::mbar_wait(&bar, 0);
+        } else {
+            for (int i = tid; i < valid; i += NTHREADS) stg[i] = src[i];
+            __syncthreads();
+        }
+        // musicdata.py:48 (x 1/32768 in fp32), :82-84 (zero-pad), :88 (mean removal)
+        float part = 0.f;
+        for (int i = tid; i < n; i += NTHREADS) {
+            float v = i < valid ? (float)stg[i] * (1.0f / 32768.0f) : 0.f;
+            x[i] = v;
+            part += v;
+        }
+        const float mean = block_sum(part, red) / (float)n;
+        for (int i = tid; i < n; i += NTHREADS) x[i] -= mean;
+        __syncthreads();
+    }
+
+    // ---- L2 normalisation factor (melspec.py:35-36, eps 1e-12) -------------------------------
+    float part = 0.f;
+    for (int i = tid; i < n; i += NTHREADS) part = fmaf(x[i], x[i], part);
+    const float ss = block_sum(part, red);
+    const float scale = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+
+    // ---- reflect padding (torch.stft center=True, pad_mode='reflect') -------------------------
+    for (int i = tid; i < pad; i += NTHREADS) {
+        xs[i] = xs[2 * pad - i];                        // padded[i] = x[pad - i]
+        xs[pad + n + i] = xs[pad + n - 2 - i];          // padded[pad+n+i] = x[n-2-i]
+    }
+    __syncthreads();
+
+    // ---- per-lane constants -------------------------------------------------------------------
+    float2 twl[16];  // W_512^(lane * k1) for the register holding k1 = bitrev4(i)
+#pragma unroll
+    for (int i = 0; i < 16; i++) twl[i] = __ldg(a.tw + ((2 * lane * bitrev4(i)) & (NFFT - 1)));
+    float2 wst[5];   // cross-lane stage twiddles W_(2 half)^(lane & (half-1)), half = 16,8,4,2,1
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+        const int half = 16 >> s;
+        wst[s] = __ldg(a.tw + (lane & (half - 1)) * (NFFT / (2 * half)));
+    }
+    const int k2 = (int)(__brev((unsigned)lane) >> 27);
+    float2 *zw = zbuf + warp * ZBUF_F2;
+    float *pw = reinterpret_cast<float *>(zw);
+    const int Tp = a.T + 1;
+
+    for (int t = warp; t < a.T; t += NWARPS) {
+        // windowed frame -> z[n'] = xw[2n'] + i xw[2n'+1], lane holds n' = 32 r + lane
+        float2 v[16];
+        const float *fr = xs + t * a.hop;
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            const int j = 64 * r + 2 * lane;
+            const float2 xv = *reinterpret_cast<const float2 *>(fr + j);
+            const float2 wv = __ldg(reinterpret_cast<const float2 *>(a.win + j));
+            v[r] = make_float2(xv.x * scale * wv.x, xv.y * scale * wv.y);
+        }
+        fft16_dif(v);
+#pragma unroll
+        for (int i = 1; i < 16; i++) v[i] = cmul(v[i], twl[i]);  // i = 0 -> k1 = 0 -> twiddle 1
+#pragma unroll
+        for (int s = 0; s < 5; s++) {
+            const int half = 16 >> s;
+            const bool upper = (lane & half) != 0;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                float2 p;
+                p.x = __shfl_xor_sync(0xffffffffu, v[i].x, half);
+                p.y = __shfl_xor_sync(0xffffffffu, v[i].y, half);
+                const float2 sum = cadd(v[i], p);
+                const float2 dif = cmul(csub(p, v[i]), wst[s]);
+                v[i] = upper ? dif : sum;
+            }
+        }
+        // Z[k1 + 16 k2] with k1 = bitrev4(i), k2 = bitrev5(lane)
+#pragma unroll
+        for (int i = 0; i < 16; i++) zw[k2 * ZSTRIDE + bitrev4(i)] = v[i];
+        __syncwarp();
+        // real-FFT recombination: X[k] = E + W_1024^k O, power spectrum
+        float P[17];
+#pragma unroll
+        for (int it = 0; it < 17; it++) {
+            const int k = lane + 32 * it;
+            P[it] = 0.f;
+            if (k <= NFFT / 2) {
+                const int ka = k & 511, kb = (512 - k) & 511;
+                const float2 A = zw[(ka >> 4) * ZSTRIDE + (ka & 15)];
+                float2 Bc = zw[(kb >> 4) * ZSTRIDE + (kb & 15)];
+                Bc.y = -Bc.y;
+                const float2 E = make_float2(0.5f * (A.x + Bc.x), 0.5f * (A.y + Bc.y));
+                const float2 D = csub(A, Bc);
+                const float2 O = make_float2(0.5f * D.y, -0.5f * D.x);
+                const float2 X = cadd(E, cmul(__ldg(a.tw + k), O));
+                P[it] = X.x * X.x + X.y * X.y;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 17; it++) {
+            const int k = lane + 32 * it;
+            if (k <= NFFT / 2) pw[k] = P[it];
+        }
+        __syncwarp();
+        // sparse HTK mel projection + log (melspec.py:41,46)
+        for (int m = lane; m < a.n_mels; m += 32) {
+            const int s0 = __ldg(a.fb_start + m), c = __ldg(a.fb_cnt + m);
+            const float *w = a.fb_w + (size_t)m * a.fb_stride;
+            float acc = 0.f;
+            for (int j = 0; j < c; j++) acc = fmaf(__ldg(w + j), pw[s0 + j], acc);
+            tile[m * Tp + t] = logf(acc + 1e-8f);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    float *o = a.out + b * (int64_t)a.n_mels * a.T;
+    const int tot = a.n_mels * a.T;
+    for (int i = tid; i < tot; i += NTHREADS) {
+        const int m = i / a.T, t = i - m * a.T;
+        o[i] = tile[m * Tp + t];
+    }
+}
+
+size_t mel_smem_bytes(int n, int n_mels, int T) {
+    size_t xs = (size_t)((n + NFFT + 3) & ~3) * 4;
+    size_t z = (size_t)NWARPS * ZBUF_F2 * 8;
+    size_t tile = (size_t)n_mels * (T + 1) * 4;
+    if (tile < (size_t)n * 2 + 16) tile = (size_t)n * 2 + 16;  // int16 staging shares the tile region
+    return xs + z + tile;
+}
+
+int launch_mel(MelPlan *p, const MelArgs &a, int64_t B, bool pcm) {
+    if (B == 0) return PFANN_OK;
+    PF_CHECK(B <= 0x7fffffffLL, PFANN_ERR_ARG, "mel: too many segments in one call (%lld)", (long long)B);
+    if (pcm)
+        mel_kernel<true><<<(unsigned)B, NTHREADS, p->smem_bytes, p->ctx->stream>>>(a);
+    else
+        mel_kernel<false><<<(unsigned)B, NTHREADS, p->smem_bytes, p->ctx->stream>>>(a);
+    p->ctx->launches++;
+    PF_CUDA(cudaGetLastError());
+    return PFANN_OK;
+}
+
+MelArgs base_args(MelPlan *p) {
+    MelArgs a = {};
+    a.n = p->seg_len;
+    a.hop = p->hop;
+    a.T = p->T;
+    a.n_mels = p->n_mels;
+    a.fb_stride = p->fb_stride;
+    a.tw = p->d_tw;
+    a.win = p->d_win;
+    a.fb_start = p->d_fb_start;
+    a.fb_cnt = p->d_fb_cnt;
+    a.fb_w = p->d_fb_w;
+    return a;
+}
+
+}  // namespace
+
+namespace pfann {
+// used by extract.cu: run stage 1 on device-resident inputs into a device buffer
+int mel_forward_dev(pfann_mel *h, const float *x_dev, int64_t B, float *out_dev) {
+    MelPlan *p = reinterpret_cast<MelPlan *>(h);
+    MelArgs a = base_args(p);
+    a.x = x_dev;
+    a.out = out_dev;
+    return launch_mel(p, a, B, false);
+}
+int mel_forward_pcm_dev(pfann_mel *h, const int16_t *pcm_dev, int64_t n_samples, const int64_t *start_dev,
+                        const int32_t *valid_dev, int64_t B, float *out_dev) {
+    MelPlan *p = reinterpret_cast<MelPlan *>(h);
+    MelArgs a = base_args(p);
+    a.pcm = pcm_dev;
+    a.pcm_len = n_samples;
+    a.seg_start = start_dev;
+    a.seg_valid = valid_dev;
+    a.out = out_dev;
+    return launch_mel(p, a, B, true);
+}
+Ctx *mel_ctx(pfann_mel *h) { return reinterpret_cast<MelPlan *>(h)->ctx; }
+void mel_dims(pfann_mel *h, int *seg_len, int *n_mels, int *T) {
+    MelPlan *p = reinterpret_cast<MelPlan *>(h);
+    *seg_len = p->seg_len;
+    *n_mels = p->n_mels;
+    *T = p->T;
+}
+}  // namespace pfann
+
+extern "C" {
+
+int pfann_mel_create(pfann_ctx *hctx, int sample_rate, int n_fft, int hop, double f_min, double f_max,
+                     int n_mels, int seg_len, pfann_mel **out) {
+    PF_CHECK(hctx && out, PFANN_ERR_ARG, "pfann_mel_create: NULL argument");
+    PF_CHECK(n_fft == NFFT, PFANN_ERR_UNSUPPORTED, "pfann_mel_create: n_fft=%d unsupported (kernel is built for 1024)",
+             n_fft);
+    PF_CHECK(hop > 0 && (hop % 2) == 0, PFANN_ERR_UNSUPPORTED, "pfann_mel_create: hop must be even (got %d)", hop);
+    PF_CHECK(seg_len > n_fft / 2 && seg_len % 4 == 0, PFANN_ERR_UNSUPPORTED,
+             "pfann_mel_create: seg_len=%d must be > n_fft/2 and a multiple of 4", seg_len);
+    PF_CHECK(n_mels > 0 && n_mels <= 1024, PFANN_ERR_ARG, "pfann_mel_create: bad n_mels %d", n_mels);
+    Ctx *ctx = reinterpret_cast<Ctx *>(hctx);
+    PF_CUDA(cudaSetDevice(ctx->device));
+    MelPlan *p = new MelPlan();
+    p->ctx = ctx;
+    p->sample_rate = sample_rate;
+    p->n_fft = n_fft;
+    p->hop = hop;
+    p->n_mels = n_mels;
+    p->seg_len = seg_len;
+    p->T = 1 + seg_len / hop;
+    // the last frame must stay inside the padded signal
+    PF_CHECK((p->T - 1) * hop + n_fft <= seg_len + n_fft, PFANN_ERR_ARG, "pfann_mel_create: bad framing");
+    p->smem_bytes = mel_smem_bytes(seg_len, n_mels, p->T);
+    PF_CHECK(p->smem_bytes <= 227 * 1024, PFANN_ERR_UNSUPPORTED,
+             "pfann_mel_create: segment of %d samples needs %zu B of shared memory (> 227 KB)", seg_len,
+             p->smem_bytes);
+
+    // tables in double, rounded once to fp32
+    std::vector<float2> tw(NFFT);
+    std::vector<float> win(NFFT);
+    const double PI = 3.14159265358979323846;
+    for (int k = 0; k < NFFT; k++) {
+        tw[k].x = (float)cos(2.0 * PI * k / NFFT);
+        tw[k].y = (float)(-sin(2.0 * PI * k / NFFT));
+        win[k] = (float)(0.5 - 0.5 * cos(2.0 * PI * k / NFFT));  // torch.hann_window(periodic=True)
+    }
+    // torchaudio.functional.melscale_fbanks(norm=None, mel_scale='htk') (melspec.py:19-31), kept sparse
+    const int n_freqs = n_fft / 2 + 1;
+    std::vector<double> f_pts(n_mels + 2);
+    const double m_min = 2595.0 * log10(1.0 + f_min / 700.0), m_max = 2595.0 * log10(1.0 + f_max / 700.0);
+    for (int i = 0; i < n_mels + 2; i++)
+        f_pts[i] = 700.0 * (pow(10.0, (m_min + (m_max - m_min) * i / (n_mels + 1)) / 2595.0) - 1.0);
+    std::vector<int> start(n_mels), cnt(n_mels);
+    std::vector<std::vector<float>> rows(n_mels);
+    int stride = 1;
+    const double nyq = (double)(sample_rate / 2);
+    for (int m = 0; m < n_mels; m++) {
+        int first = -1, last = -2;
+        std::vector<float> w(n_freqs, 0.f);
+        for (int k = 0; k < n_freqs; k++) {
+            double f = nyq * k / (n_freqs - 1);
+            double down = (f - f_pts[m]) / (f_pts[m + 1] - f_pts[m]);
+            double up = (f_pts[m + 2] - f) / (f_pts[m + 2] - f_pts[m + 1]);
+            double v = down < up ? down : up;
+            if (v > 0.0) {
+                w[k] = (float)v;
+                if (first < 0) first = k;
+                last = k;
+            }
+        }
+        start[m] = first < 0 ? 0 : first;
+        cnt[m] = first < 0 ? 0 : last - first + 1;
+        rows[m].assign(w.begin() + start[m], w.begin() + start[m] + cnt[m]);
+        if (cnt[m] > stride) stride = cnt[m];
+    }
+    p->fb_stride = stride;
+    std::vector<float> fbw((size_t)n_mels * stride, 0.f);
+    for (int m = 0; m < n_mels; m++)
+        for (int j = 0; j < cnt[m]; j++) fbw[(size_t)m * stride + j] = rows[m][j];
+
+    PF_CUDA(cudaMalloc(&p->d_tw, sizeof(float2) * NFFT));
+    PF_CUDA(cudaMalloc(&p->d_win, sizeof(float) * NFFT));
+    PF_CUDA(cudaMalloc(&p->d_fb_start, sizeof(int) * n_mels));
+    PF_CUDA(cudaMalloc(&p->d_fb_cnt, sizeof(int) * n_mels));
+    PF_CUDA(cudaMalloc(&p->d_fb_w, sizeof(float) * fbw.size()));
+    PF_CUDA(cudaMemcpy(p->d_tw, tw.data(), sizeof(float2) * NFFT, cudaMemcpyHostToDevice));
+    PF_CUDA(cudaMemcpy(p->d_win, win.data(), sizeof(float) * NFFT, cudaMemcpyHostToDevice));
+    PF_CUDA(cudaMemcpy(p->d_fb_start, start.data(), sizeof(int) * n_mels, cudaMemcpyHostToDevice));
+    PF_CUDA(cudaMemcpy(p->d_fb_cnt, cnt.data(), sizeof(int) * n_mels, cudaMemcpyHostToDevice));
+    PF_CUDA(cudaMemcpy(p->d_fb_w, fbw.data(), sizeof(float) * fbw.size(), cudaMemcpyHostToDevice));
+    PF_CUDA(cudaFuncSetAttribute(mel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
+    PF_CUDA(cudaFuncSetAttribute(mel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
+    *out = reinterpret_cast<pfann_mel *>(p);
+    return PFANN_OK;
+}
+
+void pfann_mel_destroy(pfann_mel *h) {
+    MelPlan *p = reinterpret_cast<MelPlan *>(h);
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    cudaFree(p->d_tw);
+    cudaFree(p->d_win);
+    cudaFree(p->d_fb_start);
+    cudaFree(p->d_fb_cnt);
+    cudaFree(p->d_fb_w);
+    p->seg_start.release();
+    p->seg_valid.release();
+    delete p;
+}
+
+int pfann_mel_n_frames(pfann_mel *h) { return h ? reinterpret_cast<MelPlan *>(h)->T : 0; }
+
+int pfann_mel_forward(pfann_mel *h, const float *x, int64_t B, float *out) {
+    PF_CHECK(h && (B == 0 || (x && out)), PFANN_ERR_ARG, "pfann_mel_forward: NULL argument");
+    PF_CHECK(B >= 0, PFANN_ERR_ARG, "pfann_mel_forward: negative batch");
+    MelPlan *p = reinterpret_cast<MelPlan *>(h);
+    if (B == 0) return PFANN_OK;
+    PF_CUDA(cudaSetDevice(p->ctx->device));
+    const size_t in_b = (size_t)B * p->seg_len * 4, out_b = (size_t)B * p->n_mels * p->T * 4;
+    const void *xd;
+    void *od;
+    PF_TRY(stage_input(p->ctx, 0, x, in_b, &xd));
+    PF_TRY(stage_output(p->ctx, 0, out, out_b, &od));
+    PF_TRY(mel_forward_dev(h, (const float *)xd, B, (float *)od));
+    return finish_output(p->ctx, 0, out, out_b);
+}
+
+int pfann_mel_forward_pcm16(pfann_mel *h, const int16_t *pcm, int64_t n_samples, const int64_t *seg_start,
+                            const int32_t *seg_valid, int64_t B, float *out) {
+    PF_CHECK(h && (B == 0 || (pcm && seg_start && seg_valid && out)), PFANN_ERR_ARG,
+             "pfann_mel_forward_pcm16: NULL argument");
+    MelPlan *p = reinterpret_cast<MelPlan *>(h);
+    if (B == 0) return PFANN_OK;
+    PF_CUDA(cudaSetDevice(p->ctx->device));
+    const size_t out_b = (size_t)B * p->n_mels * p->T * 4;
+    const void *pd, *sd, *vd;
+    void *od;
+    PF_TRY(stage_input(p->ctx, 0, pcm, (size_t)n_samples * 2, &pd));
+    PF_TRY(stage_input(p->ctx, 1, seg_start, (size_t)B * 8, &sd));
+    PF_TRY(stage_input(p->ctx, 2, seg_valid, (size_t)B * 4, &vd));
+    PF_TRY(stage_output(p->ctx, 0, out, out_b, &od));
+    PF_TRY(mel_forward_pcm_dev(h, (const int16_t *)pd, n_samples, (const int64_t *)sd, (const int32_t *)vd, B,
+                               (float *)od));
+    return finish_output(p->ctx, 0, out, out_b);
+}
+
+}  // extern "C"

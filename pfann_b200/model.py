@@ -1,0 +1,155 @@
+"""Drop-in for the reference's ``model.py``: ``FpNetwork(d, h, u, F, T, params)`` with the reference's
+state_dict keys, ``forward(x, norm=True)`` computed by libpfann_b200 (include/pfann_b200.h, stage 2).
+
+    model = FpNetwork(d, h, u, F_bin, T, params['model']).to(device)              # builder.py:55
+    model.load_state_dict(torch.load(os.path.join(model_dir, 'model.pt')))        # builder.py:56
+    z = model(g)                                                                  # builder.py:96
+
+The torch modules below only HOLD the parameters (so that ``load_state_dict`` / ``state_dict`` / ``.to`` /
+default initialisation behave exactly like the reference's); they are never called.  ``forward`` hands the
+weights to the native library once (re-done when they change) and then calls ``pfann_model_forward``.
+"""
+import ctypes
+import os
+
+import torch
+from torch.nn import Conv1d, Conv2d, LayerNorm, Module, ModuleList
+
+from . import _lib
+
+
+def _precision(name):
+    name = (name or os.environ.get('PFANN_B200_PRECISION', 'bf16')).lower()
+    if name in ('bf16', 'tc', 'tensor'):
+        return _lib.PRECISION_BF16
+    if name in ('fp32', 'f32', 'simt'):
+        return _lib.PRECISION_FP32
+    raise ValueError('unknown precision %r (bf16 | fp32)' % name)
+
+
+class SeparableConv2d(Module):
+    """Parameter container with the shapes of model.py:15-31 (k=3, stride (2,2))."""
+
+    def __init__(self, i, o, k, s, in_F, in_T, fuller=False, activation='ReLU', relu_after_bn=True):
+        super(SeparableConv2d, self).__init__()
+        if activation != 'ReLU' or not relu_after_bn or k != 3 or tuple(s) != (2, 2):
+            raise NotImplementedError('pfann_b200: only ReLU, relu_after_bn=True, k=3, stride 2 have a B200 kernel')
+        self.conv1 = Conv2d(i, o, kernel_size=(1, k), stride=(1, s[0]))
+        self.ln1 = LayerNorm((o, in_F, (in_T - 1) // s[0] + 1))
+        if fuller:
+            self.conv2 = Conv2d(o, o, kernel_size=(k, 1), stride=(s[1], 1))
+        else:
+            self.conv2 = Conv2d(o, o, kernel_size=(k, 1), stride=(s[1], 1), groups=o)
+        self.ln2 = LayerNorm((o, (in_F - 1) // s[1] + 1, (in_T - 1) // s[0] + 1))
+
+
+class MyF(Module):
+    def __init__(self, d, h, u, in_F, in_T, fuller=False, activation='ReLU', strides=None, relu_after_bn=True):
+        super(MyF, self).__init__()
+        if strides is not None:
+            raise NotImplementedError('pfann_b200: custom strides (NAF-converted models) are not supported yet')
+        channels = [1, d, d, 2 * d, 2 * d, 4 * d, 4 * d, h, h]
+        convs = []
+        for i in range(8):
+            convs.append(SeparableConv2d(channels[i], channels[i + 1], 3, (2, 2), in_F, in_T, fuller=fuller,
+                                         activation=activation, relu_after_bn=relu_after_bn))
+            in_F = (in_F - 1) // 2 + 1
+            in_T = (in_T - 1) // 2 + 1
+        assert in_F == in_T == 1, 'output must be 1x1'
+        self.convs = ModuleList(convs)
+
+
+class MyG(Module):
+    def __init__(self, d, h, u):
+        super(MyG, self).__init__()
+        assert h % d == 0, 'h must be divisible by d'
+        v = h // d
+        self.d, self.h, self.u, self.v = d, h, u, v
+        self.linear1 = Conv1d(d * v, d * u, kernel_size=(1,), groups=d)
+        self.linear2 = Conv1d(d * u, d, kernel_size=(1,), groups=d)
+
+
+class FpNetwork(Module):
+    """model.py:132-153.  ``params`` is ``params['model']`` of the JSON config; the extra optional key
+    ``b200_precision`` ('bf16' tensor-core path, default; 'fp32' CUDA-core validation path) picks the kernels."""
+
+    def __init__(self, d, h, u, F, T, params):
+        super(FpNetwork, self).__init__()
+        self.f = MyF(d, h, u, F, T,
+                     fuller=params.get('fuller', False),
+                     activation=params.get('conv_activation', 'ReLU'),
+                     strides=params.get('strides'),
+                     relu_after_bn=params.get('relu_after_bn', True))
+        self.g = MyG(d, h, u)
+        self.dims = (d, h, u, F, T)
+        self.fuller = bool(params.get('fuller', False))
+        self.precision = _precision(params.get('b200_precision'))
+        self.chunk = int(params.get('b200_chunk', 0))
+        self._handles = {}     # device -> (handle, weights fingerprint)
+
+    # -- native handle management ------------------------------------------------------------------
+    def _fingerprint(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters()) + (self.precision, self.chunk)
+
+    def native_handle(self, device):
+        """pfann_model* for `device`, (re)built when the parameters changed since the last call."""
+        fp = self._fingerprint()
+        ent = self._handles.get(device)
+        if ent is not None and ent[1] == fp:
+            return ent[0]
+        L = _lib.lib()
+        if ent is None:
+            d, h, u, F, T = self.dims
+            hnd = ctypes.c_void_p()
+            _lib.check(L.pfann_model_create(_lib.ctx(device), d, h, u, F, T, int(self.fuller), ctypes.byref(hnd)),
+                       'pfann_model_create')
+        else:
+            hnd = ent[0]
+        for name, p in self.state_dict().items():
+            t = p.detach().to(torch.float32).contiguous()
+            _lib.check(L.pfann_model_set_param(hnd, name.encode(), _lib.ptr(t), t.numel()), 'pfann_model_set_param')
+        if t.is_cuda:
+            torch.cuda.synchronize(t.device)
+        _lib.check(L.pfann_model_finalize(hnd, self.precision), 'pfann_model_finalize')
+        if self.chunk > 0:
+            _lib.check(L.pfann_model_set_chunk(hnd, self.chunk), 'pfann_model_set_chunk')
+        self._handles[device] = (hnd, fp)
+        return hnd
+
+    def forward(self, x, norm=True):
+        d, h, u, F, T = self.dims
+        assert x.shape[-2:] == (F, T), 'expected [B, %d, %d], got %s' % (F, T, tuple(x.shape))
+        dev = _lib.device_index(x)
+        hnd = self.native_handle(dev)
+        _lib.use_torch_stream(dev)
+        xf = x.reshape(-1, F, T).to(torch.float32).contiguous()
+        z = torch.empty((xf.shape[0], d), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().pfann_model_forward(hnd, _lib.ptr(xf), xf.shape[0], int(bool(norm)), _lib.ptr(z)),
+                   'pfann_model_forward')
+        return z
+
+    def layer_output(self, x, layer):
+        """Parity tap: output of ``self.f.convs[layer]`` as the reference module would return it (NCHW)."""
+        d, h, u, F, T = self.dims
+        dev = _lib.device_index(x)
+        hnd = self.native_handle(dev)
+        _lib.use_torch_stream(dev)
+        L = _lib.lib()
+        _lib.check(L.pfann_model_set_tap(hnd, layer), 'pfann_model_set_tap')
+        try:
+            self.forward(x)
+            conv = self.f.convs[layer]
+            shape = (x.shape[0],) + tuple(conv.ln2.normalized_shape)
+            out = torch.empty(shape, dtype=torch.float32)
+            _lib.check(L.pfann_model_get_activation(hnd, layer, _lib.ptr(out), out.numel()),
+                       'pfann_model_get_activation')
+        finally:
+            L.pfann_model_set_tap(hnd, -1)
+        return out
+
+    def __del__(self):
+        try:
+            for hnd, _ in self._handles.values():
+                _lib.lib().pfann_model_destroy(hnd)
+        except Exception:
+            pass
