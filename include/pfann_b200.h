@@ -45,6 +45,13 @@ int pfann_ctx_sync(pfann_ctx *ctx);
 /* Number of kernels of this library launched through the context so far (bench.py: gpu_launches). */
 long long pfann_ctx_launches(pfann_ctx *ctx);
 int pfann_ctx_sm_count(pfann_ctx *ctx);
+/* Optional per-kernel-class timing: when enabled every kernel launch is bracketed by a CUDA-event pair on the
+ * launching stream.  pfann_ctx_profile_read synchronises, returns the summed milliseconds and launch counts per
+ * class (0 mel, 1 conv tcgen05, 2 conv CUDA-core, 3 LayerNorm, 4 head, 5 kNN scan, 6 kNN select, 7 rerank,
+ * 8 misc) and clears the record. */
+#define PFANN_N_KERNEL_CLASSES 9
+int pfann_ctx_profile(pfann_ctx *ctx, int enable);
+int pfann_ctx_profile_read(pfann_ctx *ctx, double *ms, long long *count, int n_classes);
 
 /* ---- stage 1: log-mel front end -------------------------------------------------------------- */
 

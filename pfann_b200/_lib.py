@@ -19,7 +19,7 @@ PRECISION_FP32 = 0
 PRECISION_BF16 = 1
 
 _lib = None
-_lock = threading.Lock()
+_lock = threading.RLock()
 _ctx = {}
 
 
@@ -39,6 +39,8 @@ def _declare(L):
     L.pfann_ctx_launches.argtypes = [vp]
     L.pfann_ctx_launches.restype = c_longlong
     L.pfann_ctx_sm_count.argtypes = [vp]
+    L.pfann_ctx_profile.argtypes = [vp, c_int]
+    L.pfann_ctx_profile_read.argtypes = [vp, POINTER(c_double), POINTER(c_longlong), c_int]
     L.pfann_mel_create.argtypes = [vp, c_int, c_int, c_int, c_double, c_double, c_int, c_int, POINTER(vp)]
     L.pfann_mel_destroy.argtypes = [vp]
     L.pfann_mel_destroy.restype = None
@@ -123,6 +125,22 @@ def use_torch_stream(device):
 
 def launches(device=0):
     return int(lib().pfann_ctx_launches(ctx(device)))
+
+
+KERNEL_CLASSES = ['mel', 'conv_tc', 'conv_cc', 'layernorm', 'head', 'knn_scan', 'knn_select', 'rerank', 'misc']
+
+
+def profile(device, enable):
+    check(lib().pfann_ctx_profile(ctx(device), int(enable)), 'pfann_ctx_profile')
+
+
+def profile_read(device=0):
+    """{class: (milliseconds, launches)} accumulated since the last read (synchronises the stream)."""
+    n = len(KERNEL_CLASSES)
+    ms = (c_double * n)()
+    cnt = (c_longlong * n)()
+    check(lib().pfann_ctx_profile_read(ctx(device), ms, cnt, n), 'pfann_ctx_profile_read')
+    return {k: (ms[i], int(cnt[i])) for i, k in enumerate(KERNEL_CLASSES)}
 
 
 def ptr(a):

@@ -58,6 +58,9 @@ struct DevBuf {
     template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// kernel classes for the optional per-class CUDA-event timing (bench.py roofline)
+enum KernelClass { K_MEL = 0, K_CONV_TC, K_CONV_CC, K_LN, K_HEAD, K_KNN_SCAN, K_KNN_SELECT, K_RERANK, K_MISC, K_NCLASS };
+
 // Per-device context: device ordinal, the stream all work is enqueued on, scratch, launch counter.
 struct Ctx {
     int device = 0;
@@ -65,6 +68,18 @@ struct Ctx {
     int sm_count = 148;
     long long launches = 0;  // kernels of OURS launched through this context (bench: gpu_launches)
     DevBuf stage_in[4], stage_out[4];
+    bool profile = false;    // record a CUDA-event pair around every kernel launch, per class
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[K_NCLASS];
+    std::vector<cudaEvent_t> prof_pool;
+};
+
+// RAII: events on the launching stream around one kernel launch (no-op unless ctx->profile)
+struct ProfScope {
+    Ctx *c;
+    int k;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ProfScope(Ctx *ctx, int klass);
+    ~ProfScope();
 };
 
 // Where does a caller pointer live?  Host buffers are staged through ctx scratch.

@@ -76,6 +76,29 @@ int finish_output(Ctx *ctx, int slot, void *dst, size_t bytes) {
     return PFANN_OK;
 }
 
+static cudaEvent_t prof_get_event(Ctx *c) {
+    if (!c->prof_pool.empty()) {
+        cudaEvent_t e = c->prof_pool.back();
+        c->prof_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+ProfScope::ProfScope(Ctx *ctx, int klass) : c(ctx), k(klass) {
+    if (!c->profile) return;
+    e0 = prof_get_event(c);
+    e1 = prof_get_event(c);
+    cudaEventRecord(e0, c->stream);
+}
+ProfScope::~ProfScope() {
+    if (!e0) return;
+    cudaEventRecord(e1, c->stream);
+    c->prof_events[k].push_back({e0, e1});
+}
+
 }  // namespace pfann
 
 using namespace pfann;
@@ -134,6 +157,37 @@ int pfann_ctx_sync(pfann_ctx *h) {
     Ctx *c = reinterpret_cast<Ctx *>(h);
     PF_CUDA(cudaSetDevice(c->device));
     PF_CUDA(cudaStreamSynchronize(c->stream));
+    return PFANN_OK;
+}
+
+int pfann_ctx_profile(pfann_ctx *h, int enable) {
+    PF_CHECK(h != nullptr, PFANN_ERR_ARG, "pfann_ctx_profile: ctx is NULL");
+    reinterpret_cast<Ctx *>(h)->profile = enable != 0;
+    return PFANN_OK;
+}
+
+int pfann_ctx_profile_read(pfann_ctx *h, double *ms, long long *count, int n_classes) {
+    PF_CHECK(h && ms && count, PFANN_ERR_ARG, "pfann_ctx_profile_read: NULL argument");
+    Ctx *c = reinterpret_cast<Ctx *>(h);
+    PF_CUDA(cudaSetDevice(c->device));
+    PF_CUDA(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < n_classes; k++) {
+        ms[k] = 0.0;
+        count[k] = 0;
+    }
+    for (int k = 0; k < K_NCLASS; k++) {
+        for (auto &pr : c->prof_events[k]) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, pr.first, pr.second);
+            if (k < n_classes) {
+                ms[k] += t;
+                count[k]++;
+            }
+            c->prof_pool.push_back(pr.first);
+            c->prof_pool.push_back(pr.second);
+        }
+        c->prof_events[k].clear();
+    }
     return PFANN_OK;
 }
 

@@ -398,6 +398,7 @@ template <typename InT>
 int launch_conv_fp32(Model *m, const ConvWeights &cw, const InT *X, float *Y, int nb) {
     const ConvGeom &g = cw.g;
     cudaStream_t st = m->ctx->stream;
+    ProfScope ps(m->ctx, K_CONV_CC);
     if (g.depthwise) {
         const long long total = (long long)nb * g.out_per_sample();
         conv_dw_kernel<InT><<<cdiv(total, 256), 256, 0, st>>>(X, cw.w_kn, cw.bias, Y, total, g.Co, g.Fi, g.Ti, g.Fo,
@@ -422,6 +423,7 @@ template <typename OutT>
 int launch_ln_apply(Model *m, const ConvWeights &cw, const float *Y, OutT *X, int nb) {
     const long long E = cw.g.out_per_sample();
     dim3 grid(cdiv(E, 1024), nb);
+    ProfScope ps(m->ctx, K_LN);
     ln_apply_kernel<OutT><<<grid, 256, 0, m->ctx->stream>>>(Y, m->stats.as<float2>(), cw.gamma, cw.beta, X, E);
     m->ctx->launches++;
     PF_CUDA(cudaGetLastError());
@@ -429,6 +431,7 @@ int launch_ln_apply(Model *m, const ConvWeights &cw, const float *Y, OutT *X, in
 }
 
 int launch_stats(Model *m, const ConvWeights &cw, const float *Y, int nb) {
+    ProfScope ps(m->ctx, K_LN);
     ln_stats_kernel<<<nb, 512, 0, m->ctx->stream>>>(Y, cw.g.out_per_sample(), m->stats.as<float2>());
     m->ctx->launches++;
     PF_CUDA(cudaGetLastError());
@@ -486,6 +489,7 @@ int forward_chunk(Model *m, const float *mel, int nb, int norm, float *z) {
         PF_TRY(save_tap<ActT>(m, 7, xb, nb));
     }
     const int threads = ((m->d + 31) / 32) * 32;
+    ProfScope ps(m->ctx, K_HEAD);
     head_kernel<<<nb, threads, (m->h + 32) * sizeof(float), m->ctx->stream>>>(
         Y, m->stats.as<float2>(), last.gamma, last.beta, m->w1, m->b1, m->w2, m->b2, z, m->d, m->h, m->u, norm);
     m->ctx->launches++;

@@ -234,6 +234,7 @@ int launch_tc(Model *m, const TcConv &tc, const TcArgs &args) {
         attr_set = true;
     }
     dim3 grid(cdiv(args.M, BM), tc.NT);
+    ProfScope ps(m->ctx, K_CONV_TC);
     conv_gemm_tc_kernel<BN><<<grid, TC_THREADS, smem, m->ctx->stream>>>(tc.mapA[0], tc.mapA[1], tc.mapA[2], tc.mapB,
                                                                          args);
     m->ctx->launches++;
@@ -348,6 +349,7 @@ int tc_conv(Model *m, int idx, const __nv_bfloat16 *X, float *Y, int nb) {
     a.Co = g.Co; a.R = (int)g.rows_per_sample(); a.To = g.To; a.fdim = tc.fdim;
     a.kb_per_tap = g.Ci / BK; a.ntaps = g.ntaps; a.NT = tc.NT; a.slots = tc.slots;
     if (tc.BN == 128) PF_TRY(launch_tc<128>(m, tc, a)); else PF_TRY(launch_tc<64>(m, tc, a));
+    ProfScope ps(m->ctx, K_LN);
     ln_finalize_kernel<<<cdiv(nb, 8), 256, 0, m->ctx->stream>>>(m->partials.as<float2>(), tc.slots, g.out_per_sample(),
                                                               m->stats.as<float2>(), nb);
     m->ctx->launches++;

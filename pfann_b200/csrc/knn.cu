@@ -84,12 +84,25 @@ __global__ void __launch_bounds__(SCAN_THREADS) knn_scan_fp32_kernel(
 }
 
 // ---- per-query threshold from the sample scores ---------------------------------------------------------
-// thr[q] = (k-th best sample score) - 2*eps*|q|*max_norm ; -inf when the sample has fewer than k rows.
-// Also writes qnorm[q].
-__global__ void __launch_bounds__(256) knn_kth_kernel(const float *sample, int64_t sample_ld, int S, int Spad,
-                                                      const float *q, int d, int k, float eps_rel, float max_norm,
-                                                      float *thr, float *qnorm) {
-    extern __shared__ uint32_t keys[];  // [Spad]
+// Stage 1: grid (Qg, nchunks): every CTA sorts one chunk (<= 8192 scores) of a query's sample in shared memory
+// and keeps its k best keys.  Stage 2: one CTA per query merges the nchunks*k survivors; the k-th best of the
+// whole sample is then  thr[q] = kth - 2*eps*|q|*max_norm  (-inf when the sample has fewer than k rows).
+__global__ void __launch_bounds__(256) knn_kth_chunk_kernel(const float *sample, int64_t sample_ld, int S, int chunk,
+                                                            int cpad, int k, uint32_t *part) {
+    extern __shared__ uint32_t keys[];  // [cpad]
+    const int qi = blockIdx.x, c = blockIdx.y, nchunks = gridDim.y;
+    const int lo = c * chunk;
+    const int n = (S - lo) < chunk ? (S - lo) : chunk;
+    for (int i = threadIdx.x; i < cpad; i += blockDim.x) keys[i] = i < n ? flipf(sample[qi * sample_ld + lo + i]) : 0u;
+    bitonic_sort<uint32_t, true>(keys, cpad);
+    uint32_t *out = part + ((int64_t)qi * nchunks + c) * k;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) out[i] = i < n ? keys[i] : 0u;
+}
+
+__global__ void __launch_bounds__(256) knn_kth_merge_kernel(const uint32_t *part, int nkeys, int P, int S,
+                                                            const float *q, int d, int k, float eps_rel,
+                                                            float max_norm, float *thr, float *qnorm) {
+    extern __shared__ uint32_t keys[];  // [P]
     __shared__ float red[8];
     const int qi = blockIdx.x;
     float ss = 0.f;
@@ -97,12 +110,12 @@ __global__ void __launch_bounds__(256) knn_kth_kernel(const float *sample, int64
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
-    for (int i = threadIdx.x; i < Spad; i += blockDim.x) keys[i] = i < S ? flipf(sample[qi * sample_ld + i]) : 0u;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) keys[i] = i < nkeys ? part[(int64_t)qi * nkeys + i] : 0u;
     __syncthreads();
     float tot = 0.f;
     for (int i = 0; i < 8; i++) tot += red[i];
     const float qn = sqrtf(tot);
-    bitonic_sort<uint32_t, true>(keys, Spad);
+    bitonic_sort<uint32_t, true>(keys, P);
     if (threadIdx.x == 0) {
         qnorm[qi] = qn;
         thr[qi] = (S >= k) ? unflipf(keys[k - 1]) - 2.f * eps_rel * qn * max_norm : -INFINITY;
@@ -289,6 +302,7 @@ int scan(Db *db, bool tc, const float *q, int Qg, int64_t r0, int64_t r1, int mo
     const size_t smem = (size_t)(QG * db->d + SCAN_ROWS * (db->d + 4)) * 4;
     for (int q0 = 0; q0 < Qg; q0 += QG) {
         const int qn = (Qg - q0) < QG ? (Qg - q0) : QG;
+        ProfScope ps(db->ctx, K_KNN_SCAN);
         knn_scan_fp32_kernel<<<(unsigned)grid, SCAN_THREADS, smem, db->ctx->stream>>>(
             db->emb32, r0, r1, db->d, q + (int64_t)q0 * db->d, qn, mode, sample ? sample + q0 * sample_ld : nullptr,
             sample_ld, thr ? thr + q0 : nullptr, cnt ? cnt + q0 : nullptr, cand ? cand + (int64_t)q0 * cap : nullptr,
@@ -318,15 +332,25 @@ int db_search_dev(Db *db, const float *q, int64_t Q, int k, float *dist, int64_t
     const float eps_rel = (tc ? 4.0e-3f : 0.f) + fmaxf(1.0e-5f, 1.2e-7f * (float)d);
     const int cap = db->cand_cap;
     const int group = tc ? 128 : QG * 4;  // queries per database pass
-    int S = (int)(db->n < db->sample_rows ? db->n : db->sample_rows);
-    if (S > 8192) S = 8192;               // kth-select sorts the sample in shared memory
-    int Spad = 1;
-    while (Spad < S) Spad <<= 1;
+    // sample size: aim at ~1024 rows above the threshold (k * n / S ~ 1024), within [sample_rows, 256 Ki]
+    int64_t want = (int64_t)k * db->n / 1024;
+    if (want < db->sample_rows) want = db->sample_rows;
+    if (want > 262144) want = 262144;
+    const int chunk = 8192;  // one kth-select CTA sorts this many sample scores in shared memory
+    int64_t max_chunks = 8192 / k;  // stage 2 sorts nchunks * k keys in shared memory
+    if (want > max_chunks * chunk) want = max_chunks * chunk;
+    const int S = (int)(db->n < want ? db->n : want);
+    const int nchunks = (S + chunk - 1) / chunk;
+    int cpad = 1;
+    while (cpad < (S < chunk ? S : chunk)) cpad <<= 1;
+    int P2 = 1;
+    while (P2 < nchunks * k) P2 <<= 1;
     PF_TRY(db->thr.ensure(sizeof(float) * group));
     PF_TRY(db->qnorm.ensure(sizeof(float) * group));
     PF_TRY(db->cnt.ensure(sizeof(int) * group));
     PF_TRY(db->cand.ensure(sizeof(uint32_t) * (size_t)group * cap));
     PF_TRY(db->sample.ensure(sizeof(float) * (size_t)group * S));
+    PF_TRY(db->rr_keys.ensure(sizeof(uint32_t) * (size_t)group * nchunks * k));
     PF_TRY(db->flags.ensure(sizeof(int) * 4));
     const size_t sel_smem = (size_t)cap * 8 + (size_t)d * 4;
     PF_CUDA(cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
@@ -337,10 +361,16 @@ int db_search_dev(Db *db, const float *q, int64_t Q, int k, float *dist, int64_t
         const float *qg = q + q0 * d;
         // 1. threshold pre-pass on the first S rows
         PF_TRY(scan(db, tc, qg, Qg, 0, S, 0, db->sample.as<float>(), S, nullptr, nullptr, nullptr, 0));
-        knn_kth_kernel<<<Qg, 256, (size_t)Spad * 4, st>>>(db->sample.as<float>(), S, S, Spad, qg, d, k, eps_rel,
-                                                          db->max_norm, db->thr.as<float>(), db->qnorm.as<float>());
-        db->ctx->launches++;
-        PF_CUDA(cudaGetLastError());
+        {
+            ProfScope ps(db->ctx, K_KNN_SELECT);
+            knn_kth_chunk_kernel<<<dim3(Qg, nchunks), 256, (size_t)cpad * 4, st>>>(
+                db->sample.as<float>(), S, S, chunk, cpad, k, db->rr_keys.as<uint32_t>());
+            knn_kth_merge_kernel<<<Qg, 256, (size_t)P2 * 4, st>>>(db->rr_keys.as<uint32_t>(), nchunks * k, P2, S, qg, d, k,
+                                                                 eps_rel, db->max_norm, db->thr.as<float>(),
+                                                                 db->qnorm.as<float>());
+            db->ctx->launches += 2;
+            PF_CUDA(cudaGetLastError());
+        }
         bool done = false;
         for (int iter = 0; iter < 4 && !done; iter++) {
             PF_CUDA(cudaMemsetAsync(db->cnt.p, 0, sizeof(int) * Qg, st));
@@ -349,10 +379,13 @@ int db_search_dev(Db *db, const float *q, int64_t Q, int k, float *dist, int64_t
             PF_TRY(scan(db, tc, qg, Qg, 0, db->n, 1, nullptr, 0, db->thr.as<float>(), db->cnt.as<int>(),
                         db->cand.as<uint32_t>(), cap));
             // 3. exact rescoring + sort
+            {
+            ProfScope ps(db->ctx, K_KNN_SELECT);
             knn_select_kernel<<<Qg, 256, sel_smem, st>>>(db->emb32, d, db->id_base, qg, db->cnt.as<int>(),
                                                          db->cand.as<uint32_t>(), cap, k, eps_rel, db->max_norm,
                                                          db->qnorm.as<float>(), db->thr.as<float>(), dist + q0 * k,
                                                          labels + q0 * k, db->flags.as<int>());
+            }
             db->ctx->launches++;
             PF_CUDA(cudaGetLastError());
             int overflow = 0;

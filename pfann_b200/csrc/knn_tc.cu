@@ -194,6 +194,7 @@ int launch_scan(Db *db, KnnTcState *st, const ScanArgs &a) {
     long long grid = db->ctx->sm_count;
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) return PFANN_OK;
+    ProfScope ps(db->ctx, K_KNN_SCAN);
     knn_scan_tc_kernel<N><<<(unsigned)grid, KNN_THREADS, smem, db->ctx->stream>>>(st->mapA, a);
     db->ctx->launches++;
     PF_CUDA(cudaGetLastError());

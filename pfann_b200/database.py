@@ -69,19 +69,10 @@ class Database:
     half-open ranges) restrict this handle to a shard cut at song boundaries (see pfann_b200.dist)."""
 
     def __init__(self, dir_for_db, indexer_params, hop_size, device=None, songs=None):
-        import torch
         self.dir_for_db = dir_for_db
-        self.params = indexer_params
-        self.top_k = self.params['top_k']
-        self.frame_shift_mul = self.params.get('frame_shift_mul', 1)
-        self.hop_size = hop_size
-        self.score_alpha = self.params.get('score_alpha', 0)
-
-        self.songList = read_file_list(os.path.join(dir_for_db, 'songList.txt'))
+        songList = read_file_list(os.path.join(dir_for_db, 'songList.txt'))
         key = np.fromfile(os.path.join(dir_for_db, 'landmarkKey'), dtype=np.int32)
-        assert len(self.songList) == key.shape[0]
-        self.song_pos = np.pad(np.cumsum(key, dtype=np.int64), (1, 0))   # database.py:86
-
+        assert len(songList) == key.shape[0]
         emb_path = os.path.join(dir_for_db, 'embeddings')
         idx_path = os.path.join(dir_for_db, 'landmarkValue')
         emb = None
@@ -89,21 +80,54 @@ class Database:
             emb = read_flat_index(idx_path)
         if emb is None:
             emb = np.fromfile(emb_path, dtype=np.float32)
-            d = self.params.get('d') or (emb.shape[0] // max(int(self.song_pos[-1]), 1))
-            emb = emb.reshape([-1, d])
-        assert emb.shape[0] == self.song_pos[-1], 'landmarkKey does not match the number of embeddings'
-        self.d = emb.shape[1]
-        self.ntotal = emb.shape[0]
+            ntotal = int(key.sum())
+            emb = emb.reshape([ntotal, -1]) if ntotal else emb.reshape([0, indexer_params.get('d', 128)])
+        self._open(emb, key, songList, indexer_params, hop_size, device, songs, False)
 
+    @classmethod
+    def from_arrays(cls, emb, landmark_key, indexer_params, hop_size, song_list=None, device=None, songs=None,
+                    emb_is_shard=False):
+        """Open from memory instead of a database directory.  `emb` is fp32 [n, d] (numpy, or a torch tensor on
+        the host or on the GPU); with ``emb_is_shard`` it holds only the rows of the songs in ``songs``."""
+        self = cls.__new__(cls)
+        self.dir_for_db = None
+        key = np.ascontiguousarray(landmark_key, dtype=np.int32)
+        if song_list is None:
+            song_list = ['song%d' % i for i in range(len(key))]
+        self._open(emb, key, song_list, indexer_params, hop_size, device, songs, emb_is_shard)
+        return self
+
+    def _open(self, emb, key, song_list, indexer_params, hop_size, device, songs, emb_is_shard):
+        import torch
+        self.params = indexer_params
+        self.top_k = self.params['top_k']
+        self.frame_shift_mul = self.params.get('frame_shift_mul', 1)
+        self.hop_size = hop_size
+        self.score_alpha = self.params.get('score_alpha', 0)
+        self.songList = song_list
+        self.song_pos = np.pad(np.cumsum(key, dtype=np.int64), (1, 0))   # database.py:86
+        self.ntotal = int(self.song_pos[-1])
+        self.d = int(emb.shape[1])
         if device is None:
             if not torch.cuda.is_available():
                 raise _lib.PfannError('pfann_b200.Database needs a CUDA device (sm_100a); there is no CPU fallback')
             device = torch.cuda.current_device()
         self.device = int(device)
-        s0, s1 = (0, len(self.songList)) if songs is None else songs
+        s0, s1 = (0, len(key)) if songs is None else songs
         self.song_range = (int(s0), int(s1))
         r0, r1 = int(self.song_pos[s0]), int(self.song_pos[s1])
-        shard = np.ascontiguousarray(emb[r0:r1])
+        if emb_is_shard:
+            assert emb.shape[0] == r1 - r0, 'shard rows do not match landmarkKey'
+            shard = emb
+        else:
+            assert emb.shape[0] == self.ntotal, 'landmarkKey does not match the number of embeddings'
+            shard = emb[r0:r1]
+        if isinstance(shard, np.ndarray):
+            shard = np.ascontiguousarray(shard, dtype=np.float32)
+        else:
+            shard = shard.to(torch.float32).contiguous()
+            if shard.is_cuda:
+                torch.cuda.synchronize(shard.device)
         skey = np.ascontiguousarray(key[s0:s1])
         self._h = ctypes.c_void_p()
         _lib.check(_lib.lib().pfann_db_open(_lib.ctx(self.device), _lib.ptr(shard), shard.shape[0], self.d,

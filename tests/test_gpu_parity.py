@@ -1,0 +1,338 @@
+"""GPU (-m gpu): the CUDA path, called through the C-ABI via the reference-shaped Python mirrors, against
+the CPU oracle (oracle/) and the golden vectors produced by the reference's own code (tests/golden/)."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip('torch')
+from oracle import pfann_oracle as orc  # noqa: E402  (checker only)
+from pfann_b200 import _lib, synth  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+MEL_MAX_TOL = 3e-3     # log domain; the reference itself (fp32) differs from the double oracle by 1.4e-3
+MEL_MEAN_TOL = 3e-5
+EMB_FP32_TOL = 1e-4    # abs, unit-norm embeddings, fp32 CUDA-core path
+EMB_BF16_COS = 1e-3    # 1 - cos, bf16 tensor-core path (bf16 operands, fp32 accumulate + LayerNorm)
+
+
+@pytest.fixture(scope='module')
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    return torch.device('cuda', 0)
+
+
+def _mel_inputs():
+    return np.concatenate([synth.synth_segments(3, seed=1), np.zeros((1, 8000), np.float32)])
+
+
+# ------------------------------------------------------------------------------------------- stage 1
+def test_mel_vs_golden_and_oracle(dev, golden_dir):
+    from pfann_b200.datautil.melspec import build_mel_spec_layer
+    params = synth.read_config('default')
+    mel = build_mel_spec_layer(params).to(dev)
+    x = _mel_inputs()
+    g = np.load(os.path.join(golden_dir, 'mel_default.npz'))['mel']
+    y = mel(torch.from_numpy(x).to(dev)).cpu().numpy()
+    assert y.shape == (4, 256, 32)
+    for ref in (g, orc.melspec(x, params)):
+        err = np.abs(y[:3] - ref[:3])
+        assert err.max() < MEL_MAX_TOL, err.max()
+        assert err.mean() < MEL_MEAN_TOL, err.mean()
+    np.testing.assert_allclose(y[3], np.log(np.float32(1e-8)), atol=1e-6)      # all-zero segment
+    # host pointers go through the same kernel (staged inside the C-ABI call) and give identical bits
+    y2 = mel(torch.from_numpy(x)).numpy()
+    assert np.array_equal(y, y2)
+    # batched / leading dims like the reference module ([..., n] -> [..., n_mels, T])
+    y3 = mel(torch.from_numpy(x).to(dev).reshape(2, 2, 8000))
+    assert tuple(y3.shape) == (2, 2, 256, 32)
+    assert np.array_equal(y3.reshape(4, 256, 32).cpu().numpy(), y)
+
+
+def test_mel_many_segments_vs_oracle(dev):
+    from pfann_b200.datautil.melspec import build_mel_spec_layer
+    params = synth.read_config('default')
+    mel = build_mel_spec_layer(params).to(dev)
+    x = synth.synth_segments(300, seed=3)
+    y = mel(torch.from_numpy(x).to(dev)).cpu().numpy()
+    ref = orc.melspec(x, params)
+    err = np.abs(y - ref)
+    assert err.max() < MEL_MAX_TOL and err.mean() < MEL_MEAN_TOL, (err.max(), err.mean())
+
+
+def test_mel_pcm16_framing_vs_oracle(dev):
+    """musicdata.py:48,82-88 folded into the kernel: ragged clips incl. one shorter than a segment."""
+    import ctypes
+    from pfann_b200.datautil.melspec import build_mel_spec_layer
+    params = synth.read_config('default')
+    mel = build_mel_spec_layer(params).to(dev)
+    lens = [8000, 20000, 5000, 31999]
+    pcm = np.concatenate([synth.synth_pcm(500 + i, n) for i, n in enumerate(lens)])
+    off = np.concatenate([[0], np.cumsum(lens)])
+    for hop in (4000, 2000):
+        starts, valids, rows = [], [], []
+        for i, n in enumerate(lens):
+            r = orc.frame_pcm16(pcm[off[i]:off[i + 1]], 8000, hop)
+            rows.append(r)
+            for s in range(r.shape[0]):
+                starts.append(off[i] + s * hop)
+                valids.append(min(8000, n - s * hop))
+        rows = np.concatenate(rows)
+        B = rows.shape[0]
+        out = np.empty((B, 256, 32), np.float32)
+        h = mel.plan_handle(0, 8000)
+        _lib.use_torch_stream(0)
+        st, va = np.array(starts, np.int64), np.array(valids, np.int32)
+        _lib.check(_lib.lib().pfann_mel_forward_pcm16(h, _lib.ptr(pcm), pcm.shape[0], _lib.ptr(st), _lib.ptr(va), B,
+                                                      _lib.ptr(out)))
+        ref = orc.melspec(rows, params)
+        err = np.abs(out - ref)
+        assert err.max() < MEL_MAX_TOL and err.mean() < MEL_MEAN_TOL, (hop, err.max(), err.mean())
+
+
+# ------------------------------------------------------------------------------------------- stage 2
+def _net(name, precision, dev, seed):
+    from pfann_b200.model import FpNetwork
+    params = synth.read_config(name)
+    d, h, u, F, T = synth.model_dims(params)
+    mp = dict(params['model'], b200_precision=precision)
+    net = FpNetwork(d, h, u, F, T, mp).to(dev)
+    sd = synth.make_state_dict(params, seed=seed)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    net.eval()
+    return net, params, sd
+
+
+@pytest.mark.parametrize('name', ['tiny', 'n640d64', 'default'])
+def test_encoder_fp32_vs_golden(dev, golden_dir, name):
+    g = np.load(os.path.join(golden_dir, 'enc_%s.npz' % name))
+    mel = np.load(os.path.join(golden_dir, 'mel_default.npz'))['mel']
+    net, params, sd = _net(name, 'fp32', dev, int(g['seed']))
+    x = torch.from_numpy(mel).to(dev)
+    z = net(x).cpu().numpy()
+    zr = net(x, norm=False).cpu().numpy()
+    np.testing.assert_allclose(z, g['z'], rtol=0, atol=EMB_FP32_TOL)
+    np.testing.assert_allclose(zr, g['z_raw'], rtol=2e-3, atol=2e-4)
+    np.testing.assert_allclose(np.linalg.norm(z, axis=1), 1.0, atol=1e-5)
+    # per-layer parity taps against the reference's module outputs (mean / std / max of each layer)
+    for l in (0, 3, 7):
+        act = net.layer_output(x, l).numpy()
+        want = g['layer_stats'][l]
+        assert abs(act.mean() - want[0]) < 2e-4 * max(1, abs(want[0])), (l, act.mean(), want)
+        assert abs(act.std(ddof=1) - want[1]) < 2e-4 * max(1, want[1]), (l, act.std(ddof=1), want)
+    enc = net.layer_output(x, 7).numpy().reshape(x.shape[0], -1)
+    np.testing.assert_allclose(enc, g['enc_out'], rtol=2e-3, atol=2e-4)
+
+
+@pytest.mark.parametrize('name', ['n640d64', 'default'])
+def test_encoder_bf16_tensor_core_vs_golden(dev, golden_dir, name):
+    g = np.load(os.path.join(golden_dir, 'enc_%s.npz' % name))
+    mel = np.load(os.path.join(golden_dir, 'mel_default.npz'))['mel']
+    net, params, sd = _net(name, 'bf16', dev, int(g['seed']))
+    x = torch.from_numpy(mel).to(dev)
+    z = net(x).cpu().numpy()
+    cos = (z * g['z']).sum(1)
+    assert (1 - cos).max() < EMB_BF16_COS, 1 - cos
+    np.testing.assert_allclose(np.linalg.norm(z, axis=1), 1.0, atol=1e-5)
+    # layer-by-layer drift stays small (relative L2 error of each SeparableConv2d output vs the fp32 path)
+    ref, _, _ = _net(name, 'fp32', dev, int(g['seed']))
+    for l in range(8):
+        a = net.layer_output(x, l).numpy()
+        b = ref.layer_output(x, l).numpy()
+        rel = np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-12)
+        assert rel < 3e-2, (l, rel)
+
+
+def test_encoder_bf16_is_deterministic_and_chunk_invariant(dev):
+    """LayerNorm partial sums use fixed slots (no atomics): identical bits run to run, and the result does
+    not depend on how segments are grouped into chunks."""
+    net, params, sd = _net('default', 'bf16', dev, 5)
+    x = torch.from_numpy(orc.melspec(synth.synth_segments(37, seed=9), params)).to(dev)
+    z1 = net(x).cpu().numpy()
+    z2 = net(x).cpu().numpy()
+    assert np.array_equal(z1, z2)
+    net.chunk = 16
+    z3 = net(x).cpu().numpy()
+    assert np.array_equal(z1, z3)
+    ref = orc.fpnetwork_forward(sd, x[:2].cpu().numpy(), params)
+    assert (1 - (z1[:2] * ref).sum(1)).max() < EMB_BF16_COS
+
+
+def test_extract_pcm16_equals_mel_plus_model(dev):
+    """builder.py:88-99 fused: PCM in, fingerprints out == framing -> mel -> model done step by step."""
+    import ctypes
+    from pfann_b200.datautil.melspec import build_mel_spec_layer
+    net, params, sd = _net('n640d64', 'bf16', dev, 21)
+    mel = build_mel_spec_layer(params).to(dev)
+    lens = [30000, 8000, 5000, 44000]
+    pcm = np.concatenate([synth.synth_pcm(900 + i, n) for i, n in enumerate(lens)])
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    L = _lib.lib()
+    nseg = L.pfann_count_segments(off.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), len(lens), 8000, 4000)
+    z = np.empty((nseg, 64), np.float32)
+    counts = np.empty(len(lens), np.int32)
+    _lib.use_torch_stream(0)
+    _lib.check(L.pfann_extract_pcm16(mel.plan_handle(0, 8000), net.native_handle(0), _lib.ptr(pcm),
+                                     off.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), len(lens), 4000, 1,
+                                     _lib.ptr(z), counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+    rows = np.concatenate([orc.frame_pcm16(pcm[off[i]:off[i + 1]], 8000, 4000) for i in range(len(lens))])
+    assert list(counts) == [(max(n, 8000) - 8000) // 4000 + 1 for n in lens] and counts.sum() == nseg
+    z2 = net(mel(torch.from_numpy(rows).to(dev))).cpu().numpy()
+    assert (1 - (z * z2).sum(1)).max() < 1e-4       # same kernels; only the mean-removal rounding differs
+    z3 = np.empty_like(z)
+    _lib.check(L.pfann_extract_segments(mel.plan_handle(0, 8000), net.native_handle(0), _lib.ptr(rows), nseg, 1,
+                                        _lib.ptr(z3)))
+    assert np.array_equal(z3, z2)
+
+
+# ------------------------------------------------------------------------------------------- stage 3
+def _open_db(tmp_path, db, key, top_k, fsm=1, alpha=0):
+    from pfann_b200.database import Database, write_flat_ip_index
+    d = str(tmp_path)
+    db.tofile(os.path.join(d, 'embeddings'))
+    write_flat_ip_index(os.path.join(d, 'landmarkValue'), db)
+    np.asarray(key, np.int32).tofile(os.path.join(d, 'landmarkKey'))
+    with open(os.path.join(d, 'songList.txt'), 'w') as f:
+        f.write('\n'.join('song%d.wav' % i for i in range(len(key))) + '\n')
+    ix = {'top_k': top_k, 'frame_shift_mul': fsm}
+    if alpha:
+        ix['score_alpha'] = alpha
+    return Database(d, ix, 0.5)
+
+
+def _check_topk(D, I, Dref, Iref, db, q):
+    """Exact-search parity: distances bit-exact for equal labels; label differences only at exact ties."""
+    assert D.shape == Dref.shape
+    same = I == Iref
+    assert np.array_equal(D[same].view(np.uint32), Dref[same].view(np.uint32))
+    if not same.all():
+        # any mismatch must be a tie in score (both orders are then valid rankings up to the id rule)
+        assert np.array_equal(D.view(np.uint32), Dref.view(np.uint32))
+        assert False, 'tie order differs from (score desc, id asc)'
+
+
+@pytest.mark.parametrize('use_tc', [0, 1])
+@pytest.mark.parametrize('k', [1, 20, 100])
+def test_knn_exact_vs_oracle(dev, tmp_path, use_tc, k):
+    db, key = synth.synth_db(50000, d=128, seed=4)
+    qs, _, _ = synth.synth_queries(db, key, 3, q_len=19, seed=8)
+    q = qs.reshape(-1, 128)
+    dbo = _open_db(tmp_path, db, key, k)
+    _lib.check(_lib.lib().pfann_db_set_tuning(dbo.handle, 0, 0, use_tc))
+    D, I = dbo.search(q)
+    Dref, Iref = orc.flat_ip_search(db, q, k)
+    _check_topk(D, I, Dref, Iref, db, q)
+    assert (np.diff(D, axis=1) <= 0).all()
+
+
+@pytest.mark.parametrize('use_tc', [0, 1])
+def test_knn_edge_cases(dev, tmp_path, use_tc):
+    # fewer rows than k -> -1 / -FLT_MAX padding (faiss contract, database.py:135)
+    db, key = synth.synth_db(7, d=128, seed=1, song_len=7)
+    dbo = _open_db(tmp_path, db, key, 10)
+    _lib.check(_lib.lib().pfann_db_set_tuning(dbo.handle, 0, 0, use_tc))
+    D, I = dbo.search(db[:3])
+    Dref, Iref = orc.flat_ip_search(db, db[:3], 10)
+    assert np.array_equal(I, Iref) and np.array_equal(D.view(np.uint32), Dref.view(np.uint32))
+    assert (I[:, 7:] == -1).all()
+    dbo.close()
+    # duplicated rows: exact ties resolve to the lower id; tiny candidate lists force the overflow/backstop paths
+    base, _ = synth.synth_db(600, d=128, seed=2)
+    dup = np.concatenate([base, base, base])
+    key = np.full(dup.shape[0] // 100, 100, np.int32)
+    dbo = _open_db(tmp_path, dup, key, 8)
+    _lib.check(_lib.lib().pfann_db_set_tuning(dbo.handle, 16, 64, use_tc))
+    q = base[:40] + 0.01
+    D, I = dbo.search(q)
+    Dref, Iref = orc.flat_ip_search(dup, q, 8)
+    assert np.array_equal(I, Iref) and np.array_equal(D.view(np.uint32), Dref.view(np.uint32))
+    dbo.close()
+    # all-zero database: every score ties
+    z = np.zeros((300, 128), np.float32)
+    dbo = _open_db(tmp_path, z, np.full(3, 100, np.int32), 5)
+    _lib.check(_lib.lib().pfann_db_set_tuning(dbo.handle, 8, 32, use_tc))
+    D, I = dbo.search(base[:2])
+    assert np.array_equal(I, np.tile(np.arange(5), (2, 1))) and (D == 0).all()
+
+
+def test_knn_many_queries_batched(dev, tmp_path):
+    """> 128 queries per call (several database passes), d = 64 (n640d64), against the oracle."""
+    db, key = synth.synth_db(20000, d=64, seed=6)
+    q = synth.synth_queries(db, key, 20, q_len=19, seed=3)[0].reshape(-1, 64)
+    dbo = _open_db(tmp_path, db, key, 20)
+    D, I = dbo.search(q)
+    Dref, Iref = orc.flat_ip_search(db, q, 20)
+    _check_topk(D, I, Dref, Iref, db, q)
+
+
+def test_seq_score_bit_exact_vs_reference_build(dev, tmp_path, golden_dir):
+    """The GPU rerank behind the reference's own seq_score() signature vs the reference's own seqscore.cpp
+    (oracle/_ref) and our C restatement: song id, offsets and scores bit for bit (score_alpha = 0)."""
+    use_ref = orc.ref_lib() is not None
+    g = np.load(os.path.join(golden_dir, 'db_small.npz'))
+    db, key = g['db'], g['key']
+    pos = synth.song_pos_from_key(key)
+    for c in range(int(g['n_cases'])):
+        q, labels, fsm = g['q%d' % c], g['labels%d' % c], int(g['fsm%d' % c])
+        dbo = _open_db(tmp_path, db, key, labels.shape[1], fsm=fsm)
+        ss = np.zeros((len(key), 2), np.float32)
+        import ctypes
+        from ctypes import POINTER, c_float, c_int64
+        best = _lib.lib().seq_score(dbo.handle, pos.ctypes.data_as(POINTER(c_int64)), len(key),
+                                    q.ctypes.data_as(POINTER(c_float)), q.shape[0],
+                                    labels.ctypes.data_as(POINTER(c_int64)), labels.shape[1],
+                                    ss.ctypes.data_as(POINTER(c_float)), fsm, 0.0)
+        rbest, rss = orc.seq_score(db, pos, q, labels, fsm, 0.0, use_ref=use_ref)
+        assert best == rbest
+        assert np.array_equal(ss.view(np.uint32), rss.view(np.uint32))
+        # and the reference's Python path (database.py:117-166, golden) agrees on (song, time)
+        sco, (sid, tim), full = dbo.query_embeddings(q)
+        assert sid == int(g['song%d' % c]) and tim == float(g['time%d' % c])
+        assert abs(sco - float(g['score%d' % c])) < 1e-6
+        np.testing.assert_allclose(full, g['ss%d' % c], rtol=0, atol=1e-6)
+        dbo.close()
+
+
+@pytest.mark.parametrize('fsm,alpha', [(1, 0.0), (2, 0.0), (3, 0.0), (1, 4.0)])
+def test_database_query_vs_oracle(dev, tmp_path, fsm, alpha):
+    db, key = synth.synth_db(30000, d=128, seed=11, song_len=59)
+    pos = synth.song_pos_from_key(key)
+    qs, songs, offs = synth.synth_queries(db, key, 16, q_len=19 * fsm if fsm > 1 else 19, seed=5)
+    dbo = _open_db(tmp_path, db, key, 20, fsm=fsm, alpha=alpha)
+    use_ref = orc.ref_lib() is not None
+    flat, index = [], []
+    for i in range(qs.shape[0]):
+        q = qs[i]
+        sco, (sid, tim), ss = dbo.query_embeddings(q)
+        _, labels = orc.flat_ip_search(db, q, 20)
+        rsco, (rsid, rtim), rss = orc.query_embeddings_cpp(db, pos, q, labels, fsm, 0.5, alpha, use_ref=use_ref)
+        assert sid == rsid and tim == rtim
+        if alpha == 0.0:
+            assert sco == rsco and np.array_equal(ss.view(np.uint32), rss.view(np.uint32))
+        else:
+            assert abs(sco - rsco) < 1e-5
+            np.testing.assert_allclose(ss, rss, rtol=0, atol=1e-5)
+        if fsm == 1:
+            assert sid == songs[i] and tim == offs[i] * 0.5      # planted diagonal recovered
+        index.append([len(flat) * q.shape[0], q.shape[0]])
+        flat.append(q)
+    # batched form == per-file form
+    bs, bsong, btime, bss = dbo.query_batch(np.concatenate(flat), np.array(index), want_song_scores=True)
+    for i in range(qs.shape[0]):
+        sco, (sid, tim), ss = dbo.query_embeddings(qs[i])
+        assert bsong[i] == sid and btime[i] == tim
+        assert np.float32(sco) == bs[i]
+        assert np.array_equal(bss[i].view(np.uint32), ss.view(np.uint32))
+
+
+def test_query_edge_cases(dev, tmp_path):
+    # empty database (database.py:126-127) and queries that overhang song ends / hit zero-length songs
+    from pfann_b200.database import Database
+    db, key = synth.synth_db(0, d=128, seed=1, song_len=5) if False else (np.zeros((0, 128), np.float32), np.zeros(2, np.int32))
+    dbo = _open_db(tmp_path, db, key, 5)
+    D, I = dbo.search(np.ones((2, 128), np.float32))
+    assert (I == -1).all()
+    sco, (sid, tim), ss = dbo.query_embeddings(np.ones((3, 128), np.float32))
+    assert sid == -1 and sco == 0.0 and tim == 0.0 and not ss.any()
