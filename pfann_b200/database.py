@@ -205,7 +205,7 @@ class Database:
             self.frame_shift_mul, float(self.score_alpha), score.ctypes.data_as(POINTER(c_float)),
             song.ctypes.data_as(POINTER(c_int32)), tim.ctypes.data_as(POINTER(c_float)),
             ss.ctypes.data_as(POINTER(c_float)) if ss is not None else None, n_songs), 'pfann_db_query')
-        scale = self.hop_size / self.frame_shift_mul
         if ss is not None:
-            ss[:, :, 1] *= scale
-        return score, song, tim.astype(np.float64) * scale, ss
+            ss[:, :, 1] *= self.hop_size / self.frame_shift_mul              # database.py:193
+        # database.py:191: frames * hop_size / fsm evaluated left to right in double, like the reference
+        return score, song, tim.astype(np.float64) * self.hop_size / self.frame_shift_mul, ss

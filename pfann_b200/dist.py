@@ -75,7 +75,7 @@ class ShardedDatabase:
         if self.world == 1:
             return t.unsqueeze(0)
         out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
-        self.dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+        self.dist.all_gather(list(out.unbind(0)), t.contiguous(), group=self.group)   # nccl and gloo alike
         return out
 
     def query_batch(self, queries, query_index):
@@ -90,7 +90,7 @@ class ShardedDatabase:
         allp = self._all_gather(pack).cpu().numpy()
         score, song, tim = combine_best(allp[:, :, 0].astype(np.float32), allp[:, :, 1].astype(np.int64),
                                         allp[:, :, 2].astype(np.float32))
-        return score, song, tim.astype(np.float64) * (self.hop_size / self.fsm)
+        return score, song, tim.astype(np.float64) * self.hop_size / self.fsm               # database.py:191
 
 
 class GpuShard:
