@@ -8,6 +8,7 @@
 //     conv2 (3x1 along F, stride 2; dense if fuller else depthwise)  -> Y -> stats -> LN-apply
 // and after layer 7 the split head (model.py:122-130) fused with the last LN-apply and the L2 normalise.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "encoder.cuh"
@@ -195,36 +196,169 @@ __global__ void __launch_bounds__(512) ln_stats_kernel(const float *Y, long long
 __device__ __forceinline__ void store_out(float *p, float v) { *p = v; }
 __device__ __forceinline__ void store_out(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
 
-// X[b][e] = relu((Y[b][e] - mean_b) * rstd_b * gamma[e] + beta[e]);  4 elements per thread
-template <typename OutT>
-__global__ void __launch_bounds__(256) ln_apply_kernel(const float *Y, const float2 *stats, const float *gamma,
-                                                       const float *beta, OutT *X, long long E) {
-    const long long b = blockIdx.y;
-    const float2 st = stats[b];
+// X[b][e] = relu((Y[b][e] - mean_b) * rstd_b * gamma[e] + beta[e]).  A thread owns 4 consecutive elements e and
+// walks over the `group` samples of blockIdx.y, so the per-element affine (gamma, beta: 2.27 M parameters for
+// default.json, L2-resident) is fetched once per group instead of once per sample.
+__device__ __forceinline__ float4 ld_y4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ float4 ld_y4(const __nv_bfloat16 *p) {
+    const uint2 u = *reinterpret_cast<const uint2 *>(p);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162 *>(&u.x), b = *reinterpret_cast<const __nv_bfloat162 *>(&u.y);
+    const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ float ld_y1(const float *p) { return *p; }
+__device__ __forceinline__ float ld_y1(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
+
+template <typename YT, typename OutT>
+__global__ void __launch_bounds__(256) ln_apply_kernel(const YT *Y, const float2 *stats, const float *gamma,
+                                                       const float *beta, OutT *X, long long E, int nb, int group) {
     const long long e0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (e0 >= E) return;
-    const float *y = Y + b * E + e0;
-    OutT *x = X + b * E + e0;
+    const int b0 = blockIdx.y * group;
+    const int b1 = (b0 + group) < nb ? (b0 + group) : nb;
     if (e0 + 3 < E && (E & 3) == 0) {
-        const float4 v = *reinterpret_cast<const float4 *>(y);
         const float4 g = __ldg(reinterpret_cast<const float4 *>(gamma + e0));
         const float4 be = __ldg(reinterpret_cast<const float4 *>(beta + e0));
-        const float o0 = fmaxf(fmaf((v.x - st.x) * st.y, g.x, be.x), 0.f);
-        const float o1 = fmaxf(fmaf((v.y - st.x) * st.y, g.y, be.y), 0.f);
-        const float o2 = fmaxf(fmaf((v.z - st.x) * st.y, g.z, be.z), 0.f);
-        const float o3 = fmaxf(fmaf((v.w - st.x) * st.y, g.w, be.w), 0.f);
-        if (sizeof(OutT) == 4) {
-            *reinterpret_cast<float4 *>(x) = make_float4(o0, o1, o2, o3);
-        } else {
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(o0, o1), p1 = __floats2bfloat162_rn(o2, o3);
-            uint2 pk;
-            pk.x = *reinterpret_cast<uint32_t *>(&p0);
-            pk.y = *reinterpret_cast<uint32_t *>(&p1);
-            *reinterpret_cast<uint2 *>(x) = pk;
+        for (int b = b0; b < b1; b++) {
+            const float2 st = __ldg(stats + b);
+            const float4 v = ld_y4(Y + (long long)b * E + e0);
+            const float o0 = fmaxf(fmaf((v.x - st.x) * st.y, g.x, be.x), 0.f);
+            const float o1 = fmaxf(fmaf((v.y - st.x) * st.y, g.y, be.y), 0.f);
+            const float o2 = fmaxf(fmaf((v.z - st.x) * st.y, g.z, be.z), 0.f);
+            const float o3 = fmaxf(fmaf((v.w - st.x) * st.y, g.w, be.w), 0.f);
+            OutT *x = X + (long long)b * E + e0;
+            if (sizeof(OutT) == 4) {
+                *reinterpret_cast<float4 *>(x) = make_float4(o0, o1, o2, o3);
+            } else {
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(o0, o1), p1 = __floats2bfloat162_rn(o2, o3);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t *>(&p0);
+                pk.y = *reinterpret_cast<uint32_t *>(&p1);
+                *reinterpret_cast<uint2 *>(x) = pk;
+            }
         }
     } else {
-        for (int i = 0; i < 4 && e0 + i < E; i++)
-            store_out(x + i, fmaxf(fmaf((y[i] - st.x) * st.y, __ldg(gamma + e0 + i), __ldg(beta + e0 + i)), 0.f));
+        for (int b = b0; b < b1; b++) {
+            const float2 st = __ldg(stats + b);
+            for (int i = 0; i < 4 && e0 + i < E; i++)
+                store_out(X + (long long)b * E + e0 + i,
+                          fmaxf(fmaf((ld_y1(Y + (long long)b * E + e0 + i) - st.x) * st.y, __ldg(gamma + e0 + i),
+                                     __ldg(beta + e0 + i)), 0.f));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Layer 0, conv1 (C_in = 1, 1x3 along time) fused with ln1 + ReLU (model.py:56-60).
+// The conv output (C x F x T/2 = 524 288 values per segment for default.json, the largest activation of
+// the network) is never written: its LayerNorm statistics follow exactly from 9 moments of the mel tile,
+//   sum  y   = P*sum_c b_c + sum_j A_j S_j                         S_j  = sum_p m_j(p)
+//   sum  y^2 = sum_jj' G_jj' R_jj' + 2 sum_j H_j S_j + P*sum_c b_c^2   R_jj' = sum_p m_j(p) m_j'(p)
+// (m_j(p) = mel value under tap j at output position p, 0 in the padding; A, G, H = sums over channels of
+// w, w w', b w), so one kernel computes conv + normalise + affine + ReLU and stores the bf16 activation.
+// ------------------------------------------------------------------------------------------------
+struct L0Args {
+    const float *mel;   // [nb][F][T]
+    int F, T, To, ntaps;
+    int off[3];
+    int C;
+};
+
+__global__ void __launch_bounds__(256) l0_moments_kernel(const L0Args a, const Model::L0Consts k, float2 *stats) {
+    __shared__ double red[8];
+    const float *m = a.mel + (long long)blockIdx.x * a.F * a.T;
+    const int P = a.F * a.To;
+    double S[3] = {0, 0, 0}, R[6] = {0, 0, 0, 0, 0, 0};  // R: 00 01 02 11 12 22
+    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+        const int f = p / a.To, to = p - f * a.To;
+        float v[3] = {0.f, 0.f, 0.f};
+        for (int j = 0; j < a.ntaps; j++) {
+            const int t = 2 * to + a.off[j];
+            if (t >= 0 && t < a.T) v[j] = m[f * a.T + t];
+        }
+        S[0] += v[0]; S[1] += v[1]; S[2] += v[2];
+        R[0] += (double)v[0] * v[0]; R[1] += (double)v[0] * v[1]; R[2] += (double)v[0] * v[2];
+        R[3] += (double)v[1] * v[1]; R[4] += (double)v[1] * v[2]; R[5] += (double)v[2] * v[2];
+    }
+    for (int i = 0; i < 3; i++) S[i] = block_sum_d(S[i], red);
+    for (int i = 0; i < 6; i++) R[i] = block_sum_d(R[i], red);
+    if (threadIdx.x == 0) {
+        const double Rm[3][3] = {{R[0], R[1], R[2]}, {R[1], R[3], R[4]}, {R[2], R[4], R[5]}};
+        double s1 = (double)P * k.Bsum, s2 = (double)P * k.B2;
+        for (int j = 0; j < 3; j++) {
+            s1 += k.A[j] * S[j];
+            s2 += 2.0 * k.H[j] * S[j];
+            for (int jj = 0; jj < 3; jj++) s2 += k.G[j][jj] * Rm[j][jj];
+        }
+        const double N = (double)P * a.C;
+        const double mean = s1 / N;
+        double var = s2 / N - mean * mean;
+        if (var < 0.0) var = 0.0;
+        stats[blockIdx.x] = make_float2((float)mean, (float)(1.0 / sqrt(var + 1e-5)));
+    }
+}
+
+// thread = (output position p, group of 8 channels); loops over the samples of its group so that the
+// per-position LayerNorm affine (gamma, beta: 4 MB for default.json) is fetched once per group, not per sample
+template <typename OutT>
+__global__ void __launch_bounds__(256) l0_conv_ln_kernel(const L0Args a, const float *__restrict__ w /*[C][ntaps]*/,
+                                                         const float *__restrict__ bias, const float *__restrict__ gamma,
+                                                         const float *__restrict__ beta, const float2 *__restrict__ stats,
+                                                         OutT *__restrict__ X, int nb, int group) {
+    const int cgroups = a.C >> 3;
+    const int ppb = 256 / cgroups;  // positions per block
+    const int cg = threadIdx.x % cgroups;
+    const int p = blockIdx.x * ppb + threadIdx.x / cgroups;
+    const int P = a.F * a.To;
+    if (p >= P) return;
+    const int f = p / a.To, to = p - f * a.To;
+    float wr[8][3], br[8], gr[8], be[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        const int ch = cg * 8 + c;
+#pragma unroll
+        for (int j = 0; j < 3; j++) wr[c][j] = j < a.ntaps ? __ldg(w + ch * a.ntaps + j) : 0.f;
+        br[c] = __ldg(bias + ch);
+        gr[c] = __ldg(gamma + (long long)p * a.C + ch);
+        be[c] = __ldg(beta + (long long)p * a.C + ch);
+    }
+    int tpos[3];
+    bool tok[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        tpos[j] = 2 * to + (j < a.ntaps ? a.off[j] : 0);
+        tok[j] = j < a.ntaps && tpos[j] >= 0 && tpos[j] < a.T;
+    }
+    const int b0 = blockIdx.y * group;
+    const int b1 = (b0 + group) < nb ? (b0 + group) : nb;
+    for (int b = b0; b < b1; b++) {
+        const float *m = a.mel + ((long long)b * a.F + f) * a.T;
+        const float m0 = tok[0] ? __ldg(m + tpos[0]) : 0.f;
+        const float m1 = tok[1] ? __ldg(m + tpos[1]) : 0.f;
+        const float m2 = tok[2] ? __ldg(m + tpos[2]) : 0.f;
+        const float2 st = __ldg(stats + b);
+        float o[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            float v = br[c];
+            v = fmaf(wr[c][0], m0, v);
+            v = fmaf(wr[c][1], m1, v);
+            v = fmaf(wr[c][2], m2, v);
+            o[c] = fmaxf(fmaf((v - st.x) * st.y, gr[c], be[c]), 0.f);
+        }
+        OutT *dst = X + ((long long)b * P + p) * a.C + cg * 8;
+        if (sizeof(OutT) == 2) {
+            __nv_bfloat162 q0 = __floats2bfloat162_rn(o[0], o[1]), q1 = __floats2bfloat162_rn(o[2], o[3]);
+            __nv_bfloat162 q2 = __floats2bfloat162_rn(o[4], o[5]), q3 = __floats2bfloat162_rn(o[6], o[7]);
+            uint4 pk;
+            pk.x = *reinterpret_cast<uint32_t *>(&q0); pk.y = *reinterpret_cast<uint32_t *>(&q1);
+            pk.z = *reinterpret_cast<uint32_t *>(&q2); pk.w = *reinterpret_cast<uint32_t *>(&q3);
+            *reinterpret_cast<uint4 *>(dst) = pk;
+        } else {
+            float *d32 = reinterpret_cast<float *>(dst);
+            *reinterpret_cast<float4 *>(d32) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4 *>(d32 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        }
     }
 }
 
@@ -419,12 +553,16 @@ int launch_conv_fp32(Model *m, const ConvWeights &cw, const InT *X, float *Y, in
     return PFANN_OK;
 }
 
-template <typename OutT>
-int launch_ln_apply(Model *m, const ConvWeights &cw, const float *Y, OutT *X, int nb) {
+template <typename YT, typename OutT>
+int launch_ln_apply(Model *m, const ConvWeights &cw, const YT *Y, OutT *X, int nb) {
     const long long E = cw.g.out_per_sample();
-    dim3 grid(cdiv(E, 1024), nb);
+    // enough CTAs to fill the machine first, then amortise the affine over as many samples as possible
+    int group = 16;
+    while (group > 1 && (long long)cdiv(E, 1024) * cdiv(nb, group) < 2LL * m->ctx->sm_count) group >>= 1;
+    dim3 grid(cdiv(E, 1024), cdiv(nb, group));
     ProfScope ps(m->ctx, K_LN);
-    ln_apply_kernel<OutT><<<grid, 256, 0, m->ctx->stream>>>(Y, m->stats.as<float2>(), cw.gamma, cw.beta, X, E);
+    ln_apply_kernel<YT, OutT><<<grid, 256, 0, m->ctx->stream>>>(Y, m->stats.as<float2>(), cw.gamma, cw.beta, X, E, nb,
+                                                                group);
     m->ctx->launches++;
     PF_CUDA(cudaGetLastError());
     return PFANN_OK;
@@ -452,6 +590,31 @@ int save_tap(Model *m, int l, const ActT *X, int nb) {
     return PFANN_OK;
 }
 
+template <typename ActT>
+int launch_l0_fused(Model *m, const float *mel, ActT *X, int nb) {
+    const ConvWeights &cw = m->conv[0];
+    const ConvGeom &g = cw.g;
+    L0Args a;
+    a.mel = mel; a.F = g.Fi; a.T = g.Ti; a.To = g.To; a.ntaps = g.ntaps; a.C = g.Co;
+    for (int j = 0; j < 3; j++) a.off[j] = g.tap_off[j];
+    cudaStream_t st = m->ctx->stream;
+    {
+        ProfScope ps(m->ctx, K_LN);
+        l0_moments_kernel<<<nb, 256, 0, st>>>(a, m->l0c, m->stats.as<float2>());
+    }
+    const int cgroups = g.Co / 8, ppb = 256 / cgroups, P = g.Fi * g.To;
+    const int group = 32;
+    dim3 grid(cdiv(P, ppb), cdiv(nb, group));
+    {
+        ProfScope ps(m->ctx, K_CONV_CC);
+        l0_conv_ln_kernel<ActT><<<grid, 256, 0, st>>>(a, m->l0_w, cw.bias, cw.gamma, cw.beta, m->stats.as<float2>(), X, nb,
+                                                      group);
+    }
+    m->ctx->launches += 2;
+    PF_CUDA(cudaGetLastError());
+    return PFANN_OK;
+}
+
 // one chunk of nb <= m->chunk samples through the 8 layers + head
 template <typename ActT>
 int forward_chunk(Model *m, const float *mel, int nb, int norm, float *z) {
@@ -462,30 +625,41 @@ int forward_chunk(Model *m, const float *mel, int nb, int norm, float *z) {
         for (int which = 0; which < 2; which++) {
             const ConvWeights &cw = m->conv[2 * l + which];
             const bool first = (l == 0 && which == 0);
-            bool stats_done = false;
+            const bool last = (l == 7 && which == 1);
+            bool stats_done = false, ybf = false;
+            if (first && m->l0_fused) {
+                // conv1 + ln1 + ReLU in one pass, statistics from the mel moments: nothing else to do
+                PF_TRY(launch_l0_fused<ActT>(m, mel, xa, nb));
+                continue;
+            }
             if (first) {
                 // layer 0 conv1: C_in = 1, K = 3 -- CUDA cores in both paths, reads the fp32 mel directly
                 PF_TRY(launch_conv_fp32<float>(m, cw, mel, Y, nb));
             } else {
                 const ActT *in = which == 0 ? xb : xa;
                 if (tc && tc_supported(cw.g)) {
-                    PF_TRY(tc_conv(m, 2 * l + which, reinterpret_cast<const __nv_bfloat16 *>(in), Y, nb));
-                    stats_done = true;  // statistics come out of the GEMM epilogue
+                    ybf = m->y_bf16 && !last;  // the head reads the last raw output in fp32
+                    PF_TRY(tc_conv(m, 2 * l + which, reinterpret_cast<const __nv_bfloat16 *>(in), Y, ybf, nb));
+                    stats_done = true;  // statistics come out of the GEMM epilogue (from the fp32 accumulators)
                 } else {
                     // depthwise conv2 (fuller == false) and geometries without a tensor-core mapping
                     PF_TRY(launch_conv_fp32<ActT>(m, cw, in, Y, nb));
                 }
             }
             if (!stats_done) PF_TRY(launch_stats(m, cw, Y, nb));
-            if (l == 7 && which == 1) break;  // the head applies the last LayerNorm itself
-            PF_TRY(launch_ln_apply<ActT>(m, cw, Y, which == 0 ? xa : xb, nb));
+            if (last) break;  // the head applies the last LayerNorm itself
+            if (ybf)
+                PF_TRY((launch_ln_apply<__nv_bfloat16, ActT>(m, cw, reinterpret_cast<const __nv_bfloat16 *>(Y),
+                                                             which == 0 ? xa : xb, nb)));
+            else
+                PF_TRY((launch_ln_apply<float, ActT>(m, cw, Y, which == 0 ? xa : xb, nb)));
             if (which == 1) PF_TRY(save_tap<ActT>(m, l, xb, nb));
         }
     }
     const ConvWeights &last = m->conv[15];
     if (m->tap_layer == 7) {
         // materialise the layer-7 output only when asked for
-        PF_TRY(launch_ln_apply<ActT>(m, last, Y, xb, nb));
+        PF_TRY((launch_ln_apply<float, ActT>(m, last, Y, xb, nb)));
         PF_TRY(save_tap<ActT>(m, 7, xb, nb));
     }
     const int threads = ((m->d + 31) / 32) * 32;
@@ -561,7 +735,7 @@ void pfann_model_destroy(pfann_model *hm) {
     cudaSetDevice(m->ctx->device);
     tc_release(m);
     for (int i = 0; i < 16; i++) free_conv(m->conv[i]);
-    cudaFree(m->w1); cudaFree(m->b1); cudaFree(m->w2); cudaFree(m->b2);
+    cudaFree(m->w1); cudaFree(m->b1); cudaFree(m->w2); cudaFree(m->b2); cudaFree(m->l0_w);
     m->ybuf.release(); m->xa.release(); m->xb.release(); m->stats.release(); m->partials.release();
     m->tapbuf.release(); m->melbuf.release(); m->zbuf.release();
     delete m;
@@ -609,6 +783,31 @@ int pfann_model_finalize(pfann_model *hm, int precision) {
             return rc;
         }
         F = F2; T = T2;
+    }
+    {
+        // layer-0 fusion constants (live taps of conv1, channel sums in double)
+        const ConvGeom &g = m->conv[0].g;
+        const std::vector<float> &w = m->host["f.convs.0.conv1.weight"], &b = m->host["f.convs.0.conv1.bias"];
+        Model::L0Consts c = {};
+        std::vector<float> wt((size_t)g.Co * g.ntaps);
+        for (int o = 0; o < g.Co; o++) {
+            c.Bsum += b[o];
+            c.B2 += (double)b[o] * b[o];
+            for (int j = 0; j < g.ntaps; j++) {
+                const double wj = w[(size_t)o * 3 + g.tap_k[j]];
+                wt[(size_t)o * g.ntaps + j] = (float)wj;
+                c.A[j] += wj;
+                c.H[j] += (double)b[o] * wj;
+                for (int jj = 0; jj < g.ntaps; jj++) c.G[j][jj] += wj * (double)w[(size_t)o * 3 + g.tap_k[jj]];
+            }
+        }
+        m->l0c = c;
+        cudaFree(m->l0_w);
+        m->l0_w = nullptr;
+        PF_TRY(upload(wt, &m->l0_w));
+        m->y_bf16 = getenv("PFANN_B200_Y_FP32") == nullptr;
+        m->l0_fused = g.Ci == 1 && g.Co % 8 == 0 && (256 % (g.Co / 8)) == 0 && g.Co / 8 <= 256 &&
+                      getenv("PFANN_B200_NO_L0_FUSION") == nullptr;
     }
     const int v = m->h / m->d;
     const std::vector<float> *w1 = find_param(m, "g.linear1.weight", (size_t)m->d * m->u * v);

@@ -48,6 +48,14 @@ struct Model {
     std::map<std::string, std::vector<float>> host;  // reference-keyed fp32 parameters (as given)
     ConvWeights conv[16];                            // conv[2l] = conv1 of layer l, conv[2l+1] = conv2
     float *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;  // head (model.py:118-120)
+    // layer-0 conv1 fusion: sums over output channels that turn 9 moments of the mel tile into the exact
+    // LayerNorm statistics of the (never materialised) conv output.  Live taps only.
+    struct L0Consts {
+        double A[3], G[3][3], H[3], Bsum, B2;
+    } l0c;
+    float *l0_w = nullptr;  // [Co][ntaps] fp32 (tap-major per channel)
+    bool l0_fused = false;
+    bool y_bf16 = true;     // tensor-core convs write their raw output in bf16 (statistics stay fp32)
     DevBuf ybuf, xa, xb, stats, partials, tapbuf, melbuf, zbuf;
     int tap_layer = -1;
     long long tap_numel = 0;
@@ -58,8 +66,8 @@ struct Model {
 int tc_prepare(Model *m);                      // build per-layer state after weights are on the device
 void tc_release(Model *m);
 bool tc_supported(const ConvGeom &g);
-// Y[m][n] (fp32) = conv GEMM of X (bf16, channels-last) for `nb` samples; also writes per-sample
+// Y[m][n] (fp32 or bf16) = conv GEMM of X (bf16, channels-last) for `nb` samples; also writes per-sample
 // LayerNorm partial sums into m->partials and reduces them into m->stats (mean, rstd).
-int tc_conv(Model *m, int idx, const __nv_bfloat16 *X, float *Y, int nb);
+int tc_conv(Model *m, int idx, const __nv_bfloat16 *X, void *Y, bool y_bf16, int nb);
 
 }  // namespace pfann

@@ -160,6 +160,21 @@ def test_encoder_bf16_is_deterministic_and_chunk_invariant(dev):
     assert (1 - (z1[:2] * ref).sum(1)).max() < EMB_BF16_COS
 
 
+def test_layer0_fusion_matches_unfused(dev, monkeypatch):
+    """conv1 + ln1 + ReLU of layer 0 with statistics derived from the mel moments == conv -> two-pass LN."""
+    params = synth.read_config('default')
+    x = torch.from_numpy(orc.melspec(synth.synth_segments(5, seed=2), params)).to(dev)
+    fused, _, _ = _net('default', 'fp32', dev, 7)
+    a = fused.layer_output(x, 0).numpy()
+    za = fused(x).cpu().numpy()
+    monkeypatch.setenv('PFANN_B200_NO_L0_FUSION', '1')
+    plain, _, _ = _net('default', 'fp32', dev, 7)
+    b = plain.layer_output(x, 0).numpy()
+    zb = plain(x).cpu().numpy()
+    np.testing.assert_allclose(a, b, rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(za, zb, rtol=0, atol=2e-5)
+
+
 def test_extract_pcm16_equals_mel_plus_model(dev):
     """builder.py:88-99 fused: PCM in, fingerprints out == framing -> mel -> model done step by step."""
     import ctypes

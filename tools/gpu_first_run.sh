@@ -22,6 +22,8 @@ for t in "$@"; do
     smoke)   run t_smoke 300 python __graft_entry__.py smoke ;;
     bench_small) run bench_small 600 python bench.py --clips 500 --db-rows 1000000 --queries 1000 --steps 2 --warmup 1 ;;
     bench)   run bench 1200 python bench.py ;;
+    sweep)   for c in 128 512 2048 4096; do run sweep_$c 300 python bench.py --clips 2000 --chunk $c --steps 2 --warmup 1 --no-match --no-cpu; done ;;
+    cli)     run t_cli 300 python -m pytest tests/test_gpu_cli.py -q -m gpu ;;
     all)     run t_all 900 python -m pytest tests -q -m gpu ;;
     ncu_list) run ncu_list 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --clips 100 --chunk 1024 --db-rows 1000000 --queries 100 --no-cpu ;;
     ncu_conv) run ncu_conv 900 ncu --set full --clock-control none --import-source on -k regex:conv_gemm_tc -s 30 -c 4 -o gpurun_out/prof_conv python bench.py --steps 1 --warmup 1 --clips 100 --no-match --no-cpu ;;
