@@ -31,6 +31,7 @@ enum {
         if (_e != cudaSuccess) {                                                              \
             ::pfann::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                  \
                                cudaGetErrorString(_e));                                       \
+            cudaGetLastError(); /* do not leave a stale error for the next check */           \
             return ::pfann::PFANN_ERR_CUDA;                                                   \
         }                                                                                     \
     } while (0)

@@ -300,12 +300,12 @@ template <int BN, typename YT>
 int launch_tc(Model *m, const TcConv &tc, const TcArgs &args) {
     const size_t smem =
         (size_t)tc_stages<BN>() * (BM * BK * 2 + BN * BK * 2) + 4 * 4096 + (size_t)args.Co * 4 + 1024;
-    PF_CHECK(smem <= 227 * 1024, PFANN_ERR_UNSUPPORTED, "conv GEMM needs %zu B of shared memory", smem);
-    static bool attr_set = false;
-    if (!attr_set) {
+    PF_CHECK(smem + 2048 <= 227 * 1024, PFANN_ERR_UNSUPPORTED, "conv GEMM needs %zu B of shared memory", smem);
+    static size_t attr_smem = 0;  // per instantiation: raise the opt-in limit only when a launch needs more
+    if (smem > attr_smem) {
         PF_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, YT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     227 * 1024));
-        attr_set = true;
+                                     (int)smem));
+        attr_smem = smem;
     }
     const long long ntiles = (long long)args.m_tiles * args.NT;
     long long grid = m->ctx->sm_count;
