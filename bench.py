@@ -178,7 +178,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--clips', type=int, default=10000, help='clips per GPU (config 2: 10000)')
     ap.add_argument('--clip-seconds', type=int, default=30)
-    ap.add_argument('--chunk', type=int, default=1024, help='segments per internal pass')
+    ap.add_argument('--chunk', type=int, default=4096, help='segments per internal pass')
     ap.add_argument('--precision', default='bf16')
     ap.add_argument('--db-rows', type=int, default=10_000_000)
     ap.add_argument('--queries', type=int, default=10000)

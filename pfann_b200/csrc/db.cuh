@@ -35,6 +35,32 @@ __device__ __forceinline__ float dot_fma_seq(const float *__restrict__ a, const 
     for (int k = 0; k < d; k++) acc = __fmaf_rn(a[k], b[k], acc);
     return acc;
 }
+// Same arithmetic (one fmaf per element, k ascending -> bit-identical result), but the row is fetched one
+// 128-byte line ahead of the dependent FMA chain so a thread keeps two lines in flight.  `row` is global and
+// 16-byte aligned, `q` is in shared memory, d % 32 == 0.
+__device__ __forceinline__ float dot_fma_seq_lines(const float *__restrict__ row, const float *__restrict__ q, int d) {
+    const float4 *r4 = reinterpret_cast<const float4 *>(row);
+    float4 cur[8], nxt[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) cur[i] = __ldg(r4 + i);
+    float acc = 0.f;
+    for (int l = 0; l < d; l += 32) {
+        if (l + 32 < d) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) nxt[i] = __ldg(r4 + (l >> 2) + 8 + i);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            acc = __fmaf_rn(cur[i].x, q[l + 4 * i], acc);
+            acc = __fmaf_rn(cur[i].y, q[l + 4 * i + 1], acc);
+            acc = __fmaf_rn(cur[i].z, q[l + 4 * i + 2], acc);
+            acc = __fmaf_rn(cur[i].w, q[l + 4 * i + 3], acc);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) cur[i] = nxt[i];
+    }
+    return acc;
+}
 // order-preserving float -> uint32 (larger float -> larger key)
 __device__ __forceinline__ uint32_t flipf(float f) {
     uint32_t u = __float_as_uint(f);

@@ -331,33 +331,45 @@ __global__ void __launch_bounds__(256) l0_conv_ln_kernel(const L0Args a, const f
     }
     const int b0 = blockIdx.y * group;
     const int b1 = (b0 + group) < nb ? (b0 + group) : nb;
-    for (int b = b0; b < b1; b++) {
-        const float *m = a.mel + ((long long)b * a.F + f) * a.T;
-        const float m0 = tok[0] ? __ldg(m + tpos[0]) : 0.f;
-        const float m1 = tok[1] ? __ldg(m + tpos[1]) : 0.f;
-        const float m2 = tok[2] ? __ldg(m + tpos[2]) : 0.f;
-        const float2 st = __ldg(stats + b);
-        float o[8];
+    constexpr int UB = 4;  // samples in flight per thread: all their loads are issued before any arithmetic
+    for (int bb = b0; bb < b1; bb += UB) {
+        float mv[UB][3];
+        float2 st[UB];
 #pragma unroll
-        for (int c = 0; c < 8; c++) {
-            float v = br[c];
-            v = fmaf(wr[c][0], m0, v);
-            v = fmaf(wr[c][1], m1, v);
-            v = fmaf(wr[c][2], m2, v);
-            o[c] = fmaxf(fmaf((v - st.x) * st.y, gr[c], be[c]), 0.f);
+        for (int u = 0; u < UB; u++) {
+            const int b = (bb + u) < b1 ? (bb + u) : (b1 - 1);
+            const float *m = a.mel + ((long long)b * a.F + f) * a.T;
+            mv[u][0] = tok[0] ? __ldg(m + tpos[0]) : 0.f;
+            mv[u][1] = tok[1] ? __ldg(m + tpos[1]) : 0.f;
+            mv[u][2] = tok[2] ? __ldg(m + tpos[2]) : 0.f;
+            st[u] = __ldg(stats + b);
         }
-        OutT *dst = X + ((long long)b * P + p) * a.C + cg * 8;
-        if (sizeof(OutT) == 2) {
-            __nv_bfloat162 q0 = __floats2bfloat162_rn(o[0], o[1]), q1 = __floats2bfloat162_rn(o[2], o[3]);
-            __nv_bfloat162 q2 = __floats2bfloat162_rn(o[4], o[5]), q3 = __floats2bfloat162_rn(o[6], o[7]);
-            uint4 pk;
-            pk.x = *reinterpret_cast<uint32_t *>(&q0); pk.y = *reinterpret_cast<uint32_t *>(&q1);
-            pk.z = *reinterpret_cast<uint32_t *>(&q2); pk.w = *reinterpret_cast<uint32_t *>(&q3);
-            *reinterpret_cast<uint4 *>(dst) = pk;
-        } else {
-            float *d32 = reinterpret_cast<float *>(dst);
-            *reinterpret_cast<float4 *>(d32) = make_float4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<float4 *>(d32 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+#pragma unroll
+        for (int u = 0; u < UB; u++) {
+            const int b = bb + u;
+            if (b >= b1) break;
+            float o[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                float v = br[c];
+                v = fmaf(wr[c][0], mv[u][0], v);
+                v = fmaf(wr[c][1], mv[u][1], v);
+                v = fmaf(wr[c][2], mv[u][2], v);
+                o[c] = fmaxf(fmaf((v - st[u].x) * st[u].y, gr[c], be[c]), 0.f);
+            }
+            OutT *dst = X + ((long long)b * P + p) * a.C + cg * 8;
+            if (sizeof(OutT) == 2) {
+                __nv_bfloat162 q0 = __floats2bfloat162_rn(o[0], o[1]), q1 = __floats2bfloat162_rn(o[2], o[3]);
+                __nv_bfloat162 q2 = __floats2bfloat162_rn(o[4], o[5]), q3 = __floats2bfloat162_rn(o[6], o[7]);
+                uint4 pk;
+                pk.x = *reinterpret_cast<uint32_t *>(&q0); pk.y = *reinterpret_cast<uint32_t *>(&q1);
+                pk.z = *reinterpret_cast<uint32_t *>(&q2); pk.w = *reinterpret_cast<uint32_t *>(&q3);
+                *reinterpret_cast<uint4 *>(dst) = pk;
+            } else {
+                float *d32 = reinterpret_cast<float *>(dst);
+                *reinterpret_cast<float4 *>(d32) = make_float4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<float4 *>(d32 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+            }
         }
     }
 }
@@ -381,11 +393,74 @@ __global__ void to_nchw_kernel(const InT *X, float *out, long long total, int C,
 
 // ------------------------------------------------------------------------------------------------
 // Head: last LN-apply + ReLU, grouped h -> d*u, ELU, grouped d*u -> d, optional L2 normalise
-// (model.py:122-130).  One CTA per sample, one thread per output dimension g.
+// (model.py:122-130).  Persistent CTAs (one thread per output dimension g); the head weights (132 KB for
+// default.json) are staged ONCE per CTA into shared memory in a lane-major layout ([j][i][g], conflict-free)
+// and reused for every sample the CTA processes, instead of being re-read from L2 per sample.
 // ------------------------------------------------------------------------------------------------
 __global__ void head_kernel(const float *Y /*[nb][h]*/, const float2 *stats, const float *gamma, const float *beta,
-                            const float *w1, const float *b1, const float *w2, const float *b2, float *z, int d,
-                            int h, int u, int norm) {
+                            const float *w1, const float *b1, const float *w2, const float *b2, float *z, int nb,
+                            int d, int h, int u, int norm) {
+    extern __shared__ float hsm[];
+    const int v = h / d, dp = blockDim.x;  // dp = d rounded up to a warp multiple
+    float *w1s = hsm;                       // [u][v][dp]
+    float *b1s = w1s + (size_t)u * v * dp;  // [u][dp]
+    float *w2s = b1s + (size_t)u * dp;      // [u][dp]
+    float *xs = w2s + (size_t)u * dp;       // [v][dp]  LayerNorm'ed inputs of the current sample
+    float *red = xs + (size_t)v * dp;       // [32]
+    const int g = threadIdx.x;
+    for (int idx = threadIdx.x; idx < u * v * dp; idx += blockDim.x) {
+        const int gg = idx % dp, i = (idx / dp) % v, j = idx / (dp * v);
+        w1s[idx] = gg < d ? w1[((size_t)gg * u + j) * v + i] : 0.f;
+    }
+    for (int idx = threadIdx.x; idx < u * dp; idx += blockDim.x) {
+        const int gg = idx % dp, j = idx / dp;
+        b1s[idx] = gg < d ? b1[gg * u + j] : 0.f;
+        w2s[idx] = gg < d ? w2[gg * u + j] : 0.f;
+    }
+    const float bias2 = g < d ? b2[g] : 0.f;
+    float gam[16], bet[16];  // this thread's v LayerNorm affine values (v <= 16 on this path)
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        gam[i] = (i < v && g < d) ? gamma[g * v + i] : 0.f;
+        bet[i] = (i < v && g < d) ? beta[g * v + i] : 0.f;
+    }
+    __syncthreads();
+    for (long long b = blockIdx.x; b < nb; b += gridDim.x) {
+        const float2 st = stats[b];
+        float out = bias2;
+        if (g < d) {
+            float x[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                if (i < v) x[i] = fmaxf(fmaf((Y[b * h + g * v + i] - st.x) * st.y, gam[i], bet[i]), 0.f);
+            for (int j = 0; j < u; j++) {
+                float acc = b1s[j * dp + g];
+#pragma unroll
+                for (int i = 0; i < 16; i++)
+                    if (i < v) acc = fmaf(w1s[(j * v + i) * dp + g], x[i], acc);
+                const float e = acc > 0.f ? acc : expm1f(acc);  // ELU(alpha = 1)
+                out = fmaf(w2s[j * dp + g], e, out);
+            }
+        }
+        if (norm) {
+            float s = g < d ? out * out : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            __syncthreads();  // red[] free again
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+            __syncthreads();
+            float t = 0.f;
+            for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += red[i];
+            out = out / fmaxf(sqrtf(t), 1e-12f);  // F.normalize(p=2, eps=1e-12)
+        }
+        if (g < d) z[b * d + g] = out;
+    }
+}
+
+// generic fallback (v > 16 or weights too large for shared memory): one CTA per sample, weights from L2
+__global__ void head_kernel_generic(const float *Y, const float2 *stats, const float *gamma, const float *beta,
+                                    const float *w1, const float *b1, const float *w2, const float *b2, float *z, int d,
+                                    int h, int u, int norm) {
     extern __shared__ float hs[];  // [h] + [32]
     float *red = hs + h;
     const long long b = blockIdx.x;
@@ -401,7 +476,7 @@ __global__ void head_kernel(const float *Y /*[nb][h]*/, const float2 *stats, con
             float acc = __ldg(b1 + g * u + j);
             const float *w = w1 + (long long)(g * u + j) * v;
             for (int i = 0; i < v; i++) acc = fmaf(__ldg(w + i), hs[g * v + i], acc);
-            const float e = acc > 0.f ? acc : expm1f(acc);  // ELU(alpha = 1)
+            const float e = acc > 0.f ? acc : expm1f(acc);
             out = fmaf(__ldg(w2 + g * u + j), e, out);
         }
     }
@@ -413,7 +488,7 @@ __global__ void head_kernel(const float *Y /*[nb][h]*/, const float2 *stats, con
         __syncthreads();
         float t = 0.f;
         for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += red[i];
-        out = out / fmaxf(sqrtf(t), 1e-12f);  // F.normalize(p=2, eps=1e-12)
+        out = out / fmaxf(sqrtf(t), 1e-12f);
     }
     if (g < d) z[b * d + g] = out;
 }
@@ -664,8 +739,21 @@ int forward_chunk(Model *m, const float *mel, int nb, int norm, float *z) {
     }
     const int threads = ((m->d + 31) / 32) * 32;
     ProfScope ps(m->ctx, K_HEAD);
-    head_kernel<<<nb, threads, (m->h + 32) * sizeof(float), m->ctx->stream>>>(
-        Y, m->stats.as<float2>(), last.gamma, last.beta, m->w1, m->b1, m->w2, m->b2, z, m->d, m->h, m->u, norm);
+    const int v = m->h / m->d;
+    const size_t smem_fast = ((size_t)m->u * v * threads + 2 * (size_t)m->u * threads + (size_t)v * threads + 32) * 4;
+    if (v <= 16 && smem_fast <= 200 * 1024) {
+        static size_t attr = 0;
+        if (smem_fast > attr) {
+            PF_CUDA(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
+            attr = smem_fast;
+        }
+        const int grid = nb < m->ctx->sm_count ? nb : m->ctx->sm_count;
+        head_kernel<<<grid, threads, smem_fast, m->ctx->stream>>>(Y, m->stats.as<float2>(), last.gamma, last.beta, m->w1,
+                                                                   m->b1, m->w2, m->b2, z, nb, m->d, m->h, m->u, norm);
+    } else {
+        head_kernel_generic<<<nb, threads, (m->h + 32) * sizeof(float), m->ctx->stream>>>(
+            Y, m->stats.as<float2>(), last.gamma, last.beta, m->w1, m->b1, m->w2, m->b2, z, m->d, m->h, m->u, norm);
+    }
     m->ctx->launches++;
     PF_CUDA(cudaGetLastError());
     return PFANN_OK;
@@ -675,7 +763,7 @@ int ensure_workspace(Model *m) {
     long long maxY = 0, maxA = 0, maxB = 0;
     for (int i = 0; i < 16; i++) {
         const long long e = m->conv[i].g.out_per_sample();
-        if (e > maxY) maxY = e;
+        if (e > maxY && !(i == 0 && m->l0_fused)) maxY = e;  // fused layer 0 never stores its raw output
         if ((i & 1) == 0 && e > maxA) maxA = e;
         if ((i & 1) == 1 && e > maxB) maxB = e;
     }

@@ -346,7 +346,7 @@ int tc_prepare(Model *m) {
     long long maxY = 0, maxA = 0, maxB = 0;
     for (int i = 0; i < 16; i++) {
         const long long e = m->conv[i].g.out_per_sample();
-        if (e > maxY) maxY = e;
+        if (e > maxY && !(i == 0 && m->l0_fused)) maxY = e;
         if ((i & 1) == 0 && e > maxA) maxA = e;
         if ((i & 1) == 1 && e > maxB) maxB = e;
     }

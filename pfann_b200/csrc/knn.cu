@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256) knn_select_kernel(const float *__restrict
         unsigned long long key = 0ull;
         if (i < n) {
             const uint32_t id = cand[(int64_t)qi * cap + i];
-            const float s = dot_fma_seq(db + (int64_t)id * d, qv, d);
+            const float s = (d & 31) == 0 ? dot_fma_seq_lines(db + (int64_t)id * d, qv, d) : dot_fma_seq(db + (int64_t)id * d, qv, d);
             key = ((unsigned long long)flipf(s) << 32) | (unsigned long long)(0xFFFFFFFFu - id);
         }
         keys[i] = key;

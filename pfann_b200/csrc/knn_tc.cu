@@ -25,6 +25,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int STAGES = 4;
 constexpr int KNN_THREADS = 192;
+constexpr int QCAP = 2048;  // parked filter survivors per CTA
 
 struct KnnTcState {
     CUtensorMap mapA;  // [n][d] bf16, box (64, 128)
@@ -55,6 +56,10 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_scan_tc_kernel(const __gri
     const uint32_t B_KB_BYTES = N * BK * 2;
     unsigned char *sB = sbase;                         // [KBLK][N rows][128 B]
     unsigned char *sA = sbase + (size_t)B_KB_BYTES * KBLK;  // [STAGES][KBLK][128 rows][128 B]
+    // survivors of the filter are parked here and pushed to the global candidate lists after the scan: a
+    // global atomicAdd with return (~1 us) must not sit between the TMEM read and the buffer release
+    uint2 *queue = reinterpret_cast<uint2 *>(sA + (size_t)STAGES * STAGE_BYTES);  // [QCAP] (query, row)
+    __shared__ int qcount_s;
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ float thr_s[N];
@@ -63,6 +68,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_scan_tc_kernel(const __gri
     const long long ntiles = (a.r1 - a.r0 + BM - 1) / BM;
 
     if (tid == 0) {
+        qcount_s = 0;
         ptx::prefetch_tmap(&mapA);
         for (int s = 0; s < STAGES; s++) {
             ptx::mbar_init(&full_bar[s], 1);
@@ -172,8 +178,13 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_scan_tc_kernel(const __gri
 #pragma unroll
                         for (int i = 0; i < 32; i++) {
                             if (__uint_as_float(v[i]) >= thr_s[c + i]) {
-                                const int pos = atomicAdd(a.cnt + c + i, 1);
-                                if (pos < a.cap) a.cand[(long long)(c + i) * a.cap + pos] = (uint32_t)row;
+                                const int qp = atomicAdd(&qcount_s, 1);
+                                if (qp < QCAP) {
+                                    queue[qp] = make_uint2((uint32_t)(c + i), (uint32_t)row);
+                                } else {  // queue full (degenerate thresholds): push directly
+                                    const int pos = atomicAdd(a.cnt + c + i, 1);
+                                    if (pos < a.cap) a.cand[(long long)(c + i) * a.cap + pos] = (uint32_t)row;
+                                }
                             }
                         }
                     }
@@ -183,6 +194,16 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_scan_tc_kernel(const __gri
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tempty_bar[buf]);
+        }
+        // flush the parked survivors: the 128 epilogue threads issue their global atomics side by side
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (a.mode == 1) {
+            const int nq = qcount_s < QCAP ? qcount_s : QCAP;
+            for (int i = tid - 64; i < nq; i += 128) {
+                const uint2 e = queue[i];
+                const int pos = atomicAdd(a.cnt + e.x, 1);
+                if (pos < a.cap) a.cand[(long long)e.x * a.cap + pos] = e.y;
+            }
         }
     }
     ptx::tc_fence_before();
@@ -196,7 +217,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_scan_tc_kernel(const __gri
 template <int N>
 int launch_scan(Db *db, KnnTcState *st, const ScanArgs &a) {
     const int KBLK = db->d / BK;
-    const size_t smem = 1024 + (size_t)N * BK * 2 * KBLK + (size_t)STAGES * BM * BK * 2 * KBLK;
+    const size_t smem = 1024 + (size_t)N * BK * 2 * KBLK + (size_t)STAGES * BM * BK * 2 * KBLK + (size_t)QCAP * 8;
     PF_CUDA(cudaFuncSetAttribute(knn_scan_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long ntiles = (a.r1 - a.r0 + BM - 1) / BM;
     long long grid = db->ctx->sm_count;

@@ -22,11 +22,12 @@ for t in "$@"; do
     smoke)   run t_smoke 300 python __graft_entry__.py smoke ;;
     bench_small) run bench_small 600 python bench.py --clips 500 --db-rows 1000000 --queries 1000 --steps 2 --warmup 1 ;;
     bench)   run bench 1200 python bench.py ;;
-    sweep)   for c in 128 512 2048 4096; do run sweep_$c 300 python bench.py --clips 2000 --chunk $c --steps 2 --warmup 1 --no-match --no-cpu; done ;;
+    sweep)   for c in ${SWEEP:-2048 4096 8192}; do run sweep_$c 300 python bench.py --clips 2000 --chunk $c --steps 2 --warmup 1 --no-match --no-cpu; done ;;
     cli)     run t_cli 300 python -m pytest tests/test_gpu_cli.py -q -m gpu ;;
+    probe)   run knn_probe 600 python tools/knn_probe.py ;;
     all)     run t_all 900 python -m pytest tests -q -m gpu ;;
-    ncu_list) run ncu_list 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --clips 100 --chunk 1024 --db-rows 1000000 --queries 100 --no-cpu ;;
-    ncu_conv) run ncu_conv 900 ncu --set full --clock-control none --import-source on -k regex:conv_gemm_tc -s 30 -c 4 -o gpurun_out/prof_conv python bench.py --steps 1 --warmup 1 --clips 100 --no-match --no-cpu ;;
+    ncu_list) run ncu_list 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --clips 300 --chunk 4096 --db-rows 1000000 --queries 100 --no-cpu ;;
+    ncu_conv) run ncu_conv 900 ncu --set full --clock-control none --import-source on -k regex:conv_gemm_tc -s 30 -c 6 -o gpurun_out/prof_conv python bench.py --steps 1 --warmup 1 --clips 300 --no-match --no-cpu ;;
     ncu_knn)  run ncu_knn 900 ncu --set full --clock-control none --import-source on -k regex:knn_scan_tc -s 4 -c 2 -o gpurun_out/prof_knn python bench.py --steps 1 --warmup 1 --clips 20 --db-rows 10000000 --queries 100 --no-cpu ;;
   esac
 done
