@@ -42,6 +42,7 @@ struct ScanArgs {
     int *cnt;
     uint32_t *cand;
     int cap;
+    unsigned long long *prof;  // optional [grid][8] cycle counters (tools/knn_probe.py)
     int debug;           // probe knob (PFANN_KNN_DEBUG): 1 skip filter, 2 skip TMEM loads too, 3 also skip the MMAs
 };
 
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_scan_tc_kernel(const __gri
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    long long pc[5] = {0, 0, 0, 0, 0};  // cycle accounting: producer wait, mma wait tempty/full, epilogue wait/work
 
     if (warp == 0) {
         if (lane == 0) {
@@ -113,7 +115,9 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_scan_tc_kernel(const __gri
             long long it = 0;
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
                 const int s = (int)(it % STAGES);
+                const long long c0 = clock64();
                 if (it >= STAGES) ptx::mbar_wait(&empty_bar[s], (uint32_t)((it / STAGES) - 1) & 1);
+                pc[0] += clock64() - c0;
                 ptx::mbar_expect_tx(&full_bar[s], STAGE_BYTES);
                 const int row0 = (int)(a.r0 + tile * BM);
                 for (int kb = 0; kb < KBLK; kb++)
@@ -128,8 +132,12 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_scan_tc_kernel(const __gri
             long long it = 0;
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
                 const int s = (int)(it % STAGES), buf = (int)(it & 1);
+                const long long c0 = clock64();
                 if (it >= 2) ptx::mbar_wait(&tempty_bar[buf], (uint32_t)((it >> 1) - 1) & 1);
+                const long long c1 = clock64();
                 ptx::mbar_wait(&full_bar[s], (uint32_t)(it / STAGES) & 1);
+                pc[1] += c1 - c0;
+                pc[2] += clock64() - c1;
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N);
                 for (int kb = 0; kb < KBLK && a.debug < 3; kb++) {
@@ -149,8 +157,11 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_scan_tc_kernel(const __gri
         long long it = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
             const int buf = (int)(it & 1);
+            const long long c0 = clock64();
             ptx::mbar_wait(&tfull_bar[buf], (uint32_t)(it >> 1) & 1);
             ptx::tc_fence_after();
+            const long long c1 = clock64();
+            pc[3] += c1 - c0;
             const long long row = a.r0 + tile * BM + quarter * 32 + lane;
             const bool rvalid = row < a.r1;
 #pragma unroll 1
@@ -194,6 +205,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_scan_tc_kernel(const __gri
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tempty_bar[buf]);
+            pc[4] += clock64() - c1;
         }
         // flush the parked survivors: the 128 epilogue threads issue their global atomics side by side
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -205,6 +217,13 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_scan_tc_kernel(const __gri
                 if (pos < a.cap) a.cand[(long long)e.x * a.cap + pos] = e.y;
             }
         }
+    }
+    if (a.prof && lane == 0) {
+        unsigned long long *o = a.prof + (size_t)blockIdx.x * 8;
+        if (warp == 0) o[0] = pc[0];
+        if (warp == 1) { o[1] = pc[1]; o[2] = pc[2]; }
+        if (warp >= 2) { atomicAdd(&o[3], (unsigned long long)pc[3]); atomicAdd(&o[4], (unsigned long long)pc[4]); }
+        if (warp == 2) o[5] = (unsigned long long)ntiles;
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -275,6 +294,8 @@ int knn_tc_scan(Db *db, const float *q, int Qg, int64_t r0, int64_t r1, int mode
     a.sample = sample; a.sample_ld = sample_ld; a.thr = thr; a.cnt = cnt; a.cand = cand; a.cap = cap;
     const char *dbg = getenv("PFANN_KNN_DEBUG");
     a.debug = dbg ? atoi(dbg) : 0;
+    const char *pp = getenv("PFANN_KNN_PROF_PTR");  // probe only: device address of a zeroed [grid][8] u64 buffer
+    a.prof = pp ? reinterpret_cast<unsigned long long *>(strtoull(pp, nullptr, 0)) : nullptr;
     if (Qg <= 32) return launch_scan<32>(db, st, a);
     return launch_scan<128>(db, st, a);
 }

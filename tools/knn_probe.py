@@ -18,6 +18,8 @@ emb /= emb.norm(dim=1, keepdim=True)
 key = np.full(n // 50, 50, np.int32)
 db = Database.from_arrays(emb, key, {'top_k': 20}, 0.5, device=0)
 del emb
+prof = torch.zeros((148, 8), dtype=torch.int64, device=dev)
+os.environ['PFANN_KNN_PROF_PTR'] = str(prof.data_ptr())
 for Q in (19, 128):
     q = torch.randn((Q, 128), device=dev)
     q /= q.norm(dim=1, keepdim=True)
@@ -25,6 +27,7 @@ for Q in (19, 128):
     I = torch.empty((Q, 20), dtype=torch.int64, device=dev)
     for dbg in (0, 1, 2, 3):
         os.environ['PFANN_KNN_DEBUG'] = str(dbg)
+        prof.zero_()
         _lib.use_torch_stream(0)
         for it in range(3):
             if it == 1:
@@ -36,3 +39,7 @@ for Q in (19, 128):
         sel = p['knn_select'][0]
         print('Q=%3d debug=%d  scan %.3f ms over %d launches (%.1f GB/s of bf16 DB per full pass)  select %.3f ms'
               % (Q, dbg, ms / 2, cnt // 2, n * 256 / (ms / 2 / 1e3) / 1e9 if ms else 0, sel / 2), flush=True)
+        pr = prof.cpu().numpy().astype(np.float64)
+        tiles = n / 128 / 148 * 3  # 3 searches x (prepass + full scan) accumulate; per-CTA tiles of the full scans dominate
+        print('     cycles/tile/CTA: producer wait empty %.0f | mma wait tempty %.0f, wait full %.0f | epilogue (avg of 4 warps) wait tfull %.0f, work %.0f'
+              % tuple(pr[:, j].mean() / tiles / (4 if j >= 3 else 1) for j in range(5)), flush=True)
