@@ -340,6 +340,7 @@ def bench_match(torch, args, world, rank, local, device, barrier, max_over_ranks
         q = torch.empty((nq * q_len, d), device=device)
     if world > 1:
         torch.distributed.broadcast(q, 0)
+    emb_host = emb.cpu() if (world == 1 and not args.no_cpu) else None   # for the CPU baseline of this leg
     del emb
     torch.cuda.empty_cache()
     qi = np.stack([np.arange(nq, dtype=np.int64) * q_len, np.full(nq, q_len, np.int64)], axis=1)
@@ -377,6 +378,28 @@ def bench_match(torch, args, world, rank, local, device, barrier, max_over_ranks
             qii[:, 0] -= b0 * q_len
             db.query_batch(qh[b0 * q_len:b1 * q_len], qii)
         e2e = nq / (time.perf_counter() - t0)
+    cpu = None
+    if emb_host is not None:
+        # reference path on the host cores: exact inner-product top-k (torch-CPU matmul + topk standing in for
+        # faiss IndexFlatIP, which is not installed) + the reference's rerank arithmetic (oracle seq_score, C)
+        from oracle import pfann_oracle as orc
+        torch.set_num_threads(os.cpu_count() or 1)
+        qh_all = q.cpu()
+        dbn = emb_host.numpy()
+        ncpu = min(nq, 6)
+        t0 = time.perf_counter()
+        ok = 0
+        for i in range(ncpu):
+            qq = qh_all[i * q_len:(i + 1) * q_len]
+            _, lab = torch.topk(qq @ emb_host.T, k, dim=1)
+            best, ss = orc.seq_score(dbn, pos, qq.numpy(), lab.numpy(), 1, 0.0)
+            ok += int(best == res['song'][i] and ss[best, 1] * 0.5 == res['time'][i])
+        dt = time.perf_counter() - t0
+        cpu = {'value': ncpu / dt, 'unit': 'queries/s', 'cores': os.cpu_count(), 'kind': 'port',
+               'sample': '%d of %d query files vs the full %d-row database; torch-CPU matmul+topk stands in for faiss '
+                         'IndexFlatIP, rerank = C restatement of cpp/seqscore.cpp' % (ncpu, nq, n),
+               'answers_equal_gpu': ok == ncpu}
+        del emb_host, dbn
     scan_ms, scan_n = prof['knn_scan']
     rows_local = r1 - r0
     passes = scan_n  # each launch streams (a sample of, or all of) the shard once
@@ -387,7 +410,7 @@ def bench_match(torch, args, world, rank, local, device, barrier, max_over_ranks
             'knn_scan': {'launches': passes, 'ms': scan_ms,
                          'tflops': (2.0 * nq * q_len * rows_local * d) / (scan_ms / 1000.0) / 1e12 if scan_ms else None,
                          'frac_of_bf16_peak': ((2.0 * nq * q_len * rows_local * d) / (scan_ms / 1000.0) / 1e12) / pk['tf_sustained'] if scan_ms else None},
-            'gpu_launches': int(_lib.launches(local) - l0)}
+            'gpu_launches': int(_lib.launches(local) - l0), 'cpu_baseline': cpu}
 
 
 if __name__ == '__main__':

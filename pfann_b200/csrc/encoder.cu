@@ -298,66 +298,79 @@ __global__ void __launch_bounds__(256) l0_moments_kernel(const L0Args a, const M
     }
 }
 
-// thread = (output position p, group of 8 channels); loops over the samples of its group so that the
-// per-position LayerNorm affine (gamma, beta: 4 MB for default.json) is fetched once per group, not per sample
-template <typename OutT>
+// thread = (PP consecutive output positions along time, group of 8 channels); it loops over the samples of its
+// group so that the per-position LayerNorm affine (gamma, beta: 4 MB for default.json) and the conv weights stay
+// in registers, and the 2*PP+1 mel values a sample contributes are fetched once for all 8*PP outputs.
+template <typename OutT, int PP>
 __global__ void __launch_bounds__(256) l0_conv_ln_kernel(const L0Args a, const float *__restrict__ w /*[C][ntaps]*/,
                                                          const float *__restrict__ bias, const float *__restrict__ gamma,
                                                          const float *__restrict__ beta, const float2 *__restrict__ stats,
                                                          OutT *__restrict__ X, int nb, int group) {
     const int cgroups = a.C >> 3;
-    const int ppb = 256 / cgroups;  // positions per block
+    const int ppb = 256 / cgroups;  // position groups per block
     const int cg = threadIdx.x % cgroups;
-    const int p = blockIdx.x * ppb + threadIdx.x / cgroups;
+    const int pg = blockIdx.x * ppb + threadIdx.x / cgroups;  // position group: PP consecutive `to` of one f
     const int P = a.F * a.To;
-    if (p >= P) return;
-    const int f = p / a.To, to = p - f * a.To;
-    float wr[8][3], br[8], gr[8], be[8];
+    const int p0 = pg * PP;
+    if (p0 >= P) return;
+    const int f = p0 / a.To, to0 = p0 - f * a.To;
+    float wr[8][3], br[8], gr[PP][8], be[PP][8];
 #pragma unroll
     for (int c = 0; c < 8; c++) {
         const int ch = cg * 8 + c;
 #pragma unroll
         for (int j = 0; j < 3; j++) wr[c][j] = j < a.ntaps ? __ldg(w + ch * a.ntaps + j) : 0.f;
         br[c] = __ldg(bias + ch);
-        gr[c] = __ldg(gamma + (long long)p * a.C + ch);
-        be[c] = __ldg(beta + (long long)p * a.C + ch);
-    }
-    int tpos[3];
-    bool tok[3];
 #pragma unroll
-    for (int j = 0; j < 3; j++) {
-        tpos[j] = 2 * to + (j < a.ntaps ? a.off[j] : 0);
-        tok[j] = j < a.ntaps && tpos[j] >= 0 && tpos[j] < a.T;
+        for (int q = 0; q < PP; q++) {
+            gr[q][c] = __ldg(gamma + (long long)(p0 + q) * a.C + ch);
+            be[q][c] = __ldg(beta + (long long)(p0 + q) * a.C + ch);
+        }
     }
+    // mel columns needed: t = 2*(to0+q) + off[j]; with offsets {0,1,2} that is the run [2*to0, 2*to0 + 2*PP]
+    constexpr int NM = 2 * PP + 1;
+    const int tbase = 2 * to0 + a.off[0];
     const int b0 = blockIdx.y * group;
     const int b1 = (b0 + group) < nb ? (b0 + group) : nb;
-    constexpr int UB = 4;  // samples in flight per thread: all their loads are issued before any arithmetic
-    for (int bb = b0; bb < b1; bb += UB) {
-        float mv[UB][3];
-        float2 st[UB];
+    // software pipeline over samples: the next sample's mel run and statistics are in flight while this one is
+    // being computed
+    float nx[NM];
+    float2 nst;
+    {
+        const float *m = a.mel + ((long long)b0 * a.F + f) * a.T;
 #pragma unroll
-        for (int u = 0; u < UB; u++) {
-            const int b = (bb + u) < b1 ? (bb + u) : (b1 - 1);
-            const float *m = a.mel + ((long long)b * a.F + f) * a.T;
-            mv[u][0] = tok[0] ? __ldg(m + tpos[0]) : 0.f;
-            mv[u][1] = tok[1] ? __ldg(m + tpos[1]) : 0.f;
-            mv[u][2] = tok[2] ? __ldg(m + tpos[2]) : 0.f;
-            st[u] = __ldg(stats + b);
+        for (int i = 0; i < NM; i++) {
+            const int t = tbase + i;
+            nx[i] = (t >= 0 && t < a.T) ? __ldg(m + t) : 0.f;
+        }
+        nst = __ldg(stats + b0);
+    }
+    for (int b = b0; b < b1; b++) {
+        float mv[NM];
+#pragma unroll
+        for (int i = 0; i < NM; i++) mv[i] = nx[i];
+        const float2 st = nst;
+        if (b + 1 < b1) {
+            const float *m = a.mel + ((long long)(b + 1) * a.F + f) * a.T;
+#pragma unroll
+            for (int i = 0; i < NM; i++) {
+                const int t = tbase + i;
+                nx[i] = (t >= 0 && t < a.T) ? __ldg(m + t) : 0.f;
+            }
+            nst = __ldg(stats + b + 1);
         }
 #pragma unroll
-        for (int u = 0; u < UB; u++) {
-            const int b = bb + u;
-            if (b >= b1) break;
+        for (int q = 0; q < PP; q++) {
             float o[8];
 #pragma unroll
             for (int c = 0; c < 8; c++) {
                 float v = br[c];
-                v = fmaf(wr[c][0], mv[u][0], v);
-                v = fmaf(wr[c][1], mv[u][1], v);
-                v = fmaf(wr[c][2], mv[u][2], v);
-                o[c] = fmaxf(fmaf((v - st[u].x) * st[u].y, gr[c], be[c]), 0.f);
+                v = fmaf(wr[c][0], mv[2 * q], v);
+                v = fmaf(wr[c][1], mv[2 * q + 1], v);
+                v = fmaf(wr[c][2], mv[2 * q + 2], v);
+                o[c] = fmaxf(fmaf((v - st.x) * st.y, gr[q][c], be[q][c]), 0.f);
             }
-            OutT *dst = X + ((long long)b * P + p) * a.C + cg * 8;
+            OutT *dst = X + ((long long)b * P + p0 + q) * a.C + cg * 8;
             if (sizeof(OutT) == 2) {
                 __nv_bfloat162 q0 = __floats2bfloat162_rn(o[0], o[1]), q1 = __floats2bfloat162_rn(o[2], o[3]);
                 __nv_bfloat162 q2 = __floats2bfloat162_rn(o[4], o[5]), q3 = __floats2bfloat162_rn(o[6], o[7]);
@@ -679,11 +692,25 @@ int launch_l0_fused(Model *m, const float *mel, ActT *X, int nb) {
     }
     const int cgroups = g.Co / 8, ppb = 256 / cgroups, P = g.Fi * g.To;
     const int group = 32;
-    dim3 grid(cdiv(P, ppb), cdiv(nb, group));
+    // the 4-positions-per-thread variant needs the three taps to be the contiguous run {o, o+1, o+2}
+    const bool run3 = g.ntaps == 3 && g.tap_off[1] == g.tap_off[0] + 1 && g.tap_off[2] == g.tap_off[0] + 2;
     {
         ProfScope ps(m->ctx, K_CONV_CC);
-        l0_conv_ln_kernel<ActT><<<grid, 256, 0, st>>>(a, m->l0_w, cw.bias, cw.gamma, cw.beta, m->stats.as<float2>(), X, nb,
-                                                      group);
+        static const int pp_env = getenv("PFANN_L0_PP") ? atoi(getenv("PFANN_L0_PP")) : 4;
+        if (run3 && g.To % 4 == 0 && pp_env == 4) {
+            dim3 grid(cdiv(P / 4, ppb), cdiv(nb, group));
+            l0_conv_ln_kernel<ActT, 4><<<grid, 256, 0, st>>>(a, m->l0_w, cw.bias, cw.gamma, cw.beta,
+                                                             m->stats.as<float2>(), X, nb, group);
+        } else if (run3 && g.To % 2 == 0 && pp_env == 2) {
+            dim3 grid(cdiv(P / 2, ppb), cdiv(nb, group));
+            l0_conv_ln_kernel<ActT, 2><<<grid, 256, 0, st>>>(a, m->l0_w, cw.bias, cw.gamma, cw.beta,
+                                                             m->stats.as<float2>(), X, nb, group);
+        } else {
+            // one position per thread: mel run = [2 to + off0, +2]; other tap sets go through wr = 0 columns
+            dim3 grid(cdiv(P, ppb), cdiv(nb, group));
+            l0_conv_ln_kernel<ActT, 1><<<grid, 256, 0, st>>>(a, m->l0_w, cw.bias, cw.gamma, cw.beta,
+                                                             m->stats.as<float2>(), X, nb, group);
+        }
     }
     m->ctx->launches += 2;
     PF_CUDA(cudaGetLastError());
@@ -894,7 +921,9 @@ int pfann_model_finalize(pfann_model *hm, int precision) {
         m->l0_w = nullptr;
         PF_TRY(upload(wt, &m->l0_w));
         m->y_bf16 = getenv("PFANN_B200_Y_FP32") == nullptr;
-        m->l0_fused = g.Ci == 1 && g.Co % 8 == 0 && (256 % (g.Co / 8)) == 0 && g.Co / 8 <= 256 &&
+        bool taps_run = true;  // the fused kernel reads the mel run off[0], off[0]+1, off[0]+2
+        for (int j = 1; j < g.ntaps; j++) taps_run = taps_run && g.tap_off[j] == g.tap_off[0] + j;
+        m->l0_fused = taps_run && g.Ci == 1 && g.Co % 8 == 0 && (256 % (g.Co / 8)) == 0 && g.Co / 8 <= 256 &&
                       getenv("PFANN_B200_NO_L0_FUSION") == nullptr;
     }
     const int v = m->h / m->d;

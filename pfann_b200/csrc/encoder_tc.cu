@@ -182,11 +182,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
                 ptx::tmem_ld_wait();
                 float o[32];
 #pragma unroll
-                for (int i = 0; i < 32; i++) {
-                    o[i] = __uint_as_float(v[i]) + bias_s[n0 + c + i];
-                    s1 += o[i];
-                    s2 = fmaf(o[i], o[i], s2);
+                for (int j = 0; j < 8; j++) {  // bias by vector loads into distinct registers (no LDS serialisation)
+                    const float4 b4 = *reinterpret_cast<const float4 *>(&bias_s[n0 + c + 4 * j]);
+                    o[4 * j] = __uint_as_float(v[4 * j]) + b4.x;
+                    o[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
+                    o[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z;
+                    o[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
                 }
+                float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};  // 4 independent chains
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    p1[i & 3] += o[i];
+                    p2[i & 3] = fmaf(o[i], o[i], p2[i & 3]);
+                }
+                s1 += (p1[0] + p1[1]) + (p1[2] + p1[3]);
+                s2 += (p2[0] + p2[1]) + (p2[2] + p2[3]);
                 // registers (row = lane) -> XOR-swizzled smem (conflict-free both ways) -> row-contiguous stores
                 const int sw = sizeof(YT) == 4 ? (lane & 7) : ((lane >> 1) & 3);
                 if (sizeof(YT) == 4) {
