@@ -190,9 +190,17 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_scan_tc_kernel(const __gri
                         const float4 t4 = *reinterpret_cast<const float4 *>(&thr_s[c + 4 * j]);
                         th[4 * j] = t4.x; th[4 * j + 1] = t4.y; th[4 * j + 2] = t4.z; th[4 * j + 3] = t4.w;
                     }
-                    bool any = false;
+                    // "does any score reach its threshold" as a max-tree over (score - threshold): 32 independent
+                    // subtractions + a depth-5 tree; an OR-chain of 32 predicate compares is one long dependency
+                    // chain (measured ~16 cycles per compare)
+                    float mx[32];
 #pragma unroll
-                    for (int i = 0; i < 32; i++) any |= (__uint_as_float(v[i]) >= th[i]);
+                    for (int i = 0; i < 32; i++) mx[i] = __uint_as_float(v[i]) - th[i];
+#pragma unroll
+                    for (int w = 16; w > 0; w >>= 1)
+#pragma unroll
+                        for (int i = 0; i < w; i++) mx[i] = fmaxf(mx[i], mx[i + w]);
+                    const bool any = mx[0] >= 0.f;
                     if (any && rvalid) {
 #pragma unroll
                         for (int i = 0; i < 32; i++) {
