@@ -193,25 +193,29 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_scan_tc_kernel(const __gri
                     // "does any score reach its threshold" as a max-tree over (score - threshold): 32 independent
                     // subtractions + a depth-5 tree; an OR-chain of 32 predicate compares is one long dependency
                     // chain (measured ~16 cycles per compare)
-                    float mx[32];
+                    float df[32], mx[16];
 #pragma unroll
-                    for (int i = 0; i < 32; i++) mx[i] = __uint_as_float(v[i]) - th[i];
+                    for (int i = 0; i < 32; i++) df[i] = __uint_as_float(v[i]) - th[i];
 #pragma unroll
-                    for (int w = 16; w > 0; w >>= 1)
+                    for (int i = 0; i < 16; i++) mx[i] = fmaxf(df[i], df[i + 16]);
+#pragma unroll
+                    for (int w = 8; w > 0; w >>= 1)
 #pragma unroll
                         for (int i = 0; i < w; i++) mx[i] = fmaxf(mx[i], mx[i + w]);
-                    const bool any = mx[0] >= 0.f;
-                    if (any && rvalid) {
+                    if (mx[0] >= 0.f && rvalid) {
+                        // rare path (a few lanes per tile): branch-free hit mask, then one iteration per hit
+                        uint32_t mask = 0;
 #pragma unroll
-                        for (int i = 0; i < 32; i++) {
-                            if (__uint_as_float(v[i]) >= th[i]) {
-                                const int qp = atomicAdd(&qcount_s, 1);
-                                if (qp < QCAP) {
-                                    queue[qp] = make_uint2((uint32_t)(c + i), (uint32_t)row);
-                                } else {  // queue full (degenerate thresholds): push directly
-                                    const int pos = atomicAdd(a.cnt + c + i, 1);
-                                    if (pos < a.cap) a.cand[(long long)(c + i) * a.cap + pos] = (uint32_t)row;
-                                }
+                        for (int i = 0; i < 32; i++) mask |= (df[i] >= 0.f ? 1u : 0u) << i;
+                        while (mask) {
+                            const int i = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            const int qp = atomicAdd(&qcount_s, 1);
+                            if (qp < QCAP) {
+                                queue[qp] = make_uint2((uint32_t)(c + i), (uint32_t)row);
+                            } else {  // queue full (degenerate thresholds): push directly
+                                const int pos = atomicAdd(a.cnt + c + i, 1);
+                                if (pos < a.cap) a.cand[(long long)(c + i) * a.cap + pos] = (uint32_t)row;
                             }
                         }
                     }
