@@ -89,13 +89,27 @@ __global__ void __launch_bounds__(SCAN_THREADS) knn_scan_fp32_kernel(
 // whole sample is then  thr[q] = kth - 2*eps*|q|*max_norm  (-inf when the sample has fewer than k rows).
 __global__ void __launch_bounds__(256) knn_kth_chunk_kernel(const float *sample, int64_t sample_ld, int S, int chunk,
                                                             int cpad, int k, uint32_t *part) {
-    extern __shared__ uint32_t keys[];  // [cpad]
+    extern __shared__ uint32_t keys[];  // [cpad] (full sort) or [256] (thread-max path)
     const int qi = blockIdx.x, c = blockIdx.y, nchunks = gridDim.y;
     const int lo = c * chunk;
     const int n = (S - lo) < chunk ? (S - lo) : chunk;
+    uint32_t *out = part + ((int64_t)qi * nchunks + c) * k;
+    if (k <= 128) {
+        // Cheap and still safe: every thread keeps the maximum of its strided slice; the k-th largest of those 256
+        // maxima is an actual sample score that is <= the chunk's true k-th largest (each maximum is a distinct
+        // element), i.e. still a valid lower bound -- and nearly tight, since the top k rarely share a slice.
+        uint32_t m = 0u;
+        for (int i = threadIdx.x; i < n; i += 256) {
+            const uint32_t key = flipf(sample[qi * sample_ld + lo + i]);
+            m = key > m ? key : m;
+        }
+        keys[threadIdx.x] = m;
+        bitonic_sort<uint32_t, true>(keys, 256);
+        for (int i = threadIdx.x; i < k; i += blockDim.x) out[i] = keys[i];
+        return;
+    }
     for (int i = threadIdx.x; i < cpad; i += blockDim.x) keys[i] = i < n ? flipf(sample[qi * sample_ld + lo + i]) : 0u;
     bitonic_sort<uint32_t, true>(keys, cpad);
-    uint32_t *out = part + ((int64_t)qi * nchunks + c) * k;
     for (int i = threadIdx.x; i < k; i += blockDim.x) out[i] = i < n ? keys[i] : 0u;
 }
 
@@ -363,7 +377,7 @@ int db_search_dev(Db *db, const float *q, int64_t Q, int k, float *dist, int64_t
         PF_TRY(scan(db, tc, qg, Qg, 0, S, 0, db->sample.as<float>(), S, nullptr, nullptr, nullptr, 0));
         {
             ProfScope ps(db->ctx, K_KNN_SELECT);
-            knn_kth_chunk_kernel<<<dim3(Qg, nchunks), 256, (size_t)cpad * 4, st>>>(
+            knn_kth_chunk_kernel<<<dim3(Qg, nchunks), 256, (size_t)(cpad > 256 ? cpad : 256) * 4, st>>>(
                 db->sample.as<float>(), S, S, chunk, cpad, k, db->rr_keys.as<uint32_t>());
             knn_kth_merge_kernel<<<Qg, 256, (size_t)P2 * 4, st>>>(db->rr_keys.as<uint32_t>(), nchunks * k, P2, S, qg, d, k,
                                                                  eps_rel, db->max_norm, db->thr.as<float>(),
