@@ -649,7 +649,7 @@ int launch_ln_apply(Model *m, const ConvWeights &cw, const YT *Y, OutT *X, int n
     while (group > 1 && (long long)cdiv(E, 1024) * cdiv(nb, group) < 2LL * m->ctx->sm_count) group >>= 1;
     dim3 grid(cdiv(E, 1024), cdiv(nb, group));
     ProfScope ps(m->ctx, K_LN);
-    ln_apply_kernel<YT, OutT><<<grid, 256, 0, m->ctx->stream>>>(Y, m->stats.as<float2>(), cw.gamma, cw.beta, X, E, nb,
+    ln_apply_kernel<YT, OutT><<<grid, 256, 0, m->ctx->stream>>>(Y, m->cur_stats, cw.gamma, cw.beta, X, E, nb,
                                                                 group);
     m->ctx->launches++;
     PF_CUDA(cudaGetLastError());
@@ -658,23 +658,24 @@ int launch_ln_apply(Model *m, const ConvWeights &cw, const YT *Y, OutT *X, int n
 
 int launch_stats(Model *m, const ConvWeights &cw, const float *Y, int nb) {
     ProfScope ps(m->ctx, K_LN);
-    ln_stats_kernel<<<nb, 512, 0, m->ctx->stream>>>(Y, cw.g.out_per_sample(), m->stats.as<float2>());
+    ln_stats_kernel<<<nb, 512, 0, m->ctx->stream>>>(Y, cw.g.out_per_sample(), m->cur_stats);
     m->ctx->launches++;
     PF_CUDA(cudaGetLastError());
     return PFANN_OK;
 }
 
 template <typename ActT>
-int save_tap(Model *m, int l, const ActT *X, int nb) {
+int save_tap(Model *m, int l, const ActT *X, int nb, int total_nb = -1, int s0 = 0) {
     if (m->tap_layer != l) return PFANN_OK;
     const ConvGeom &g = m->conv[2 * l + 1].g;
+    if (total_nb < 0) total_nb = nb;
     const long long total = (long long)nb * g.out_per_sample();
-    PF_TRY(m->tapbuf.ensure((size_t)total * 4));
-    to_nchw_kernel<ActT><<<cdiv(total, 256), 256, 0, m->ctx->stream>>>(X, m->tapbuf.as<float>(), total, g.Co, g.Fo,
-                                                                        g.To);
+    PF_TRY(m->tapbuf.ensure((size_t)total_nb * g.out_per_sample() * 4));  // sized once for the whole call
+    to_nchw_kernel<ActT><<<cdiv(total, 256), 256, 0, m->ctx->stream>>>(
+        X, m->tapbuf.as<float>() + (long long)s0 * g.out_per_sample(), total, g.Co, g.Fo, g.To);
     m->ctx->launches++;
     PF_CUDA(cudaGetLastError());
-    m->tap_numel = total;
+    m->tap_numel = (long long)total_nb * g.out_per_sample();
     return PFANN_OK;
 }
 
@@ -688,7 +689,7 @@ int launch_l0_fused(Model *m, const float *mel, ActT *X, int nb) {
     cudaStream_t st = m->ctx->stream;
     {
         ProfScope ps(m->ctx, K_LN);
-        l0_moments_kernel<<<nb, 256, 0, st>>>(a, m->l0c, m->stats.as<float2>());
+        l0_moments_kernel<<<nb, 256, 0, st>>>(a, m->l0c, m->cur_stats);
     }
     const int cgroups = g.Co / 8, ppb = 256 / cgroups, P = g.Fi * g.To;
     const int group = 32;
@@ -700,20 +701,49 @@ int launch_l0_fused(Model *m, const float *mel, ActT *X, int nb) {
         if (run3 && g.To % 4 == 0 && pp_env == 4) {
             dim3 grid(cdiv(P / 4, ppb), cdiv(nb, group));
             l0_conv_ln_kernel<ActT, 4><<<grid, 256, 0, st>>>(a, m->l0_w, cw.bias, cw.gamma, cw.beta,
-                                                             m->stats.as<float2>(), X, nb, group);
+                                                             m->cur_stats, X, nb, group);
         } else if (run3 && g.To % 2 == 0 && pp_env == 2) {
             dim3 grid(cdiv(P / 2, ppb), cdiv(nb, group));
             l0_conv_ln_kernel<ActT, 2><<<grid, 256, 0, st>>>(a, m->l0_w, cw.bias, cw.gamma, cw.beta,
-                                                             m->stats.as<float2>(), X, nb, group);
+                                                             m->cur_stats, X, nb, group);
         } else {
             // one position per thread: mel run = [2 to + off0, +2]; other tap sets go through wr = 0 columns
             dim3 grid(cdiv(P, ppb), cdiv(nb, group));
             l0_conv_ln_kernel<ActT, 1><<<grid, 256, 0, st>>>(a, m->l0_w, cw.bias, cw.gamma, cw.beta,
-                                                             m->stats.as<float2>(), X, nb, group);
+                                                             m->cur_stats, X, nb, group);
         }
     }
     m->ctx->launches += 2;
     PF_CUDA(cudaGetLastError());
+    return PFANN_OK;
+}
+
+// Front phase (tensor-core path): layers [0, front_layers) depth-first over sub-chunks in the small re-used
+// workspace; the last apply writes the chunk-level input of layer `front_layers` (m->xb).
+int forward_front(Model *m, const float *mel, int nb) {
+    typedef __nv_bfloat16 bf;
+    const int LF = m->front_layers, SB = m->front_sub;
+    const long long mel_per = (long long)m->F * m->T;
+    m->cur_stats = m->fstats.as<float2>();
+    m->cur_partials = m->fpartials.as<float2>();
+    if (m->tap_layer >= 0 && m->tap_layer < LF)  // reserve the whole tap buffer before the first sub-chunk writes
+        PF_TRY(m->tapbuf.ensure((size_t)nb * m->conv[2 * m->tap_layer + 1].g.out_per_sample() * 4));
+    for (int s0 = 0; s0 < nb; s0 += SB) {
+        const int ns = (nb - s0) < SB ? (nb - s0) : SB;
+        PF_TRY(launch_l0_fused<bf>(m, mel + (long long)s0 * mel_per, m->fxa.as<bf>(), ns));
+        for (int idx = 1; idx < 2 * LF; idx++) {
+            const ConvWeights &cw = m->conv[idx];
+            const bf *in = (idx & 1) ? m->fxa.as<bf>() : m->fxb.as<bf>();
+            PF_TRY(tc_conv(m, idx, in, m->fy.p, m->y_bf16, ns));
+            bf *out = (idx & 1) ? m->fxb.as<bf>() : m->fxa.as<bf>();
+            if (idx == 2 * LF - 1) out = m->xb.as<bf>() + (long long)s0 * cw.g.out_per_sample();
+            if (m->y_bf16)
+                PF_TRY((launch_ln_apply<bf, bf>(m, cw, m->fy.as<bf>(), out, ns)));
+            else
+                PF_TRY((launch_ln_apply<float, bf>(m, cw, m->fy.as<float>(), out, ns)));
+            if (idx & 1) PF_TRY(save_tap<bf>(m, idx >> 1, out, ns, nb, s0));
+        }
+    }
     return PFANN_OK;
 }
 
@@ -723,7 +753,14 @@ int forward_chunk(Model *m, const float *mel, int nb, int norm, float *z) {
     const bool tc = (sizeof(ActT) == 2);
     float *Y = m->ybuf.as<float>();
     ActT *xa = m->xa.as<ActT>(), *xb = m->xb.as<ActT>();
-    for (int l = 0; l < 8; l++) {
+    int l_begin = 0;
+    if (tc && m->front_layers > 0) {
+        PF_TRY(forward_front(m, mel, nb));
+        l_begin = m->front_layers;
+    }
+    m->cur_stats = m->stats.as<float2>();
+    m->cur_partials = m->partials.as<float2>();
+    for (int l = l_begin; l < 8; l++) {
         for (int which = 0; which < 2; which++) {
             const ConvWeights &cw = m->conv[2 * l + which];
             const bool first = (l == 0 && which == 0);
@@ -775,30 +812,14 @@ int forward_chunk(Model *m, const float *mel, int nb, int norm, float *z) {
             attr = smem_fast;
         }
         const int grid = nb < m->ctx->sm_count ? nb : m->ctx->sm_count;
-        head_kernel<<<grid, threads, smem_fast, m->ctx->stream>>>(Y, m->stats.as<float2>(), last.gamma, last.beta, m->w1,
+        head_kernel<<<grid, threads, smem_fast, m->ctx->stream>>>(Y, m->cur_stats, last.gamma, last.beta, m->w1,
                                                                    m->b1, m->w2, m->b2, z, nb, m->d, m->h, m->u, norm);
     } else {
         head_kernel_generic<<<nb, threads, (m->h + 32) * sizeof(float), m->ctx->stream>>>(
-            Y, m->stats.as<float2>(), last.gamma, last.beta, m->w1, m->b1, m->w2, m->b2, z, m->d, m->h, m->u, norm);
+            Y, m->cur_stats, last.gamma, last.beta, m->w1, m->b1, m->w2, m->b2, z, m->d, m->h, m->u, norm);
     }
     m->ctx->launches++;
     PF_CUDA(cudaGetLastError());
-    return PFANN_OK;
-}
-
-int ensure_workspace(Model *m) {
-    long long maxY = 0, maxA = 0, maxB = 0;
-    for (int i = 0; i < 16; i++) {
-        const long long e = m->conv[i].g.out_per_sample();
-        if (e > maxY && !(i == 0 && m->l0_fused)) maxY = e;  // fused layer 0 never stores its raw output
-        if ((i & 1) == 0 && e > maxA) maxA = e;
-        if ((i & 1) == 1 && e > maxB) maxB = e;
-    }
-    const size_t act = m->precision == PFANN_PRECISION_BF16 ? 2 : 4;
-    PF_TRY(m->ybuf.ensure((size_t)maxY * m->chunk * 4));
-    PF_TRY(m->xa.ensure((size_t)maxA * m->chunk * act));
-    PF_TRY(m->xb.ensure((size_t)maxB * m->chunk * act));
-    PF_TRY(m->stats.ensure((size_t)m->chunk * sizeof(float2)));
     return PFANN_OK;
 }
 
@@ -806,10 +827,49 @@ int ensure_workspace(Model *m) {
 
 namespace pfann {
 
+int plan_workspace(Model *m) {
+    const int LF = m->precision == PFANN_PRECISION_BF16 ? m->front_layers : 0;
+    const size_t act = m->precision == PFANN_PRECISION_BF16 ? 2 : 4;
+    long long tY = 0, tA = 0, tB = 0, fY = 0, fA = 0, fB = 0;
+    for (int i = 0; i < 16; i++) {
+        const long long e = m->conv[i].g.out_per_sample();
+        const bool front = i < 2 * LF;
+        const bool stores_y = !(i == 0 && m->l0_fused);  // fused layer 0 never stores its raw output
+        if (front) {
+            if (stores_y && e > fY) fY = e;
+            if ((i & 1) == 0 && e > fA) fA = e;
+            if ((i & 1) == 1 && i != 2 * LF - 1 && e > fB) fB = e;
+            if (i == 2 * LF - 1 && e > tB) tB = e;  // the front's last output is the tail's first input
+        } else {
+            if (stores_y && e > tY) tY = e;
+            if ((i & 1) == 0 && e > tA) tA = e;
+            if ((i & 1) == 1 && e > tB) tB = e;
+        }
+    }
+    PF_TRY(m->ybuf.ensure((size_t)(tY ? tY : 1) * m->chunk * 4));
+    PF_TRY(m->xa.ensure((size_t)(tA ? tA : 1) * m->chunk * act));
+    PF_TRY(m->xb.ensure((size_t)(tB ? tB : 1) * m->chunk * act));
+    PF_TRY(m->stats.ensure((size_t)m->chunk * sizeof(float2)));
+    if (LF > 0) {
+        PF_TRY(m->fy.ensure((size_t)(fY ? fY : 1) * m->front_sub * 4));
+        PF_TRY(m->fxa.ensure((size_t)(fA ? fA : 1) * m->front_sub * 2));
+        PF_TRY(m->fxb.ensure((size_t)(fB ? fB : 1) * m->front_sub * 2));
+        PF_TRY(m->fstats.ensure((size_t)m->front_sub * sizeof(float2)));
+    }
+    return PFANN_OK;
+}
+
+}  // namespace pfann
+
+namespace {
+}  // namespace
+
+namespace pfann {
+
 // device-pointer forward used by the C-ABI wrappers and by extract.cu
 int model_forward_dev(Model *m, const float *mel, int64_t B, int norm, float *z) {
     PF_CHECK(m->precision >= 0, PFANN_ERR_STATE, "pfann_model_forward: call pfann_model_finalize first");
-    PF_TRY(ensure_workspace(m));
+    PF_TRY(plan_workspace(m));
     const long long mel_per = (long long)m->F * m->T;
     for (int64_t b0 = 0; b0 < B; b0 += m->chunk) {
         const int nb = (int)((B - b0) < m->chunk ? (B - b0) : m->chunk);
@@ -852,6 +912,7 @@ void pfann_model_destroy(pfann_model *hm) {
     for (int i = 0; i < 16; i++) free_conv(m->conv[i]);
     cudaFree(m->w1); cudaFree(m->b1); cudaFree(m->w2); cudaFree(m->b2); cudaFree(m->l0_w);
     m->ybuf.release(); m->xa.release(); m->xb.release(); m->stats.release(); m->partials.release();
+    m->fy.release(); m->fxa.release(); m->fxb.release(); m->fstats.release(); m->fpartials.release();
     m->tapbuf.release(); m->melbuf.release(); m->zbuf.release();
     delete m;
 }
@@ -940,6 +1001,19 @@ int pfann_model_finalize(pfann_model *hm, int precision) {
     PF_TRY(upload(*b1, &m->b1));
     PF_TRY(upload(*w2, &m->w2));
     PF_TRY(upload(*b2, &m->b2));
+    m->front_layers = 0;
+    m->front_sub = 0;
+    if (precision == PFANN_PRECISION_BF16 && m->l0_fused) {
+        int lf = getenv("PFANN_B200_FRONT_LAYERS") ? atoi(getenv("PFANN_B200_FRONT_LAYERS")) : 3;
+        int sb = getenv("PFANN_B200_FRONT_SUB") ? atoi(getenv("PFANN_B200_FRONT_SUB")) : 48;
+        if (lf > 7) lf = 7;
+        for (int i = 1; i < 2 * lf; i++)
+            if (!tc_supported(m->conv[i].g)) lf = 0;  // e.g. depthwise conv2 (fuller == false)
+        if (lf > 0 && sb > 0 && sb < m->chunk) {
+            m->front_layers = lf;
+            m->front_sub = sb;
+        }
+    }
     if (precision == PFANN_PRECISION_BF16) {
         int rc = tc_prepare(m);
         if (rc != PFANN_OK) {
@@ -954,10 +1028,7 @@ int pfann_model_set_chunk(pfann_model *hm, int chunk) {
     PF_CHECK(hm && chunk > 0 && chunk <= 65535, PFANN_ERR_ARG, "pfann_model_set_chunk: chunk must be in 1..65535");
     Model *m = reinterpret_cast<Model *>(hm);
     m->chunk = chunk;
-    if (m->precision == PFANN_PRECISION_BF16) {
-        tc_release(m);
-        return tc_prepare(m);
-    }
+    if (m->precision >= 0) return pfann_model_finalize(hm, m->precision);  // workspaces, tensor maps, front phase
     return PFANN_OK;
 }
 

@@ -56,7 +56,13 @@ struct Model {
     float *l0_w = nullptr;  // [Co][ntaps] fp32 (tap-major per channel)
     bool l0_fused = false;
     bool y_bf16 = true;     // tensor-core convs write their raw output in bf16 (statistics stay fp32)
-    DevBuf ybuf, xa, xb, stats, partials, tapbuf, melbuf, zbuf;
+    DevBuf ybuf, xa, xb, stats, partials, tapbuf, melbuf, zbuf;   // chunk-sized workspace ("tail" phase)
+    // "front" phase (tensor-core path): the first `front_layers` SeparableConv2d run depth-first over sub-chunks
+    // of `front_sub` samples in a small, re-used workspace, so that their activations (1 MB/sample after layer-0
+    // conv1, ...) live and die in the 126 MB L2 instead of making round trips to HBM.  0 = disabled.
+    int front_layers = 0, front_sub = 0;
+    DevBuf fy, fxa, fxb, fstats, fpartials;
+    float2 *cur_stats = nullptr, *cur_partials = nullptr;  // statistics buffers of the phase being executed
     int tap_layer = -1;
     long long tap_numel = 0;
     void *tc_state = nullptr;  // tensor maps etc., owned by encoder_tc.cu
@@ -69,5 +75,7 @@ bool tc_supported(const ConvGeom &g);
 // Y[m][n] (fp32 or bf16) = conv GEMM of X (bf16, channels-last) for `nb` samples; also writes per-sample
 // LayerNorm partial sums into m->partials and reduces them into m->stats (mean, rstd).
 int tc_conv(Model *m, int idx, const __nv_bfloat16 *X, void *Y, bool y_bf16, int nb);
+// encoder.cu: size both workspaces (needs conv geometries and front_* decided)
+int plan_workspace(Model *m);
 
 }  // namespace pfann

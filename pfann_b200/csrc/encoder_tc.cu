@@ -39,6 +39,7 @@ struct TcConv {
     int BN = 0, NT = 0;  // N tile, number of N tiles
     int box_to = 0, box_f = 0, box_b = 0, fdim = 0;
     int slots = 0;       // LayerNorm partial slots per sample
+    const void *x_base = nullptr;  // activation buffer the A tensor maps point into
 };
 
 struct TcState {
@@ -352,25 +353,18 @@ int tc_prepare(Model *m) {
     PF_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess, PFANN_ERR_CUDA,
              "cuTensorMapEncodeTiled is not available from the driver");
     st->encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
-    // workspace must exist before tensor maps can point into it
-    long long maxY = 0, maxA = 0, maxB = 0;
-    for (int i = 0; i < 16; i++) {
-        const long long e = m->conv[i].g.out_per_sample();
-        if (e > maxY && !(i == 0 && m->l0_fused)) maxY = e;
-        if ((i & 1) == 0 && e > maxA) maxA = e;
-        if ((i & 1) == 1 && e > maxB) maxB = e;
-    }
-    PF_TRY(m->ybuf.ensure((size_t)maxY * m->chunk * 4));
-    PF_TRY(m->xa.ensure((size_t)maxA * m->chunk * 2));
-    PF_TRY(m->xb.ensure((size_t)maxB * m->chunk * 2));
-    PF_TRY(m->stats.ensure((size_t)m->chunk * sizeof(float2)));
-    const cuuint64_t nb = (cuuint64_t)m->chunk;
+    // workspaces must exist before tensor maps can point into them
+    PF_TRY(plan_workspace(m));
     for (int i = 1; i < 16; i++) {
+        const bool front = i < 2 * m->front_layers;
+        const cuuint64_t nb = (cuuint64_t)(front ? m->front_sub : m->chunk);
         const ConvGeom &g = m->conv[i].g;
         TcConv &tc = st->conv[i];
         tc.supported = tc_supported(g);
         if (!tc.supported) continue;
-        const __nv_bfloat16 *X = reinterpret_cast<const __nv_bfloat16 *>((i & 1) == 0 ? m->xb.p : m->xa.p);
+        const __nv_bfloat16 *X = reinterpret_cast<const __nv_bfloat16 *>(
+            front ? ((i & 1) == 0 ? m->fxb.p : m->fxa.p) : ((i & 1) == 0 ? m->xb.p : m->xa.p));
+        tc.x_base = X;
         tc.BN = g.Co >= 256 ? 256 : (g.Co >= 128 ? 128 : 64);
         tc.NT = g.Co / tc.BN;
         tc.fdim = g.axis == 0 ? g.Fi : g.Fo;
@@ -411,6 +405,7 @@ int tc_prepare(Model *m) {
         }
     }
     PF_TRY(m->partials.ensure((size_t)m->chunk * st->max_slots * sizeof(float2)));
+    if (m->front_layers > 0) PF_TRY(m->fpartials.ensure((size_t)m->front_sub * st->max_slots * sizeof(float2)));
     return PFANN_OK;
 }
 
@@ -425,10 +420,9 @@ int tc_conv(Model *m, int idx, const __nv_bfloat16 *X, void *Y, bool y_bf16, int
     const TcConv &tc = st->conv[idx];
     const ConvGeom &g = m->conv[idx].g;
     PF_CHECK(tc.supported, PFANN_ERR_UNSUPPORTED, "tc_conv: conv %d has no tensor-core geometry", idx);
-    PF_CHECK(X == reinterpret_cast<const __nv_bfloat16 *>((idx & 1) == 0 ? m->xb.p : m->xa.p), PFANN_ERR_STATE,
-             "tc_conv: input buffer moved since the tensor maps were built");
+    PF_CHECK(X == tc.x_base, PFANN_ERR_STATE, "tc_conv: input buffer moved since the tensor maps were built");
     TcArgs a;
-    a.Y = Y; a.bias = m->conv[idx].bias; a.partials = m->partials.as<float2>();
+    a.Y = Y; a.bias = m->conv[idx].bias; a.partials = m->cur_partials;
     a.M = (long long)nb * g.rows_per_sample();
     a.m_tiles = (int)((a.M + BM - 1) / BM);
     a.Co = g.Co; a.R = (int)g.rows_per_sample(); a.To = g.To; a.fdim = tc.fdim;
@@ -443,8 +437,8 @@ int tc_conv(Model *m, int idx, const __nv_bfloat16 *X, void *Y, bool y_bf16, int
         else PF_TRY((launch_tc<64, float>(m, tc, a)));
     }
     ProfScope ps(m->ctx, K_LN);
-    ln_finalize_kernel<<<cdiv(nb, 8), 256, 0, m->ctx->stream>>>(m->partials.as<float2>(), tc.slots, g.out_per_sample(),
-                                                              m->stats.as<float2>(), nb);
+    ln_finalize_kernel<<<cdiv(nb, 8), 256, 0, m->ctx->stream>>>(m->cur_partials, tc.slots, g.out_per_sample(),
+                                                              m->cur_stats, nb);
     m->ctx->launches++;
     PF_CUDA(cudaGetLastError());
     return PFANN_OK;
