@@ -1004,7 +1004,9 @@ int pfann_model_finalize(pfann_model *hm, int precision) {
     m->front_layers = 0;
     m->front_sub = 0;
     if (precision == PFANN_PRECISION_BF16 && m->l0_fused) {
-        int lf = getenv("PFANN_B200_FRONT_LAYERS") ? atoi(getenv("PFANN_B200_FRONT_LAYERS")) : 3;
+        // off by default: measured slower on B200 (profiles/r01/front_phase_sweep.md) -- per-kernel fixed costs at
+        // L2-sized sub-chunks (<= 64 samples) outweigh the saved HBM round trips
+        int lf = getenv("PFANN_B200_FRONT_LAYERS") ? atoi(getenv("PFANN_B200_FRONT_LAYERS")) : 0;
         int sb = getenv("PFANN_B200_FRONT_SUB") ? atoi(getenv("PFANN_B200_FRONT_SUB")) : 48;
         if (lf > 7) lf = 7;
         for (int i = 1; i < 2 * lf; i++)

@@ -24,14 +24,14 @@ for t in "$@"; do
     bench)   run bench 1200 python bench.py ;;
     sweep)   for c in ${SWEEP:-2048 4096 8192}; do run sweep_$c 300 python bench.py --clips 2000 --chunk $c --steps 2 --warmup 1 --no-match --no-cpu; done ;;
     cli)     run t_cli 300 python -m pytest tests/test_gpu_cli.py -q -m gpu ;;
-    ncu_l0)  run ncu_l0 600 ncu --set full --clock-control none --import-source on -k regex:'l0_conv_ln|ln_apply|mel_kernel' -s 4 -c 5 -o gpurun_out/prof_l0 python bench.py --steps 1 --warmup 1 --clips 300 --no-match --no-cpu ;;
+    ncu_l0)  run ncu_l0 600 ncu --set full --clock-control none --import-source on -k regex:'l0_conv_ln|mel_kernel|head_kernel|l0_moments' -c 4 -o gpurun_out/prof_l0 python bench.py --steps 1 --warmup 1 --clips 300 --no-match --no-cpu ;;
     full)    run t_full 600 python -m pytest tests/test_gpu_fullsize.py -q -m gpu ;;
     front)   for sb in ${FRONT:-0 32 48 64 96}; do export PFANN_B200_FRONT_SUB=$sb; [ $sb = 0 ] && export PFANN_B200_FRONT_LAYERS=0 || export PFANN_B200_FRONT_LAYERS=${FL:-3}; run front_${FL:-3}_$sb 300 python bench.py --clips 2000 --steps 2 --warmup 1 --no-match --no-cpu; done; unset PFANN_B200_FRONT_SUB PFANN_B200_FRONT_LAYERS ;;
     probe)   run knn_probe 600 python tools/knn_probe.py ;;
     all)     run t_all 900 python -m pytest tests -q -m gpu ;;
     ncu_list) run ncu_list 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --clips 300 --chunk 4096 --db-rows 1000000 --queries 100 --no-cpu ;;
-    ncu_conv) run ncu_conv 900 ncu --set full --clock-control none --import-source on -k regex:conv_gemm_tc -s 30 -c 6 -o gpurun_out/prof_conv python bench.py --steps 1 --warmup 1 --clips 300 --no-match --no-cpu ;;
-    ncu_knn)  run ncu_knn 900 ncu --set full --clock-control none --import-source on -k regex:knn_scan_tc -s 4 -c 2 -o gpurun_out/prof_knn python bench.py --steps 1 --warmup 1 --clips 20 --db-rows 10000000 --queries 100 --no-cpu ;;
+    ncu_conv) run ncu_conv 900 ncu --set full --clock-control none --import-source on -k regex:conv_gemm_tc -s 15 -c 15 -o gpurun_out/prof_conv python bench.py --steps 1 --warmup 1 --clips 300 --no-match --no-cpu ;;
+    ncu_knn)  run ncu_knn 900 ncu --set full --clock-control none --import-source on -k regex:'knn_scan_tc|knn_select|rerank' -s 6 -c 6 -o gpurun_out/prof_knn python bench.py --steps 1 --warmup 1 --clips 20 --db-rows 10000000 --queries 128 --match-batch 128 --no-cpu ;;
   esac
 done
 cat gpurun_out/summary.txt
