@@ -529,6 +529,8 @@ void free_conv(ConvWeights &c) {
     cudaFree(c.bias);
     cudaFree(c.gamma);
     cudaFree(c.beta);
+    cudaFree(c.gamma16);
+    cudaFree(c.beta16);
     c = ConvWeights();
 }
 
@@ -613,6 +615,10 @@ int finalize_conv(Model *m, int l, int which, const ConvGeom &g) {
             }
     PF_TRY(upload(gp, &cw.gamma));
     PF_TRY(upload(bp, &cw.beta));
+    if (m->precision == PFANN_PRECISION_BF16) {
+        PF_TRY(upload_bf16(gp, &cw.gamma16));
+        PF_TRY(upload_bf16(bp, &cw.beta16));
+    }
     return PFANN_OK;
 }
 
@@ -776,6 +782,13 @@ int forward_chunk(Model *m, const float *mel, int nb, int norm, float *z) {
                 PF_TRY(launch_conv_fp32<float>(m, cw, mel, Y, nb));
             } else {
                 const ActT *in = which == 0 ? xb : xa;
+                if (tc && !last && tc_ln_supported(m, 2 * l + which)) {
+                    // conv + LayerNorm + ReLU in one kernel (accumulators stay in TMEM, no raw output)
+                    PF_TRY(tc_conv_ln(m, 2 * l + which, reinterpret_cast<const __nv_bfloat16 *>(in),
+                                      reinterpret_cast<__nv_bfloat16 *>(which == 0 ? xa : xb), nb));
+                    if (which == 1) PF_TRY(save_tap<ActT>(m, l, xb, nb));
+                    continue;
+                }
                 if (tc && tc_supported(cw.g)) {
                     ybf = m->y_bf16 && !last;  // the head reads the last raw output in fp32
                     PF_TRY(tc_conv(m, 2 * l + which, reinterpret_cast<const __nv_bfloat16 *>(in), Y, ybf, nb));

@@ -37,6 +37,7 @@ struct ConvWeights {
     float *bias = nullptr;           // [Co]
     float *gamma = nullptr;          // LayerNorm affine permuted to channels-last [Fo][To][Co]
     float *beta = nullptr;
+    __nv_bfloat16 *gamma16 = nullptr, *beta16 = nullptr;  // same, bf16 (fused conv+LayerNorm epilogue)
 };
 
 struct Model {
@@ -75,6 +76,10 @@ bool tc_supported(const ConvGeom &g);
 // Y[m][n] (fp32 or bf16) = conv GEMM of X (bf16, channels-last) for `nb` samples; also writes per-sample
 // LayerNorm partial sums into m->partials and reduces them into m->stats (mean, rstd).
 int tc_conv(Model *m, int idx, const __nv_bfloat16 *X, void *Y, bool y_bf16, int nb);
+// Fused conv + LayerNorm + ReLU (TMEM-resident accumulators, no raw output): Xout[m][n] bf16.  Returns
+// PFANN_ERR_UNSUPPORTED (without touching anything) when the geometry has no fused mapping.
+bool tc_ln_supported(Model *m, int idx);
+int tc_conv_ln(Model *m, int idx, const __nv_bfloat16 *X, __nv_bfloat16 *Xout, int nb);
 // encoder.cu: size both workspaces (needs conv geometries and front_* decided)
 int plan_workspace(Model *m);
 

@@ -20,6 +20,7 @@
 // ln_apply_kernel in encoder.cu.
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 #include "encoder.cuh"
 #include "pfann_b200.h"
@@ -265,6 +266,297 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Fused convolution + LayerNorm + ReLU: the raw convolution output never leaves the SM.
+//
+// A cluster of CS CTAs owns whole samples: every CTA accumulates its TM x NT tiles of a "group" (CS*TM*128
+// consecutive output rows = one or more complete samples) in TMEM (up to 512 columns), then
+//   pass 1: epilogue warps read the accumulators (tcgen05.ld) and reduce (sum, sum of squares) per sample, in a
+//           fixed order; when a sample spans several CTAs (CS > 1) the partial sums are exchanged through
+//           distributed shared memory (st.shared::cluster + a cluster-scope mbarrier);
+//   pass 2: the accumulators are read again, normalised, scaled by the per-element affine (bf16 gamma/beta),
+//           ReLU'd, converted to bf16 and stored coalesced -- directly the operand of the next GEMM.
+// TMEM slot j is handed back to the MMA issuer as soon as its pass 2 is done, so the tensor core already works on
+// the next group's tile j while later slots are still being normalised.  Compared with conv -> raw Y -> apply this
+// removes one HBM write and one HBM read of every activation and two kernel launches per convolution.
+// ------------------------------------------------------------------------------------------------------------
+struct TcLnArgs {
+    __nv_bfloat16 *X;                    // [M][Co] normalised output
+    const float *bias;                   // [Co]
+    const __nv_bfloat16 *gamma, *beta;   // [R][Co]
+    long long M;                         // valid rows
+    int n_groups;
+    int Co, R, To, fdim, kb_per_tap, ntaps, NT, TM, CS;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA0,
+                                                                   const __grid_constant__ CUtensorMap mapA1,
+                                                                   const __grid_constant__ CUtensorMap mapA2,
+                                                                   const __grid_constant__ CUtensorMap mapB,
+                                                                   const TcLnArgs a) {
+    constexpr int STAGES = tc_stages<BN>();
+    constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *sbase =
+        reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char *stage_out = sbase + (size_t)STAGES * STAGE_BYTES;     // 4 warps x 2 KB (bf16 rows)
+    float *bias_s = reinterpret_cast<float *>(stage_out + 4 * 2048);    // [Co]
+    float2 *rs = reinterpret_cast<float2 *>(bias_s + a.Co);             // [512] per-row (sum, sumsq)
+    double2 *cta_part = reinterpret_cast<double2 *>(rs + 512);          // [512] per-sample partial of this CTA
+    float2 *stat_s = reinterpret_cast<float2 *>(cta_part + 512);        // [512] (mean, rstd)
+    __shared__ __align__(16) double2 xchg[2][4];                        // [parity][rank] partials of the cluster
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[4], tempty_bar[4], xbar;
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int KB = a.kb_per_tap * a.ntaps;
+    const int slots = a.TM * a.NT;
+    const int rows_cta = a.TM * BM;
+    const long long GR = (long long)a.CS * rows_cta;
+    const int rank = (int)ptx::cluster_ctarank();
+    const int cluster_id = blockIdx.x / a.CS, n_clusters = gridDim.x / a.CS;
+
+    if (tid == 0) {
+        ptx::prefetch_tmap(&mapA0);
+        ptx::prefetch_tmap(&mapB);
+        for (int s = 0; s < STAGES; s++) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 4; s++) {
+            ptx::mbar_init(&tfull_bar[s], 1);
+            ptx::mbar_init(&tempty_bar[s], 4);
+        }
+        ptx::mbar_init(&xbar, (uint32_t)a.CS);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(&tmem_base_s, 512);
+        ptx::tmem_relinquish();
+    }
+    for (int i = tid; i < a.Co; i += TC_THREADS) bias_s[i] = a.bias[i];
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (a.CS > 1) {  // peers must have initialised their barriers before anyone arrives on them remotely
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            long long it = 0;
+            for (long long g = cluster_id; g < a.n_groups; g += n_clusters) {
+                for (int j = 0; j < slots; j++) {
+                    const int tm = j / a.NT, nt = j - tm * a.NT;
+                    const long long m0 = g * GR + (long long)rank * rows_cta + (long long)tm * BM;
+                    const int n0 = nt * BN;
+                    const int f0 = (int)((m0 / a.To) % a.fdim);
+                    const int b0 = (int)(m0 / ((long long)a.To * a.fdim));
+                    for (int kb = 0; kb < KB; kb++, it++) {
+                        const int s = (int)(it % STAGES);
+                        if (it >= STAGES) ptx::mbar_wait(&empty_bar[s], (uint32_t)((it / STAGES) - 1) & 1);
+                        unsigned char *sa = sbase + (size_t)s * STAGE_BYTES;
+                        ptx::mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                        const int tap = kb / a.kb_per_tap, c0 = (kb - tap * a.kb_per_tap) * BK;
+                        const CUtensorMap *mA = tap == 0 ? &mapA0 : (tap == 1 ? &mapA1 : &mapA2);
+                        ptx::tma_load_4d(sa, mA, &full_bar[s], c0, 0, f0, b0);
+                        ptx::tma_load_2d(sa + A_BYTES, &mapB, &full_bar[s], kb * BK, n0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN);
+            long long it = 0, git = 0;
+            for (long long g = cluster_id; g < a.n_groups; g += n_clusters, git++) {
+                for (int j = 0; j < slots; j++) {
+                    if (git >= 1) ptx::mbar_wait(&tempty_bar[j], (uint32_t)(git - 1) & 1);
+                    ptx::tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(j * BN);
+                    for (int kb = 0; kb < KB; kb++, it++) {
+                        const int s = (int)(it % STAGES);
+                        ptx::mbar_wait(&full_bar[s], (uint32_t)(it / STAGES) & 1);
+                        ptx::tc_fence_after();
+                        const uint32_t sa = ptx::smem_u32(sbase + (size_t)s * STAGE_BYTES);
+                        const uint64_t da = ptx::umma_desc_k_sw128(sa), db = ptx::umma_desc_k_sw128(sa + A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; k++)
+                            ptx::umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        ptx::umma_commit(&empty_bar[s]);
+                    }
+                    ptx::umma_commit(&tfull_bar[j]);
+                }
+            }
+        }
+    } else {
+        // ===== epilogue warps =====
+        const int quarter = warp & 3, ew = warp - 2, tid_e = tid - 64;
+        uint4 *stg = reinterpret_cast<uint4 *>(stage_out + (size_t)ew * 2048);
+        const int Rc = a.R < rows_cta ? a.R : rows_cta;  // rows of one sample inside this CTA
+        const int n_s = rows_cta / Rc;                    // samples (or the one partial sample) of this CTA
+        const double invE = 1.0 / ((double)a.R * (double)a.Co);
+        long long git = 0;
+        for (long long g = cluster_id; g < a.n_groups; g += n_clusters, git++) {
+            const long long row_cta0 = g * GR + (long long)rank * rows_cta;
+            // ---------------- pass 1: per-row sums over all channels ----------------
+#pragma unroll
+            for (int tm = 0; tm < 4; tm++) {
+                if (tm < a.TM) {
+                    float s1 = 0.f, s2 = 0.f;
+                    for (int nt = 0; nt < a.NT; nt++) {
+                        const int j = tm * a.NT + nt, n0 = nt * BN;
+                        ptx::mbar_wait(&tfull_bar[j], (uint32_t)git & 1);
+                        ptx::tc_fence_after();
+#pragma unroll 1
+                        for (int c = 0; c < BN; c += 32) {
+                            uint32_t v[32];
+                            ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * BN + c), v);
+                            ptx::tmem_ld_wait();
+                            float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                            for (int q = 0; q < 8; q++) {
+                                const float4 b4 = *reinterpret_cast<const float4 *>(&bias_s[n0 + c + 4 * q]);
+                                const float o0 = __uint_as_float(v[4 * q]) + b4.x, o1 = __uint_as_float(v[4 * q + 1]) + b4.y;
+                                const float o2 = __uint_as_float(v[4 * q + 2]) + b4.z, o3 = __uint_as_float(v[4 * q + 3]) + b4.w;
+                                p1[0] += o0; p1[1] += o1; p1[2] += o2; p1[3] += o3;
+                                p2[0] = fmaf(o0, o0, p2[0]); p2[1] = fmaf(o1, o1, p2[1]);
+                                p2[2] = fmaf(o2, o2, p2[2]); p2[3] = fmaf(o3, o3, p2[3]);
+                            }
+                            s1 += (p1[0] + p1[1]) + (p1[2] + p1[3]);
+                            s2 += (p2[0] + p2[1]) + (p2[2] + p2[3]);
+                        }
+                    }
+                    rs[tm * BM + quarter * 32 + lane] = make_float2(s1, s2);
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            // ---------------- per-sample sums of this CTA, fixed order, double ----------------
+            for (int s = ew; s < n_s; s += 4) {
+                double d1 = 0.0, d2 = 0.0;
+                for (int i = lane; i < Rc; i += 32) {
+                    const float2 v2 = rs[s * Rc + i];
+                    d1 += (double)v2.x;
+                    d2 += (double)v2.y;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+                    d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+                }
+                if (lane == 0) cta_part[s] = make_double2(d1, d2);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (a.CS > 1) {
+                // one sample spans the cluster: push this CTA's partial into every member's exchange slot
+                const int par = (int)(git & 1);
+                if (ew == 0 && lane < a.CS) {
+                    const double2 mine = cta_part[0];
+                    ptx::st_cluster_f64x2(ptx::mapa_u32(ptx::smem_u32(&xchg[par][rank]), (uint32_t)lane), mine.x, mine.y);
+                    ptx::mbar_arrive_cluster(ptx::mapa_u32(ptx::smem_u32(&xbar), (uint32_t)lane));
+                }
+                ptx::mbar_wait_cluster(&xbar, (uint32_t)par);
+                if (tid_e == 0) {
+                    double t1 = 0.0, t2 = 0.0;
+                    for (int r = 0; r < a.CS; r++) {
+                        t1 += xchg[par][r].x;
+                        t2 += xchg[par][r].y;
+                    }
+                    const double mean = t1 * invE;
+                    double var = t2 * invE - mean * mean;
+                    if (var < 0.0) var = 0.0;
+                    stat_s[0] = make_float2((float)mean, (float)(1.0 / sqrt(var + 1e-5)));
+                }
+            } else {
+                for (int s = tid_e; s < n_s; s += 128) {
+                    const double mean = cta_part[s].x * invE;
+                    double var = cta_part[s].y * invE - mean * mean;
+                    if (var < 0.0) var = 0.0;
+                    stat_s[s] = make_float2((float)mean, (float)(1.0 / sqrt(var + 1e-5)));
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            // ---------------- pass 2: normalise + affine + ReLU + bf16 store ----------------
+#pragma unroll
+            for (int tm = 0; tm < 4; tm++) {
+                if (tm < a.TM) {
+                    const int rr = tm * BM + quarter * 32 + lane;
+                    const long long mrow0 = row_cta0 + (long long)tm * BM + quarter * 32;
+                    const long long m = mrow0 + lane;
+                    const bool valid = m < a.M;
+                    const float2 st = stat_s[rr / Rc];
+                    const long long pos = valid ? (m % a.R) : 0;  // position inside the sample -> affine row
+                    for (int nt = 0; nt < a.NT; nt++) {
+                        const int j = tm * a.NT + nt, n0 = nt * BN;
+#pragma unroll 1
+                        for (int c = 0; c < BN; c += 32) {
+                            uint32_t v[32];
+                            ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * BN + c), v);
+                            const uint4 *g4 = reinterpret_cast<const uint4 *>(a.gamma + pos * a.Co + n0 + c);
+                            const uint4 *b4p = reinterpret_cast<const uint4 *>(a.beta + pos * a.Co + n0 + c);
+                            uint4 gq[4], bq[4];
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                gq[q] = __ldg(g4 + q);
+                                bq[q] = __ldg(b4p + q);
+                            }
+                            ptx::tmem_ld_wait();
+                            const int sw = (lane >> 1) & 3;
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const float4 ba = *reinterpret_cast<const float4 *>(&bias_s[n0 + c + 8 * q]);
+                                const float4 bb = *reinterpret_cast<const float4 *>(&bias_s[n0 + c + 8 * q + 4]);
+                                const float bia[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+                                const uint32_t gw[4] = {gq[q].x, gq[q].y, gq[q].z, gq[q].w};
+                                const uint32_t bw[4] = {bq[q].x, bq[q].y, bq[q].z, bq[q].w};
+                                uint32_t pk[4];
+#pragma unroll
+                                for (int e = 0; e < 4; e++) {
+                                    const float2 gf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&gw[e]));
+                                    const float2 bf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&bw[e]));
+                                    const float x0 = (__uint_as_float(v[8 * q + 2 * e]) + bia[2 * e] - st.x) * st.y;
+                                    const float x1 = (__uint_as_float(v[8 * q + 2 * e + 1]) + bia[2 * e + 1] - st.x) * st.y;
+                                    const __nv_bfloat162 o2 =
+                                        __floats2bfloat162_rn(fmaxf(fmaf(x0, gf.x, bf.x), 0.f), fmaxf(fmaf(x1, gf.y, bf.y), 0.f));
+                                    pk[e] = *reinterpret_cast<const uint32_t *>(&o2);
+                                }
+                                stg[lane * 4 + (q ^ sw)] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            }
+                            __syncwarp();
+#pragma unroll
+                            for (int r0 = 0; r0 < 32; r0 += 8) {
+                                const int r = r0 + (lane >> 2), ch = lane & 3;
+                                const uint4 val = stg[r * 4 + (ch ^ ((r >> 1) & 3))];
+                                if (mrow0 + r < a.M)
+                                    *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(a.X) +
+                                                               ((mrow0 + r) * a.Co + n0 + c) * 2 + ch * 16) = val;
+                            }
+                            __syncwarp();
+                        }
+                        // slot j fully consumed: the next group's MMAs may overwrite it
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(&tempty_bar[j]);
+                    }
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (a.CS > 1) {  // nobody leaves while a peer may still write into its shared memory
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 512);
+    }
+}
+
 // stats[b] = (mean, rstd) from the partial slots; one warp per sample, fixed summation order
 __global__ void ln_finalize_kernel(const float2 *partials, int slots, long long E, float2 *stats, int nb) {
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -326,6 +618,65 @@ int launch_tc(Model *m, const TcConv &tc, const TcArgs &args) {
                                                                                        tc.mapA[2], tc.mapB, args);
     m->ctx->launches++;
     PF_CUDA(cudaGetLastError());
+    return PFANN_OK;
+}
+
+
+struct LnGeom {
+    bool ok = false;
+    int TM = 0, CS = 0, BN = 0, NT = 0;
+};
+
+LnGeom ln_geom(const ConvGeom &g) {
+    LnGeom r;
+    if (!pfann::tc_supported(g)) return r;
+    r.BN = g.Co >= 256 ? 256 : 128;
+    if (g.Co % r.BN) return r;
+    r.NT = g.Co / r.BN;
+    const int slots_max = 512 / r.BN;
+    if (r.NT > slots_max) return r;           // Co = 1024: a sample's channels do not fit one CTA's TMEM
+    r.TM = slots_max / r.NT;
+    const long long R = g.rows_per_sample();
+    const long long rows_cta = (long long)r.TM * BM;
+    if (R > rows_cta) {
+        if (R % rows_cta) return r;
+        r.CS = (int)(R / rows_cta);
+        if (r.CS > 4) return r;
+    } else {
+        if (rows_cta % R) return r;
+        r.CS = 1;
+    }
+    r.ok = true;
+    return r;
+}
+
+template <int BN>
+int launch_tc_ln(Model *m, const TcConv &tc, const TcLnArgs &args) {
+    const size_t smem = (size_t)tc_stages<BN>() * (BM * BK * 2 + BN * BK * 2) + 4 * 2048 + (size_t)args.Co * 4 +
+                        512 * 8 + 512 * 16 + 512 * 8 + 1024;
+    PF_CHECK(smem + 2048 <= 227 * 1024, PFANN_ERR_UNSUPPORTED, "fused conv+LN needs %zu B of shared memory", smem);
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        PF_CUDA(cudaFuncSetAttribute(conv_ln_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
+    long long n_clusters = m->ctx->sm_count / args.CS;
+    if (n_clusters > args.n_groups) n_clusters = args.n_groups;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_clusters * args.CS));
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = m->ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)args.CS;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    ProfScope ps(m->ctx, K_CONV_TC);
+    PF_CUDA(cudaLaunchKernelEx(&cfg, conv_ln_tc_kernel<BN>, tc.mapA[0], tc.mapA[1], tc.mapA[2], tc.mapB, args));
+    m->ctx->launches++;
     return PFANN_OK;
 }
 
@@ -442,6 +793,33 @@ int tc_conv(Model *m, int idx, const __nv_bfloat16 *X, void *Y, bool y_bf16, int
     m->ctx->launches++;
     PF_CUDA(cudaGetLastError());
     return PFANN_OK;
+}
+
+bool tc_ln_supported(Model *m, int idx) {
+    if (idx < 1 || idx > 14 || m->tc_state == nullptr) return false;
+    static const bool off = getenv("PFANN_B200_NO_FUSED_LN") != nullptr;
+    if (off) return false;
+    return ln_geom(m->conv[idx].g).ok;
+}
+
+int tc_conv_ln(Model *m, int idx, const __nv_bfloat16 *X, __nv_bfloat16 *Xout, int nb) {
+    TcState *st = reinterpret_cast<TcState *>(m->tc_state);
+    PF_CHECK(st != nullptr, PFANN_ERR_STATE, "tc_conv_ln: tensor-core state missing");
+    const TcConv &tc = st->conv[idx];
+    const ConvGeom &g = m->conv[idx].g;
+    const LnGeom lg = ln_geom(g);
+    PF_CHECK(tc.supported && lg.ok, PFANN_ERR_UNSUPPORTED, "tc_conv_ln: conv %d has no fused geometry", idx);
+    PF_CHECK(lg.BN == tc.BN, PFANN_ERR_STATE, "tc_conv_ln: tile width mismatch");
+    PF_CHECK(X == tc.x_base, PFANN_ERR_STATE, "tc_conv_ln: input buffer moved since the tensor maps were built");
+    TcLnArgs a;
+    a.X = Xout; a.bias = m->conv[idx].bias; a.gamma = m->conv[idx].gamma16; a.beta = m->conv[idx].beta16;
+    a.M = (long long)nb * g.rows_per_sample();
+    const long long GR = (long long)lg.CS * lg.TM * BM;
+    a.n_groups = (int)((a.M + GR - 1) / GR);
+    a.Co = g.Co; a.R = (int)g.rows_per_sample(); a.To = g.To; a.fdim = tc.fdim;
+    a.kb_per_tap = g.Ci / BK; a.ntaps = g.ntaps; a.NT = lg.NT; a.TM = lg.TM; a.CS = lg.CS;
+    if (lg.BN == 256) return launch_tc_ln<256>(m, tc, a);
+    return launch_tc_ln<128>(m, tc, a);
 }
 
 }  // namespace pfann
