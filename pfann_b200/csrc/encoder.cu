@@ -615,9 +615,25 @@ int finalize_conv(Model *m, int l, int which, const ConvGeom &g) {
             }
     PF_TRY(upload(gp, &cw.gamma));
     PF_TRY(upload(bp, &cw.beta));
-    if (m->precision == PFANN_PRECISION_BF16) {
-        PF_TRY(upload_bf16(gp, &cw.gamma16));
-        PF_TRY(upload_bf16(bp, &cw.beta16));
+    if (m->precision == PFANN_PRECISION_BF16 && g.Co % 32 == 0) {
+        // lane-major blocked copy for the fused conv+LayerNorm epilogue (thread = row, 8 channels per 16-byte
+        // load): [row block of 32][column block of 32][4 x 8 columns][32 rows][8].  Blocks of samples with
+        // fewer than 32 rows repeat the rows cyclically, so lane r always finds row (r mod R) in slot r.
+        const int R = g.Fo * g.To, RB = (R + 31) / 32, CB = g.Co / 32;
+        std::vector<float> gl((size_t)RB * CB * 1024), bl((size_t)RB * CB * 1024);
+        for (int rb = 0; rb < RB; rb++)
+            for (int cb = 0; cb < CB; cb++)
+                for (int q = 0; q < 4; q++)
+                    for (int r = 0; r < 32; r++)
+                        for (int e = 0; e < 8; e++) {
+                            const int row = R >= 32 ? (rb * 32 + r) : (r % R);
+                            const size_t src = (size_t)(row < R ? row : 0) * g.Co + cb * 32 + q * 8 + e;
+                            const size_t dst = ((((size_t)rb * CB + cb) * 4 + q) * 32 + r) * 8 + e;
+                            gl[dst] = gp[src];
+                            bl[dst] = bp[src];
+                        }
+        PF_TRY(upload_bf16(gl, &cw.gamma16));
+        PF_TRY(upload_bf16(bl, &cw.beta16));
     }
     return PFANN_OK;
 }

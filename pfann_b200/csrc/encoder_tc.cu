@@ -287,6 +287,7 @@ struct TcLnArgs {
     long long M;                         // valid rows
     int n_groups;
     int Co, R, To, fdim, kb_per_tap, ntaps, NT, TM, CS;
+    unsigned long long *prof;            // optional cycle counters [grid][8] (tools/ln_probe.py)
 };
 
 template <int BN>
@@ -401,8 +402,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_ln_tc_kernel(const __grid_
         const int n_s = rows_cta / Rc;                    // samples (or the one partial sample) of this CTA
         const double invE = 1.0 / ((double)a.R * (double)a.Co);
         long long git = 0;
+        long long pc[4] = {0, 0, 0, 0};
         for (long long g = cluster_id; g < a.n_groups; g += n_clusters, git++) {
             const long long row_cta0 = g * GR + (long long)rank * rows_cta;
+            const long long t0 = clock64();
             // ---------------- pass 1: per-row sums over all channels ----------------
 #pragma unroll
             for (int tm = 0; tm < 4; tm++) {
@@ -410,8 +413,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_ln_tc_kernel(const __grid_
                     float s1 = 0.f, s2 = 0.f;
                     for (int nt = 0; nt < a.NT; nt++) {
                         const int j = tm * a.NT + nt, n0 = nt * BN;
+                        const long long tw = clock64();
                         ptx::mbar_wait(&tfull_bar[j], (uint32_t)git & 1);
                         ptx::tc_fence_after();
+                        pc[0] += clock64() - tw;
 #pragma unroll 1
                         for (int c = 0; c < BN; c += 32) {
                             uint32_t v[32];
@@ -434,6 +439,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_ln_tc_kernel(const __grid_
                     rs[tm * BM + quarter * 32 + lane] = make_float2(s1, s2);
                 }
             }
+            const long long t1 = clock64();
             asm volatile("bar.sync 1, 128;" ::: "memory");
             // ---------------- per-sample sums of this CTA, fixed order, double ----------------
             for (int s = ew; s < n_s; s += 4) {
@@ -480,70 +486,106 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_ln_tc_kernel(const __grid_
                 }
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
+            const long long t2 = clock64();
             // ---------------- pass 2: normalise + affine + ReLU + bf16 store ----------------
+            // Software-pipelined over 32-column chunks: while chunk i is being normalised, the TMEM read and the
+            // gamma/beta loads of chunk i+1 are already in flight.  gamma/beta are stored lane-major
+            // ([row block][col block][4][32 lanes][8]) so each warp load is one fully used 512-byte request.
 #pragma unroll
             for (int tm = 0; tm < 4; tm++) {
                 if (tm < a.TM) {
                     const int rr = tm * BM + quarter * 32 + lane;
                     const long long mrow0 = row_cta0 + (long long)tm * BM + quarter * 32;
-                    const long long m = mrow0 + lane;
-                    const bool valid = m < a.M;
+                    const bool valid = (mrow0 + lane) < a.M;
                     const float2 st = stat_s[rr / Rc];
-                    const long long pos = valid ? (m % a.R) : 0;  // position inside the sample -> affine row
-                    for (int nt = 0; nt < a.NT; nt++) {
-                        const int j = tm * a.NT + nt, n0 = nt * BN;
-#pragma unroll 1
-                        for (int c = 0; c < BN; c += 32) {
-                            uint32_t v[32];
-                            ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * BN + c), v);
-                            const uint4 *g4 = reinterpret_cast<const uint4 *>(a.gamma + pos * a.Co + n0 + c);
-                            const uint4 *b4p = reinterpret_cast<const uint4 *>(a.beta + pos * a.Co + n0 + c);
-                            uint4 gq[4], bq[4];
+                    const long long rb = valid ? (((mrow0 + lane) % a.R) >> 5) : 0;  // 32-row block of the affine
+                    const uint4 *gl = reinterpret_cast<const uint4 *>(a.gamma) + rb * (a.Co >> 5) * 128 + lane;
+                    const uint4 *bl = reinterpret_cast<const uint4 *>(a.beta) + rb * (a.Co >> 5) * 128 + lane;
+                    constexpr int CPT = BN / 32;  // chunks per tile
+                    const int nch = a.NT * CPT;
+                    uint32_t vA[32], vB[32];
+                    uint4 gA[4], bA[4], gB[4], bB[4];
+                    auto issue = [&](int ci, uint32_t (&v)[32], uint4 (&gq)[4], uint4 (&bq)[4]) {
+                        const int nt = ci / CPT, c = (ci - nt * CPT) * 32;
+                        const int j = tm * a.NT + nt, col = nt * BN + c;
+                        ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * BN + c), v);
 #pragma unroll
-                            for (int q = 0; q < 4; q++) {
-                                gq[q] = __ldg(g4 + q);
-                                bq[q] = __ldg(b4p + q);
-                            }
-                            ptx::tmem_ld_wait();
-                            const int sw = (lane >> 1) & 3;
-#pragma unroll
-                            for (int q = 0; q < 4; q++) {
-                                const float4 ba = *reinterpret_cast<const float4 *>(&bias_s[n0 + c + 8 * q]);
-                                const float4 bb = *reinterpret_cast<const float4 *>(&bias_s[n0 + c + 8 * q + 4]);
-                                const float bia[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-                                const uint32_t gw[4] = {gq[q].x, gq[q].y, gq[q].z, gq[q].w};
-                                const uint32_t bw[4] = {bq[q].x, bq[q].y, bq[q].z, bq[q].w};
-                                uint32_t pk[4];
-#pragma unroll
-                                for (int e = 0; e < 4; e++) {
-                                    const float2 gf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&gw[e]));
-                                    const float2 bf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&bw[e]));
-                                    const float x0 = (__uint_as_float(v[8 * q + 2 * e]) + bia[2 * e] - st.x) * st.y;
-                                    const float x1 = (__uint_as_float(v[8 * q + 2 * e + 1]) + bia[2 * e + 1] - st.x) * st.y;
-                                    const __nv_bfloat162 o2 =
-                                        __floats2bfloat162_rn(fmaxf(fmaf(x0, gf.x, bf.x), 0.f), fmaxf(fmaf(x1, gf.y, bf.y), 0.f));
-                                    pk[e] = *reinterpret_cast<const uint32_t *>(&o2);
-                                }
-                                stg[lane * 4 + (q ^ sw)] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                            }
-                            __syncwarp();
-#pragma unroll
-                            for (int r0 = 0; r0 < 32; r0 += 8) {
-                                const int r = r0 + (lane >> 2), ch = lane & 3;
-                                const uint4 val = stg[r * 4 + (ch ^ ((r >> 1) & 3))];
-                                if (mrow0 + r < a.M)
-                                    *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(a.X) +
-                                                               ((mrow0 + r) * a.Co + n0 + c) * 2 + ch * 16) = val;
-                            }
-                            __syncwarp();
+                        for (int q = 0; q < 4; q++) {
+                            gq[q] = __ldg(gl + ((col >> 5) * 4 + q) * 32);
+                            bq[q] = __ldg(bl + ((col >> 5) * 4 + q) * 32);
                         }
-                        // slot j fully consumed: the next group's MMAs may overwrite it
-                        ptx::tc_fence_before();
+                    };
+                    auto finish = [&](int ci, const uint32_t (&v)[32], const uint4 (&gq)[4], const uint4 (&bq)[4]) {
+                        const int nt = ci / CPT, c = (ci - nt * CPT) * 32;
+                        const int n0 = nt * BN;
+                        const int sw = (lane >> 1) & 3;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const float4 ba = *reinterpret_cast<const float4 *>(&bias_s[n0 + c + 8 * q]);
+                            const float4 bb = *reinterpret_cast<const float4 *>(&bias_s[n0 + c + 8 * q + 4]);
+                            const float bia[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+                            const uint32_t gw[4] = {gq[q].x, gq[q].y, gq[q].z, gq[q].w};
+                            const uint32_t bw[4] = {bq[q].x, bq[q].y, bq[q].z, bq[q].w};
+                            uint32_t pk[4];
+#pragma unroll
+                            for (int e = 0; e < 4; e++) {
+                                const float2 gf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&gw[e]));
+                                const float2 bf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&bw[e]));
+                                const float x0 = (__uint_as_float(v[8 * q + 2 * e]) + bia[2 * e] - st.x) * st.y;
+                                const float x1 = (__uint_as_float(v[8 * q + 2 * e + 1]) + bia[2 * e + 1] - st.x) * st.y;
+                                const __nv_bfloat162 o2 =
+                                    __floats2bfloat162_rn(fmaxf(fmaf(x0, gf.x, bf.x), 0.f), fmaxf(fmaf(x1, gf.y, bf.y), 0.f));
+                                pk[e] = *reinterpret_cast<const uint32_t *>(&o2);
+                            }
+                            stg[lane * 4 + (q ^ sw)] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        }
                         __syncwarp();
-                        if (lane == 0) ptx::mbar_arrive(&tempty_bar[j]);
+#pragma unroll
+                        for (int r0 = 0; r0 < 32; r0 += 8) {
+                            const int r = r0 + (lane >> 2), ch = lane & 3;
+                            const uint4 val = stg[r * 4 + (ch ^ ((r >> 1) & 3))];
+                            if (mrow0 + r < a.M)
+                                *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(a.X) +
+                                                           ((mrow0 + r) * a.Co + n0 + c) * 2 + ch * 16) = val;
+                        }
+                        __syncwarp();
+                    };
+                    auto release = [&](int ci) {  // after the last chunk of a tile: hand its TMEM slot back
+                        if ((ci + 1) % CPT == 0) {
+                            ptx::tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) ptx::mbar_arrive(&tempty_bar[tm * a.NT + ci / CPT]);
+                        }
+                    };
+                    issue(0, vA, gA, bA);
+                    ptx::tmem_ld_wait();
+#pragma unroll 1
+                    for (int ci = 0; ci < nch; ci += 2) {
+                        if (ci + 1 < nch) issue(ci + 1, vB, gB, bB);
+                        finish(ci, vA, gA, bA);
+                        ptx::tmem_ld_wait();
+                        release(ci);
+                        if (ci + 1 < nch) {
+                            if (ci + 2 < nch) issue(ci + 2, vA, gA, bA);
+                            finish(ci + 1, vB, gB, bB);
+                            ptx::tmem_ld_wait();
+                            release(ci + 1);
+                        }
                     }
                 }
             }
+            const long long t3 = clock64();
+            pc[1] += t1 - t0;  // pass 1 incl. waiting for the MMAs
+            pc[2] += t2 - t1;  // reductions, barriers, cluster exchange
+            pc[3] += t3 - t2;  // pass 2
+        }
+        if (a.prof && lane == 0) {
+            unsigned long long *o = a.prof + (size_t)blockIdx.x * 8;
+            atomicAdd(&o[0], (unsigned long long)pc[0]);
+            atomicAdd(&o[1], (unsigned long long)pc[1]);
+            atomicAdd(&o[2], (unsigned long long)pc[2]);
+            atomicAdd(&o[3], (unsigned long long)pc[3]);
+            if (warp == 2) atomicAdd(&o[4], (unsigned long long)git);
         }
     }
     ptx::tc_fence_before();
@@ -818,6 +860,8 @@ int tc_conv_ln(Model *m, int idx, const __nv_bfloat16 *X, __nv_bfloat16 *Xout, i
     a.n_groups = (int)((a.M + GR - 1) / GR);
     a.Co = g.Co; a.R = (int)g.rows_per_sample(); a.To = g.To; a.fdim = tc.fdim;
     a.kb_per_tap = g.Ci / BK; a.ntaps = g.ntaps; a.NT = lg.NT; a.TM = lg.TM; a.CS = lg.CS;
+    const char *pp = getenv("PFANN_LN_PROF_PTR");  // probe only: zeroed device buffer [16][grid<=148][8] u64
+    a.prof = pp ? reinterpret_cast<unsigned long long *>(strtoull(pp, nullptr, 0)) + (size_t)idx * 148 * 8 : nullptr;
     if (lg.BN == 256) return launch_tc_ln<256>(m, tc, a);
     return launch_tc_ln<128>(m, tc, a);
 }
