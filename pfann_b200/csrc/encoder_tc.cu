@@ -290,8 +290,10 @@ struct TcLnArgs {
     unsigned long long *prof;            // optional cycle counters [grid][8] (tools/ln_probe.py)
 };
 
+constexpr int LN_THREADS = 320;  // warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 epilogue (two per TMEM lane quarter)
+
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA0,
+__global__ void __launch_bounds__(LN_THREADS, 1) conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA0,
                                                                    const __grid_constant__ CUtensorMap mapA1,
                                                                    const __grid_constant__ CUtensorMap mapA2,
                                                                    const __grid_constant__ CUtensorMap mapB,
@@ -301,10 +303,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_ln_tc_kernel(const __grid_
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *sbase =
         reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char *stage_out = sbase + (size_t)STAGES * STAGE_BYTES;     // 4 warps x 2 KB (bf16 rows)
-    float *bias_s = reinterpret_cast<float *>(stage_out + 4 * 2048);    // [Co]
-    float2 *rs = reinterpret_cast<float2 *>(bias_s + a.Co);             // [512] per-row (sum, sumsq)
-    double2 *cta_part = reinterpret_cast<double2 *>(rs + 512);          // [512] per-sample partial of this CTA
+    unsigned char *stage_out = sbase + (size_t)STAGES * STAGE_BYTES;     // 8 warps x 2 KB (bf16 rows)
+    float *bias_s = reinterpret_cast<float *>(stage_out + 8 * 2048);    // [Co]
+    float2 *rs = reinterpret_cast<float2 *>(bias_s + a.Co);             // [2][512] per-row (sum, sumsq) per column half
+    double2 *cta_part = reinterpret_cast<double2 *>(rs + 1024);         // [512] per-sample partial of this CTA
     float2 *stat_s = reinterpret_cast<float2 *>(cta_part + 512);        // [512] (mean, rstd)
     __shared__ __align__(16) double2 xchg[2][4];                        // [parity][rank] partials of the cluster
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[4], tempty_bar[4], xbar;
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_ln_tc_kernel(const __grid_
         }
         for (int s = 0; s < 4; s++) {
             ptx::mbar_init(&tfull_bar[s], 1);
-            ptx::mbar_init(&tempty_bar[s], 4);
+            ptx::mbar_init(&tempty_bar[s], 8);  // one arrive per epilogue warp
         }
         ptx::mbar_init(&xbar, (uint32_t)a.CS);
         ptx::fence_mbar_init();
@@ -336,7 +338,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_ln_tc_kernel(const __grid_
         ptx::tmem_alloc(&tmem_base_s, 512);
         ptx::tmem_relinquish();
     }
-    for (int i = tid; i < a.Co; i += TC_THREADS) bias_s[i] = a.bias[i];
+    for (int i = tid; i < a.Co; i += LN_THREADS) bias_s[i] = a.bias[i];
     ptx::tc_fence_before();
     __syncthreads();
     if (a.CS > 1) {  // peers must have initialised their barriers before anyone arrives on them remotely
@@ -395,18 +397,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_ln_tc_kernel(const __grid_
             }
         }
     } else {
-        // ===== epilogue warps =====
-        const int quarter = warp & 3, ew = warp - 2, tid_e = tid - 64;
+        // ===== epilogue warps: 8 warps, two per TMEM lane quarter; `half` picks the even / odd 32-column chunks =====
+        const int quarter = warp & 3, ew = warp - 2, half = ew >> 2, tid_e = tid - 64;
         uint4 *stg = reinterpret_cast<uint4 *>(stage_out + (size_t)ew * 2048);
         const int Rc = a.R < rows_cta ? a.R : rows_cta;  // rows of one sample inside this CTA
         const int n_s = rows_cta / Rc;                    // samples (or the one partial sample) of this CTA
         const double invE = 1.0 / ((double)a.R * (double)a.Co);
+        constexpr int CPT = BN / 32;  // chunks per tile
         long long git = 0;
         long long pc[4] = {0, 0, 0, 0};
         for (long long g = cluster_id; g < a.n_groups; g += n_clusters, git++) {
             const long long row_cta0 = g * GR + (long long)rank * rows_cta;
             const long long t0 = clock64();
-            // ---------------- pass 1: per-row sums over all channels ----------------
+            // ---------------- pass 1: per-row sums over this warp's chunks ----------------
 #pragma unroll
             for (int tm = 0; tm < 4; tm++) {
                 if (tm < a.TM) {
@@ -418,7 +421,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_ln_tc_kernel(const __grid_
                         ptx::tc_fence_after();
                         pc[0] += clock64() - tw;
 #pragma unroll 1
-                        for (int c = 0; c < BN; c += 32) {
+                        for (int c = half * 32; c < BN; c += 64) {
                             uint32_t v[32];
                             ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * BN + c), v);
                             ptx::tmem_ld_wait();
@@ -436,18 +439,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_ln_tc_kernel(const __grid_
                             s2 += (p2[0] + p2[1]) + (p2[2] + p2[3]);
                         }
                     }
-                    rs[tm * BM + quarter * 32 + lane] = make_float2(s1, s2);
+                    rs[half * 512 + tm * BM + quarter * 32 + lane] = make_float2(s1, s2);
                 }
             }
             const long long t1 = clock64();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             // ---------------- per-sample sums of this CTA, fixed order, double ----------------
-            for (int s = ew; s < n_s; s += 4) {
+            for (int s = ew; s < n_s; s += 8) {
                 double d1 = 0.0, d2 = 0.0;
                 for (int i = lane; i < Rc; i += 32) {
-                    const float2 v2 = rs[s * Rc + i];
-                    d1 += (double)v2.x;
-                    d2 += (double)v2.y;
+                    const float2 va = rs[s * Rc + i], vb = rs[512 + s * Rc + i];
+                    d1 += (double)va.x + (double)vb.x;
+                    d2 += (double)va.y + (double)vb.y;
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
@@ -456,7 +459,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_ln_tc_kernel(const __grid_
                 }
                 if (lane == 0) cta_part[s] = make_double2(d1, d2);
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             if (a.CS > 1) {
                 // one sample spans the cluster: push this CTA's partial into every member's exchange slot
                 const int par = (int)(git & 1);
@@ -467,30 +470,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_ln_tc_kernel(const __grid_
                 }
                 ptx::mbar_wait_cluster(&xbar, (uint32_t)par);
                 if (tid_e == 0) {
-                    double t1 = 0.0, t2 = 0.0;
+                    double t1s = 0.0, t2s = 0.0;
                     for (int r = 0; r < a.CS; r++) {
-                        t1 += xchg[par][r].x;
-                        t2 += xchg[par][r].y;
+                        t1s += xchg[par][r].x;
+                        t2s += xchg[par][r].y;
                     }
-                    const double mean = t1 * invE;
-                    double var = t2 * invE - mean * mean;
+                    const double mean = t1s * invE;
+                    double var = t2s * invE - mean * mean;
                     if (var < 0.0) var = 0.0;
                     stat_s[0] = make_float2((float)mean, (float)(1.0 / sqrt(var + 1e-5)));
                 }
             } else {
-                for (int s = tid_e; s < n_s; s += 128) {
+                for (int s = tid_e; s < n_s; s += 256) {
                     const double mean = cta_part[s].x * invE;
                     double var = cta_part[s].y * invE - mean * mean;
                     if (var < 0.0) var = 0.0;
                     stat_s[s] = make_float2((float)mean, (float)(1.0 / sqrt(var + 1e-5)));
                 }
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             const long long t2 = clock64();
             // ---------------- pass 2: normalise + affine + ReLU + bf16 store ----------------
-            // Software-pipelined over 32-column chunks: while chunk i is being normalised, the TMEM read and the
-            // gamma/beta loads of chunk i+1 are already in flight.  gamma/beta are stored lane-major
-            // ([row block][col block][4][32 lanes][8]) so each warp load is one fully used 512-byte request.
+            // gamma/beta are stored lane-major ([row block][col block][4][32 lanes][8]): one fully used 512-byte
+            // request per warp load; the affine + ReLU run as packed bf16x2 HFMA2 / HMNMX2.
 #pragma unroll
             for (int tm = 0; tm < 4; tm++) {
                 if (tm < a.TM) {
@@ -498,79 +500,61 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_ln_tc_kernel(const __grid_
                     const long long mrow0 = row_cta0 + (long long)tm * BM + quarter * 32;
                     const bool valid = (mrow0 + lane) < a.M;
                     const float2 st = stat_s[rr / Rc];
+                    const float rstd = st.y, nmr = -st.x * st.y;
                     const long long rb = valid ? (((mrow0 + lane) % a.R) >> 5) : 0;  // 32-row block of the affine
                     const uint4 *gl = reinterpret_cast<const uint4 *>(a.gamma) + rb * (a.Co >> 5) * 128 + lane;
                     const uint4 *bl = reinterpret_cast<const uint4 *>(a.beta) + rb * (a.Co >> 5) * 128 + lane;
-                    constexpr int CPT = BN / 32;  // chunks per tile
-                    const int nch = a.NT * CPT;
-                    uint32_t vA[32], vB[32];
-                    uint4 gA[4], bA[4], gB[4], bB[4];
-                    auto issue = [&](int ci, uint32_t (&v)[32], uint4 (&gq)[4], uint4 (&bq)[4]) {
-                        const int nt = ci / CPT, c = (ci - nt * CPT) * 32;
-                        const int j = tm * a.NT + nt, col = nt * BN + c;
-                        ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * BN + c), v);
-#pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            gq[q] = __ldg(gl + ((col >> 5) * 4 + q) * 32);
-                            bq[q] = __ldg(bl + ((col >> 5) * 4 + q) * 32);
-                        }
-                    };
-                    auto finish = [&](int ci, const uint32_t (&v)[32], const uint4 (&gq)[4], const uint4 (&bq)[4]) {
-                        const int nt = ci / CPT, c = (ci - nt * CPT) * 32;
-                        const int n0 = nt * BN;
-                        const int sw = (lane >> 1) & 3;
-#pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            const float4 ba = *reinterpret_cast<const float4 *>(&bias_s[n0 + c + 8 * q]);
-                            const float4 bb = *reinterpret_cast<const float4 *>(&bias_s[n0 + c + 8 * q + 4]);
-                            const float bia[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-                            const uint32_t gw[4] = {gq[q].x, gq[q].y, gq[q].z, gq[q].w};
-                            const uint32_t bw[4] = {bq[q].x, bq[q].y, bq[q].z, bq[q].w};
-                            uint32_t pk[4];
-#pragma unroll
-                            for (int e = 0; e < 4; e++) {
-                                const float2 gf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&gw[e]));
-                                const float2 bf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&bw[e]));
-                                const float x0 = (__uint_as_float(v[8 * q + 2 * e]) + bia[2 * e] - st.x) * st.y;
-                                const float x1 = (__uint_as_float(v[8 * q + 2 * e + 1]) + bia[2 * e + 1] - st.x) * st.y;
-                                const __nv_bfloat162 o2 =
-                                    __floats2bfloat162_rn(fmaxf(fmaf(x0, gf.x, bf.x), 0.f), fmaxf(fmaf(x1, gf.y, bf.y), 0.f));
-                                pk[e] = *reinterpret_cast<const uint32_t *>(&o2);
-                            }
-                            stg[lane * 4 + (q ^ sw)] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                        }
-                        __syncwarp();
-#pragma unroll
-                        for (int r0 = 0; r0 < 32; r0 += 8) {
-                            const int r = r0 + (lane >> 2), ch = lane & 3;
-                            const uint4 val = stg[r * 4 + (ch ^ ((r >> 1) & 3))];
-                            if (mrow0 + r < a.M)
-                                *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(a.X) +
-                                                           ((mrow0 + r) * a.Co + n0 + c) * 2 + ch * 16) = val;
-                        }
-                        __syncwarp();
-                    };
-                    auto release = [&](int ci) {  // after the last chunk of a tile: hand its TMEM slot back
-                        if ((ci + 1) % CPT == 0) {
-                            ptx::tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) ptx::mbar_arrive(&tempty_bar[tm * a.NT + ci / CPT]);
-                        }
-                    };
-                    issue(0, vA, gA, bA);
-                    ptx::tmem_ld_wait();
+                    const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+                    for (int nt = 0; nt < a.NT; nt++) {
+                        const int j = tm * a.NT + nt, n0 = nt * BN;
 #pragma unroll 1
-                    for (int ci = 0; ci < nch; ci += 2) {
-                        if (ci + 1 < nch) issue(ci + 1, vB, gB, bB);
-                        finish(ci, vA, gA, bA);
-                        ptx::tmem_ld_wait();
-                        release(ci);
-                        if (ci + 1 < nch) {
-                            if (ci + 2 < nch) issue(ci + 2, vA, gA, bA);
-                            finish(ci + 1, vB, gB, bB);
+                        for (int c = half * 32; c < BN; c += 64) {
+                            uint32_t v[32];
+                            ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * BN + c), v);
+                            uint4 gq[4], bq[4];
+                            const int cb = (n0 + c) >> 5;
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                gq[q] = __ldg(gl + (cb * 4 + q) * 32);
+                                bq[q] = __ldg(bl + (cb * 4 + q) * 32);
+                            }
                             ptx::tmem_ld_wait();
-                            release(ci + 1);
+                            const int sw = (lane >> 1) & 3;
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const float4 ba = *reinterpret_cast<const float4 *>(&bias_s[n0 + c + 8 * q]);
+                                const float4 bb = *reinterpret_cast<const float4 *>(&bias_s[n0 + c + 8 * q + 4]);
+                                const float bia[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+                                const uint32_t gw[4] = {gq[q].x, gq[q].y, gq[q].z, gq[q].w};
+                                const uint32_t bw[4] = {bq[q].x, bq[q].y, bq[q].z, bq[q].w};
+                                uint32_t pk[4];
+#pragma unroll
+                                for (int e = 0; e < 4; e++) {
+                                    const float x0 = fmaf(__uint_as_float(v[8 * q + 2 * e]) + bia[2 * e], rstd, nmr);
+                                    const float x1 = fmaf(__uint_as_float(v[8 * q + 2 * e + 1]) + bia[2 * e + 1], rstd, nmr);
+                                    __nv_bfloat162 y2 = __hfma2(__floats2bfloat162_rn(x0, x1),
+                                                                *reinterpret_cast<const __nv_bfloat162 *>(&gw[e]),
+                                                                *reinterpret_cast<const __nv_bfloat162 *>(&bw[e]));
+                                    y2 = __hmax2(y2, zero2);
+                                    pk[e] = *reinterpret_cast<const uint32_t *>(&y2);
+                                }
+                                stg[lane * 4 + (q ^ sw)] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            }
+                            __syncwarp();
+#pragma unroll
+                            for (int r0 = 0; r0 < 32; r0 += 8) {
+                                const int r = r0 + (lane >> 2), ch = lane & 3;
+                                const uint4 val = stg[r * 4 + (ch ^ ((r >> 1) & 3))];
+                                if (mrow0 + r < a.M)
+                                    *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(a.X) +
+                                                               ((mrow0 + r) * a.Co + n0 + c) * 2 + ch * 16) = val;
+                            }
+                            __syncwarp();
                         }
+                        // this warp's share of slot j is consumed; with all 8 arrivals the MMAs may overwrite it
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(&tempty_bar[j]);
                     }
                 }
             }
@@ -694,8 +678,8 @@ LnGeom ln_geom(const ConvGeom &g) {
 
 template <int BN>
 int launch_tc_ln(Model *m, const TcConv &tc, const TcLnArgs &args) {
-    const size_t smem = (size_t)tc_stages<BN>() * (BM * BK * 2 + BN * BK * 2) + 4 * 2048 + (size_t)args.Co * 4 +
-                        512 * 8 + 512 * 16 + 512 * 8 + 1024;
+    const size_t smem = (size_t)tc_stages<BN>() * (BM * BK * 2 + BN * BK * 2) + 8 * 2048 + (size_t)args.Co * 4 +
+                        1024 * 8 + 512 * 16 + 512 * 8 + 1024;
     PF_CHECK(smem + 2048 <= 227 * 1024, PFANN_ERR_UNSUPPORTED, "fused conv+LN needs %zu B of shared memory", smem);
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
@@ -706,7 +690,7 @@ int launch_tc_ln(Model *m, const TcConv &tc, const TcLnArgs &args) {
     if (n_clusters > args.n_groups) n_clusters = args.n_groups;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(n_clusters * args.CS));
-    cfg.blockDim = dim3(TC_THREADS);
+    cfg.blockDim = dim3(LN_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = m->ctx->stream;
     cudaLaunchAttribute at[1];

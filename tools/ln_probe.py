@@ -29,5 +29,5 @@ for idx in range(1, 15):
     g = pr[idx, :, 4].sum() / 1.0
     if g == 0:
         continue
-    per = [pr[idx, :, j].sum() / 4.0 / g for j in range(4)]   # cycles per group per CTA (avg of 4 warps)
+    per = [pr[idx, :, j].sum() / 8.0 / g for j in range(4)]   # cycles per group per CTA (avg of 8 warps)
     print('conv %2d: groups/CTA %.0f | cycles per group: %s' % (idx, g / 148, ', '.join('%s %.0f' % (n, v) for n, v in zip(names, per))))
