@@ -65,6 +65,10 @@ template <int BN>
 __host__ __device__ constexpr int tc_stages() {
     return BN >= 256 ? 4 : 6;
 }
+template <int BN>
+__host__ __device__ constexpr int ln_stages() {  // the fused kernel keeps ~40 KB of epilogue state in smem
+    return BN >= 256 ? 3 : 5;
+}
 
 // Persistent: grid = #SMs, every CTA walks tiles t = blockIdx.x, +gridDim.x, ... of the (m_tile, n_tile) space.
 //   warp 0      TMA producer  -- runs ahead of the MMAs by up to STAGES K-blocks, across tile boundaries
@@ -298,7 +302,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) conv_ln_tc_kernel(const __grid_
                                                                    const __grid_constant__ CUtensorMap mapA2,
                                                                    const __grid_constant__ CUtensorMap mapB,
                                                                    const TcLnArgs a) {
-    constexpr int STAGES = tc_stages<BN>();
+    constexpr int STAGES = ln_stages<BN>();
     constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *sbase =
@@ -678,7 +682,7 @@ LnGeom ln_geom(const ConvGeom &g) {
 
 template <int BN>
 int launch_tc_ln(Model *m, const TcConv &tc, const TcLnArgs &args) {
-    const size_t smem = (size_t)tc_stages<BN>() * (BM * BK * 2 + BN * BK * 2) + 8 * 2048 + (size_t)args.Co * 4 +
+    const size_t smem = (size_t)ln_stages<BN>() * (BM * BK * 2 + BN * BK * 2) + 8 * 2048 + (size_t)args.Co * 4 +
                         1024 * 8 + 512 * 16 + 512 * 8 + 1024;
     PF_CHECK(smem + 2048 <= 227 * 1024, PFANN_ERR_UNSUPPORTED, "fused conv+LN needs %zu B of shared memory", smem);
     static size_t attr_smem = 0;
