@@ -59,6 +59,7 @@ struct TcArgs {
     int To, fdim;       // tile -> tensor coordinates
     int kb_per_tap, ntaps;
     int NT, slots;
+    int n_stages, b_res;  // smem ring depth; 1 = the whole weight matrix stays resident in shared memory
 };
 
 template <int BN>
@@ -81,15 +82,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
                                                                      const __grid_constant__ CUtensorMap mapA2,
                                                                      const __grid_constant__ CUtensorMap mapB,
                                                                      const TcArgs a) {
-    constexpr int STAGES = tc_stages<BN>();
-    constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int MAX_STAGES = 12;
+    const int STAGES = a.n_stages;
+    constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+    // weights either stream through the ring next to A, or (when K x BN fits) are loaded once and stay resident:
+    // that halves the L2 -> SM traffic of the small-K layers, which is what paces them (measured ~40 B/cycle/SM)
+    const uint32_t STAGE_BYTES = A_BYTES + (a.b_res ? 0u : B_BYTES);
     constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *sbase =
         reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char *stage_out = sbase + (size_t)STAGES * STAGE_BYTES;   // 4 warps x 4 KB epilogue staging
+    const int KBall = a.kb_per_tap * a.ntaps;
+    unsigned char *sBres = sbase + (size_t)STAGES * STAGE_BYTES;       // [KB][BN x 128 B] when b_res
+    unsigned char *stage_out = sBres + (a.b_res ? (size_t)KBall * B_BYTES : 0);  // 4 warps x 4 KB epilogue staging
     float *bias_s = reinterpret_cast<float *>(stage_out + 4 * 4096);  // [Co]
-    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], bres_bar, tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -107,6 +114,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
             ptx::mbar_init(&tfull_bar[s], 1);
             ptx::mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
         }
+        ptx::mbar_init(&bres_bar, 1);
         ptx::fence_mbar_init();
     }
     if (warp == 1) {
@@ -123,6 +131,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
         if (lane == 0) {
             // ===== TMA producer =====
             long long it = 0;
+            if (a.b_res) {  // the whole [Co x K] weight matrix, once
+                ptx::mbar_expect_tx(&bres_bar, (uint32_t)KB * B_BYTES);
+                for (int kb = 0; kb < KB; kb++) ptx::tma_load_2d(sBres + (size_t)kb * B_BYTES, &mapB, &bres_bar, kb * BK, 0);
+            }
             for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
                 const long long m0 = (t / a.NT) * BM;
                 const int n0 = (int)(t % a.NT) * BN;
@@ -136,7 +148,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
                     const int tap = kb / a.kb_per_tap, c0 = (kb - tap * a.kb_per_tap) * BK;
                     const CUtensorMap *mA = tap == 0 ? &mapA0 : (tap == 1 ? &mapA1 : &mapA2);
                     ptx::tma_load_4d(sa, mA, &full_bar[s], c0, 0, f0, b0);
-                    ptx::tma_load_2d(sa + A_BYTES, &mapB, &full_bar[s], kb * BK, n0);
+                    if (!a.b_res) ptx::tma_load_2d(sa + A_BYTES, &mapB, &full_bar[s], kb * BK, n0);
                 }
             }
         }
@@ -145,6 +157,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
             // ===== MMA issuer =====
             constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN);
             long long it = 0, ti = 0;
+            if (a.b_res) ptx::mbar_wait(&bres_bar, 0);
             for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ti++) {
                 const int buf = (int)(ti & 1);
                 if (ti >= 2) ptx::mbar_wait(&tempty_bar[buf], (uint32_t)((ti >> 1) - 1) & 1);
@@ -155,7 +168,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
                     ptx::mbar_wait(&full_bar[s], (uint32_t)(it / STAGES) & 1);
                     ptx::tc_fence_after();
                     const uint32_t sa = ptx::smem_u32(sbase + (size_t)s * STAGE_BYTES);
-                    const uint64_t da = ptx::umma_desc_k_sw128(sa), db = ptx::umma_desc_k_sw128(sa + A_BYTES);
+                    const uint64_t da = ptx::umma_desc_k_sw128(sa);
+                    const uint64_t db = ptx::umma_desc_k_sw128(a.b_res ? ptx::smem_u32(sBres + (size_t)kb * B_BYTES) : sa + A_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / 16; k++)
                         ptx::umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
@@ -291,6 +305,7 @@ struct TcLnArgs {
     long long M;                         // valid rows
     int n_groups;
     int Co, R, To, fdim, kb_per_tap, ntaps, NT, TM, CS;
+    int n_stages, b_res;                 // smem ring depth; 1 = weights resident in shared memory
     unsigned long long *prof;            // optional cycle counters [grid][8] (tools/ln_probe.py)
 };
 
@@ -302,18 +317,24 @@ __global__ void __launch_bounds__(LN_THREADS, 1) conv_ln_tc_kernel(const __grid_
                                                                    const __grid_constant__ CUtensorMap mapA2,
                                                                    const __grid_constant__ CUtensorMap mapB,
                                                                    const TcLnArgs a) {
-    constexpr int STAGES = ln_stages<BN>();
-    constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int MAX_STAGES = 12;
+    const int STAGES = a.n_stages;
+    constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+    // weights either stream through the ring next to A, or (when K x BN fits) are loaded once and stay resident:
+    // that halves the L2 -> SM traffic of the small-K layers, which is what paces them (measured ~40 B/cycle/SM)
+    const uint32_t STAGE_BYTES = A_BYTES + (a.b_res ? 0u : B_BYTES);
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *sbase =
         reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char *stage_out = sbase + (size_t)STAGES * STAGE_BYTES;     // 8 warps x 2 KB (bf16 rows)
+    const int KBall = a.kb_per_tap * a.ntaps;
+    unsigned char *sBres = sbase + (size_t)STAGES * STAGE_BYTES;         // [KB][BN x 128 B] when b_res
+    unsigned char *stage_out = sBres + (a.b_res ? (size_t)KBall * B_BYTES : 0);  // 8 warps x 2 KB (bf16 rows)
     float *bias_s = reinterpret_cast<float *>(stage_out + 8 * 2048);    // [Co]
     float2 *rs = reinterpret_cast<float2 *>(bias_s + a.Co);             // [2][512] per-row (sum, sumsq) per column half
     double2 *cta_part = reinterpret_cast<double2 *>(rs + 1024);         // [512] per-sample partial of this CTA
     float2 *stat_s = reinterpret_cast<float2 *>(cta_part + 512);        // [512] (mean, rstd)
     __shared__ __align__(16) double2 xchg[2][4];                        // [parity][rank] partials of the cluster
-    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[4], tempty_bar[4], xbar;
+    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], bres_bar, tfull_bar[4], tempty_bar[4], xbar;
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -336,6 +357,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) conv_ln_tc_kernel(const __grid_
             ptx::mbar_init(&tempty_bar[s], 8);  // one arrive per epilogue warp
         }
         ptx::mbar_init(&xbar, (uint32_t)a.CS);
+        ptx::mbar_init(&bres_bar, 1);
         ptx::fence_mbar_init();
     }
     if (warp == 1) {
@@ -355,6 +377,10 @@ __global__ void __launch_bounds__(LN_THREADS, 1) conv_ln_tc_kernel(const __grid_
         if (lane == 0) {
             // ===== TMA producer =====
             long long it = 0;
+            if (a.b_res) {  // the whole [Co x K] weight matrix, once (b_res implies NT == 1)
+                ptx::mbar_expect_tx(&bres_bar, (uint32_t)KB * B_BYTES);
+                for (int kb = 0; kb < KB; kb++) ptx::tma_load_2d(sBres + (size_t)kb * B_BYTES, &mapB, &bres_bar, kb * BK, 0);
+            }
             for (long long g = cluster_id; g < a.n_groups; g += n_clusters) {
                 for (int j = 0; j < slots; j++) {
                     const int tm = j / a.NT, nt = j - tm * a.NT;
@@ -370,7 +396,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) conv_ln_tc_kernel(const __grid_
                         const int tap = kb / a.kb_per_tap, c0 = (kb - tap * a.kb_per_tap) * BK;
                         const CUtensorMap *mA = tap == 0 ? &mapA0 : (tap == 1 ? &mapA1 : &mapA2);
                         ptx::tma_load_4d(sa, mA, &full_bar[s], c0, 0, f0, b0);
-                        ptx::tma_load_2d(sa + A_BYTES, &mapB, &full_bar[s], kb * BK, n0);
+                        if (!a.b_res) ptx::tma_load_2d(sa + A_BYTES, &mapB, &full_bar[s], kb * BK, n0);
                     }
                 }
             }
@@ -380,6 +406,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) conv_ln_tc_kernel(const __grid_
             // ===== MMA issuer =====
             constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN);
             long long it = 0, git = 0;
+            if (a.b_res) ptx::mbar_wait(&bres_bar, 0);
             for (long long g = cluster_id; g < a.n_groups; g += n_clusters, git++) {
                 for (int j = 0; j < slots; j++) {
                     if (git >= 1) ptx::mbar_wait(&tempty_bar[j], (uint32_t)(git - 1) & 1);
@@ -390,7 +417,8 @@ __global__ void __launch_bounds__(LN_THREADS, 1) conv_ln_tc_kernel(const __grid_
                         ptx::mbar_wait(&full_bar[s], (uint32_t)(it / STAGES) & 1);
                         ptx::tc_fence_after();
                         const uint32_t sa = ptx::smem_u32(sbase + (size_t)s * STAGE_BYTES);
-                        const uint64_t da = ptx::umma_desc_k_sw128(sa), db = ptx::umma_desc_k_sw128(sa + A_BYTES);
+                        const uint64_t da = ptx::umma_desc_k_sw128(sa);
+                        const uint64_t db = ptx::umma_desc_k_sw128(a.b_res ? ptx::smem_u32(sBres + (size_t)kb * B_BYTES) : sa + A_BYTES);
 #pragma unroll
                         for (int k = 0; k < BK / 16; k++)
                             ptx::umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
@@ -629,11 +657,31 @@ int encode_map(TcState *st, CUtensorMap *map, const void *base, int rank, const 
     return PFANN_OK;
 }
 
+// Shared-memory plan: resident weights when K x BN x 2 B leaves room for >= 4 A stages, else A+B stream together.
+static void plan_ring(int BN, int KB, int NT, size_t fixed_bytes, int *n_stages, int *b_res, size_t *smem) {
+    const size_t budget = 225 * 1024 - 1024;  // dynamic smem available next to the static barriers
+    const size_t A = (size_t)BM * BK * 2, B = (size_t)BN * BK * 2;
+    const size_t bres = (size_t)KB * B;
+    static const bool off = getenv("PFANN_B200_NO_BRES") != nullptr;
+    if (!off && NT == 1 && fixed_bytes + bres + 4 * A <= budget) {
+        size_t st = (budget - fixed_bytes - bres) / A;
+        if (st > 12) st = 12;
+        *n_stages = (int)st; *b_res = 1;
+        *smem = st * A + bres + fixed_bytes + 1024;
+        return;
+    }
+    size_t st = (budget - fixed_bytes) / (A + B);
+    if (st > 12) st = 12;
+    *n_stages = (int)st; *b_res = 0;
+    *smem = st * (A + B) + fixed_bytes + 1024;
+}
+
 template <int BN, typename YT>
-int launch_tc(Model *m, const TcConv &tc, const TcArgs &args) {
-    const size_t smem =
-        (size_t)tc_stages<BN>() * (BM * BK * 2 + BN * BK * 2) + 4 * 4096 + (size_t)args.Co * 4 + 1024;
-    PF_CHECK(smem + 2048 <= 227 * 1024, PFANN_ERR_UNSUPPORTED, "conv GEMM needs %zu B of shared memory", smem);
+int launch_tc(Model *m, const TcConv &tc, const TcArgs &args_in) {
+    TcArgs args = args_in;
+    size_t smem = 0;
+    plan_ring(BN, args.kb_per_tap * args.ntaps, args.NT, 4 * 4096 + (size_t)args.Co * 4, &args.n_stages, &args.b_res, &smem);
+    PF_CHECK(args.n_stages >= 2, PFANN_ERR_UNSUPPORTED, "conv GEMM: no room for a shared-memory ring");
     static size_t attr_smem = 0;  // per instantiation: raise the opt-in limit only when a launch needs more
     if (smem > attr_smem) {
         PF_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, YT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -681,10 +729,12 @@ LnGeom ln_geom(const ConvGeom &g) {
 }
 
 template <int BN>
-int launch_tc_ln(Model *m, const TcConv &tc, const TcLnArgs &args) {
-    const size_t smem = (size_t)ln_stages<BN>() * (BM * BK * 2 + BN * BK * 2) + 8 * 2048 + (size_t)args.Co * 4 +
-                        1024 * 8 + 512 * 16 + 512 * 8 + 1024;
-    PF_CHECK(smem + 2048 <= 227 * 1024, PFANN_ERR_UNSUPPORTED, "fused conv+LN needs %zu B of shared memory", smem);
+int launch_tc_ln(Model *m, const TcConv &tc, const TcLnArgs &args_in) {
+    TcLnArgs args = args_in;
+    size_t smem = 0;
+    plan_ring(BN, args.kb_per_tap * args.ntaps, args.NT, 8 * 2048 + (size_t)args.Co * 4 + 1024 * 8 + 512 * 16 + 512 * 8,
+              &args.n_stages, &args.b_res, &smem);
+    PF_CHECK(args.n_stages >= 2, PFANN_ERR_UNSUPPORTED, "fused conv+LN: no room for a shared-memory ring");
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
         PF_CUDA(cudaFuncSetAttribute(conv_ln_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
