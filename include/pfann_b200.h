@@ -52,6 +52,11 @@ int pfann_ctx_sm_count(pfann_ctx *ctx);
 #define PFANN_N_KERNEL_CLASSES 9
 int pfann_ctx_profile(pfann_ctx *ctx, int enable);
 int pfann_ctx_profile_read(pfann_ctx *ctx, double *ms, long long *count, int n_classes);
+/* Finer breakdown of the record consumed by the LAST pfann_ctx_profile_read: slot i < 16 = convolution i
+ * (2*layer + {0: conv1, 1: conv2}; fused conv+LayerNorm kernels included), 16 + i = LayerNorm kernels that follow
+ * convolution i, 32 = mel, 33 = head, 34 = layer-0 moments. */
+#define PFANN_N_PROFILE_DETAIL 48
+int pfann_ctx_profile_detail(pfann_ctx *ctx, double *ms, long long *count, int n);
 
 /* ---- stage 1: log-mel front end -------------------------------------------------------------- */
 

@@ -41,6 +41,7 @@ def _declare(L):
     L.pfann_ctx_sm_count.argtypes = [vp]
     L.pfann_ctx_profile.argtypes = [vp, c_int]
     L.pfann_ctx_profile_read.argtypes = [vp, POINTER(c_double), POINTER(c_longlong), c_int]
+    L.pfann_ctx_profile_detail.argtypes = [vp, POINTER(c_double), POINTER(c_longlong), c_int]
     L.pfann_mel_create.argtypes = [vp, c_int, c_int, c_int, c_double, c_double, c_int, c_int, POINTER(vp)]
     L.pfann_mel_destroy.argtypes = [vp]
     L.pfann_mel_destroy.restype = None
@@ -141,6 +142,16 @@ def profile_read(device=0):
     cnt = (c_longlong * n)()
     check(lib().pfann_ctx_profile_read(ctx(device), ms, cnt, n), 'pfann_ctx_profile_read')
     return {k: (ms[i], int(cnt[i])) for i, k in enumerate(KERNEL_CLASSES)}
+
+
+def profile_detail(device=0):
+    """Per-kernel breakdown of the record consumed by the last profile_read(): {name: (ms, launches)}."""
+    n = 48
+    ms = (c_double * n)()
+    cnt = (c_longlong * n)()
+    check(lib().pfann_ctx_profile_detail(ctx(device), ms, cnt, n), 'pfann_ctx_profile_detail')
+    names = ['conv%d' % i for i in range(16)] + ['ln%d' % i for i in range(16)] + ['mel', 'head', 'l0_moments']
+    return {k: (ms[i], int(cnt[i])) for i, k in enumerate(names) if cnt[i]}
 
 
 def ptr(a):

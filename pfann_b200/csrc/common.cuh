@@ -71,15 +71,20 @@ struct Ctx {
     DevBuf stage_in[4], stage_out[4];
     bool profile = false;    // record a CUDA-event pair around every kernel launch, per class
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[K_NCLASS];
+    // finer breakdown of the same event pairs: (detail slot, index into prof_events[class]); slots are
+    // 0-15 conv idx, 16-31 LayerNorm kernels after conv idx, 32 mel, 33 head, 34 layer-0 moments
+    std::vector<std::pair<int, std::pair<int, int>>> prof_detail;
     std::vector<cudaEvent_t> prof_pool;
+    double detail_ms[48] = {};       // filled by pfann_ctx_profile_read, returned by pfann_ctx_profile_detail
+    long long detail_count[48] = {};
 };
 
 // RAII: events on the launching stream around one kernel launch (no-op unless ctx->profile)
 struct ProfScope {
     Ctx *c;
-    int k;
+    int k, sub;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    ProfScope(Ctx *ctx, int klass);
+    ProfScope(Ctx *ctx, int klass, int detail = -1);
     ~ProfScope();
 };
 
@@ -251,6 +256,15 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
           "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr)
         : "memory");
 }

@@ -87,7 +87,7 @@ static cudaEvent_t prof_get_event(Ctx *c) {
     return e;
 }
 
-ProfScope::ProfScope(Ctx *ctx, int klass) : c(ctx), k(klass) {
+ProfScope::ProfScope(Ctx *ctx, int klass, int detail) : c(ctx), k(klass), sub(detail) {
     if (!c->profile) return;
     e0 = prof_get_event(c);
     e1 = prof_get_event(c);
@@ -96,6 +96,7 @@ ProfScope::ProfScope(Ctx *ctx, int klass) : c(ctx), k(klass) {
 ProfScope::~ProfScope() {
     if (!e0) return;
     cudaEventRecord(e1, c->stream);
+    if (sub >= 0) c->prof_detail.push_back({sub, {k, (int)c->prof_events[k].size()}});
     c->prof_events[k].push_back({e0, e1});
 }
 
@@ -175,6 +176,14 @@ int pfann_ctx_profile_read(pfann_ctx *h, double *ms, long long *count, int n_cla
         ms[k] = 0.0;
         count[k] = 0;
     }
+    for (int i = 0; i < PFANN_N_PROFILE_DETAIL; i++) c->detail_ms[i] = 0.0, c->detail_count[i] = 0;
+    for (auto &d : c->prof_detail) {
+        auto &pr = c->prof_events[d.second.first][d.second.second];
+        float t = 0.f;
+        cudaEventElapsedTime(&t, pr.first, pr.second);
+        if (d.first < PFANN_N_PROFILE_DETAIL) c->detail_ms[d.first] += t, c->detail_count[d.first]++;
+    }
+    c->prof_detail.clear();
     for (int k = 0; k < K_NCLASS; k++) {
         for (auto &pr : c->prof_events[k]) {
             float t = 0.f;
@@ -187,6 +196,16 @@ int pfann_ctx_profile_read(pfann_ctx *h, double *ms, long long *count, int n_cla
             c->prof_pool.push_back(pr.second);
         }
         c->prof_events[k].clear();
+    }
+    return PFANN_OK;
+}
+
+int pfann_ctx_profile_detail(pfann_ctx *h, double *ms, long long *count, int n) {
+    PF_CHECK(h && ms && count, PFANN_ERR_ARG, "pfann_ctx_profile_detail: NULL argument");
+    Ctx *c = reinterpret_cast<Ctx *>(h);
+    for (int i = 0; i < n; i++) {
+        ms[i] = i < PFANN_N_PROFILE_DETAIL ? c->detail_ms[i] : 0.0;
+        count[i] = i < PFANN_N_PROFILE_DETAIL ? c->detail_count[i] : 0;
     }
     return PFANN_OK;
 }

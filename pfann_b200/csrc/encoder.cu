@@ -410,63 +410,115 @@ __global__ void to_nchw_kernel(const InT *X, float *out, long long total, int C,
 // default.json) are staged ONCE per CTA into shared memory in a lane-major layout ([j][i][g], conflict-free)
 // and reused for every sample the CTA processes, instead of being re-read from L2 per sample.
 // ------------------------------------------------------------------------------------------------
-__global__ void head_kernel(const float *Y /*[nb][h]*/, const float2 *stats, const float *gamma, const float *beta,
-                            const float *w1, const float *b1, const float *w2, const float *b2, float *z, int nb,
-                            int d, int h, int u, int norm) {
+// HG groups of dp threads per CTA; every group handles HS samples per iteration so that one shared-memory read of a
+// weight feeds HS FMAs, and the loads of the next iteration's inputs are independent of the current arithmetic.
+constexpr int HEAD_HG = 2, HEAD_HS = 4;
+
+template <int V>
+__global__ void __launch_bounds__(256) head_kernel(const float *Y /*[nb][h]*/, const float2 *stats, const float *gamma,
+                                                   const float *beta, const float *w1, const float *b1, const float *w2,
+                                                   const float *b2, float *z, int nb, int d, int h, int u, int norm) {
     extern __shared__ float hsm[];
-    const int v = h / d, dp = blockDim.x;  // dp = d rounded up to a warp multiple
-    float *w1s = hsm;                       // [u][v][dp]
-    float *b1s = w1s + (size_t)u * v * dp;  // [u][dp]
+    const int dp = blockDim.x / HEAD_HG;    // d rounded up to a warp multiple
+    float *w1s = hsm;                       // [u][V][dp]
+    float *b1s = w1s + (size_t)u * V * dp;  // [u][dp]
     float *w2s = b1s + (size_t)u * dp;      // [u][dp]
-    float *xs = w2s + (size_t)u * dp;       // [v][dp]  LayerNorm'ed inputs of the current sample
-    float *red = xs + (size_t)v * dp;       // [32]
-    const int g = threadIdx.x;
-    for (int idx = threadIdx.x; idx < u * v * dp; idx += blockDim.x) {
-        const int gg = idx % dp, i = (idx / dp) % v, j = idx / (dp * v);
-        w1s[idx] = gg < d ? w1[((size_t)gg * u + j) * v + i] : 0.f;
-    }
-    for (int idx = threadIdx.x; idx < u * dp; idx += blockDim.x) {
-        const int gg = idx % dp, j = idx / dp;
-        b1s[idx] = gg < d ? b1[gg * u + j] : 0.f;
-        w2s[idx] = gg < d ? w2[gg * u + j] : 0.f;
-    }
-    const float bias2 = g < d ? b2[g] : 0.f;
-    float gam[16], bet[16];  // this thread's v LayerNorm affine values (v <= 16 on this path)
+    float *red = w2s + (size_t)u * dp;      // [HG][HS][dp / 32]
+    const int grp = threadIdx.x / dp, g = threadIdx.x - grp * dp;
+    const int nw = dp >> 5;
+    // staging: thread (grp, g) copies rows j = grp, grp + HG, ... of output dimension g: V contiguous floats each
+    for (int j = grp; j < u; j += HEAD_HG) {
+        float wv[V];
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-        gam[i] = (i < v && g < d) ? gamma[g * v + i] : 0.f;
-        bet[i] = (i < v && g < d) ? beta[g * v + i] : 0.f;
+        for (int i = 0; i < V; i++) wv[i] = 0.f;
+        if (g < d) {
+            const float4 *src = reinterpret_cast<const float4 *>(w1 + ((size_t)g * u + j) * V);
+#pragma unroll
+            for (int i = 0; i < V / 4; i++) {
+                const float4 t = __ldg(src + i);
+                wv[4 * i] = t.x; wv[4 * i + 1] = t.y; wv[4 * i + 2] = t.z; wv[4 * i + 3] = t.w;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < V; i++) w1s[(j * V + i) * dp + g] = wv[i];
+        b1s[j * dp + g] = g < d ? __ldg(b1 + g * u + j) : 0.f;
+        w2s[j * dp + g] = g < d ? __ldg(w2 + g * u + j) : 0.f;
+    }
+    const float bias2 = g < d ? __ldg(b2 + g) : 0.f;
+    float gam[V], bet[V];  // this thread's LayerNorm affine values
+#pragma unroll
+    for (int i = 0; i < V; i++) {
+        gam[i] = g < d ? __ldg(gamma + g * V + i) : 0.f;
+        bet[i] = g < d ? __ldg(beta + g * V + i) : 0.f;
     }
     __syncthreads();
-    for (long long b = blockIdx.x; b < nb; b += gridDim.x) {
-        const float2 st = stats[b];
-        float out = bias2;
-        if (g < d) {
-            float x[16];
+    const long long step = (long long)gridDim.x * HEAD_HG * HEAD_HS;
+    for (long long bb = ((long long)blockIdx.x * HEAD_HG + grp) * HEAD_HS; bb < nb; bb += step) {
+        float x[HEAD_HS][V], out[HEAD_HS];
 #pragma unroll
-            for (int i = 0; i < 16; i++)
-                if (i < v) x[i] = fmaxf(fmaf((Y[b * h + g * v + i] - st.x) * st.y, gam[i], bet[i]), 0.f);
-            for (int j = 0; j < u; j++) {
-                float acc = b1s[j * dp + g];
+        for (int s = 0; s < HEAD_HS; s++) {
+            const long long b = bb + s < nb ? bb + s : nb - 1;  // tail: recompute the last sample, store is guarded
+            const float2 st = __ldg(stats + b);
+            out[s] = bias2;
+            if (g < d) {
+                const float4 *src = reinterpret_cast<const float4 *>(Y + b * h + g * V);
 #pragma unroll
-                for (int i = 0; i < 16; i++)
-                    if (i < v) acc = fmaf(w1s[(j * v + i) * dp + g], x[i], acc);
-                const float e = acc > 0.f ? acc : expm1f(acc);  // ELU(alpha = 1)
-                out = fmaf(w2s[j * dp + g], e, out);
+                for (int i = 0; i < V / 4; i++) {
+                    const float4 t = __ldg(src + i);
+                    x[s][4 * i] = fmaxf(fmaf((t.x - st.x) * st.y, gam[4 * i], bet[4 * i]), 0.f);
+                    x[s][4 * i + 1] = fmaxf(fmaf((t.y - st.x) * st.y, gam[4 * i + 1], bet[4 * i + 1]), 0.f);
+                    x[s][4 * i + 2] = fmaxf(fmaf((t.z - st.x) * st.y, gam[4 * i + 2], bet[4 * i + 2]), 0.f);
+                    x[s][4 * i + 3] = fmaxf(fmaf((t.w - st.x) * st.y, gam[4 * i + 3], bet[4 * i + 3]), 0.f);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < V; i++) x[s][i] = 0.f;
+            }
+        }
+        for (int j = 0; j < u; j++) {
+            float acc[HEAD_HS];
+            const float bj = b1s[j * dp + g], wj = w2s[j * dp + g];
+#pragma unroll
+            for (int s = 0; s < HEAD_HS; s++) acc[s] = bj;
+#pragma unroll
+            for (int i = 0; i < V; i++) {
+                const float w = w1s[(j * V + i) * dp + g];
+#pragma unroll
+                for (int s = 0; s < HEAD_HS; s++) acc[s] = fmaf(w, x[s][i], acc[s]);
+            }
+#pragma unroll
+            for (int s = 0; s < HEAD_HS; s++) {
+                const float e = acc[s] > 0.f ? acc[s] : expm1f(acc[s]);  // ELU(alpha = 1)
+                out[s] = fmaf(wj, e, out[s]);
             }
         }
         if (norm) {
-            float s = g < d ? out * out : 0.f;
+            float sq[HEAD_HS];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            __syncthreads();  // red[] free again
-            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-            __syncthreads();
-            float t = 0.f;
-            for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += red[i];
-            out = out / fmaxf(sqrtf(t), 1e-12f);  // F.normalize(p=2, eps=1e-12)
+            for (int s = 0; s < HEAD_HS; s++) {
+                sq[s] = g < d ? out[s] * out[s] : 0.f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sq[s] += __shfl_xor_sync(0xffffffffu, sq[s], o);
+            }
+            float *rg = red + (size_t)grp * HEAD_HS * nw;
+            if ((g & 31) == 0) {
+#pragma unroll
+                for (int s = 0; s < HEAD_HS; s++) rg[s * nw + (g >> 5)] = sq[s];
+            }
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(dp) : "memory");
+#pragma unroll
+            for (int s = 0; s < HEAD_HS; s++) {
+                float t = 0.f;
+                for (int i = 0; i < nw; i++) t += rg[s * nw + i];
+                out[s] = out[s] / fmaxf(sqrtf(t), 1e-12f);  // F.normalize(p=2, eps=1e-12)
+            }
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(dp) : "memory");  // red[] free again
         }
-        if (g < d) z[b * d + g] = out;
+        if (g < d) {
+#pragma unroll
+            for (int s = 0; s < HEAD_HS; s++)
+                if (bb + s < nb) z[(bb + s) * d + g] = out[s];
+        }
     }
 }
 
@@ -529,8 +581,7 @@ void free_conv(ConvWeights &c) {
     cudaFree(c.bias);
     cudaFree(c.gamma);
     cudaFree(c.beta);
-    cudaFree(c.gamma16);
-    cudaFree(c.beta16);
+    cudaFree(c.gb16);
     c = ConvWeights();
 }
 
@@ -615,25 +666,27 @@ int finalize_conv(Model *m, int l, int which, const ConvGeom &g) {
             }
     PF_TRY(upload(gp, &cw.gamma));
     PF_TRY(upload(bp, &cw.beta));
-    if (m->precision == PFANN_PRECISION_BF16 && g.Co % 32 == 0) {
-        // lane-major blocked copy for the fused conv+LayerNorm epilogue (thread = row, 8 channels per 16-byte
-        // load): [row block of 32][column block of 32][4 x 8 columns][32 rows][8].  Blocks of samples with
-        // fewer than 32 rows repeat the rows cyclically, so lane r always finds row (r mod R) in slot r.
-        const int R = g.Fo * g.To, RB = (R + 31) / 32, CB = g.Co / 32;
-        std::vector<float> gl((size_t)RB * CB * 1024), bl((size_t)RB * CB * 1024);
-        for (int rb = 0; rb < RB; rb++)
-            for (int cb = 0; cb < CB; cb++)
+    const LnGeom lg = ln_geom(g);
+    if (m->precision == PFANN_PRECISION_BF16 && lg.ok) {
+        // gamma/beta of every CTA position (rb, nh) of the fused conv+LayerNorm kernel, in the order its epilogue
+        // reads shared memory: [32-column chunk][lane quarter][4 x 16 B gamma, 4 x 16 B beta][lane = row][8 channels].
+        // Samples shorter than 128 rows repeat cyclically inside the 128-row tile.
+        const int R = g.Fo * g.To;
+        std::vector<float> gb((size_t)lg.P * 32768);
+        for (int p = 0; p < lg.P; p++) {
+            const int rb = p / lg.NT, nh = p % lg.NT;
+            for (int cb = 0; cb < 4; cb++)
                 for (int q = 0; q < 4; q++)
-                    for (int r = 0; r < 32; r++)
-                        for (int e = 0; e < 8; e++) {
-                            const int row = R >= 32 ? (rb * 32 + r) : (r % R);
-                            const size_t src = (size_t)(row < R ? row : 0) * g.Co + cb * 32 + q * 8 + e;
-                            const size_t dst = ((((size_t)rb * CB + cb) * 4 + q) * 32 + r) * 8 + e;
-                            gl[dst] = gp[src];
-                            bl[dst] = bp[src];
-                        }
-        PF_TRY(upload_bf16(gl, &cw.gamma16));
-        PF_TRY(upload_bf16(bl, &cw.beta16));
+                    for (int jj = 0; jj < 8; jj++)
+                        for (int r = 0; r < 32; r++)
+                            for (int e = 0; e < 8; e++) {
+                                const int row = (rb * 128 + q * 32 + r) % R;
+                                const size_t src = (size_t)row * g.Co + nh * 128 + cb * 32 + (jj & 3) * 8 + e;
+                                const size_t dst = (size_t)p * 32768 + ((((size_t)cb * 4 + q) * 8 + jj) * 32 + r) * 8 + e;
+                                gb[dst] = jj < 4 ? gp[src] : bp[src];
+                            }
+        }
+        PF_TRY(upload_bf16(gb, &cw.gb16));
     }
     return PFANN_OK;
 }
@@ -642,7 +695,7 @@ template <typename InT>
 int launch_conv_fp32(Model *m, const ConvWeights &cw, const InT *X, float *Y, int nb) {
     const ConvGeom &g = cw.g;
     cudaStream_t st = m->ctx->stream;
-    ProfScope ps(m->ctx, K_CONV_CC);
+    ProfScope ps(m->ctx, K_CONV_CC, m->prof_idx);
     if (g.depthwise) {
         const long long total = (long long)nb * g.out_per_sample();
         conv_dw_kernel<InT><<<cdiv(total, 256), 256, 0, st>>>(X, cw.w_kn, cw.bias, Y, total, g.Co, g.Fi, g.Ti, g.Fo,
@@ -670,7 +723,7 @@ int launch_ln_apply(Model *m, const ConvWeights &cw, const YT *Y, OutT *X, int n
     int group = 16;
     while (group > 1 && (long long)cdiv(E, 1024) * cdiv(nb, group) < 2LL * m->ctx->sm_count) group >>= 1;
     dim3 grid(cdiv(E, 1024), cdiv(nb, group));
-    ProfScope ps(m->ctx, K_LN);
+    ProfScope ps(m->ctx, K_LN, 16 + m->prof_idx);
     ln_apply_kernel<YT, OutT><<<grid, 256, 0, m->ctx->stream>>>(Y, m->cur_stats, cw.gamma, cw.beta, X, E, nb,
                                                                 group);
     m->ctx->launches++;
@@ -679,7 +732,7 @@ int launch_ln_apply(Model *m, const ConvWeights &cw, const YT *Y, OutT *X, int n
 }
 
 int launch_stats(Model *m, const ConvWeights &cw, const float *Y, int nb) {
-    ProfScope ps(m->ctx, K_LN);
+    ProfScope ps(m->ctx, K_LN, 16 + m->prof_idx);
     ln_stats_kernel<<<nb, 512, 0, m->ctx->stream>>>(Y, cw.g.out_per_sample(), m->cur_stats);
     m->ctx->launches++;
     PF_CUDA(cudaGetLastError());
@@ -710,7 +763,7 @@ int launch_l0_fused(Model *m, const float *mel, ActT *X, int nb) {
     for (int j = 0; j < 3; j++) a.off[j] = g.tap_off[j];
     cudaStream_t st = m->ctx->stream;
     {
-        ProfScope ps(m->ctx, K_LN);
+        ProfScope ps(m->ctx, K_LN, 34);
         l0_moments_kernel<<<nb, 256, 0, st>>>(a, m->l0c, m->cur_stats);
     }
     const int cgroups = g.Co / 8, ppb = 256 / cgroups, P = g.Fi * g.To;
@@ -718,7 +771,7 @@ int launch_l0_fused(Model *m, const float *mel, ActT *X, int nb) {
     // the 4-positions-per-thread variant needs the three taps to be the contiguous run {o, o+1, o+2}
     const bool run3 = g.ntaps == 3 && g.tap_off[1] == g.tap_off[0] + 1 && g.tap_off[2] == g.tap_off[0] + 2;
     {
-        ProfScope ps(m->ctx, K_CONV_CC);
+        ProfScope ps(m->ctx, K_CONV_CC, 0);
         static const int pp_env = getenv("PFANN_L0_PP") ? atoi(getenv("PFANN_L0_PP")) : 4;
         if (run3 && g.To % 4 == 0 && pp_env == 4) {
             dim3 grid(cdiv(P / 4, ppb), cdiv(nb, group));
@@ -755,6 +808,7 @@ int forward_front(Model *m, const float *mel, int nb) {
         PF_TRY(launch_l0_fused<bf>(m, mel + (long long)s0 * mel_per, m->fxa.as<bf>(), ns));
         for (int idx = 1; idx < 2 * LF; idx++) {
             const ConvWeights &cw = m->conv[idx];
+            m->prof_idx = idx;
             const bf *in = (idx & 1) ? m->fxa.as<bf>() : m->fxb.as<bf>();
             PF_TRY(tc_conv(m, idx, in, m->fy.p, m->y_bf16, ns));
             bf *out = (idx & 1) ? m->fxb.as<bf>() : m->fxa.as<bf>();
@@ -785,6 +839,7 @@ int forward_chunk(Model *m, const float *mel, int nb, int norm, float *z) {
     for (int l = l_begin; l < 8; l++) {
         for (int which = 0; which < 2; which++) {
             const ConvWeights &cw = m->conv[2 * l + which];
+            m->prof_idx = 2 * l + which;
             const bool first = (l == 0 && which == 0);
             const bool last = (l == 7 && which == 1);
             bool stats_done = false, ybf = false;
@@ -831,18 +886,25 @@ int forward_chunk(Model *m, const float *mel, int nb, int norm, float *z) {
         PF_TRY(save_tap<ActT>(m, 7, xb, nb));
     }
     const int threads = ((m->d + 31) / 32) * 32;
-    ProfScope ps(m->ctx, K_HEAD);
+    ProfScope ps(m->ctx, K_HEAD, 33);
     const int v = m->h / m->d;
-    const size_t smem_fast = ((size_t)m->u * v * threads + 2 * (size_t)m->u * threads + (size_t)v * threads + 32) * 4;
-    if (v <= 16 && smem_fast <= 200 * 1024) {
+    const size_t smem_fast =
+        ((size_t)m->u * v * threads + 2 * (size_t)m->u * threads + (size_t)HEAD_HG * HEAD_HS * (threads / 32)) * 4;
+    if ((v == 8 || v == 16) && threads * HEAD_HG <= 256 && smem_fast <= 200 * 1024) {
         static size_t attr = 0;
         if (smem_fast > attr) {
-            PF_CUDA(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
+            PF_CUDA(cudaFuncSetAttribute(head_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
+            PF_CUDA(cudaFuncSetAttribute(head_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
             attr = smem_fast;
         }
-        const int grid = nb < m->ctx->sm_count ? nb : m->ctx->sm_count;
-        head_kernel<<<grid, threads, smem_fast, m->ctx->stream>>>(Y, m->cur_stats, last.gamma, last.beta, m->w1,
-                                                                   m->b1, m->w2, m->b2, z, nb, m->d, m->h, m->u, norm);
+        const int want = (nb + HEAD_HG * HEAD_HS - 1) / (HEAD_HG * HEAD_HS);
+        const int grid = want < m->ctx->sm_count ? want : m->ctx->sm_count;
+        if (v == 8)
+            head_kernel<8><<<grid, threads * HEAD_HG, smem_fast, m->ctx->stream>>>(
+                Y, m->cur_stats, last.gamma, last.beta, m->w1, m->b1, m->w2, m->b2, z, nb, m->d, m->h, m->u, norm);
+        else
+            head_kernel<16><<<grid, threads * HEAD_HG, smem_fast, m->ctx->stream>>>(
+                Y, m->cur_stats, last.gamma, last.beta, m->w1, m->b1, m->w2, m->b2, z, nb, m->d, m->h, m->u, norm);
     } else {
         head_kernel_generic<<<nb, threads, (m->h + 32) * sizeof(float), m->ctx->stream>>>(
             Y, m->cur_stats, last.gamma, last.beta, m->w1, m->b1, m->w2, m->b2, z, m->d, m->h, m->u, norm);
@@ -942,7 +1004,7 @@ void pfann_model_destroy(pfann_model *hm) {
     cudaFree(m->w1); cudaFree(m->b1); cudaFree(m->w2); cudaFree(m->b2); cudaFree(m->l0_w);
     m->ybuf.release(); m->xa.release(); m->xb.release(); m->stats.release(); m->partials.release();
     m->fy.release(); m->fxa.release(); m->fxb.release(); m->fstats.release(); m->fpartials.release();
-    m->tapbuf.release(); m->melbuf.release(); m->zbuf.release();
+    m->tapbuf.release(); m->melbuf.release(); m->zbuf.release(); m->ln_part.release(); m->ln_err.release();
     delete m;
 }
 
@@ -1080,7 +1142,8 @@ int pfann_model_forward(pfann_model *hm, const float *mel, int64_t B, int norm, 
     PF_TRY(stage_input(m->ctx, 0, mel, in_b, &xd));
     PF_TRY(stage_output(m->ctx, 0, z, out_b, &zd));
     PF_TRY(model_forward_dev(m, (const float *)xd, B, norm, (float *)zd));
-    return finish_output(m->ctx, 0, z, out_b);
+    PF_TRY(finish_output(m->ctx, 0, z, out_b));
+    return is_device_ptr(z) ? PFANN_OK : tc_ln_check(m);
 }
 
 int pfann_model_get_activation(pfann_model *hm, int layer, float *out, int64_t numel) {

@@ -37,7 +37,7 @@ struct ConvWeights {
     float *bias = nullptr;           // [Co]
     float *gamma = nullptr;          // LayerNorm affine permuted to channels-last [Fo][To][Co]
     float *beta = nullptr;
-    __nv_bfloat16 *gamma16 = nullptr, *beta16 = nullptr;  // same, bf16 (fused conv+LayerNorm epilogue)
+    __nv_bfloat16 *gb16 = nullptr;   // gamma/beta per CTA position of the fused conv+LayerNorm kernel (bf16)
 };
 
 struct Model {
@@ -63,7 +63,9 @@ struct Model {
     // conv1, ...) live and die in the 126 MB L2 instead of making round trips to HBM.  0 = disabled.
     int front_layers = 0, front_sub = 0;
     DevBuf fy, fxa, fxb, fstats, fpartials;
+    DevBuf ln_part, ln_err;  // fused conv+LayerNorm: statistics exchange table, time-out flag
     float2 *cur_stats = nullptr, *cur_partials = nullptr;  // statistics buffers of the phase being executed
+    int prof_idx = 0;      // convolution being executed (detail slot of the optional event profile)
     int tap_layer = -1;
     long long tap_numel = 0;
     void *tc_state = nullptr;  // tensor maps etc., owned by encoder_tc.cu
@@ -78,7 +80,14 @@ bool tc_supported(const ConvGeom &g);
 int tc_conv(Model *m, int idx, const __nv_bfloat16 *X, void *Y, bool y_bf16, int nb);
 // Fused conv + LayerNorm + ReLU (TMEM-resident accumulators, no raw output): Xout[m][n] bf16.  Returns
 // PFANN_ERR_UNSUPPORTED (without touching anything) when the geometry has no fused mapping.
+struct LnGeom {
+    bool ok = false;
+    int NT = 0, RB = 0, P = 0;  // 128-channel slices, 128-row blocks per sample, CTA positions per sample group
+    int sg_shift = 0;           // log2(samples per 128-row tile)
+};
+LnGeom ln_geom(const ConvGeom &g);
 bool tc_ln_supported(Model *m, int idx);
+int tc_ln_check(Model *m);
 int tc_conv_ln(Model *m, int idx, const __nv_bfloat16 *X, __nv_bfloat16 *Xout, int nb);
 // encoder.cu: size both workspaces (needs conv geometries and front_* decided)
 int plan_workspace(Model *m);

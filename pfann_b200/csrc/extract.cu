@@ -59,7 +59,8 @@ int pfann_extract_segments(pfann_mel *mel, pfann_model *hm, const float *x, int6
         PF_TRY(mel_forward_dev(mel, (const float *)xd + b0 * seg_len, nb, m->melbuf.as<float>()));
         PF_TRY(model_forward_dev(m, m->melbuf.as<float>(), nb, norm, (float *)zd + b0 * m->d));
     }
-    return finish_output(m->ctx, 0, z, out_b);
+    PF_TRY(finish_output(m->ctx, 0, z, out_b));
+    return is_device_ptr(z) ? PFANN_OK : tc_ln_check(m);
 }
 
 int pfann_extract_pcm16(pfann_mel *mel, pfann_model *hm, const int16_t *pcm, const int64_t *clip_off, int n_clips,
@@ -104,7 +105,8 @@ int pfann_extract_pcm16(pfann_mel *mel, pfann_model *hm, const int16_t *pcm, con
     }
     // the descriptor vectors are host temporaries: make sure their H2D copies are done before they die
     PF_CUDA(cudaStreamSynchronize(m->ctx->stream));
-    return finish_output(m->ctx, 0, z, out_b);
+    PF_TRY(finish_output(m->ctx, 0, z, out_b));
+    return tc_ln_check(m);
 }
 
 }  // extern "C"

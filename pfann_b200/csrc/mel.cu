@@ -281,7 +281,7 @@ size_t mel_smem_bytes(int n, int n_mels, int T) {
 int launch_mel(MelPlan *p, const MelArgs &a, int64_t B, bool pcm) {
     if (B == 0) return PFANN_OK;
     PF_CHECK(B <= 0x7fffffffLL, PFANN_ERR_ARG, "mel: too many segments in one call (%lld)", (long long)B);
-    ProfScope ps(p->ctx, K_MEL);
+    ProfScope ps(p->ctx, K_MEL, 32);
     if (pcm)
         mel_kernel<true><<<(unsigned)B, NTHREADS, p->smem_bytes, p->ctx->stream>>>(a);
     else
