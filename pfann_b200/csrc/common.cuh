@@ -66,6 +66,7 @@ enum KernelClass { K_MEL = 0, K_CONV_TC, K_CONV_CC, K_LN, K_HEAD, K_KNN_SCAN, K_
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;  // H2D / D2H pipelines of pfann_extract_pcm16 (host buffers)
     int sm_count = 148;
     long long launches = 0;  // kernels of OURS launched through this context (bench: gpu_launches)
     DevBuf stage_in[4], stage_out[4];

@@ -140,6 +140,8 @@ void pfann_ctx_destroy(pfann_ctx *h) {
     Ctx *c = reinterpret_cast<Ctx *>(h);
     if (!c) return;
     cudaSetDevice(c->device);
+    if (c->copy_in) cudaStreamDestroy(c->copy_in);
+    if (c->copy_out) cudaStreamDestroy(c->copy_out);
     for (int i = 0; i < 4; i++) {
         c->stage_in[i].release();
         c->stage_out[i].release();

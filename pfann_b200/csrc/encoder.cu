@@ -766,6 +766,11 @@ int launch_l0_fused(Model *m, const float *mel, ActT *X, int nb) {
         ProfScope ps(m->ctx, K_LN, 34);
         l0_moments_kernel<<<nb, 256, 0, st>>>(a, m->l0c, m->cur_stats);
     }
+    if (sizeof(ActT) == 2 && tc_l0_supported(m)) {
+        m->ctx->launches++;
+        PF_CUDA(cudaGetLastError());
+        return tc_l0(m, mel, m->cur_stats, reinterpret_cast<__nv_bfloat16 *>(X), nb);
+    }
     const int cgroups = g.Co / 8, ppb = 256 / cgroups, P = g.Fi * g.To;
     const int group = 32;
     // the 4-positions-per-thread variant needs the three taps to be the contiguous run {o, o+1, o+2}
@@ -1002,6 +1007,7 @@ void pfann_model_destroy(pfann_model *hm) {
     tc_release(m);
     for (int i = 0; i < 16; i++) free_conv(m->conv[i]);
     cudaFree(m->w1); cudaFree(m->b1); cudaFree(m->w2); cudaFree(m->b2); cudaFree(m->l0_w);
+    cudaFree(m->l0_gb16); cudaFree(m->l0_btile);
     m->ybuf.release(); m->xa.release(); m->xb.release(); m->stats.release(); m->partials.release();
     m->fy.release(); m->fxa.release(); m->fxb.release(); m->fstats.release(); m->fpartials.release();
     m->tapbuf.release(); m->melbuf.release(); m->zbuf.release(); m->ln_part.release(); m->ln_err.release();
@@ -1072,6 +1078,48 @@ int pfann_model_finalize(pfann_model *hm, int precision) {
         cudaFree(m->l0_w);
         m->l0_w = nullptr;
         PF_TRY(upload(wt, &m->l0_w));
+        cudaFree(m->l0_gb16); cudaFree(m->l0_btile);
+        m->l0_gb16 = nullptr; m->l0_btile = nullptr;
+        if (precision == PFANN_PRECISION_BF16 && g.Co == 128 && (g.Fo * g.To) % 128 == 0) {
+            // tensor-core layer-0 kernel: weight tile [128 channels][64 K] bf16 in the 128-byte-swizzled K-major
+            // layout (only K columns 0-15 are read): [wh0 wh1 wh2 | wh0 wh1 wh2 | wl0 wl1 wl2 | bh bm bl 0 0 0 0]
+            std::vector<__nv_bfloat16> bt(128 * 64, __float2bfloat16_rn(0.f));
+            for (int n = 0; n < 128; n++) {
+                float wv[3] = {0.f, 0.f, 0.f};
+                for (int j = 0; j < g.ntaps; j++) wv[j] = wt[(size_t)n * g.ntaps + j];
+                __nv_bfloat16 k[16];
+                for (int i = 0; i < 16; i++) k[i] = __float2bfloat16_rn(0.f);
+                for (int j = 0; j < 3; j++) {
+                    const __nv_bfloat16 wh = __float2bfloat16_rn(wv[j]);
+                    const __nv_bfloat16 wl = __float2bfloat16_rn(wv[j] - __bfloat162float(wh));
+                    k[j] = wh; k[3 + j] = wh; k[6 + j] = wl;
+                }
+                const __nv_bfloat16 bh = __float2bfloat16_rn(b[n]);
+                const __nv_bfloat16 bm = __float2bfloat16_rn(b[n] - __bfloat162float(bh));
+                const __nv_bfloat16 bl = __float2bfloat16_rn(b[n] - __bfloat162float(bh) - __bfloat162float(bm));
+                k[9] = bh; k[10] = bm; k[11] = bl;
+                for (int c = 0; c < 2; c++)       // logical 16-byte chunk c of row n lives at chunk c ^ (n % 8)
+                    for (int e = 0; e < 8; e++) bt[(size_t)n * 64 + ((c ^ (n & 7)) * 8) + e] = k[c * 8 + e];
+            }
+            PF_CUDA(cudaMalloc(&m->l0_btile, bt.size() * sizeof(__nv_bfloat16)));
+            PF_CUDA(cudaMemcpy(m->l0_btile, bt.data(), bt.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+            // ln1 affine per block of 128 positions in the epilogue's register layout (see finalize_conv)
+            const int PB = g.Fo * g.To / 128;
+            const std::vector<float> &ga = m->host["f.convs.0.ln1.weight"], &be = m->host["f.convs.0.ln1.bias"];
+            std::vector<float> gb((size_t)PB * 32768);
+            for (int pb = 0; pb < PB; pb++)
+                for (int cb = 0; cb < 4; cb++)
+                    for (int q = 0; q < 4; q++)
+                        for (int jj = 0; jj < 8; jj++)
+                            for (int r = 0; r < 32; r++)
+                                for (int e = 0; e < 8; e++) {
+                                    const int pos = pb * 128 + q * 32 + r, ch = cb * 32 + (jj & 3) * 8 + e;
+                                    const size_t src = (size_t)ch * g.Fo * g.To + pos;  // reference order [C][F][T]
+                                    const size_t dst = (size_t)pb * 32768 + ((((size_t)cb * 4 + q) * 8 + jj) * 32 + r) * 8 + e;
+                                    gb[dst] = jj < 4 ? ga[src] : be[src];
+                                }
+            PF_TRY(upload_bf16(gb, &m->l0_gb16));
+        }
         m->y_bf16 = getenv("PFANN_B200_Y_FP32") == nullptr;
         bool taps_run = true;  // the fused kernel reads the mel run off[0], off[0]+1, off[0]+2
         for (int j = 1; j < g.ntaps; j++) taps_run = taps_run && g.tap_off[j] == g.tap_off[0] + j;

@@ -55,6 +55,8 @@ struct Model {
         double A[3], G[3][3], H[3], Bsum, B2;
     } l0c;
     float *l0_w = nullptr;  // [Co][ntaps] fp32 (tap-major per channel)
+    __nv_bfloat16 *l0_gb16 = nullptr;  // layer-0 ln1 affine per block of 128 positions (tensor-core layer-0 kernel)
+    void *l0_btile = nullptr;          // its 16 KB weight tile (bf16 hi/lo split, shared-memory layout)
     bool l0_fused = false;
     bool y_bf16 = true;     // tensor-core convs write their raw output in bf16 (statistics stay fp32)
     DevBuf ybuf, xa, xb, stats, partials, tapbuf, melbuf, zbuf;   // chunk-sized workspace ("tail" phase)
@@ -88,6 +90,9 @@ struct LnGeom {
 LnGeom ln_geom(const ConvGeom &g);
 bool tc_ln_supported(Model *m, int idx);
 int tc_ln_check(Model *m);
+// layer-0 conv1 + ln1 + ReLU as one K = 16 MMA per 128 positions (statistics from the moments kernel)
+bool tc_l0_supported(Model *m);
+int tc_l0(Model *m, const float *mel, const float2 *stats, __nv_bfloat16 *X, int nb);
 int tc_conv_ln(Model *m, int idx, const __nv_bfloat16 *X, __nv_bfloat16 *Xout, int nb);
 // encoder.cu: size both workspaces (needs conv geometries and front_* decided)
 int plan_workspace(Model *m);

@@ -355,8 +355,12 @@ __global__ void __launch_bounds__(LN_THREADS, 1) conv_ln_tc_kernel(const __grid_
         reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int KB = a.kb_per_tap * a.ntaps;
     unsigned char *sBres = sbase + (size_t)STAGES * STAGE_BYTES;                 // [KB][128 x 128 B] when b_res
-    unsigned char *stage_out = sBres + (a.b_res ? (size_t)KB * B_BYTES : 0);      // 16 warps x 1 KB store staging
-    float *bias_s = reinterpret_cast<float *>(stage_out + LN_EPI_WARPS * 1024);  // [128]
+    // bias tile: row r holds [1 1 1 0..] in K columns 0-15 and [b_hi b_mid b_lo 0..] of channel n0 + r in K columns
+    // 16-31 (same swizzled K-major layout as the operands).  One extra MMA per tile, A = columns 0-15 of every row,
+    // B = columns 16-31, initialises the accumulator with the bias -- the epilogue never touches it (bias reads
+    // from shared memory used to cost more L1 data-pipe cycles than the tensor core's own operand reads).
+    unsigned char *cb_s = sBres + (a.b_res ? (size_t)KB * B_BYTES : 0);
+    unsigned char *stage_out = cb_s + 16384;                                      // 16 warps x 1 KB store staging
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], bres_bar;
     __shared__ __align__(8) uint64_t tfull_bar[4], tempty_bar[4], sready_bar[4];
     __shared__ float2 stat_s[4][4];                                               // [slot][sample of the tile] (mean, rstd)
@@ -388,7 +392,21 @@ __global__ void __launch_bounds__(LN_THREADS, 1) conv_ln_tc_kernel(const __grid_
         ptx::tmem_alloc(&tmem_base_s, 512);
         ptx::tmem_relinquish();
     }
-    for (int i = tid; i < BN; i += LN_THREADS) bias_s[i] = a.bias[n0 + i];
+    if (tid < BN) {
+        const float b = a.bias[n0 + tid];
+        const __nv_bfloat16 bh = __float2bfloat16_rn(b);
+        const __nv_bfloat16 bm = __float2bfloat16_rn(b - __bfloat162float(bh));
+        const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh) - __bfloat162float(bm));
+        const uint32_t one = 0x3F80u;  // bf16 1.0
+        uint4 *row = reinterpret_cast<uint4 *>(cb_s + (size_t)tid * 128);
+        const int x = tid & 7;         // 128-byte swizzle: logical 16-byte chunk c lives at chunk c ^ (row % 8)
+        row[0 ^ x] = make_uint4(one | (one << 16), one, 0u, 0u);
+        row[1 ^ x] = make_uint4(0u, 0u, 0u, 0u);
+        row[2 ^ x] = make_uint4((uint32_t)__bfloat16_as_ushort(bh) | ((uint32_t)__bfloat16_as_ushort(bm) << 16),
+                                (uint32_t)__bfloat16_as_ushort(bl), 0u, 0u);
+        row[3 ^ x] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    ptx::fence_proxy_async();  // the tensor core reads the bias tile through the async proxy
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -432,6 +450,10 @@ __global__ void __launch_bounds__(LN_THREADS, 1) conv_ln_tc_kernel(const __grid_
                 if (i >= 4) ptx::mbar_wait(&tempty_bar[slot], (uint32_t)((i >> 2) - 1) & 1);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(slot * BN);
+                {   // accumulator := bias (ones x bias rows)
+                    const uint64_t dc = ptx::umma_desc_k_sw128(ptx::smem_u32(cb_s));
+                    ptx::umma_f16(d_tmem, dc, dc + 2, idesc, 0);
+                }
                 for (int kb = 0; kb < KB; kb++) {
                     ptx::mbar_wait(&full_bar[s], round & 1);
                     ptx::tc_fence_after();
@@ -440,7 +462,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) conv_ln_tc_kernel(const __grid_
                     const uint64_t db = ptx::umma_desc_k_sw128(a.b_res ? ptx::smem_u32(sBres + (size_t)kb * B_BYTES) : sa + A_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / 16; k++)
-                        ptx::umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        ptx::umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, 1);
                     ptx::umma_commit(&empty_bar[s]);
                     if (++s == STAGES) s = 0, round++;
                 }
@@ -487,9 +509,8 @@ __global__ void __launch_bounds__(LN_THREADS, 1) conv_ln_tc_kernel(const __grid_
                 float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int q = 0; q < 8; q++) {
-                    const float4 b4 = *reinterpret_cast<const float4 *>(&bias_s[cc + 4 * q]);
-                    const float o0 = __uint_as_float(v[4 * q]) + b4.x, o1 = __uint_as_float(v[4 * q + 1]) + b4.y;
-                    const float o2 = __uint_as_float(v[4 * q + 2]) + b4.z, o3 = __uint_as_float(v[4 * q + 3]) + b4.w;
+                    const float o0 = __uint_as_float(v[4 * q]), o1 = __uint_as_float(v[4 * q + 1]);
+                    const float o2 = __uint_as_float(v[4 * q + 2]), o3 = __uint_as_float(v[4 * q + 3]);
                     p1[0] += o0; p1[1] += o1; p1[2] += o2; p1[3] += o3;
                     p2[0] = fmaf(o0, o0, p2[0]); p2[1] = fmaf(o1, o1, p2[1]);
                     p2[2] = fmaf(o2, o2, p2[2]); p2[3] = fmaf(o3, o3, p2[3]);
@@ -538,15 +559,12 @@ __global__ void __launch_bounds__(LN_THREADS, 1) conv_ln_tc_kernel(const __grid_
                         const uint4 g4 = gq[2 * hh + q], b4 = bq[2 * hh + q];
                         const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w};
                         const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
-                        const float4 ba = *reinterpret_cast<const float4 *>(&bias_s[cc + 16 * hh + 8 * q]);
-                        const float4 bb = *reinterpret_cast<const float4 *>(&bias_s[cc + 16 * hh + 8 * q + 4]);
-                        const float bia[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
                         for (int e = 0; e < 4; e++) {
                             const int c = 8 * q + 2 * e;
                             const float a0 = __uint_as_float(hh ? vb[c] : va[c]), a1 = __uint_as_float(hh ? vb[c + 1] : va[c + 1]);
-                            const float x0 = fmaf(a0 + bia[2 * e], rstd, nmr);
-                            const float x1 = fmaf(a1 + bia[2 * e + 1], rstd, nmr);
+                            const float x0 = fmaf(a0, rstd, nmr);
+                            const float x1 = fmaf(a1, rstd, nmr);
                             __nv_bfloat162 y2 = __hfma2(__floats2bfloat162_rn(x0, x1),
                                                         *reinterpret_cast<const __nv_bfloat162 *>(&gw[e]),
                                                         *reinterpret_cast<const __nv_bfloat162 *>(&bw[e]));
@@ -646,6 +664,225 @@ __global__ void __launch_bounds__(LN_THREADS, 1) conv_ln_tc_kernel(const __grid_
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Layer 0: conv1 (C_in = 1, three taps along time, model.py:20) + ln1 + ReLU on the tensor core.
+//
+// K = 3 is far too small for a GEMM -- but one 128 x 128 x 16 tcgen05.mma per 128 output positions costs 64 tensor
+// cycles and replaces 3 FMAs + bias per output on the CUDA cores.  The 16 K-columns carry a bf16 hi/lo split of both
+// operands so that the product is exact to ~2^-17 (fp32 accumulation in TMEM):
+//     A row (position p): [mh0 mh1 mh2 | ml0 ml1 ml2 | mh0 mh1 mh2 | 1  1  1  0 ...]      m_j = mel under tap j
+//     B row (channel  n): [wh0 wh1 wh2 | wh0 wh1 wh2 | wl0 wl1 wl2 | bh bm bl 0 ...]      bias as three bf16 terms
+// Builder warps assemble the A tiles (two 16-byte stores per row, swizzled K-major layout) from the fp32 log-mel,
+// one thread issues the MMAs into a ring of four TMEM accumulators, and sixteen epilogue warps read them back
+// (tcgen05.ld), normalise with the statistics the moments kernel derived analytically, apply the per-element affine
+// (register-resident per position block: tiles are walked position-block-major) and ReLU, and store bf16 rows.
+// ------------------------------------------------------------------------------------------------------------
+struct L0TcArgs {
+    const float *mel;          // [nb][F][T]
+    const float2 *stats;       // [nb] (mean, rstd)
+    const __nv_bfloat16 *gb;   // [PB][64 KB] gamma/beta per block of 128 positions, epilogue register layout
+    const uint4 *btile;        // 16 KB weight tile in the tensor core's shared-memory layout
+    __nv_bfloat16 *X;          // [nb][P][128]
+    int nb, F, T, To, ntaps, off[3];
+    int PB;                    // position blocks per sample (P / 128)
+};
+constexpr int L0_BUILD_WARPS = 2;
+constexpr int L0_THREADS = 32 * (L0_BUILD_WARPS + 1 + 16);
+constexpr int L0_STAGES = 8;
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t *>(&v);
+}
+
+__global__ void __launch_bounds__(L0_THREADS, 1) l0_tc_kernel(const L0TcArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *sbase =
+        reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char *sA = sbase;                         // L0_STAGES x (128 rows x 128 B); 32 B per row are used
+    unsigned char *sB = sA + L0_STAGES * 16384;        // 16 KB weight tile
+    unsigned char *stage_out = sB + 16384;             // 16 warps x 1 KB store staging
+    __shared__ __align__(8) uint64_t a_full[L0_STAGES], a_empty[L0_STAGES], tfull_bar[4], tempty_bar[4];
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // tiles in position-block-major order t = pb * nb + s; every CTA takes one contiguous range
+    const long long T_total = (long long)a.PB * a.nb;
+    const long long t_begin = T_total * blockIdx.x / gridDim.x, t_end = T_total * (blockIdx.x + 1) / gridDim.x;
+    const int nt = (int)(t_end - t_begin);
+    const int pb_begin = (int)(t_begin / a.nb), s_begin = (int)(t_begin - (long long)pb_begin * a.nb);
+
+    if (tid == 0) {
+        for (int s = 0; s < L0_STAGES; s++) {
+            ptx::mbar_init(&a_full[s], 32 * L0_BUILD_WARPS);
+            ptx::mbar_init(&a_empty[s], 1);
+        }
+        for (int s = 0; s < 4; s++) {
+            ptx::mbar_init(&tfull_bar[s], 1);
+            ptx::mbar_init(&tempty_bar[s], 16);
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == L0_BUILD_WARPS) {
+        ptx::tmem_alloc(&tmem_base_s, 512);
+        ptx::tmem_relinquish();
+    }
+    for (int i = tid; i < 1024; i += L0_THREADS) reinterpret_cast<uint4 *>(sB)[i] = a.btile[i];
+    ptx::fence_proxy_async();
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp < L0_BUILD_WARPS) {
+        // ===== A-tile builders: thread bt assembles rows bt and bt + 64 of every tile =====
+        int pb = pb_begin, s = s_begin, stage = 0;
+        uint32_t round = 0;
+        float mv[2][3];
+        auto load_rows = [&](int pbi, int si, float(&out)[2][3]) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int p = pbi * 128 + tid + 64 * h;
+                const int f = p / a.To, to = p - f * a.To;
+                const float *row = a.mel + ((long long)si * a.F + f) * a.T;
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    const int t = 2 * to + a.off[j];
+                    out[h][j] = (j < a.ntaps && t >= 0 && t < a.T) ? __ldg(row + t) : 0.f;
+                }
+            }
+        };
+        if (nt > 0) load_rows(pb, s, mv);
+        for (int i = 0; i < nt; i++) {
+            float cur[2][3];
+#pragma unroll
+            for (int h = 0; h < 2; h++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) cur[h][j] = mv[h][j];
+            int pbn = pb, sn = s + 1;
+            if (sn == a.nb) sn = 0, pbn++;
+            if (i + 1 < nt) load_rows(pbn, sn, mv);  // next tile's inputs are in flight while this one is assembled
+            if (round > 0) ptx::mbar_wait(&a_empty[stage], (round - 1) & 1);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int r = tid + 64 * h;
+                float mh[3], ml[3];
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    mh[j] = __bfloat162float(__float2bfloat16_rn(cur[h][j]));
+                    ml[j] = cur[h][j] - mh[j];
+                }
+                uint4 *row = reinterpret_cast<uint4 *>(sA + (size_t)stage * 16384 + (size_t)r * 128);
+                const int x = r & 7;  // 128-byte swizzle: logical 16-byte chunk c lives at chunk c ^ (row % 8)
+                row[0 ^ x] = make_uint4(pack_bf16(mh[0], mh[1]), pack_bf16(mh[2], ml[0]), pack_bf16(ml[1], ml[2]),
+                                        pack_bf16(mh[0], mh[1]));
+                row[1 ^ x] = make_uint4(pack_bf16(mh[2], 1.f), pack_bf16(1.f, 1.f), 0u, 0u);
+            }
+            ptx::fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+            ptx::mbar_arrive(&a_full[stage]);
+            pb = pbn; s = sn;
+            if (++stage == L0_STAGES) stage = 0, round++;
+        }
+    } else if (warp == L0_BUILD_WARPS) {
+        if (lane == 0) {
+            // ===== MMA issuer: one 128 x 128 x 16 MMA per tile =====
+            constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, 128);
+            const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(sB));
+            int stage = 0;
+            uint32_t round = 0;
+            for (int i = 0; i < nt; i++) {
+                const int slot = i & 3;
+                if (i >= 4) ptx::mbar_wait(&tempty_bar[slot], (uint32_t)((i >> 2) - 1) & 1);
+                ptx::mbar_wait(&a_full[stage], round & 1);
+                ptx::tc_fence_after();
+                const uint64_t da = ptx::umma_desc_k_sw128(ptx::smem_u32(sA + (size_t)stage * 16384));
+                ptx::umma_f16(tmem_base + (uint32_t)(slot * 128), da, db, idesc, 0);
+                ptx::umma_commit(&a_empty[stage]);
+                ptx::umma_commit(&tfull_bar[slot]);
+                if (++stage == L0_STAGES) stage = 0, round++;
+            }
+        }
+    } else {
+        // ===== epilogue: 16 warps, four per TMEM lane quarter; warp `wc` of a quarter owns columns [32 wc, 32 wc + 32) =====
+        const int quarter = warp & 3, ew = warp - (L0_BUILD_WARPS + 1), wc = ew >> 2;
+        const int cc = wc * 32;
+        uint4 *stg = reinterpret_cast<uint4 *>(stage_out + (size_t)ew * 1024);
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)cc;
+        const long long P = (long long)a.PB * 128;
+        const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+        const int sw = (lane >> 2) & 1;
+        uint4 gq[4], bq[4];
+        int pb = pb_begin, s = s_begin, cur_pb = -1;
+        float2 st_next = nt > 0 ? __ldg(a.stats + s) : make_float2(0.f, 1.f);
+        for (int i = 0; i < nt; i++) {
+            const int slot = i & 3;
+            if (pb != cur_pb) {  // at most once inside a CTA's range: gamma/beta of this position block
+                const uint4 *gl = reinterpret_cast<const uint4 *>(a.gb) + (size_t)pb * (LN_GB_BYTES / 16) +
+                                  ((wc * 4 + quarter) * 8) * 32 + lane;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    gq[q] = __ldg(gl + q * 32);
+                    bq[q] = __ldg(gl + (4 + q) * 32);
+                }
+                cur_pb = pb;
+            }
+            const float2 st = st_next;
+            int pbn = pb, sn = s + 1;
+            if (sn == a.nb) sn = 0, pbn++;
+            if (i + 1 < nt) st_next = __ldg(a.stats + sn);
+            const float rstd = st.y, nmr = -st.x * st.y;
+            const long long mrow0 = (long long)s * P + (long long)pb * 128 + quarter * 32;
+            ptx::mbar_wait(&tfull_bar[slot], (uint32_t)(i >> 2) & 1);
+            ptx::tc_fence_after();
+            uint32_t va[16], vb[16];
+            ptx::tmem_ld_32x32b_x16(t_lane + (uint32_t)(slot * 128), va);
+            ptx::tmem_ld_32x32b_x16(t_lane + (uint32_t)(slot * 128 + 16), vb);
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty_bar[slot]);
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) {
+                uint32_t pk[8];
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    const uint4 g4 = gq[2 * hh + q], b4 = bq[2 * hh + q];
+                    const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w};
+                    const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const int c = 8 * q + 2 * e;
+                        const float a0 = __uint_as_float(hh ? vb[c] : va[c]), a1 = __uint_as_float(hh ? vb[c + 1] : va[c + 1]);
+                        __nv_bfloat162 y2 = __hfma2(__floats2bfloat162_rn(fmaf(a0, rstd, nmr), fmaf(a1, rstd, nmr)),
+                                                    *reinterpret_cast<const __nv_bfloat162 *>(&gw[e]),
+                                                    *reinterpret_cast<const __nv_bfloat162 *>(&bw[e]));
+                        y2 = __hmax2(y2, zero2);
+                        pk[4 * q + e] = *reinterpret_cast<const uint32_t *>(&y2);
+                    }
+                }
+                stg[lane * 2 + (0 ^ sw)] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                stg[lane * 2 + (1 ^ sw)] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                __syncwarp();
+#pragma unroll
+                for (int r0 = 0; r0 < 32; r0 += 16) {
+                    const int r = r0 + (lane >> 1), ch = lane & 1;
+                    const uint4 val = stg[r * 2 + (ch ^ ((r >> 2) & 1))];
+                    *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(a.X) +
+                                               ((mrow0 + r) * 128 + cc + hh * 16) * 2 + ch * 16) = val;
+                }
+                __syncwarp();
+            }
+            pb = pbn; s = sn;
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == L0_BUILD_WARPS) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 512);
+    }
+}
+
 // stats[b] = (mean, rstd) from the partial slots; one warp per sample, fixed summation order
 __global__ void ln_finalize_kernel(const float2 *partials, int slots, long long E, float2 *stats, int nb) {
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -733,9 +970,9 @@ int launch_tc(Model *m, const TcConv &tc, const TcArgs &args_in) {
 
 int launch_tc_ln(Model *m, const TcConv &tc, const LnGeom &lg, const TcLnArgs &args_in) {
     TcLnArgs args = args_in;
-    // shared-memory plan: 16 KB store staging + bias are fixed; the weight slice stays resident
+    // shared-memory plan: 16 KB bias tile + 16 KB store staging are fixed; the weight slice stays resident
     // when that leaves room for >= 3 activation stages, otherwise weights stream through the ring next to them
-    const size_t budget = 225 * 1024, fixed = LN_EPI_WARPS * 1024 + LN_BN * 4;
+    const size_t budget = 225 * 1024, fixed = 16384 + LN_EPI_WARPS * 1024;
     const size_t A = (size_t)BM * BK * 2, B = (size_t)LN_BN * BK * 2;
     const size_t bres = (size_t)args.kb_per_tap * args.ntaps * B;
     static const char *env_bres = getenv("PFANN_B200_LN_BRES");
@@ -948,6 +1185,36 @@ int tc_conv_ln(Model *m, int idx, const __nv_bfloat16 *X, __nv_bfloat16 *Xout, i
     const char *pp = getenv("PFANN_LN_PROF_PTR");  // probe only: zeroed device buffer [16][grid<=148][8] u64
     a.prof = pp ? reinterpret_cast<unsigned long long *>(strtoull(pp, nullptr, 0)) + (size_t)idx * 148 * 8 : nullptr;
     return launch_tc_ln(m, tc, lg, a);
+}
+
+bool tc_l0_supported(Model *m) {
+    static const bool off = getenv("PFANN_B200_NO_L0_TC") != nullptr;
+    const ConvGeom &g = m->conv[0].g;
+    return !off && m->l0_gb16 != nullptr && m->l0_btile != nullptr && g.Co == 128 && (g.Fo * g.To) % 128 == 0;
+}
+
+// layer-0 conv1 + ln1 + ReLU on the tensor core; `stats` = per-sample (mean, rstd) from the moments kernel
+int tc_l0(Model *m, const float *mel, const float2 *stats, __nv_bfloat16 *X, int nb) {
+    const ConvGeom &g = m->conv[0].g;
+    L0TcArgs a = {};
+    a.mel = mel; a.stats = stats; a.gb = m->l0_gb16; a.btile = reinterpret_cast<const uint4 *>(m->l0_btile); a.X = X;
+    a.nb = nb; a.F = g.Fi; a.T = g.Ti; a.To = g.To; a.ntaps = g.ntaps;
+    for (int j = 0; j < 3; j++) a.off[j] = j < g.ntaps ? g.tap_off[j] : 0;
+    a.PB = g.Fo * g.To / 128;
+    const size_t smem = (size_t)L0_STAGES * 16384 + 16384 + 16 * 1024 + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PF_CUDA(cudaFuncSetAttribute(l0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    long long grid = m->ctx->sm_count;
+    const long long tiles = (long long)a.PB * nb;
+    if (grid > tiles) grid = tiles;
+    ProfScope ps(m->ctx, K_CONV_TC, 0);
+    l0_tc_kernel<<<(unsigned)grid, L0_THREADS, smem, m->ctx->stream>>>(a);
+    m->ctx->launches++;
+    PF_CUDA(cudaGetLastError());
+    return PFANN_OK;
 }
 
 // 1 when a statistics exchange of the fused conv+LayerNorm kernel ever timed out (synchronises the stream)

@@ -91,21 +91,73 @@ int pfann_extract_pcm16(pfann_mel *mel, pfann_model *hm, const int16_t *pcm, con
     const size_t out_b = (size_t)B * m->d * 4;
     const void *pd, *sd, *vd;
     void *zd;
-    PF_TRY(stage_input(m->ctx, 0, pcm + clip_off[0], (size_t)n_samples * 2, &pd));
-    PF_TRY(stage_input(m->ctx, 1, start.data(), (size_t)B * 8, &sd));
-    PF_TRY(stage_input(m->ctx, 2, valid.data(), (size_t)B * 4, &vd));
-    PF_TRY(stage_output(m->ctx, 0, z, out_b, &zd));
+    Ctx *ctx = m->ctx;
+    // Host PCM: the copy is pipelined with the compute -- chunk k + 1's samples travel on a copy stream while chunk
+    // k is being fingerprinted, and finished fingerprints go back on a third stream (PCIe is full duplex).
+    const bool pipe_in = !is_device_ptr(pcm), pipe_out = !is_device_ptr(z);
+    const int64_t n_chunks = (B + m->chunk - 1) / m->chunk;
+    if (pipe_in) {
+        PF_TRY(ctx->stage_in[0].ensure((size_t)n_samples * 2));
+        pd = ctx->stage_in[0].p;
+    } else {
+        pd = pcm + clip_off[0];
+    }
+    PF_TRY(stage_input(ctx, 1, start.data(), (size_t)B * 8, &sd));
+    PF_TRY(stage_input(ctx, 2, valid.data(), (size_t)B * 4, &vd));
+    PF_TRY(stage_output(ctx, 0, z, out_b, &zd));
+    if ((pipe_in || pipe_out) && ctx->copy_in == nullptr) {
+        PF_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+        PF_CUDA(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    }
+    std::vector<cudaEvent_t> ev_in(pipe_in ? n_chunks : 0), ev_done(pipe_out ? n_chunks : 0);
+    for (auto &e : ev_in) PF_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &e : ev_done) PF_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    int64_t copied = 0;  // samples already enqueued for upload
+    auto upload_for_chunk = [&](int64_t k) -> int {
+        const int64_t last = ((k + 1) * m->chunk < B ? (k + 1) * m->chunk : B) - 1;
+        int64_t need = start[last] + seg_len;
+        if (need > n_samples) need = n_samples;
+        if (need > copied) {
+            PF_CUDA(cudaMemcpyAsync((int16_t *)ctx->stage_in[0].p + copied, pcm + clip_off[0] + copied,
+                                    (size_t)(need - copied) * 2, cudaMemcpyHostToDevice, ctx->copy_in));
+            copied = need;
+        }
+        PF_CUDA(cudaEventRecord(ev_in[k], ctx->copy_in));
+        return PFANN_OK;
+    };
+    if (pipe_in) {
+        // the staging buffer may still be read by work enqueued earlier on the compute stream
+        cudaEvent_t ev0;
+        PF_CUDA(cudaEventCreateWithFlags(&ev0, cudaEventDisableTiming));
+        PF_CUDA(cudaEventRecord(ev0, ctx->stream));
+        PF_CUDA(cudaStreamWaitEvent(ctx->copy_in, ev0, 0));
+        PF_CUDA(cudaEventDestroy(ev0));
+        PF_TRY(upload_for_chunk(0));
+    }
     const size_t mel_per = (size_t)m->F * m->T;
     PF_TRY(m->melbuf.ensure(mel_per * 4 * (size_t)m->chunk));
-    for (int64_t b0 = 0; b0 < B; b0 += m->chunk) {
+    for (int64_t b0 = 0, k = 0; b0 < B; b0 += m->chunk, k++) {
         const int64_t nb = (B - b0) < m->chunk ? (B - b0) : m->chunk;
+        if (pipe_in) {
+            if (k + 1 < n_chunks) PF_TRY(upload_for_chunk(k + 1));
+            PF_CUDA(cudaStreamWaitEvent(ctx->stream, ev_in[k], 0));
+        }
         PF_TRY(mel_forward_pcm_dev(mel, (const int16_t *)pd, n_samples, (const int64_t *)sd + b0,
                                    (const int32_t *)vd + b0, nb, m->melbuf.as<float>()));
         PF_TRY(model_forward_dev(m, m->melbuf.as<float>(), nb, norm, (float *)zd + b0 * m->d));
+        if (pipe_out) {
+            PF_CUDA(cudaEventRecord(ev_done[k], ctx->stream));
+            PF_CUDA(cudaStreamWaitEvent(ctx->copy_out, ev_done[k], 0));
+            PF_CUDA(cudaMemcpyAsync(z + b0 * m->d, (float *)zd + b0 * m->d, (size_t)nb * m->d * 4,
+                                    cudaMemcpyDeviceToHost, ctx->copy_out));
+        }
     }
     // the descriptor vectors are host temporaries: make sure their H2D copies are done before they die
-    PF_CUDA(cudaStreamSynchronize(m->ctx->stream));
-    PF_TRY(finish_output(m->ctx, 0, z, out_b));
+    PF_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (pipe_in) PF_CUDA(cudaStreamSynchronize(ctx->copy_in));
+    if (pipe_out) PF_CUDA(cudaStreamSynchronize(ctx->copy_out));
+    for (auto &e : ev_in) cudaEventDestroy(e);
+    for (auto &e : ev_done) cudaEventDestroy(e);
     return tc_ln_check(m);
 }
 
