@@ -364,6 +364,7 @@ def bench_match(torch, args, world, rank, local, device, barrier, max_over_ranks
     _lib.profile(local, True)
     t = max_over_ranks(timed(torch, step, 1, 1, barrier))
     prof = _lib.profile_read(local)
+    detail = _lib.profile_detail(local)
     _lib.profile(local, False)
     acc = float(np.mean((res['song'] == qsong.cpu().numpy()) & (res['time'] == qoff.cpu().numpy() * 0.5)))
     # the same through the single-call host API with host buffers (only meaningful at world == 1)
@@ -407,6 +408,7 @@ def bench_match(torch, args, world, rank, local, device, barrier, max_over_ranks
             'vectors_per_query': q_len, 'top_k': k, 'shard_rows': rows_local, 'accuracy_vs_planted': acc,
             'query_files_per_db_pass': B, 'regime': 'batched (tensor-bound): 128 query vectors per database pass',
             'classes_ms': {kk: round(v[0], 3) for kk, v in prof.items() if v[1]},
+            'kernels_ms': {kk: [round(v[0], 3), v[1]] for kk, v in detail.items()},
             'knn_scan': {'launches': passes, 'ms': scan_ms,
                          'tflops': (2.0 * nq * q_len * rows_local * d) / (scan_ms / 1000.0) / 1e12 if scan_ms else None,
                          'frac_of_bf16_peak': ((2.0 * nq * q_len * rows_local * d) / (scan_ms / 1000.0) / 1e12) / pk['tf_sustained'] if scan_ms else None},

@@ -54,7 +54,8 @@ int pfann_ctx_profile(pfann_ctx *ctx, int enable);
 int pfann_ctx_profile_read(pfann_ctx *ctx, double *ms, long long *count, int n_classes);
 /* Finer breakdown of the record consumed by the LAST pfann_ctx_profile_read: slot i < 16 = convolution i
  * (2*layer + {0: conv1, 1: conv2}; fused conv+LayerNorm kernels included), 16 + i = LayerNorm kernels that follow
- * convolution i, 32 = mel, 33 = head, 34 = layer-0 moments. */
+ * convolution i, 32 = mel, 33 = head, 34 = layer-0 moments, 35 = kNN sample scan, 36 = kNN filtered scan,
+ * 37 = k-th selection of the sample, 38 = kNN select, 39 = rerank. */
 #define PFANN_N_PROFILE_DETAIL 48
 int pfann_ctx_profile_detail(pfann_ctx *ctx, double *ms, long long *count, int n);
 

@@ -150,7 +150,7 @@ def profile_detail(device=0):
     ms = (c_double * n)()
     cnt = (c_longlong * n)()
     check(lib().pfann_ctx_profile_detail(ctx(device), ms, cnt, n), 'pfann_ctx_profile_detail')
-    names = ['conv%d' % i for i in range(16)] + ['ln%d' % i for i in range(16)] + ['mel', 'head', 'l0_moments']
+    names = ['conv%d' % i for i in range(16)] + ['ln%d' % i for i in range(16)] + ['mel', 'head', 'l0_moments', 'knn_scan_sample', 'knn_scan_full', 'knn_kth', 'knn_select', 'rerank']
     return {k: (ms[i], int(cnt[i])) for i, k in enumerate(names) if cnt[i]}
 
 

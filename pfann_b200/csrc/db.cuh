@@ -23,7 +23,7 @@ struct Db {
     int sample_rows = 16384;         // rows scanned in the threshold pre-pass
     int use_tc = 1;                  // tensor-core bf16 scan when available, else fp32 CUDA-core scan
     // scratch
-    DevBuf qbuf, qnorm, thr, cnt, cand, sample, flags, dist, labels, rr_keys, rr_scores, rr_out, lab_stage;
+    DevBuf qbuf, qnorm, thr, cnt, cand, cand_v, sample, flags, dist, labels, rr_keys, rr_scores, rr_out, lab_stage;
     void *tc_state = nullptr;
 };
 
@@ -101,6 +101,6 @@ void knn_tc_release(Db *db);
 // approximate scan of rows [r0, r1) against Qg <= 128 queries; mode 0: store all scores to
 // sample[q][row - r0] (ld = sample_ld); mode 1: push row ids with score >= thr[q] into cand/cnt
 int knn_tc_scan(Db *db, const float *q, int Qg, int64_t r0, int64_t r1, int mode, float *sample, int64_t sample_ld,
-                const float *thr, int *cnt, uint32_t *cand, int cap);
+                const float *thr, int *cnt, uint32_t *cand, uint32_t *cand_v, int cap);
 
 }  // namespace pfann

@@ -30,7 +30,8 @@ constexpr int SCAN_THREADS = 256;
 // grid.x = row tiles (grid-stride), 256 threads; thread -> (row r = tid % 64, query octet qs = tid / 64)
 __global__ void __launch_bounds__(SCAN_THREADS) knn_scan_fp32_kernel(
     const float *__restrict__ db, int64_t r0, int64_t r1, int d, const float *__restrict__ q, int Qg, int mode,
-    float *sample, int64_t sample_ld, const float *__restrict__ thr, int *cnt, uint32_t *cand, int cap) {
+    float *sample, int64_t sample_ld, const float *__restrict__ thr, int *cnt, uint32_t *cand, uint32_t *cand_v,
+    int cap) {
     extern __shared__ __align__(16) float sm[];
     const int ldr = d + 4;                 // padded row stride (16-byte aligned, conflict-free for float4)
     float *qs_ = sm;                       // [QG][d]
@@ -76,7 +77,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) knn_scan_fp32_kernel(
                     sample[qi * sample_ld + (row - r0)] = acc[j];
                 } else if (acc[j] >= thr[qi]) {
                     const int pos = atomicAdd(cnt + qi, 1);
-                    if (pos < cap) cand[(int64_t)qi * cap + pos] = (uint32_t)row;
+                    if (pos < cap) {
+                        cand[(int64_t)qi * cap + pos] = (uint32_t)row;
+                        cand_v[(int64_t)qi * cap + pos] = __float_as_uint(fmaxf(acc[j] - thr[qi], 0.f));
+                    }
                 }
             }
         }
@@ -136,43 +140,67 @@ __global__ void __launch_bounds__(256) knn_kth_merge_kernel(const uint32_t *part
     }
 }
 
-// ---- select: exact rescoring + sort + emit --------------------------------------------------------------
+// ---- select: rank by scan score, exact rescoring of the few that can matter, sort, emit ------------------------
+// The scan leaves ~1-2 k survivors per query, each with v = (scan score - threshold).  |scan - exact| <= delta =
+// eps_rel |q| max|x|, so with a_k the k-th best scan score every true top-k row has a scan score >= a_k - 2 delta:
+// only that prefix of the ranking (a few dozen rows) is re-scored exactly in fp32 (gathering 512-byte rows of the
+// fp32 database is what used to dominate this kernel), sorted by (score desc, id asc) and emitted.
 // flags[0] += 1 for every query whose candidate list overflowed (its threshold is tightened in place).
 __global__ void __launch_bounds__(256) knn_select_kernel(const float *__restrict__ db, int d, int64_t id_base,
                                                          const float *__restrict__ q, const int *cnt,
-                                                         const uint32_t *cand, int cap, int k, float eps_rel,
-                                                         float max_norm, const float *qnorm, float *thr,
+                                                         const uint32_t *cand, const uint32_t *cand_v, int cap, int k,
+                                                         float eps_rel, float max_norm, const float *qnorm, float *thr,
                                                          float *dist, int64_t *labels, int *flags) {
     extern __shared__ __align__(16) unsigned char smraw[];
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(smraw);  // [cap]
     float *qv = reinterpret_cast<float *>(keys + cap);                         // [d]
+    __shared__ int m_s;
     const int qi = blockIdx.x;
     const int total = cnt[qi];
     const int n = total < cap ? total : cap;
     int P = 1;
     while (P < n) P <<= 1;
     for (int i = threadIdx.x; i < d; i += blockDim.x) qv[i] = q[(int64_t)qi * d + i];
-    __syncthreads();
+    if (threadIdx.x == 0) m_s = 0;
     for (int i = threadIdx.x; i < P; i += blockDim.x) {
         unsigned long long key = 0ull;
         if (i < n) {
             const uint32_t id = cand[(int64_t)qi * cap + i];
-            const float s = (d & 31) == 0 ? dot_fma_seq_lines(db + (int64_t)id * d, qv, d) : dot_fma_seq(db + (int64_t)id * d, qv, d);
-            key = ((unsigned long long)flipf(s) << 32) | (unsigned long long)(0xFFFFFFFFu - id);
+            key = ((unsigned long long)flipf(__uint_as_float(cand_v[(int64_t)qi * cap + i])) << 32) |
+                  (unsigned long long)(0xFFFFFFFFu - id);
         }
         keys[i] = key;
     }
     bitonic_sort<unsigned long long, true>(keys, P);
+    const float delta2 = 2.f * eps_rel * qnorm[qi] * max_norm;
     if (total > cap) {
-        // overflow: the stored subset still bounds the true k-th score from below (exact scores)
+        // overflow: the stored subset still bounds the k-th best scan score from below
         if (threadIdx.x == 0) {
             atomicAdd(flags, 1);
-            if (n >= k) thr[qi] = fmaxf(thr[qi], unflipf((uint32_t)(keys[k - 1] >> 32)) - eps_rel * qnorm[qi] * max_norm);
+            if (n >= k) thr[qi] = fmaxf(thr[qi], thr[qi] + unflipf((uint32_t)(keys[k - 1] >> 32)) - delta2);
         }
         return;
     }
+    // prefix of the ranking that can contain a true top-k row
+    const float vmin = n >= k ? unflipf((uint32_t)(keys[k - 1] >> 32)) - delta2 : -INFINITY;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        if (unflipf((uint32_t)(keys[i] >> 32)) >= vmin) atomicMax(&m_s, i + 1);
+    __syncthreads();
+    const int m = m_s;
+    int P2 = 1;
+    while (P2 < m) P2 <<= 1;
+    for (int i = threadIdx.x; i < P2; i += blockDim.x) {
+        unsigned long long key = 0ull;
+        if (i < m) {
+            const uint32_t id = 0xFFFFFFFFu - (uint32_t)(keys[i] & 0xFFFFFFFFull);
+            const float s = (d & 31) == 0 ? dot_fma_seq_lines(db + (int64_t)id * d, qv, d) : dot_fma_seq(db + (int64_t)id * d, qv, d);
+            key = ((unsigned long long)flipf(s) << 32) | (unsigned long long)(0xFFFFFFFFu - id);
+        }
+        keys[i] = key;  // slot i is read and written by this thread only
+    }
+    bitonic_sort<unsigned long long, true>(keys, P2);
     for (int j = threadIdx.x; j < k; j += blockDim.x) {
-        if (j < n) {
+        if (j < m) {
             dist[(int64_t)qi * k + j] = unflipf((uint32_t)(keys[j] >> 32));
             labels[(int64_t)qi * k + j] = id_base + (int64_t)(0xFFFFFFFFu - (uint32_t)(keys[j] & 0xFFFFFFFFull));
         } else {
@@ -308,19 +336,19 @@ __global__ void topk_merge_kernel(const float *dist_g, const int64_t *labels_g, 
 }
 
 int scan(Db *db, bool tc, const float *q, int Qg, int64_t r0, int64_t r1, int mode, float *sample, int64_t sample_ld,
-         const float *thr, int *cnt, uint32_t *cand, int cap) {
-    if (tc) return knn_tc_scan(db, q, Qg, r0, r1, mode, sample, sample_ld, thr, cnt, cand, cap);
+         const float *thr, int *cnt, uint32_t *cand, uint32_t *cand_v, int cap) {
+    if (tc) return knn_tc_scan(db, q, Qg, r0, r1, mode, sample, sample_ld, thr, cnt, cand, cand_v, cap);
     const int64_t ntiles = (r1 - r0 + SCAN_ROWS - 1) / SCAN_ROWS;
     int64_t grid = (int64_t)db->ctx->sm_count * 4;
     if (grid > ntiles) grid = ntiles;
     const size_t smem = (size_t)(QG * db->d + SCAN_ROWS * (db->d + 4)) * 4;
     for (int q0 = 0; q0 < Qg; q0 += QG) {
         const int qn = (Qg - q0) < QG ? (Qg - q0) : QG;
-        ProfScope ps(db->ctx, K_KNN_SCAN);
+        ProfScope ps(db->ctx, K_KNN_SCAN, mode == 0 ? 35 : 36);
         knn_scan_fp32_kernel<<<(unsigned)grid, SCAN_THREADS, smem, db->ctx->stream>>>(
             db->emb32, r0, r1, db->d, q + (int64_t)q0 * db->d, qn, mode, sample ? sample + q0 * sample_ld : nullptr,
             sample_ld, thr ? thr + q0 : nullptr, cnt ? cnt + q0 : nullptr, cand ? cand + (int64_t)q0 * cap : nullptr,
-            cap);
+            cand_v ? cand_v + (int64_t)q0 * cap : nullptr, cap);
         db->ctx->launches++;
     }
     PF_CUDA(cudaGetLastError());
@@ -345,7 +373,7 @@ int db_search_dev(Db *db, const float *q, int64_t Q, int k, float *dist, int64_t
     // |scan score - exact score| <= eps_rel * |q| * |x|: bf16 operand rounding 2^-8 (+ fp32 accumulation order)
     const float eps_rel = (tc ? 4.0e-3f : 0.f) + fmaxf(1.0e-5f, 1.2e-7f * (float)d);
     const int cap = db->cand_cap;
-    const int group = tc ? 128 : QG * 4;  // queries per database pass
+    const int group = tc ? (d <= 128 ? 256 : 128) : QG * 4;  // queries per database pass
     // sample size: aim at ~1024 rows above the threshold (k * n / S ~ 1024), within [sample_rows, 256 Ki]
     int64_t want = (int64_t)k * db->n / 1024;
     if (want < db->sample_rows) want = db->sample_rows;
@@ -363,6 +391,7 @@ int db_search_dev(Db *db, const float *q, int64_t Q, int k, float *dist, int64_t
     PF_TRY(db->qnorm.ensure(sizeof(float) * group));
     PF_TRY(db->cnt.ensure(sizeof(int) * group));
     PF_TRY(db->cand.ensure(sizeof(uint32_t) * (size_t)group * cap));
+    PF_TRY(db->cand_v.ensure(sizeof(uint32_t) * (size_t)group * cap));
     PF_TRY(db->sample.ensure(sizeof(float) * (size_t)group * S));
     PF_TRY(db->rr_keys.ensure(sizeof(uint32_t) * (size_t)group * nchunks * k));
     PF_TRY(db->flags.ensure(sizeof(int) * 4));
@@ -374,9 +403,9 @@ int db_search_dev(Db *db, const float *q, int64_t Q, int k, float *dist, int64_t
         const int Qg = (int)((Q - q0) < group ? (Q - q0) : group);
         const float *qg = q + q0 * d;
         // 1. threshold pre-pass on the first S rows
-        PF_TRY(scan(db, tc, qg, Qg, 0, S, 0, db->sample.as<float>(), S, nullptr, nullptr, nullptr, 0));
+        PF_TRY(scan(db, tc, qg, Qg, 0, S, 0, db->sample.as<float>(), S, nullptr, nullptr, nullptr, nullptr, 0));
         {
-            ProfScope ps(db->ctx, K_KNN_SELECT);
+            ProfScope ps(db->ctx, K_KNN_SELECT, 37);
             knn_kth_chunk_kernel<<<dim3(Qg, nchunks), 256, (size_t)(cpad > 256 ? cpad : 256) * 4, st>>>(
                 db->sample.as<float>(), S, S, chunk, cpad, k, db->rr_keys.as<uint32_t>());
             knn_kth_merge_kernel<<<Qg, 256, (size_t)P2 * 4, st>>>(db->rr_keys.as<uint32_t>(), nchunks * k, P2, S, qg, d, k,
@@ -391,12 +420,13 @@ int db_search_dev(Db *db, const float *q, int64_t Q, int k, float *dist, int64_t
             PF_CUDA(cudaMemsetAsync(db->flags.p, 0, sizeof(int) * 4, st));
             // 2. filtered scan of the whole shard
             PF_TRY(scan(db, tc, qg, Qg, 0, db->n, 1, nullptr, 0, db->thr.as<float>(), db->cnt.as<int>(),
-                        db->cand.as<uint32_t>(), cap));
+                        db->cand.as<uint32_t>(), db->cand_v.as<uint32_t>(), cap));
             // 3. exact rescoring + sort
             {
-            ProfScope ps(db->ctx, K_KNN_SELECT);
+            ProfScope ps(db->ctx, K_KNN_SELECT, 38);
             knn_select_kernel<<<Qg, 256, sel_smem, st>>>(db->emb32, d, db->id_base, qg, db->cnt.as<int>(),
-                                                         db->cand.as<uint32_t>(), cap, k, eps_rel, db->max_norm,
+                                                         db->cand.as<uint32_t>(), db->cand_v.as<uint32_t>(), cap, k,
+                                                         eps_rel, db->max_norm,
                                                          db->qnorm.as<float>(), db->thr.as<float>(), dist + q0 * k,
                                                          labels + q0 * k, db->flags.as<int>());
             }

@@ -23,9 +23,8 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int STAGES = 4;
-constexpr int KNN_THREADS = 192;
-constexpr int QCAP = 2048;  // parked filter survivors per CTA
+constexpr int KNN_EPI_WARPS = 16;  // four per TMEM lane quarter, 32 query columns each
+constexpr int KNN_THREADS = 32 * (2 + KNN_EPI_WARPS);
 
 struct KnnTcState {
     CUtensorMap mapA;  // [n][d] bf16, box (64, 128)
@@ -40,15 +39,25 @@ struct ScanArgs {
     long long sample_ld;
     const float *thr;    // mode 1
     int *cnt;
-    uint32_t *cand;
+    uint32_t *cand;      // [Qg][cap] row ids of the filter survivors ...
+    uint32_t *cand_v;    // ... and their (scan score - threshold) as fp32 bits: the select kernel ranks by it
     int cap;
     unsigned long long *prof;  // optional [grid][8] cycle counters (tools/knn_probe.py)
     int debug;           // probe knob (PFANN_KNN_DEBUG): 1 skip filter, 2 skip TMEM loads too, 3 also skip the MMAs
 };
 
+// shared-memory budget: N = 256 queries per pass take 64 KB (queries) + 32 KB (threshold tile), leaving three
+// 32 KB database stages and 2560 parked survivors; up to 128 queries: four stages, 2048 survivors
+template <int N> struct ScanCfg {
+    static constexpr int STAGES = N > 128 ? 3 : 4;
+    static constexpr int QCAP = N > 128 ? 2560 : 2048;   // parked filter survivors per CTA
+    static constexpr int TROWS = N > 128 ? N : 128;      // rows of the threshold tile
+};
+
 template <int N>
 __global__ void __launch_bounds__(KNN_THREADS, 1) knn_scan_tc_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                      const ScanArgs a) {
+    constexpr int STAGES = ScanCfg<N>::STAGES, QCAP = ScanCfg<N>::QCAP, TROWS = ScanCfg<N>::TROWS;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *sbase = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int KBLK = a.d / BK;                         // K blocks per tile (d = 128 -> 2)
@@ -59,11 +68,15 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_scan_tc_kernel(const __gri
     unsigned char *sA = sbase + (size_t)B_KB_BYTES * KBLK;  // [STAGES][KBLK][128 rows][128 B]
     // survivors of the filter are parked here and pushed to the global candidate lists after the scan: a
     // global atomicAdd with return (~1 us) must not sit between the TMEM read and the buffer release
-    uint2 *queue = reinterpret_cast<uint2 *>(sA + (size_t)STAGES * STAGE_BYTES);  // [QCAP] (query, row)
+    uint2 *queue = reinterpret_cast<uint2 *>(sA + (size_t)STAGES * STAGE_BYTES + (size_t)TROWS * 128);  // [QCAP] (query, row)
+    uint32_t *queue_v = reinterpret_cast<uint32_t *>(queue + QCAP);                         // [QCAP] score - threshold
+    // threshold tile: row r holds [1 1 1 0..] in K columns 0-15 and [-thr_hi -thr_mid -thr_lo 0..] of query r in K
+    // columns 16-31.  One extra MMA per tile (A = columns 0-15, B = columns 16-31 of the same rows) starts the
+    // accumulator at -threshold, so "score reaches its threshold" is just a clear sign bit in TMEM.
+    unsigned char *cthr = sA + (size_t)STAGES * STAGE_BYTES;
     __shared__ int qcount_s;
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_s;
-    __shared__ __align__(16) float thr_s[N];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long ntiles = (a.r1 - a.r0 + BM - 1) / BM;
@@ -77,7 +90,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_scan_tc_kernel(const __gri
         }
         for (int s = 0; s < 2; s++) {
             ptx::mbar_init(&tfull_bar[s], 1);
-            ptx::mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+            ptx::mbar_init(&tempty_bar[s], N >= 128 ? KNN_EPI_WARPS : 4 * (N / 32));  // one arrive per participating warp
         }
         ptx::fence_mbar_init();
     }
@@ -101,7 +114,30 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_scan_tc_kernel(const __gri
         }
         *reinterpret_cast<uint4 *>(sB + (size_t)kb * B_KB_BYTES + (size_t)n * 128 + ((c ^ (n & 7)) << 4)) = pk;
     }
-    for (int i = tid; i < N; i += KNN_THREADS) thr_s[i] = (a.mode == 1 && i < a.Qg) ? a.thr[i] : INFINITY;
+    if (tid < TROWS) {
+        uint32_t w0 = 0u, w1 = 0u;  // (-thr) as three bf16 terms; queries beyond Qg: -inf (can never be reached)
+        if (a.mode == 1) {
+            if (tid < a.Qg) {
+                // a hair below the threshold so that the 3-term bf16 representation can only admit MORE rows
+                const float t = -(a.thr[tid] - 1e-6f * fabsf(a.thr[tid]) - 1e-30f);
+                const __nv_bfloat16 h = __float2bfloat16_rn(t);
+                const __nv_bfloat16 m = __float2bfloat16_rn(t - __bfloat162float(h));
+                const __nv_bfloat16 l = __float2bfloat16_rn(t - __bfloat162float(h) - __bfloat162float(m));
+                w0 = (uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(m) << 16);
+                w1 = (uint32_t)__bfloat16_as_ushort(l);
+                if (!(fabsf(t) < 3.0e38f)) w0 = t > 0.f ? 0x7F80u : 0xFF80u, w1 = 0u;  // infinite threshold
+            } else {
+                w0 = 0xFF80u;
+            }
+        }
+        const uint32_t one = 0x3F80u;
+        uint4 *row = reinterpret_cast<uint4 *>(cthr + (size_t)tid * 128);
+        const int x = tid & 7;  // 128-byte swizzle: logical 16-byte chunk c lives at chunk c ^ (row % 8)
+        row[0 ^ x] = make_uint4(one | (one << 16), one, 0u, 0u);
+        row[1 ^ x] = make_uint4(0u, 0u, 0u, 0u);
+        row[2 ^ x] = make_uint4(w0, w1, 0u, 0u);
+        row[3 ^ x] = make_uint4(0u, 0u, 0u, 0u);
+    }
     ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
     ptx::tc_fence_before();
     __syncthreads();
@@ -140,37 +176,52 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_scan_tc_kernel(const __gri
                 pc[2] += clock64() - c1;
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N);
+                {   // accumulator := -threshold (zero in the sample pre-pass)
+                    const uint64_t dc = ptx::umma_desc_k_sw128(ptx::smem_u32(cthr));
+                    ptx::umma_f16(d_tmem, dc, dc + 2, idesc, 0);
+                }
                 for (int kb = 0; kb < KBLK && a.debug < 3; kb++) {
                     const uint64_t da = ptx::umma_desc_k_sw128(ptx::smem_u32(sA + (size_t)s * STAGE_BYTES + (size_t)kb * A_KB_BYTES));
                     const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(sB + (size_t)kb * B_KB_BYTES));
 #pragma unroll
                     for (int k = 0; k < BK / 16; k++)
-                        ptx::umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        ptx::umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, 1);
                 }
                 ptx::umma_commit(&empty_bar[s]);
                 ptx::umma_commit(&tfull_bar[buf]);
             }
         }
     } else {
-        // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
-        const int quarter = warp & 3;
+        // ===== epilogue: 16 warps, four per TMEM lane quarter (= warp % 4); warp `wc` of a quarter owns query columns
+        // [32 wc, 32 wc + 32).  Warps whose columns do not exist (N = 32) only take part in the final flush. =====
+        const int quarter = warp & 3, wc = (warp - 2) >> 2;
+        const uint32_t t_quarter = tmem_base + ((uint32_t)(quarter * 32) << 16);
         long long it = 0;
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
-            const int buf = (int)(it & 1);
-            const long long c0 = clock64();
-            ptx::mbar_wait(&tfull_bar[buf], (uint32_t)(it >> 1) & 1);
-            ptx::tc_fence_after();
-            const long long c1 = clock64();
-            pc[3] += c1 - c0;
-            const long long row = a.r0 + tile * BM + quarter * 32 + lane;
-            const bool rvalid = row < a.r1;
-#pragma unroll 1
-            for (int c = 0; c < N; c += 32) {
-                if (a.debug >= 2) break;
+        if (wc * 32 < N) {
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+                const int buf = (int)(it & 1);
+                const long long c0 = clock64();
+                ptx::mbar_wait(&tfull_bar[buf], (uint32_t)(it >> 1) & 1);
+                ptx::tc_fence_after();
+                const long long c1 = clock64();
+                pc[3] += c1 - c0;
+                const long long row = a.r0 + tile * BM + quarter * 32 + lane;
+                const bool rvalid = row < a.r1;
+#pragma unroll
+              for (int c = wc * 32; c < N; c += 128) {   // N = 256: two 32-column chunks per warp
                 uint32_t v[32];
-                ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * N + c), v);
-                ptx::tmem_ld_wait();
-                if (a.debug >= 1) {
+                if (a.debug < 2) {
+                    ptx::tmem_ld_32x32b_x32(t_quarter + (uint32_t)(buf * N + c), v);
+                    ptx::tmem_ld_wait();
+                }
+                if (c + 128 >= N) {
+                    // the last values are in registers: hand the buffer back to the MMA issuer right away
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&tempty_bar[buf]);
+                }
+                if (a.debug >= 2) {
+                } else if (a.debug >= 1) {
                     uint32_t x = 0;
 #pragma unroll
                     for (int i = 0; i < 32; i++) x ^= v[i];
@@ -182,59 +233,51 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_scan_tc_kernel(const __gri
                             if (c + i < a.Qg) a.sample[(long long)(c + i) * a.sample_ld + (row - a.r0)] = __uint_as_float(v[i]);
                     }
                 } else {
-                    // thresholds of this chunk: 8 vector loads into distinct registers (32 scalar LDS through one
-                    // register serialise on the shared-memory latency: measured 2500 cycles per tile)
-                    float th[32];
+                    // accumulator = score - threshold: a hit is a clear sign bit.  AND-tree of the 32 words (3-input
+                    // LOP3s), then the rare per-hit path.
+                    uint32_t m8[8];
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const float4 t4 = *reinterpret_cast<const float4 *>(&thr_s[c + 4 * j]);
-                        th[4 * j] = t4.x; th[4 * j + 1] = t4.y; th[4 * j + 2] = t4.z; th[4 * j + 3] = t4.w;
-                    }
-                    // "does any score reach its threshold" as a max-tree over (score - threshold): 32 independent
-                    // subtractions + a depth-5 tree; an OR-chain of 32 predicate compares is one long dependency
-                    // chain (measured ~16 cycles per compare)
-                    float df[32], mx[16];
-#pragma unroll
-                    for (int i = 0; i < 32; i++) df[i] = __uint_as_float(v[i]) - th[i];
-#pragma unroll
-                    for (int i = 0; i < 16; i++) mx[i] = fmaxf(df[i], df[i + 16]);
-#pragma unroll
-                    for (int w = 8; w > 0; w >>= 1)
-#pragma unroll
-                        for (int i = 0; i < w; i++) mx[i] = fmaxf(mx[i], mx[i + w]);
-                    if (mx[0] >= 0.f && rvalid) {
-                        // rare path (a few lanes per tile): branch-free hit mask, then one iteration per hit
+                    for (int i = 0; i < 8; i++) m8[i] = v[4 * i] & v[4 * i + 1] & v[4 * i + 2] & v[4 * i + 3];
+                    const uint32_t all = (m8[0] & m8[1] & m8[2] & m8[3]) & (m8[4] & m8[5] & m8[6] & m8[7]);
+                    if (!(all & 0x80000000u) && rvalid) {
                         uint32_t mask = 0;
 #pragma unroll
-                        for (int i = 0; i < 32; i++) mask |= (df[i] >= 0.f ? 1u : 0u) << i;
+                        for (int i = 0; i < 32; i++) mask |= ((~v[i]) >> 31) << i;
                         while (mask) {
                             const int i = __ffs(mask) - 1;
                             mask &= mask - 1;
                             const int qp = atomicAdd(&qcount_s, 1);
+                            uint32_t vi = v[0];  // v[i] without dynamic register indexing
+#pragma unroll
+                            for (int j = 1; j < 32; j++) vi = (i == j) ? v[j] : vi;
                             if (qp < QCAP) {
                                 queue[qp] = make_uint2((uint32_t)(c + i), (uint32_t)row);
+                                queue_v[qp] = vi;
                             } else {  // queue full (degenerate thresholds): push directly
                                 const int pos = atomicAdd(a.cnt + c + i, 1);
-                                if (pos < a.cap) a.cand[(long long)(c + i) * a.cap + pos] = (uint32_t)row;
+                                if (pos < a.cap) {
+                                    a.cand[(long long)(c + i) * a.cap + pos] = (uint32_t)row;
+                                    a.cand_v[(long long)(c + i) * a.cap + pos] = vi;
+                                }
                             }
                         }
                     }
                 }
+              }
+                pc[4] += clock64() - c1;
             }
-            // this warp is done reading the buffer: hand it back to the MMA issuer
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tempty_bar[buf]);
-            pc[4] += clock64() - c1;
         }
         // flush the parked survivors: the 128 epilogue threads issue their global atomics side by side
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * KNN_EPI_WARPS) : "memory");
         if (a.mode == 1) {
             const int nq = qcount_s < QCAP ? qcount_s : QCAP;
-            for (int i = tid - 64; i < nq; i += 128) {
+            for (int i = tid - 64; i < nq; i += 32 * KNN_EPI_WARPS) {
                 const uint2 e = queue[i];
                 const int pos = atomicAdd(a.cnt + e.x, 1);
-                if (pos < a.cap) a.cand[(long long)e.x * a.cap + pos] = e.y;
+                if (pos < a.cap) {
+                    a.cand[(long long)e.x * a.cap + pos] = e.y;
+                    a.cand_v[(long long)e.x * a.cap + pos] = queue_v[i];
+                }
             }
         }
     }
@@ -256,13 +299,14 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_scan_tc_kernel(const __gri
 template <int N>
 int launch_scan(Db *db, KnnTcState *st, const ScanArgs &a) {
     const int KBLK = db->d / BK;
-    const size_t smem = 1024 + (size_t)N * BK * 2 * KBLK + (size_t)STAGES * BM * BK * 2 * KBLK + (size_t)QCAP * 8;
+    const size_t smem = 1024 + (size_t)N * BK * 2 * KBLK + (size_t)ScanCfg<N>::STAGES * BM * BK * 2 * KBLK +
+                        (size_t)ScanCfg<N>::QCAP * 12 + (size_t)ScanCfg<N>::TROWS * 128;
     PF_CUDA(cudaFuncSetAttribute(knn_scan_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long ntiles = (a.r1 - a.r0 + BM - 1) / BM;
     long long grid = db->ctx->sm_count;
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) return PFANN_OK;
-    ProfScope ps(db->ctx, K_KNN_SCAN);
+    ProfScope ps(db->ctx, K_KNN_SCAN, a.mode == 0 ? 35 : 36);
     knn_scan_tc_kernel<N><<<(unsigned)grid, KNN_THREADS, smem, db->ctx->stream>>>(st->mapA, a);
     db->ctx->launches++;
     PF_CUDA(cudaGetLastError());
@@ -305,19 +349,20 @@ void knn_tc_release(Db *db) {
 }
 
 int knn_tc_scan(Db *db, const float *q, int Qg, int64_t r0, int64_t r1, int mode, float *sample, int64_t sample_ld,
-                const float *thr, int *cnt, uint32_t *cand, int cap) {
+                const float *thr, int *cnt, uint32_t *cand, uint32_t *cand_v, int cap) {
     KnnTcState *st = reinterpret_cast<KnnTcState *>(db->tc_state);
     PF_CHECK(st != nullptr, PFANN_ERR_STATE, "knn_tc_scan: tensor-core state missing");
-    PF_CHECK(Qg >= 1 && Qg <= 128, PFANN_ERR_ARG, "knn_tc_scan: 1..128 queries per pass");
+    PF_CHECK(Qg >= 1 && Qg <= 256, PFANN_ERR_ARG, "knn_tc_scan: 1..256 queries per pass");
     ScanArgs a;
     a.q = q; a.Qg = Qg; a.d = db->d; a.r0 = r0; a.r1 = r1; a.mode = mode;
-    a.sample = sample; a.sample_ld = sample_ld; a.thr = thr; a.cnt = cnt; a.cand = cand; a.cap = cap;
+    a.sample = sample; a.sample_ld = sample_ld; a.thr = thr; a.cnt = cnt; a.cand = cand; a.cand_v = cand_v; a.cap = cap;
     const char *dbg = getenv("PFANN_KNN_DEBUG");
     a.debug = dbg ? atoi(dbg) : 0;
     const char *pp = getenv("PFANN_KNN_PROF_PTR");  // probe only: device address of a zeroed [grid][8] u64 buffer
     a.prof = pp ? reinterpret_cast<unsigned long long *>(strtoull(pp, nullptr, 0)) : nullptr;
     if (Qg <= 32) return launch_scan<32>(db, st, a);
-    return launch_scan<128>(db, st, a);
+    if (Qg <= 128 || db->d > 128) return launch_scan<128>(db, st, a);
+    return launch_scan<256>(db, st, a);
 }
 
 }  // namespace pfann

@@ -238,7 +238,7 @@ int rerank_dev(Db *db, const float *queries, const int64_t *query_index, int nq,
         a.gscores = db->rr_scores.as<float>();
     }
     PF_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_CAND_MAX * 12)));
-    ProfScope ps(db->ctx, K_RERANK);
+    ProfScope ps(db->ctx, K_RERANK, 39);
     rerank_kernel<<<nq, RR_THREADS, smem, db->ctx->stream>>>(a);
     db->ctx->launches++;
     PF_CUDA(cudaGetLastError());
