@@ -34,7 +34,10 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
 FLOP_PER_SEG = 0.533e9        # algorithmic FLOPs/segment, default.json, zero-pad taps excluded
-FLOP_L0C1 = 3.1e6             # layer-0 conv1 (C_in = 1) runs on CUDA cores, not in the GEMM kernel
+# conv_ln_tc_kernel (convolutions 1-7 of default.json): input + output activations per segment, bf16
+CONVLN_BYTES_PER_SEG = 2 * sum(i + o for i, o in [(524288, 262144), (262144, 131072), (131072, 65536), (65536, 65536),
+                                                  (65536, 32768), (32768, 16384), (16384, 8192)])
+CONVLN_NCU_TRAFFIC_PER_SEG = 13.529e9 / 4096   # ncu dram__bytes_read+write.sum of the 7 launches of a 4096-segment chunk
 SEG_BYTES_MEL = 64768         # stage-1 algorithmic bytes per segment (fp32 entry point)
 
 
@@ -178,7 +181,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--clips', type=int, default=10000, help='clips per GPU (config 2: 10000)')
     ap.add_argument('--clip-seconds', type=int, default=30)
-    ap.add_argument('--chunk', type=int, default=4096, help='segments per internal pass')
+    ap.add_argument('--chunk', type=int, default=16384, help='segments per internal pass')
     ap.add_argument('--precision', default='bf16')
     ap.add_argument('--db-rows', type=int, default=10_000_000)
     ap.add_argument('--queries', type=int, default=10000)
@@ -238,6 +241,7 @@ def main():
     _lib.profile(local, True)
     t_dev = timed(torch, step_dev, args.steps, 0, barrier)
     prof = _lib.profile_read(local)
+    detail = _lib.profile_detail(local)
     _lib.profile(local, False)
     launches = _lib.launches(local) - l0
     t_dev = max_over_ranks(t_dev)
@@ -259,15 +263,30 @@ def main():
     assert abs(float(np.linalg.norm(z_host[:16].numpy(), axis=1).mean()) - 1.0) < 1e-3
     del pcm_host
 
+    # Dominant kernel: conv_ln_tc_kernel, the fused conv + LayerNorm + ReLU of convolutions 1-7 (7 launches per
+    # chunk).  Its big layers move 1.5 MB of activations per segment for 0.2 GFLOP: HBM-bound (ncu: DRAM 78 %,
+    # tensor pipe 32 %, profiles/r01/v4).  Algorithmic bytes = every input and output activation once (bf16).
+    fused_ms = sum(detail.get('conv%d' % i, (0.0, 0))[0] for i in range(1, 8))
+    fused_n = sum(detail.get('conv%d' % i, (0.0, 0))[1] for i in range(1, 8))
     conv_ms, conv_n = prof['conv_tc']
-    flops = (FLOP_PER_SEG - FLOP_L0C1) * n_seg * args.steps
-    achieved = flops / (conv_ms / 1000.0) / 1e12 if conv_ms > 0 else 0.0
-    roofline = {'bound': 'tensor', 'kernel': 'conv_gemm_tc_kernel (tcgen05 implicit-GEMM convolutions)',
-                'achieved': achieved, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s',
-                'frac': achieved / pk['tf_sustained'], 'traffic': None, 'peak_source': pk['source'],
-                'launches': conv_n, 'avg_launch_ms': conv_ms / max(conv_n, 1),
-                'share_of_step': conv_ms / (t_dev * 1000.0),
-                'classes_ms_per_step': {k: round(v[0] / args.steps, 3) for k, v in prof.items() if v[1]}}
+    bytes_alg = CONVLN_BYTES_PER_SEG * n_seg * args.steps
+    achieved = bytes_alg / (fused_ms / 1000.0) / 1e9 if fused_ms > 0 else 0.0
+    flops = FLOP_PER_SEG * n_seg * args.steps
+    tens = flops / (conv_ms / 1000.0) / 1e12 if conv_ms > 0 else 0.0
+    roofline = {'bound': 'hbm', 'kernel': 'conv_ln_tc_kernel (tcgen05 implicit-GEMM convolutions 1-7 fused with LayerNorm + ReLU)',
+                'achieved': achieved, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+                'frac': achieved / pk['hbm_gbs'],
+                'traffic': CONVLN_NCU_TRAFFIC_PER_SEG * n_seg * args.steps / max(fused_n, 1),
+                'traffic_source': 'ncu dram__bytes_read+write of the 7 launches of one 4096-segment chunk, per segment '
+                                  '(profiles/r01/v4/ncu_convln.csv), scaled to the average launch of this run',
+                'algorithmic_bytes_per_launch': bytes_alg / max(fused_n, 1),
+                'peak_source': pk['source'],
+                'launches': fused_n, 'avg_launch_ms': fused_ms / max(fused_n, 1),
+                'share_of_step': fused_ms / (t_dev * 1000.0),
+                'all_tensor_core_kernels': {'tflops': tens, 'frac_of_bf16_sustained': tens / pk['tf_sustained'],
+                                            'ms_per_step': conv_ms / args.steps, 'launches': conv_n},
+                'classes_ms_per_step': {k: round(v[0] / args.steps, 3) for k, v in prof.items() if v[1]},
+                'kernels_ms_per_step': {k: round(v[0] / args.steps, 3) for k, v in detail.items()}}
     mel_ms, _ = prof['mel']
     if mel_ms > 0:
         roofline['mel_hbm_frac'] = (SEG_BYTES_MEL * n_seg * args.steps / (mel_ms / 1000.0) / 1e9) / pk['hbm_gbs']
@@ -406,7 +425,7 @@ def bench_match(torch, args, world, rank, local, device, barrier, max_over_ranks
     passes = scan_n  # each launch streams (a sample of, or all of) the shard once
     return {'metric': 'queries/s', 'value': nq / t, 'unit': 'queries/s', 'e2e': e2e, 'db_rows': n, 'queries': nq,
             'vectors_per_query': q_len, 'top_k': k, 'shard_rows': rows_local, 'accuracy_vs_planted': acc,
-            'query_files_per_db_pass': B, 'regime': 'batched (tensor-bound): 128 query vectors per database pass',
+            'query_files_per_db_pass': B, 'regime': 'batched: 256 query vectors per database pass (TMEM-read-bound epilogue, see DESIGN.md)',
             'classes_ms': {kk: round(v[0], 3) for kk, v in prof.items() if v[1]},
             'kernels_ms': {kk: [round(v[0], 3), v[1]] for kk, v in detail.items()},
             'knn_scan': {'launches': passes, 'ms': scan_ms,

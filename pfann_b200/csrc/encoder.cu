@@ -930,7 +930,8 @@ int plan_workspace(Model *m) {
     for (int i = 0; i < 16; i++) {
         const long long e = m->conv[i].g.out_per_sample();
         const bool front = i < 2 * LF;
-        const bool stores_y = !(i == 0 && m->l0_fused);  // fused layer 0 never stores its raw output
+        // fused layer 0 and the fused conv+LayerNorm kernels never store a raw convolution output
+        const bool stores_y = !(i == 0 && m->l0_fused) && !(m->precision == PFANN_PRECISION_BF16 && tc_ln_supported(m, i));
         if (front) {
             if (stores_y && e > fY) fY = e;
             if ((i & 1) == 0 && e > fA) fA = e;
