@@ -97,6 +97,7 @@ __device__ void bitonic_sort(K *keys, int n) {
 int db_search_dev(Db *db, const float *q, int64_t Q, int k, float *dist, int64_t *labels);
 // knn_tc.cu
 int knn_tc_prepare(Db *db);
+int64_t knn_tc_sample_slots(Db *db, int64_t r0, int64_t r1);
 void knn_tc_release(Db *db);
 // approximate scan of rows [r0, r1) against Qg <= 128 queries; mode 0: store all scores to
 // sample[q][row - r0] (ld = sample_ld); mode 1: push row ids with score >= thr[q] into cand/cnt

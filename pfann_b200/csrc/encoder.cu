@@ -798,47 +798,13 @@ int launch_l0_fused(Model *m, const float *mel, ActT *X, int nb) {
     return PFANN_OK;
 }
 
-// Front phase (tensor-core path): layers [0, front_layers) depth-first over sub-chunks in the small re-used
-// workspace; the last apply writes the chunk-level input of layer `front_layers` (m->xb).
-int forward_front(Model *m, const float *mel, int nb) {
-    typedef __nv_bfloat16 bf;
-    const int LF = m->front_layers, SB = m->front_sub;
-    const long long mel_per = (long long)m->F * m->T;
-    m->cur_stats = m->fstats.as<float2>();
-    m->cur_partials = m->fpartials.as<float2>();
-    if (m->tap_layer >= 0 && m->tap_layer < LF)  // reserve the whole tap buffer before the first sub-chunk writes
-        PF_TRY(m->tapbuf.ensure((size_t)nb * m->conv[2 * m->tap_layer + 1].g.out_per_sample() * 4));
-    for (int s0 = 0; s0 < nb; s0 += SB) {
-        const int ns = (nb - s0) < SB ? (nb - s0) : SB;
-        PF_TRY(launch_l0_fused<bf>(m, mel + (long long)s0 * mel_per, m->fxa.as<bf>(), ns));
-        for (int idx = 1; idx < 2 * LF; idx++) {
-            const ConvWeights &cw = m->conv[idx];
-            m->prof_idx = idx;
-            const bf *in = (idx & 1) ? m->fxa.as<bf>() : m->fxb.as<bf>();
-            PF_TRY(tc_conv(m, idx, in, m->fy.p, m->y_bf16, ns));
-            bf *out = (idx & 1) ? m->fxb.as<bf>() : m->fxa.as<bf>();
-            if (idx == 2 * LF - 1) out = m->xb.as<bf>() + (long long)s0 * cw.g.out_per_sample();
-            if (m->y_bf16)
-                PF_TRY((launch_ln_apply<bf, bf>(m, cw, m->fy.as<bf>(), out, ns)));
-            else
-                PF_TRY((launch_ln_apply<float, bf>(m, cw, m->fy.as<float>(), out, ns)));
-            if (idx & 1) PF_TRY(save_tap<bf>(m, idx >> 1, out, ns, nb, s0));
-        }
-    }
-    return PFANN_OK;
-}
-
 // one chunk of nb <= m->chunk samples through the 8 layers + head
 template <typename ActT>
 int forward_chunk(Model *m, const float *mel, int nb, int norm, float *z) {
     const bool tc = (sizeof(ActT) == 2);
     float *Y = m->ybuf.as<float>();
     ActT *xa = m->xa.as<ActT>(), *xb = m->xb.as<ActT>();
-    int l_begin = 0;
-    if (tc && m->front_layers > 0) {
-        PF_TRY(forward_front(m, mel, nb));
-        l_begin = m->front_layers;
-    }
+    const int l_begin = 0;
     m->cur_stats = m->stats.as<float2>();
     m->cur_partials = m->partials.as<float2>();
     for (int l = l_begin; l < 8; l++) {
@@ -924,35 +890,20 @@ int forward_chunk(Model *m, const float *mel, int nb, int norm, float *z) {
 namespace pfann {
 
 int plan_workspace(Model *m) {
-    const int LF = m->precision == PFANN_PRECISION_BF16 ? m->front_layers : 0;
     const size_t act = m->precision == PFANN_PRECISION_BF16 ? 2 : 4;
-    long long tY = 0, tA = 0, tB = 0, fY = 0, fA = 0, fB = 0;
+    long long tY = 0, tA = 0, tB = 0;
     for (int i = 0; i < 16; i++) {
         const long long e = m->conv[i].g.out_per_sample();
-        const bool front = i < 2 * LF;
         // fused layer 0 and the fused conv+LayerNorm kernels never store a raw convolution output
         const bool stores_y = !(i == 0 && m->l0_fused) && !(m->precision == PFANN_PRECISION_BF16 && tc_ln_supported(m, i));
-        if (front) {
-            if (stores_y && e > fY) fY = e;
-            if ((i & 1) == 0 && e > fA) fA = e;
-            if ((i & 1) == 1 && i != 2 * LF - 1 && e > fB) fB = e;
-            if (i == 2 * LF - 1 && e > tB) tB = e;  // the front's last output is the tail's first input
-        } else {
-            if (stores_y && e > tY) tY = e;
-            if ((i & 1) == 0 && e > tA) tA = e;
-            if ((i & 1) == 1 && e > tB) tB = e;
-        }
+        if (stores_y && e > tY) tY = e;
+        if ((i & 1) == 0 && e > tA) tA = e;
+        if ((i & 1) == 1 && e > tB) tB = e;
     }
     PF_TRY(m->ybuf.ensure((size_t)(tY ? tY : 1) * m->chunk * 4));
     PF_TRY(m->xa.ensure((size_t)(tA ? tA : 1) * m->chunk * act));
     PF_TRY(m->xb.ensure((size_t)(tB ? tB : 1) * m->chunk * act));
     PF_TRY(m->stats.ensure((size_t)m->chunk * sizeof(float2)));
-    if (LF > 0) {
-        PF_TRY(m->fy.ensure((size_t)(fY ? fY : 1) * m->front_sub * 4));
-        PF_TRY(m->fxa.ensure((size_t)(fA ? fA : 1) * m->front_sub * 2));
-        PF_TRY(m->fxb.ensure((size_t)(fB ? fB : 1) * m->front_sub * 2));
-        PF_TRY(m->fstats.ensure((size_t)m->front_sub * sizeof(float2)));
-    }
     return PFANN_OK;
 }
 
@@ -1010,7 +961,6 @@ void pfann_model_destroy(pfann_model *hm) {
     cudaFree(m->w1); cudaFree(m->b1); cudaFree(m->w2); cudaFree(m->b2); cudaFree(m->l0_w);
     cudaFree(m->l0_gb16); cudaFree(m->l0_btile);
     m->ybuf.release(); m->xa.release(); m->xb.release(); m->stats.release(); m->partials.release();
-    m->fy.release(); m->fxa.release(); m->fxb.release(); m->fstats.release(); m->fpartials.release();
     m->tapbuf.release(); m->melbuf.release(); m->zbuf.release(); m->ln_part.release(); m->ln_err.release();
     delete m;
 }
@@ -1141,21 +1091,6 @@ int pfann_model_finalize(pfann_model *hm, int precision) {
     PF_TRY(upload(*b1, &m->b1));
     PF_TRY(upload(*w2, &m->w2));
     PF_TRY(upload(*b2, &m->b2));
-    m->front_layers = 0;
-    m->front_sub = 0;
-    if (precision == PFANN_PRECISION_BF16 && m->l0_fused) {
-        // off by default: measured slower on B200 (profiles/r01/front_phase_sweep.md) -- per-kernel fixed costs at
-        // L2-sized sub-chunks (<= 64 samples) outweigh the saved HBM round trips
-        int lf = getenv("PFANN_B200_FRONT_LAYERS") ? atoi(getenv("PFANN_B200_FRONT_LAYERS")) : 0;
-        int sb = getenv("PFANN_B200_FRONT_SUB") ? atoi(getenv("PFANN_B200_FRONT_SUB")) : 48;
-        if (lf > 7) lf = 7;
-        for (int i = 1; i < 2 * lf; i++)
-            if (!tc_supported(m->conv[i].g)) lf = 0;  // e.g. depthwise conv2 (fuller == false)
-        if (lf > 0 && sb > 0 && sb < m->chunk) {
-            m->front_layers = lf;
-            m->front_sub = sb;
-        }
-    }
     if (precision == PFANN_PRECISION_BF16) {
         int rc = tc_prepare(m);
         if (rc != PFANN_OK) {
@@ -1170,7 +1105,7 @@ int pfann_model_set_chunk(pfann_model *hm, int chunk) {
     PF_CHECK(hm && chunk > 0 && chunk <= 65535, PFANN_ERR_ARG, "pfann_model_set_chunk: chunk must be in 1..65535");
     Model *m = reinterpret_cast<Model *>(hm);
     m->chunk = chunk;
-    if (m->precision >= 0) return pfann_model_finalize(hm, m->precision);  // workspaces, tensor maps, front phase
+    if (m->precision >= 0) return pfann_model_finalize(hm, m->precision);  // workspaces, tensor maps
     return PFANN_OK;
 }
 

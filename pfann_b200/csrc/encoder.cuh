@@ -60,11 +60,6 @@ struct Model {
     bool l0_fused = false;
     bool y_bf16 = true;     // tensor-core convs write their raw output in bf16 (statistics stay fp32)
     DevBuf ybuf, xa, xb, stats, partials, tapbuf, melbuf, zbuf;   // chunk-sized workspace ("tail" phase)
-    // "front" phase (tensor-core path): the first `front_layers` SeparableConv2d run depth-first over sub-chunks
-    // of `front_sub` samples in a small, re-used workspace, so that their activations (1 MB/sample after layer-0
-    // conv1, ...) live and die in the 126 MB L2 instead of making round trips to HBM.  0 = disabled.
-    int front_layers = 0, front_sub = 0;
-    DevBuf fy, fxa, fxb, fstats, fpartials;
     DevBuf ln_part, ln_err;  // fused conv+LayerNorm: statistics exchange table, time-out flag
     float2 *cur_stats = nullptr, *cur_partials = nullptr;  // statistics buffers of the phase being executed
     int prof_idx = 0;      // convolution being executed (detail slot of the optional event profile)
@@ -94,7 +89,7 @@ int tc_ln_check(Model *m);
 bool tc_l0_supported(Model *m);
 int tc_l0(Model *m, const float *mel, const float2 *stats, __nv_bfloat16 *X, int nb);
 int tc_conv_ln(Model *m, int idx, const __nv_bfloat16 *X, __nv_bfloat16 *Xout, int nb);
-// encoder.cu: size both workspaces (needs conv geometries and front_* decided)
+// encoder.cu: size the chunk workspace (needs the conv geometries)
 int plan_workspace(Model *m);
 
 }  // namespace pfann

@@ -1055,14 +1055,13 @@ int tc_prepare(Model *m) {
     // workspaces must exist before tensor maps can point into them
     PF_TRY(plan_workspace(m));
     for (int i = 1; i < 16; i++) {
-        const bool front = i < 2 * m->front_layers;
-        const cuuint64_t nb = (cuuint64_t)(front ? m->front_sub : m->chunk);
+        const cuuint64_t nb = (cuuint64_t)m->chunk;
         const ConvGeom &g = m->conv[i].g;
         TcConv &tc = st->conv[i];
         tc.supported = tc_supported(g);
         if (!tc.supported) continue;
         const __nv_bfloat16 *X = reinterpret_cast<const __nv_bfloat16 *>(
-            front ? ((i & 1) == 0 ? m->fxb.p : m->fxa.p) : ((i & 1) == 0 ? m->xb.p : m->xa.p));
+            (i & 1) == 0 ? m->xb.p : m->xa.p);
         tc.x_base = X;
         tc.BN = g.Co >= 256 ? 256 : (g.Co >= 128 ? 128 : 64);
         tc.NT = g.Co / tc.BN;
@@ -1106,7 +1105,6 @@ int tc_prepare(Model *m) {
         }
     }
     PF_TRY(m->partials.ensure((size_t)m->chunk * st->max_slots * sizeof(float2)));
-    if (m->front_layers > 0) PF_TRY(m->fpartials.ensure((size_t)m->front_sub * st->max_slots * sizeof(float2)));
     return PFANN_OK;
 }
 
@@ -1162,8 +1160,7 @@ LnGeom ln_geom(const ConvGeom &g) {
 
 bool tc_ln_supported(Model *m, int idx) {
     if (idx < 1 || idx > 14 || m->tc_state == nullptr) return false;
-    static const bool off = getenv("PFANN_B200_NO_FUSED_LN") != nullptr;
-    if (off) return false;
+    if (getenv("PFANN_B200_NO_FUSED_LN") != nullptr) return false;  // read per call: tests toggle it
     return m->conv[idx].gb16 != nullptr && ln_geom(m->conv[idx].g).ok;
 }
 
@@ -1188,7 +1185,7 @@ int tc_conv_ln(Model *m, int idx, const __nv_bfloat16 *X, __nv_bfloat16 *Xout, i
 }
 
 bool tc_l0_supported(Model *m) {
-    static const bool off = getenv("PFANN_B200_NO_L0_TC") != nullptr;
+    const bool off = getenv("PFANN_B200_NO_L0_TC") != nullptr;  // read per call: tests toggle it
     const ConvGeom &g = m->conv[0].g;
     return !off && m->l0_gb16 != nullptr && m->l0_btile != nullptr && g.Co == 128 && (g.Fo * g.To) % 128 == 0;
 }

@@ -152,54 +152,111 @@ __global__ void __launch_bounds__(256) knn_select_kernel(const float *__restrict
                                                          float eps_rel, float max_norm, const float *qnorm, float *thr,
                                                          float *dist, int64_t *labels, int *flags) {
     extern __shared__ __align__(16) unsigned char smraw[];
-    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smraw);  // [cap]
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smraw);  // [cap] survivors of the ranking
     float *qv = reinterpret_cast<float *>(keys + cap);                         // [d]
-    __shared__ int m_s;
-    const int qi = blockIdx.x;
+    __shared__ int hist[8][256];   // per-warp digit histograms of the radix select
+    __shared__ uint32_t sel_prefix;
+    __shared__ int sel_k, m_s;
+    const int qi = blockIdx.x, tid = threadIdx.x, warp = tid >> 5;
     const int total = cnt[qi];
     const int n = total < cap ? total : cap;
-    int P = 1;
-    while (P < n) P <<= 1;
-    for (int i = threadIdx.x; i < d; i += blockDim.x) qv[i] = q[(int64_t)qi * d + i];
-    if (threadIdx.x == 0) m_s = 0;
-    for (int i = threadIdx.x; i < P; i += blockDim.x) {
-        unsigned long long key = 0ull;
-        if (i < n) {
-            const uint32_t id = cand[(int64_t)qi * cap + i];
-            key = ((unsigned long long)flipf(__uint_as_float(cand_v[(int64_t)qi * cap + i])) << 32) |
-                  (unsigned long long)(0xFFFFFFFFu - id);
-        }
-        keys[i] = key;
+    for (int i = tid; i < d; i += blockDim.x) qv[i] = q[(int64_t)qi * d + i];
+    // this thread's share of the scan scores as order-preserving integer keys (cap <= 4096 -> at most 16)
+    uint32_t kv[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const int i = tid + 256 * j;
+        kv[j] = i < n ? flipf(__uint_as_float(cand_v[(int64_t)qi * cap + i])) : 0u;
     }
-    bitonic_sort<unsigned long long, true>(keys, P);
+    // k-th largest key by a most-significant-digit radix select, 8 bits per round: no sort of the ~2 k candidates
+    uint32_t prefix = 0u, mask = 0u;
+    if (tid == 0) {
+        sel_k = k;
+        m_s = 0;
+    }
+    const bool have_k = n >= k;
+    for (int shift = 24; shift >= 0 && have_k; shift -= 8) {
+        for (int i = tid; i < 8 * 256; i += 256) (&hist[0][0])[i] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 16; j++)
+            if (tid + 256 * j < n && (kv[j] & mask) == prefix) atomicAdd(&hist[warp][(kv[j] >> shift) & 255u], 1);
+        __syncthreads();
+        if (warp == 0) {
+            // lane l owns digits [8 l, 8 l + 8); walk from the largest digit down to the one holding the k-th key
+            const int lane = tid;
+            int c8[8], mine = 0;
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                int c = 0;
+#pragma unroll
+                for (int w = 0; w < 8; w++) c += hist[w][8 * lane + e];
+                c8[e] = c;
+                mine += c;
+            }
+            int suf = mine;  // inclusive suffix sum over lanes: keys in this lane's digits and all larger ones
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_down_sync(0xffffffffu, suf, o);
+                if (lane + o < 32) suf += t;
+            }
+            const int above = suf - mine;
+            const int kk = sel_k;
+            if (above < kk && kk <= above + mine) {  // exactly one lane
+                int acc = above;
+                int digit = 0, newk = kk;
+#pragma unroll
+                for (int e = 7; e >= 0; e--) {
+                    if (acc < kk && kk <= acc + c8[e]) {
+                        digit = 8 * lane + e;
+                        newk = kk - acc;
+                    }
+                    acc += c8[e];
+                }
+                sel_prefix = prefix | ((uint32_t)digit << shift);
+                sel_k = newk;
+            }
+        }
+        __syncthreads();
+        prefix = sel_prefix;
+        mask |= 255u << shift;
+    }
+    __syncthreads();
     const float delta2 = 2.f * eps_rel * qnorm[qi] * max_norm;
+    const float vk = have_k ? unflipf(prefix) : -INFINITY;  // k-th best (scan score - threshold)
     if (total > cap) {
         // overflow: the stored subset still bounds the k-th best scan score from below
-        if (threadIdx.x == 0) {
+        if (tid == 0) {
             atomicAdd(flags, 1);
-            if (n >= k) thr[qi] = fmaxf(thr[qi], thr[qi] + unflipf((uint32_t)(keys[k - 1] >> 32)) - delta2);
+            if (have_k) thr[qi] = fmaxf(thr[qi], thr[qi] + vk - delta2);
         }
         return;
     }
-    // prefix of the ranking that can contain a true top-k row
-    const float vmin = n >= k ? unflipf((uint32_t)(keys[k - 1] >> 32)) - delta2 : -INFINITY;
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
-        if (unflipf((uint32_t)(keys[i] >> 32)) >= vmin) atomicMax(&m_s, i + 1);
+    // every candidate that can still be a true top-k row: scan score >= k-th best - 2 delta
+    const uint32_t kmin = have_k ? flipf(vk - delta2) : 0u;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const int i = tid + 256 * j;
+        if (i < n && kv[j] >= kmin) {
+            const int pos = atomicAdd(&m_s, 1);
+            keys[pos] = (unsigned long long)cand[(int64_t)qi * cap + i];
+        }
+    }
     __syncthreads();
     const int m = m_s;
     int P2 = 1;
     while (P2 < m) P2 <<= 1;
-    for (int i = threadIdx.x; i < P2; i += blockDim.x) {
+    for (int i = tid; i < P2; i += blockDim.x) {
         unsigned long long key = 0ull;
         if (i < m) {
-            const uint32_t id = 0xFFFFFFFFu - (uint32_t)(keys[i] & 0xFFFFFFFFull);
+            const uint32_t id = (uint32_t)keys[i];
             const float s = (d & 31) == 0 ? dot_fma_seq_lines(db + (int64_t)id * d, qv, d) : dot_fma_seq(db + (int64_t)id * d, qv, d);
             key = ((unsigned long long)flipf(s) << 32) | (unsigned long long)(0xFFFFFFFFu - id);
         }
         keys[i] = key;  // slot i is read and written by this thread only
     }
     bitonic_sort<unsigned long long, true>(keys, P2);
-    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    for (int j = tid; j < k; j += blockDim.x) {
         if (j < m) {
             dist[(int64_t)qi * k + j] = unflipf((uint32_t)(keys[j] >> 32));
             labels[(int64_t)qi * k + j] = id_base + (int64_t)(0xFFFFFFFFu - (uint32_t)(keys[j] & 0xFFFFFFFFull));
@@ -382,58 +439,78 @@ int db_search_dev(Db *db, const float *q, int64_t Q, int k, float *dist, int64_t
     int64_t max_chunks = 8192 / k;  // stage 2 sorts nchunks * k keys in shared memory
     if (want > max_chunks * chunk) want = max_chunks * chunk;
     const int S = (int)(db->n < want ? db->n : want);
-    const int nchunks = (S + chunk - 1) / chunk;
+    // the tensor-core pre-pass leaves per-thread maxima (one per CTA and accumulator row) instead of every score
+    const int S_keys = tc ? (int)knn_tc_sample_slots(db, 0, S) : S;
+    const int nchunks = (S_keys + chunk - 1) / chunk;
     int cpad = 1;
-    while (cpad < (S < chunk ? S : chunk)) cpad <<= 1;
+    while (cpad < (S_keys < chunk ? S_keys : chunk)) cpad <<= 1;
     int P2 = 1;
     while (P2 < nchunks * k) P2 <<= 1;
+    const int64_t ngroups = (Q + group - 1) / group;
     PF_TRY(db->thr.ensure(sizeof(float) * group));
     PF_TRY(db->qnorm.ensure(sizeof(float) * group));
     PF_TRY(db->cnt.ensure(sizeof(int) * group));
     PF_TRY(db->cand.ensure(sizeof(uint32_t) * (size_t)group * cap));
     PF_TRY(db->cand_v.ensure(sizeof(uint32_t) * (size_t)group * cap));
-    PF_TRY(db->sample.ensure(sizeof(float) * (size_t)group * S));
+    PF_TRY(db->sample.ensure(sizeof(float) * (size_t)group * S_keys));
     PF_TRY(db->rr_keys.ensure(sizeof(uint32_t) * (size_t)group * nchunks * k));
-    PF_TRY(db->flags.ensure(sizeof(int) * 4));
+    PF_TRY(db->flags.ensure(sizeof(int) * (size_t)(ngroups + 4)));
     const size_t sel_smem = (size_t)cap * 8 + (size_t)d * 4;
     PF_CUDA(cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
     PF_CUDA(cudaFuncSetAttribute(knn_scan_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)((QG * d + SCAN_ROWS * (d + 4)) * 4)));
-    for (int64_t q0 = 0; q0 < Q; q0 += group) {
+    // 1. threshold pre-pass on the first S rows
+    auto prepass = [&](const float *qg, int Qg) -> int {
+        PF_TRY(scan(db, tc, qg, Qg, 0, S, 0, db->sample.as<float>(), S_keys, nullptr, nullptr, nullptr, nullptr, 0));
+        ProfScope ps(db->ctx, K_KNN_SELECT, 37);
+        knn_kth_chunk_kernel<<<dim3(Qg, nchunks), 256, (size_t)(cpad > 256 ? cpad : 256) * 4, st>>>(
+            db->sample.as<float>(), S_keys, S_keys, chunk, cpad, k, db->rr_keys.as<uint32_t>());
+        knn_kth_merge_kernel<<<Qg, 256, (size_t)P2 * 4, st>>>(db->rr_keys.as<uint32_t>(), nchunks * k, P2, S_keys, qg, d, k,
+                                                             eps_rel, db->max_norm, db->thr.as<float>(),
+                                                             db->qnorm.as<float>());
+        db->ctx->launches += 2;
+        PF_CUDA(cudaGetLastError());
+        return PFANN_OK;
+    };
+    // 2. filtered scan of the whole shard, 3. ranking + exact rescoring; *flag += 1 per overflowed query
+    auto filtered = [&](const float *qg, int Qg, int64_t q0, int *flag) -> int {
+        PF_CUDA(cudaMemsetAsync(db->cnt.p, 0, sizeof(int) * Qg, st));
+        PF_TRY(scan(db, tc, qg, Qg, 0, db->n, 1, nullptr, 0, db->thr.as<float>(), db->cnt.as<int>(),
+                    db->cand.as<uint32_t>(), db->cand_v.as<uint32_t>(), cap));
+        ProfScope ps(db->ctx, K_KNN_SELECT, 38);
+        knn_select_kernel<<<Qg, 256, sel_smem, st>>>(db->emb32, d, db->id_base, qg, db->cnt.as<int>(),
+                                                     db->cand.as<uint32_t>(), db->cand_v.as<uint32_t>(), cap, k,
+                                                     eps_rel, db->max_norm, db->qnorm.as<float>(), db->thr.as<float>(),
+                                                     dist + q0 * k, labels + q0 * k, flag);
+        db->ctx->launches++;
+        PF_CUDA(cudaGetLastError());
+        return PFANN_OK;
+    };
+    // Every group runs once without any host synchronisation; the (rare) groups whose candidate lists overflowed
+    // are found with ONE read-back of the per-group flags and redone with tightened thresholds.
+    int *flags = db->flags.as<int>();
+    PF_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)(ngroups + 4), st));
+    for (int64_t g = 0; g < ngroups; g++) {
+        const int64_t q0 = g * group;
+        const int Qg = (int)((Q - q0) < group ? (Q - q0) : group);
+        PF_TRY(prepass(q + q0 * d, Qg));
+        PF_TRY(filtered(q + q0 * d, Qg, q0, flags + g));
+    }
+    std::vector<int> hflags((size_t)ngroups);
+    PF_CUDA(cudaMemcpyAsync(hflags.data(), flags, sizeof(int) * (size_t)ngroups, cudaMemcpyDeviceToHost, st));
+    PF_CUDA(cudaStreamSynchronize(st));
+    for (int64_t g = 0; g < ngroups; g++) {
+        if (hflags[g] == 0) continue;
+        const int64_t q0 = g * group;
         const int Qg = (int)((Q - q0) < group ? (Q - q0) : group);
         const float *qg = q + q0 * d;
-        // 1. threshold pre-pass on the first S rows
-        PF_TRY(scan(db, tc, qg, Qg, 0, S, 0, db->sample.as<float>(), S, nullptr, nullptr, nullptr, nullptr, 0));
-        {
-            ProfScope ps(db->ctx, K_KNN_SELECT, 37);
-            knn_kth_chunk_kernel<<<dim3(Qg, nchunks), 256, (size_t)(cpad > 256 ? cpad : 256) * 4, st>>>(
-                db->sample.as<float>(), S, S, chunk, cpad, k, db->rr_keys.as<uint32_t>());
-            knn_kth_merge_kernel<<<Qg, 256, (size_t)P2 * 4, st>>>(db->rr_keys.as<uint32_t>(), nchunks * k, P2, S, qg, d, k,
-                                                                 eps_rel, db->max_norm, db->thr.as<float>(),
-                                                                 db->qnorm.as<float>());
-            db->ctx->launches += 2;
-            PF_CUDA(cudaGetLastError());
-        }
+        PF_TRY(prepass(qg, Qg));
         bool done = false;
-        for (int iter = 0; iter < 4 && !done; iter++) {
-            PF_CUDA(cudaMemsetAsync(db->cnt.p, 0, sizeof(int) * Qg, st));
-            PF_CUDA(cudaMemsetAsync(db->flags.p, 0, sizeof(int) * 4, st));
-            // 2. filtered scan of the whole shard
-            PF_TRY(scan(db, tc, qg, Qg, 0, db->n, 1, nullptr, 0, db->thr.as<float>(), db->cnt.as<int>(),
-                        db->cand.as<uint32_t>(), db->cand_v.as<uint32_t>(), cap));
-            // 3. exact rescoring + sort
-            {
-            ProfScope ps(db->ctx, K_KNN_SELECT, 38);
-            knn_select_kernel<<<Qg, 256, sel_smem, st>>>(db->emb32, d, db->id_base, qg, db->cnt.as<int>(),
-                                                         db->cand.as<uint32_t>(), db->cand_v.as<uint32_t>(), cap, k,
-                                                         eps_rel, db->max_norm,
-                                                         db->qnorm.as<float>(), db->thr.as<float>(), dist + q0 * k,
-                                                         labels + q0 * k, db->flags.as<int>());
-            }
-            db->ctx->launches++;
-            PF_CUDA(cudaGetLastError());
+        for (int iter = 0; iter < 5 && !done; iter++) {  // iteration 0 repeats the overflow and tightens the thresholds
+            PF_CUDA(cudaMemsetAsync(flags + g, 0, sizeof(int), st));
+            PF_TRY(filtered(qg, Qg, q0, flags + g));
             int overflow = 0;
-            PF_CUDA(cudaMemcpyAsync(&overflow, db->flags.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            PF_CUDA(cudaMemcpyAsync(&overflow, flags + g, sizeof(int), cudaMemcpyDeviceToHost, st));
             PF_CUDA(cudaStreamSynchronize(st));
             done = (overflow == 0);
         }

@@ -54,7 +54,7 @@ template <int N> struct ScanCfg {
     static constexpr int TROWS = N > 128 ? N : 128;      // rows of the threshold tile
 };
 
-template <int N>
+template <int N, bool SAMPLE>
 __global__ void __launch_bounds__(KNN_THREADS, 1) knn_scan_tc_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                      const ScanArgs a) {
     constexpr int STAGES = ScanCfg<N>::STAGES, QCAP = ScanCfg<N>::QCAP, TROWS = ScanCfg<N>::TROWS;
@@ -197,6 +197,12 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_scan_tc_kernel(const __gri
         const int quarter = warp & 3, wc = (warp - 2) >> 2;
         const uint32_t t_quarter = tmem_base + ((uint32_t)(quarter * 32) << 16);
         long long it = 0;
+        // sample pre-pass: every thread keeps, per query column, the maximum over the rows it has seen.  The k-th
+        // largest of these maxima (each over a distinct subset of the sample) is a lower bound of the sample's k-th
+        // largest score -- 148 x 128 values per query leave the kernel instead of one per sampled row.
+        float mx[SAMPLE ? (N > 128 ? 64 : 32) : 1];
+#pragma unroll
+        for (int i = 0; i < (SAMPLE ? (N > 128 ? 64 : 32) : 1); i++) mx[i] = -INFINITY;
         if (wc * 32 < N) {
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
                 const int buf = (int)(it & 1);
@@ -208,13 +214,14 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_scan_tc_kernel(const __gri
                 const long long row = a.r0 + tile * BM + quarter * 32 + lane;
                 const bool rvalid = row < a.r1;
 #pragma unroll
-              for (int c = wc * 32; c < N; c += 128) {   // N = 256: two 32-column chunks per warp
+              for (int ci = 0; ci < (N > 128 ? 2 : 1); ci++) {   // N = 256: two 32-column chunks per warp
+                const int c = wc * 32 + ci * 128;
                 uint32_t v[32];
                 if (a.debug < 2) {
                     ptx::tmem_ld_32x32b_x32(t_quarter + (uint32_t)(buf * N + c), v);
                     ptx::tmem_ld_wait();
                 }
-                if (c + 128 >= N) {
+                if (ci == (N > 128 ? 1 : 0)) {
                     // the last values are in registers: hand the buffer back to the MMA issuer right away
                     ptx::tc_fence_before();
                     __syncwarp();
@@ -226,11 +233,13 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_scan_tc_kernel(const __gri
 #pragma unroll
                     for (int i = 0; i < 32; i++) x ^= v[i];
                     if (x == 0x12345678u && a.cnt) a.cnt[0] = 1;  // keep the load alive
-                } else if (a.mode == 0) {
+                } else if (SAMPLE) {
                     if (rvalid) {
 #pragma unroll
-                        for (int i = 0; i < 32; i++)
-                            if (c + i < a.Qg) a.sample[(long long)(c + i) * a.sample_ld + (row - a.r0)] = __uint_as_float(v[i]);
+                        for (int i = 0; i < 32; i++) {
+                            mx[(SAMPLE ? ci * 32 : 0) + (SAMPLE ? i : 0)] =
+                                fmaxf(mx[(SAMPLE ? ci * 32 : 0) + (SAMPLE ? i : 0)], __uint_as_float(v[i]));
+                        }
                     }
                 } else {
                     // accumulator = score - threshold: a hit is a clear sign bit.  AND-tree of the 32 words (3-input
@@ -266,6 +275,17 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_scan_tc_kernel(const __gri
               }
                 pc[4] += clock64() - c1;
             }
+            if (SAMPLE) {
+#pragma unroll
+                for (int ci = 0; ci < (N > 128 ? 2 : 1); ci++)
+#pragma unroll
+                    for (int i = 0; i < 32; i++) {
+                        const int c = wc * 32 + ci * 128;
+                        if (c + i < a.Qg)
+                            a.sample[(long long)(c + i) * a.sample_ld + (long long)blockIdx.x * BM + quarter * 32 + lane] =
+                                mx[(SAMPLE ? ci * 32 : 0) + (SAMPLE ? i : 0)];
+                    }
+            }
         }
         // flush the parked survivors: the 128 epilogue threads issue their global atomics side by side
         asm volatile("bar.sync 1, %0;" ::"n"(32 * KNN_EPI_WARPS) : "memory");
@@ -296,18 +316,18 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_scan_tc_kernel(const __gri
     }
 }
 
-template <int N>
+template <int N, bool SAMPLE>
 int launch_scan(Db *db, KnnTcState *st, const ScanArgs &a) {
     const int KBLK = db->d / BK;
     const size_t smem = 1024 + (size_t)N * BK * 2 * KBLK + (size_t)ScanCfg<N>::STAGES * BM * BK * 2 * KBLK +
                         (size_t)ScanCfg<N>::QCAP * 12 + (size_t)ScanCfg<N>::TROWS * 128;
-    PF_CUDA(cudaFuncSetAttribute(knn_scan_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PF_CUDA(cudaFuncSetAttribute(knn_scan_tc_kernel<N, SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long ntiles = (a.r1 - a.r0 + BM - 1) / BM;
     long long grid = db->ctx->sm_count;
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) return PFANN_OK;
     ProfScope ps(db->ctx, K_KNN_SCAN, a.mode == 0 ? 35 : 36);
-    knn_scan_tc_kernel<N><<<(unsigned)grid, KNN_THREADS, smem, db->ctx->stream>>>(st->mapA, a);
+    knn_scan_tc_kernel<N, SAMPLE><<<(unsigned)grid, KNN_THREADS, smem, db->ctx->stream>>>(st->mapA, a);
     db->ctx->launches++;
     PF_CUDA(cudaGetLastError());
     return PFANN_OK;
@@ -348,6 +368,14 @@ void knn_tc_release(Db *db) {
     db->tc_state = nullptr;
 }
 
+// sample pre-pass (mode 0): number of per-thread maxima written per query for a row range
+int64_t knn_tc_sample_slots(Db *db, int64_t r0, int64_t r1) {
+    const long long ntiles = (r1 - r0 + BM - 1) / BM;
+    long long grid = db->ctx->sm_count;
+    if (grid > ntiles) grid = ntiles;
+    return grid * BM;
+}
+
 int knn_tc_scan(Db *db, const float *q, int Qg, int64_t r0, int64_t r1, int mode, float *sample, int64_t sample_ld,
                 const float *thr, int *cnt, uint32_t *cand, uint32_t *cand_v, int cap) {
     KnnTcState *st = reinterpret_cast<KnnTcState *>(db->tc_state);
@@ -360,9 +388,14 @@ int knn_tc_scan(Db *db, const float *q, int Qg, int64_t r0, int64_t r1, int mode
     a.debug = dbg ? atoi(dbg) : 0;
     const char *pp = getenv("PFANN_KNN_PROF_PTR");  // probe only: device address of a zeroed [grid][8] u64 buffer
     a.prof = pp ? reinterpret_cast<unsigned long long *>(strtoull(pp, nullptr, 0)) : nullptr;
-    if (Qg <= 32) return launch_scan<32>(db, st, a);
-    if (Qg <= 128 || db->d > 128) return launch_scan<128>(db, st, a);
-    return launch_scan<256>(db, st, a);
+    if (mode == 0) {
+        if (Qg <= 32) return launch_scan<32, true>(db, st, a);
+        if (Qg <= 128 || db->d > 128) return launch_scan<128, true>(db, st, a);
+        return launch_scan<256, true>(db, st, a);
+    }
+    if (Qg <= 32) return launch_scan<32, false>(db, st, a);
+    if (Qg <= 128 || db->d > 128) return launch_scan<128, false>(db, st, a);
+    return launch_scan<256, false>(db, st, a);
 }
 
 }  // namespace pfann

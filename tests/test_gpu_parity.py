@@ -175,6 +175,55 @@ def test_layer0_fusion_matches_unfused(dev, monkeypatch):
     np.testing.assert_allclose(za, zb, rtol=0, atol=2e-5)
 
 
+def test_fused_conv_layernorm_matches_unfused(dev, monkeypatch):
+    """conv_ln_tc_kernel (LayerNorm inside the GEMM epilogue, statistics exchanged between CTAs) against the
+    conv -> partial sums -> finalize -> apply chain on the same bf16 operands, for a batch that spans several
+    tiles per CTA position and is not a multiple of the samples-per-tile of the late layers."""
+    net, params, sd = _net('default', 'bf16', dev, 5)
+    x = torch.from_numpy(orc.melspec(synth.synth_segments(43, seed=12), params)).to(dev)
+    fused = [net.layer_output(x, l).numpy() for l in range(8)]
+    zf = net(x).cpu().numpy()
+    monkeypatch.setenv('PFANN_B200_NO_FUSED_LN', '1')
+    plain = [net.layer_output(x, l).numpy() for l in range(8)]
+    zp = net(x).cpu().numpy()
+    for l in range(8):
+        rel = np.linalg.norm(fused[l] - plain[l]) / np.linalg.norm(plain[l])
+        assert rel < 2e-2, (l, rel)      # both round activations to bf16, at different points of the arithmetic
+    assert (1 - (zf * zp).sum(1)).max() < 2e-4
+    monkeypatch.delenv('PFANN_B200_NO_FUSED_LN')
+    assert np.array_equal(net(x).cpu().numpy(), zf)     # and the fused path is bit-reproducible
+
+
+def test_layer0_tensor_core_matches_cuda_core(dev, monkeypatch):
+    """l0_tc_kernel (conv1 of layer 0 as one K = 16 bf16 hi/lo split MMA per 128 positions) against the CUDA-core
+    fp32 formulation: same statistics, same bf16 output up to rounding."""
+    net, params, sd = _net('default', 'bf16', dev, 9)
+    x = torch.from_numpy(orc.melspec(synth.synth_segments(6, seed=4), params)).to(dev)
+    a = net.layer_output(x, 0).numpy()
+    monkeypatch.setenv('PFANN_B200_NO_L0_TC', '1')
+    b = net.layer_output(x, 0).numpy()
+    assert np.linalg.norm(a - b) / np.linalg.norm(b) < 5e-3
+
+
+def test_extract_host_buffers_pipeline_equals_device_buffers(dev):
+    """pfann_extract_pcm16 with host buffers overlaps H2D / compute / D2H chunk by chunk; the fingerprints must be
+    the bits the device-buffer call produces (several chunks, ragged clip lengths, a clip shorter than a segment)."""
+    from pfann_b200.extract import Extractor
+    params = synth.read_config('default')
+    ex = Extractor(params, synth.make_state_dict(params, seed=3), device=0, precision='bf16', chunk=16)
+    lens = [52000, 8000, 3000, 91000, 24000, 40001]
+    pcm = np.concatenate([synth.synth_pcm(300 + i, n) for i, n in enumerate(lens)])
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    z_host, c_host = ex.extract_pcm16(pcm, off)
+    z_dev, c_dev = ex.extract_pcm16(torch.from_numpy(pcm).to(dev), off)
+    assert z_host.shape[0] > 3 * 16 and np.array_equal(c_host, c_dev)
+    assert np.array_equal(z_host, z_dev.cpu().numpy())
+    pinned = torch.from_numpy(pcm).pin_memory()
+    out = torch.empty(z_host.shape, dtype=torch.float32).pin_memory()
+    ex.extract_pcm16(pinned, off, out=out)
+    assert np.array_equal(out.numpy(), z_host)
+
+
 def test_extract_pcm16_equals_mel_plus_model(dev):
     """builder.py:88-99 fused: PCM in, fingerprints out == framing -> mel -> model done step by step."""
     import ctypes
@@ -276,6 +325,16 @@ def test_knn_many_queries_batched(dev, tmp_path):
     """> 128 queries per call (several database passes), d = 64 (n640d64), against the oracle."""
     db, key = synth.synth_db(20000, d=64, seed=6)
     q = synth.synth_queries(db, key, 20, q_len=19, seed=3)[0].reshape(-1, 64)
+    dbo = _open_db(tmp_path, db, key, 20)
+    D, I = dbo.search(q)
+    Dref, Iref = orc.flat_ip_search(db, q, 20)
+    _check_topk(D, I, Dref, Iref, db, q)
+
+
+def test_knn_256_queries_per_pass(dev, tmp_path):
+    """d = 128 and 300 queries: one 256-query pass (two TMEM chunks per epilogue warp) + one 44-query pass."""
+    db, key = synth.synth_db(60000, d=128, seed=16)
+    q = synth.synth_queries(db, key, 16, q_len=19, seed=5)[0].reshape(-1, 128)[:300]
     dbo = _open_db(tmp_path, db, key, 20)
     D, I = dbo.search(q)
     Dref, Iref = orc.flat_ip_search(db, q, 20)

@@ -26,7 +26,6 @@ for t in "$@"; do
     cli)     run t_cli 300 python -m pytest tests/test_gpu_cli.py -q -m gpu ;;
     ncu_l0)  run ncu_l0 600 ncu --set full --clock-control none --import-source on -k regex:'l0_conv_ln|mel_kernel|head_kernel|l0_moments' -c 4 -o gpurun_out/prof_l0 python bench.py --steps 1 --warmup 1 --clips 300 --no-match --no-cpu ;;
     full)    run t_full 600 python -m pytest tests/test_gpu_fullsize.py -q -m gpu ;;
-    front)   for sb in ${FRONT:-0 32 48 64 96}; do export PFANN_B200_FRONT_SUB=$sb; [ $sb = 0 ] && export PFANN_B200_FRONT_LAYERS=0 || export PFANN_B200_FRONT_LAYERS=${FL:-3}; run front_${FL:-3}_$sb 300 python bench.py --clips 2000 --steps 2 --warmup 1 --no-match --no-cpu; done; unset PFANN_B200_FRONT_SUB PFANN_B200_FRONT_LAYERS ;;
     probe)   run knn_probe 600 python tools/knn_probe.py ;;
     all)     run t_all 900 python -m pytest tests -q -m gpu ;;
     ncu_list) run ncu_list 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --clips 300 --chunk 4096 --db-rows 1000000 --queries 100 --no-cpu ;;
