@@ -32,6 +32,7 @@ constexpr unsigned long long SENTINEL = ~0ull;
 constexpr int OFF_BIAS = 1 << 27;
 constexpr int RR_THREADS = 256;
 constexpr int SMEM_CAND_MAX = 8192;  // candidates sorted in shared memory; larger lists use global scratch
+constexpr int RR_DH = 64;            // columns staged per step of the diagonal dot products
 
 __device__ __forceinline__ unsigned long long pack_key(int64_t song, int off, int shift) {
     return ((unsigned long long)song << 36) | ((unsigned long long)(unsigned)(off + OFF_BIAS) << 8) |
@@ -55,6 +56,7 @@ struct RerankArgs {
     int capK;                    // power of two >= max len * k
     unsigned long long *gkeys;   // [nq][capK] or nullptr when shared memory is used
     float *gscores;              // [nq][capK] or nullptr
+    unsigned stage_off;          // byte offset of the row staging tiles in dynamic shared memory, 0 = none
     // outputs
     float *best_score;           // [nq] raw best candidate score (-inf if none)
     int *best_song;              // [nq] global song id or -1
@@ -84,6 +86,9 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(const RerankArgs a) 
         keys = reinterpret_cast<unsigned long long *>(smraw);
         scores = reinterpret_cast<float *>(keys + a.capK);
     }
+    // per-warp staging tile [32 rows][RR_DH + 1] behind the candidate arrays (d a multiple of RR_DH only)
+    float *stage = nullptr;
+    if (a.stage_off != 0) stage = reinterpret_cast<float *>(smraw + a.stage_off) + warp * (32 * (RR_DH + 1));
     if (tid == 0) n_valid_s = 0;
     __syncthreads();
     // (1) candidate keys (seqscore.cpp:49-58)
@@ -130,9 +135,49 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(const RerankArgs a) 
             const int j = jb + lane;
             const bool ok = (j < my_len) && (off + j >= 0) && (off + j < song_len);
             float ip = 0.f;
-            if (ok) {
-                const float *vec = a.emb + (song_start - a.id_base + off + j) * a.d;
-                const float *qv = a.queries + (start + (int64_t)j * a.fsm + shift) * a.d;
+            const float *vec = a.emb + (song_start - a.id_base + off + j) * a.d;
+            const float *qv = a.queries + (start + (int64_t)j * a.fsm + shift) * a.d;
+            if (stage != nullptr) {
+                // The rows of a diagonal are consecutive database rows: the warp fetches them with coalesced 16-byte
+                // loads (16 independent requests in flight per lane) into a padded shared-memory tile, 64 columns
+                // at a time, and every lane then runs the reference's k-sequential multiply/add chain on its own
+                // row from shared memory.  (One scalar global load per multiply left the kernel waiting on DRAM.)
+                const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+                const float *base = a.emb + (song_start - a.id_base + off + jb) * a.d;  // row jb of this block
+                for (int h0 = 0; h0 < a.d; h0 += RR_DH) {
+                    float4 ld[16];
+#pragma unroll
+                    for (int r2 = 0; r2 < 16; r2++) {
+                        const int row = 2 * r2 + (lane >> 4);
+                        ld[r2] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if ((okmask >> row) & 1u)
+                            ld[r2] = __ldg(reinterpret_cast<const float4 *>(base + (int64_t)row * a.d + h0) + (lane & 15));
+                    }
+#pragma unroll
+                    for (int r2 = 0; r2 < 16; r2++) {
+                        float *dst = stage + (2 * r2 + (lane >> 4)) * (RR_DH + 1) + (lane & 15) * 4;
+                        dst[0] = ld[r2].x; dst[1] = ld[r2].y; dst[2] = ld[r2].z; dst[3] = ld[r2].w;
+                    }
+                    __syncwarp();
+                    if (ok) {
+                        const float *sv = stage + lane * (RR_DH + 1);
+#pragma unroll
+                        for (int kk0 = 0; kk0 < RR_DH; kk0 += 8) {
+                            const float4 qa = __ldg(reinterpret_cast<const float4 *>(qv + h0 + kk0));
+                            const float4 qb = __ldg(reinterpret_cast<const float4 *>(qv + h0 + kk0 + 4));
+                            ip = __fadd_rn(ip, __fmul_rn(sv[kk0], qa.x));
+                            ip = __fadd_rn(ip, __fmul_rn(sv[kk0 + 1], qa.y));
+                            ip = __fadd_rn(ip, __fmul_rn(sv[kk0 + 2], qa.z));
+                            ip = __fadd_rn(ip, __fmul_rn(sv[kk0 + 3], qa.w));
+                            ip = __fadd_rn(ip, __fmul_rn(sv[kk0 + 4], qb.x));
+                            ip = __fadd_rn(ip, __fmul_rn(sv[kk0 + 5], qb.y));
+                            ip = __fadd_rn(ip, __fmul_rn(sv[kk0 + 6], qb.z));
+                            ip = __fadd_rn(ip, __fmul_rn(sv[kk0 + 7], qb.w));
+                        }
+                    }
+                    __syncwarp();
+                }
+            } else if (ok) {
                 for (int kk = 0; kk < a.d; kk++) ip = __fadd_rn(ip, __fmul_rn(vec[kk], qv[kk]));
             }
             for (int l = 0; l < 32; l++) {
@@ -237,7 +282,14 @@ int rerank_dev(Db *db, const float *queries, const int64_t *query_index, int nq,
         a.gkeys = db->rr_keys.as<unsigned long long>();
         a.gscores = db->rr_scores.as<float>();
     }
-    PF_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_CAND_MAX * 12)));
+    const size_t stage_bytes = (size_t)(RR_THREADS / 32) * 32 * (RR_DH + 1) * sizeof(float);
+    if (db->d % RR_DH == 0) {  // staged, coalesced diagonal fetch; dynamic shared memory starts 16-byte aligned
+        a.stage_off = (unsigned)((smem + 15) & ~(size_t)15);
+        if (a.stage_off == 0) a.stage_off = 16;
+        smem = a.stage_off + stage_bytes;
+    }
+    PF_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(SMEM_CAND_MAX * 12 + 16 + stage_bytes)));
     ProfScope ps(db->ctx, K_RERANK, 39);
     rerank_kernel<<<nq, RR_THREADS, smem, db->ctx->stream>>>(a);
     db->ctx->launches++;
