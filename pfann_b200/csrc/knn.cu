@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(256) knn_select_kernel(const float *__restrict
             }
             const int above = suf - mine;
             const int kk = sel_k;
+            __syncwarp();  // every lane has read sel_k before the owning lane replaces it
             if (above < kk && kk <= above + mine) {  // exactly one lane
                 int acc = above;
                 int digit = 0, newk = kk;
