@@ -701,7 +701,7 @@ __global__ void __launch_bounds__(L0_THREADS, 1) l0_tc_kernel(const L0TcArgs a) 
         reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char *sA = sbase;                         // L0_STAGES x (128 rows x 128 B); 32 B per row are used
     unsigned char *sB = sA + L0_STAGES * 16384;        // 16 KB weight tile
-    unsigned char *stage_out = sB + 16384;             // 16 warps x 1 KB store staging
+    unsigned char *stage_out = sB + 16384;             // 16 warps x 2 KB store staging
     __shared__ __align__(8) uint64_t a_full[L0_STAGES], a_empty[L0_STAGES], tfull_bar[4], tempty_bar[4];
     __shared__ uint32_t tmem_base_s;
 
@@ -806,11 +806,11 @@ __global__ void __launch_bounds__(L0_THREADS, 1) l0_tc_kernel(const L0TcArgs a) 
         // ===== epilogue: 16 warps, four per TMEM lane quarter; warp `wc` of a quarter owns columns [32 wc, 32 wc + 32) =====
         const int quarter = warp & 3, ew = warp - (L0_BUILD_WARPS + 1), wc = ew >> 2;
         const int cc = wc * 32;
-        uint4 *stg = reinterpret_cast<uint4 *>(stage_out + (size_t)ew * 1024);
+        uint4 *stg = reinterpret_cast<uint4 *>(stage_out + (size_t)ew * 2048);
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)cc;
         const long long P = (long long)a.PB * 128;
         const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
-        const int sw = (lane >> 2) & 1;
+        const int sw = (lane >> 1) & 3;
         uint4 gq[4], bq[4];
         int pb = pb_begin, s = s_begin, cur_pb = -1;
         float2 st_next = nt > 0 ? __ldg(a.stats + s) : make_float2(0.f, 1.f);
@@ -842,36 +842,31 @@ __global__ void __launch_bounds__(L0_THREADS, 1) l0_tc_kernel(const L0TcArgs a) 
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tempty_bar[slot]);
 #pragma unroll
-            for (int hh = 0; hh < 2; hh++) {
-                uint32_t pk[8];
+            for (int q = 0; q < 4; q++) {
+                const uint4 g4 = gq[q], b4 = bq[q];
+                const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w};
+                const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
+                uint32_t pk[4];
 #pragma unroll
-                for (int q = 0; q < 2; q++) {
-                    const uint4 g4 = gq[2 * hh + q], b4 = bq[2 * hh + q];
-                    const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w};
-                    const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        const int c = 8 * q + 2 * e;
-                        const float a0 = __uint_as_float(hh ? vb[c] : va[c]), a1 = __uint_as_float(hh ? vb[c + 1] : va[c + 1]);
-                        __nv_bfloat162 y2 = __hfma2(__floats2bfloat162_rn(fmaf(a0, rstd, nmr), fmaf(a1, rstd, nmr)),
-                                                    *reinterpret_cast<const __nv_bfloat162 *>(&gw[e]),
-                                                    *reinterpret_cast<const __nv_bfloat162 *>(&bw[e]));
-                        y2 = __hmax2(y2, zero2);
-                        pk[4 * q + e] = *reinterpret_cast<const uint32_t *>(&y2);
-                    }
+                for (int e = 0; e < 4; e++) {
+                    const int c = 8 * (q & 1) + 2 * e;
+                    const float a0 = __uint_as_float(q >= 2 ? vb[c] : va[c]), a1 = __uint_as_float(q >= 2 ? vb[c + 1] : va[c + 1]);
+                    __nv_bfloat162 y2 = __hfma2(__floats2bfloat162_rn(fmaf(a0, rstd, nmr), fmaf(a1, rstd, nmr)),
+                                                *reinterpret_cast<const __nv_bfloat162 *>(&gw[e]),
+                                                *reinterpret_cast<const __nv_bfloat162 *>(&bw[e]));
+                    y2 = __hmax2(y2, zero2);
+                    pk[e] = *reinterpret_cast<const uint32_t *>(&y2);
                 }
-                stg[lane * 2 + (0 ^ sw)] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                stg[lane * 2 + (1 ^ sw)] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                __syncwarp();
-#pragma unroll
-                for (int r0 = 0; r0 < 32; r0 += 16) {
-                    const int r = r0 + (lane >> 1), ch = lane & 1;
-                    const uint4 val = stg[r * 2 + (ch ^ ((r >> 2) & 1))];
-                    *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(a.X) +
-                                               ((mrow0 + r) * 128 + cc + hh * 16) * 2 + ch * 16) = val;
-                }
-                __syncwarp();
+                stg[lane * 4 + (q ^ sw)] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
+            __syncwarp();
+#pragma unroll
+            for (int r0 = 0; r0 < 32; r0 += 8) {
+                const int r = r0 + (lane >> 2), ch = lane & 3;
+                const uint4 val = stg[r * 4 + (ch ^ ((r >> 1) & 3))];
+                *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(a.X) + ((mrow0 + r) * 128 + cc) * 2 + ch * 16) = val;
+            }
+            __syncwarp();
             pb = pbn; s = sn;
         }
     }
@@ -986,6 +981,10 @@ int launch_tc_ln(Model *m, const TcConv &tc, const LnGeom &lg, const TcLnArgs &a
         args.b_res = 0;
     }
     if (st > 12) st = 12;
+    if (const char *e = getenv("PFANN_B200_LN_STAGES")) {  // experiment knob: shallower ring
+        const size_t cap = (size_t)atoi(e);
+        if (cap >= 2 && cap < st) st = cap;
+    }
     PF_CHECK(st >= 2, PFANN_ERR_UNSUPPORTED, "fused conv+LN: no room for a shared-memory ring");
     args.n_stages = (int)st;
     const size_t smem = st * (A + (args.b_res ? 0 : B)) + (args.b_res ? bres : 0) + fixed + 1024;
@@ -1198,7 +1197,7 @@ int tc_l0(Model *m, const float *mel, const float2 *stats, __nv_bfloat16 *X, int
     a.nb = nb; a.F = g.Fi; a.T = g.Ti; a.To = g.To; a.ntaps = g.ntaps;
     for (int j = 0; j < 3; j++) a.off[j] = j < g.ntaps ? g.tap_off[j] : 0;
     a.PB = g.Fo * g.To / 128;
-    const size_t smem = (size_t)L0_STAGES * 16384 + 16384 + 16 * 1024 + 1024;
+    const size_t smem = (size_t)L0_STAGES * 16384 + 16384 + 16 * 2048 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         PF_CUDA(cudaFuncSetAttribute(l0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
