@@ -386,6 +386,22 @@ def bench_match(torch, args, world, rank, local, device, barrier, max_over_ranks
     detail = _lib.profile_detail(local)
     _lib.profile(local, False)
     acc = float(np.mean((res['song'] == qsong.cpu().numpy()) & (res['time'] == qoff.cpu().numpy() * 0.5)))
+    # per-file regime (matcher.py:136 issues one search per query file: 19 vectors per database pass): the scan is
+    # HBM-bound there -- report it against the measured copy bandwidth (north_star: >= 70 % of the HBM roofline)
+    q1 = q[:q_len].cpu().numpy()
+    for _ in range(3):
+        db.search(q1, k)
+    _lib.profile(local, True)
+    for _ in range(10):
+        db.search(q1, k)
+    _lib.profile_read(local)
+    d1 = _lib.profile_detail(local)
+    _lib.profile(local, False)
+    pf_ms = d1.get('knn_scan_full', (0.0, 1))[0] / max(d1.get('knn_scan_full', (0.0, 1))[1], 1)
+    pf_all = sum(v[0] for v in d1.values()) / 10.0
+    per_file = {'queries_per_pass': q_len, 'scan_ms': pf_ms, 'search_ms_all_kernels': pf_all,
+                'scan_gbs': (r1 - r0) * d * 2 / (pf_ms / 1e3) / 1e9 if pf_ms else None,
+                'frac_of_hbm_peak': ((r1 - r0) * d * 2 / (pf_ms / 1e3) / 1e9) / pk['hbm_gbs'] if pf_ms else None}
     # the same through the single-call host API with host buffers (only meaningful at world == 1)
     e2e = None
     if world == 1:
@@ -431,6 +447,7 @@ def bench_match(torch, args, world, rank, local, device, barrier, max_over_ranks
             'knn_scan': {'launches': passes, 'ms': scan_ms,
                          'tflops': (2.0 * nq * q_len * rows_local * d) / (scan_ms / 1000.0) / 1e12 if scan_ms else None,
                          'frac_of_bf16_peak': ((2.0 * nq * q_len * rows_local * d) / (scan_ms / 1000.0) / 1e12) / pk['tf_sustained'] if scan_ms else None},
+            'per_file_regime': per_file,
             'gpu_launches': int(_lib.launches(local) - l0), 'cpu_baseline': cpu}
 
 
