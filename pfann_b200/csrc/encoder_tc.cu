@@ -300,10 +300,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
 // Four 128 x 128 fp32 accumulators rotate through TMEM.  Per tile i the sixteen epilogue warps run
 //   pass 1 (tile i)     tcgen05.ld, + bias, per-warp (sum, sum of squares); each warp publishes its pair as ONE
 //                       64-bit word into a global exchange table (all-ones = not written yet);
-//   pass 2 (tile i - 2) tcgen05.ld again, normalise with the sample statistics, affine, ReLU, bf16, coalesced store;
+//   pass 2 (tile i - 3) tcgen05.ld again, normalise with the sample statistics, affine, ReLU, bf16, coalesced store;
 // one more "statistics" warp polls the table until the P * 16 words of a sample group are there, adds them in a fixed
 // order (double) and hands (mean, rstd) to pass 2 through shared memory.  The exchange latency (a few microseconds
-// through L2) is hidden behind two tiles of work, the tensor core runs one to two tiles ahead of the epilogue, and no
+// through L2) is hidden behind three tiles of work, the tensor core runs one tile ahead of the epilogue, and no
 // cluster launch is needed: the only requirement is that the <= 148 CTAs are co-resident (cooperative launch).
 // A poll that does not complete (never observed; would mean a peer CTA is not running) times out, raises a flag
 // and lets the kernel finish instead of hanging the GPU.
@@ -326,7 +326,7 @@ struct TcLnArgs {
 constexpr int LN_EPI_WARPS = 16;  // four per TMEM lane quarter, 32 columns each
 constexpr int LN_THREADS = 32 * (3 + LN_EPI_WARPS);  // warp 0 TMA producer, 1 MMA issuer, 2-17 epilogue, 18 statistics
 constexpr int LN_BN = 128;        // accumulator width: 4 x 128 columns = all of TMEM
-constexpr int LN_DEFER = 2;       // pass 2 runs this many tiles behind pass 1
+constexpr int LN_DEFER = 3;       // pass 2 runs this many tiles behind pass 1 (4 TMEM slots: 3 waiting + 1 accumulating)
 constexpr uint32_t LN_GB_BYTES = 128 * 128 * 2 * 2;
 constexpr unsigned long long LN_UNSET = ~0ull;
 
@@ -490,9 +490,10 @@ __global__ void __launch_bounds__(LN_THREADS, 1) conv_ln_tc_kernel(const __grid_
         }
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)cc;
         long long pc[4] = {0, 0, 0, 0};
-        // Half of the warps run pass 2 before pass 1 inside an iteration: TMEM reads (64 B/cycle/SM, the scarcest
-        // resource of this epilogue) of one half then overlap the arithmetic and stores of the other half.
-        const int p2_first = wc & 1;
+        // Inside an iteration pass 2 (tile i - 3) runs BEFORE pass 1 (tile i): its TMEM slot is the one the tensor
+        // core needs for tile i + 1, so it is released first, and the statistics exchange of a tile gets three tile
+        // times to complete (the CTAs of a lane drift against each other; with two it cost ~20 % of the epilogue).
+        const int p2_first = 1;
         for (int hs = 0; hs < 2 * (nt_cta + LN_DEFER); hs++) {
             const int i = hs >> 1;
             const bool do_p1 = ((hs & 1) ^ p2_first) == 0;
