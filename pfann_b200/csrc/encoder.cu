@@ -268,11 +268,7 @@ __global__ void __launch_bounds__(256) l0_moments_kernel(const L0Args a, const M
     __shared__ double red[8];
     const float *m = a.mel + (long long)blockIdx.x * a.F * a.T;
     const int P = a.F * a.To;
-    // per-thread partial sums over its <= 16 positions in fp32 (fp64 runs at 1/64 rate on this part and the kernel
-    // was bound by it); everything across threads and the final statistics stay in double
-    float Sf[3] = {0.f, 0.f, 0.f}, Rf[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // R: 00 01 02 11 12 22
-    double S[3] = {0, 0, 0}, R[6] = {0, 0, 0, 0, 0, 0};
-    int cnt = 0;
+    double S[3] = {0, 0, 0}, R[6] = {0, 0, 0, 0, 0, 0};  // R: 00 01 02 11 12 22
     for (int p = threadIdx.x; p < P; p += blockDim.x) {
         const int f = p / a.To, to = p - f * a.To;
         float v[3] = {0.f, 0.f, 0.f};
@@ -280,17 +276,10 @@ __global__ void __launch_bounds__(256) l0_moments_kernel(const L0Args a, const M
             const int t = 2 * to + a.off[j];
             if (t >= 0 && t < a.T) v[j] = m[f * a.T + t];
         }
-        Sf[0] += v[0]; Sf[1] += v[1]; Sf[2] += v[2];
-        Rf[0] = fmaf(v[0], v[0], Rf[0]); Rf[1] = fmaf(v[0], v[1], Rf[1]); Rf[2] = fmaf(v[0], v[2], Rf[2]);
-        Rf[3] = fmaf(v[1], v[1], Rf[3]); Rf[4] = fmaf(v[1], v[2], Rf[4]); Rf[5] = fmaf(v[2], v[2], Rf[5]);
-        if (++cnt == 16) {  // flush: keeps every fp32 partial sum short
-            for (int i = 0; i < 3; i++) S[i] += (double)Sf[i], Sf[i] = 0.f;
-            for (int i = 0; i < 6; i++) R[i] += (double)Rf[i], Rf[i] = 0.f;
-            cnt = 0;
-        }
+        S[0] += v[0]; S[1] += v[1]; S[2] += v[2];
+        R[0] += (double)v[0] * v[0]; R[1] += (double)v[0] * v[1]; R[2] += (double)v[0] * v[2];
+        R[3] += (double)v[1] * v[1]; R[4] += (double)v[1] * v[2]; R[5] += (double)v[2] * v[2];
     }
-    for (int i = 0; i < 3; i++) S[i] += (double)Sf[i];
-    for (int i = 0; i < 6; i++) R[i] += (double)Rf[i];
     for (int i = 0; i < 3; i++) S[i] = block_sum_d(S[i], red);
     for (int i = 0; i < 6; i++) R[i] = block_sum_d(R[i], red);
     if (threadIdx.x == 0) {
