@@ -447,79 +447,91 @@ int db_search_dev(Db *db, const float *q, int64_t Q, int k, float *dist, int64_t
     while (cpad < (S_keys < chunk ? S_keys : chunk)) cpad <<= 1;
     int P2 = 1;
     while (P2 < nchunks * k) P2 <<= 1;
-    const int64_t ngroups = (Q + group - 1) / group;
-    PF_TRY(db->thr.ensure(sizeof(float) * group));
-    PF_TRY(db->qnorm.ensure(sizeof(float) * group));
-    PF_TRY(db->cnt.ensure(sizeof(int) * group));
-    PF_TRY(db->cand.ensure(sizeof(uint32_t) * (size_t)group * cap));
-    PF_TRY(db->cand_v.ensure(sizeof(uint32_t) * (size_t)group * cap));
-    PF_TRY(db->sample.ensure(sizeof(float) * (size_t)group * S_keys));
-    PF_TRY(db->rr_keys.ensure(sizeof(uint32_t) * (size_t)group * nchunks * k));
+    // A "super-group" = up to SG database passes (SG * group queries) that share ONE launch of each small kernel
+    // (k-th selection of the sample, candidate ranking + exact rescoring): on a shard of a million rows a pass is
+    // ~90 us and the launch gaps of the small kernels would otherwise cost as much again.
+    const int SG = 4, sgroup = SG * group;
+    const int64_t ngroups = (Q + sgroup - 1) / sgroup;
+    PF_TRY(db->thr.ensure(sizeof(float) * sgroup));
+    PF_TRY(db->qnorm.ensure(sizeof(float) * sgroup));
+    PF_TRY(db->cnt.ensure(sizeof(int) * sgroup));
+    PF_TRY(db->cand.ensure(sizeof(uint32_t) * (size_t)sgroup * cap));
+    PF_TRY(db->cand_v.ensure(sizeof(uint32_t) * (size_t)sgroup * cap));
+    PF_TRY(db->sample.ensure(sizeof(float) * (size_t)sgroup * S_keys));
+    PF_TRY(db->rr_keys.ensure(sizeof(uint32_t) * (size_t)sgroup * nchunks * k));
     PF_TRY(db->flags.ensure(sizeof(int) * (size_t)(ngroups + 4)));
     const size_t sel_smem = (size_t)cap * 8 + (size_t)d * 4;
     PF_CUDA(cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
     PF_CUDA(cudaFuncSetAttribute(knn_scan_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)((QG * d + SCAN_ROWS * (d + 4)) * 4)));
-    // 1. threshold pre-pass on the first S rows
-    auto prepass = [&](const float *qg, int Qg) -> int {
-        PF_TRY(scan(db, tc, qg, Qg, 0, S, 0, db->sample.as<float>(), S_keys, nullptr, nullptr, nullptr, nullptr, 0));
+    float *thr = db->thr.as<float>();
+    int *cnt = db->cnt.as<int>();
+    uint32_t *cand = db->cand.as<uint32_t>(), *cand_v = db->cand_v.as<uint32_t>();
+    // 1. threshold pre-pass on the first S rows (one scan per `group` queries, one k-th selection for all)
+    auto prepass = [&](const float *qs, int Qs) -> int {
+        for (int g0 = 0; g0 < Qs; g0 += group) {
+            const int Qg = (Qs - g0) < group ? (Qs - g0) : group;
+            PF_TRY(scan(db, tc, qs + (int64_t)g0 * d, Qg, 0, S, 0, db->sample.as<float>() + (size_t)g0 * S_keys, S_keys,
+                        nullptr, nullptr, nullptr, nullptr, 0));
+        }
         ProfScope ps(db->ctx, K_KNN_SELECT, 37);
-        knn_kth_chunk_kernel<<<dim3(Qg, nchunks), 256, (size_t)(cpad > 256 ? cpad : 256) * 4, st>>>(
+        knn_kth_chunk_kernel<<<dim3(Qs, nchunks), 256, (size_t)(cpad > 256 ? cpad : 256) * 4, st>>>(
             db->sample.as<float>(), S_keys, S_keys, chunk, cpad, k, db->rr_keys.as<uint32_t>());
-        knn_kth_merge_kernel<<<Qg, 256, (size_t)P2 * 4, st>>>(db->rr_keys.as<uint32_t>(), nchunks * k, P2, S_keys, qg, d, k,
-                                                             eps_rel, db->max_norm, db->thr.as<float>(),
-                                                             db->qnorm.as<float>());
+        knn_kth_merge_kernel<<<Qs, 256, (size_t)P2 * 4, st>>>(db->rr_keys.as<uint32_t>(), nchunks * k, P2, S_keys, qs, d, k,
+                                                             eps_rel, db->max_norm, thr, db->qnorm.as<float>());
         db->ctx->launches += 2;
         PF_CUDA(cudaGetLastError());
         return PFANN_OK;
     };
-    // 2. filtered scan of the whole shard, 3. ranking + exact rescoring; *flag += 1 per overflowed query
-    auto filtered = [&](const float *qg, int Qg, int64_t q0, int *flag) -> int {
-        PF_CUDA(cudaMemsetAsync(db->cnt.p, 0, sizeof(int) * Qg, st));
-        PF_TRY(scan(db, tc, qg, Qg, 0, db->n, 1, nullptr, 0, db->thr.as<float>(), db->cnt.as<int>(),
-                    db->cand.as<uint32_t>(), db->cand_v.as<uint32_t>(), cap));
+    // 2. filtered scans of the whole shard, 3. ranking + exact rescoring; *flag += 1 per overflowed query
+    auto filtered = [&](const float *qs, int Qs, int64_t q0, int *flag) -> int {
+        PF_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * Qs, st));
+        for (int g0 = 0; g0 < Qs; g0 += group) {
+            const int Qg = (Qs - g0) < group ? (Qs - g0) : group;
+            PF_TRY(scan(db, tc, qs + (int64_t)g0 * d, Qg, 0, db->n, 1, nullptr, 0, thr + g0, cnt + g0,
+                        cand + (size_t)g0 * cap, cand_v + (size_t)g0 * cap, cap));
+        }
         ProfScope ps(db->ctx, K_KNN_SELECT, 38);
-        knn_select_kernel<<<Qg, 256, sel_smem, st>>>(db->emb32, d, db->id_base, qg, db->cnt.as<int>(),
-                                                     db->cand.as<uint32_t>(), db->cand_v.as<uint32_t>(), cap, k,
-                                                     eps_rel, db->max_norm, db->qnorm.as<float>(), db->thr.as<float>(),
-                                                     dist + q0 * k, labels + q0 * k, flag);
+        knn_select_kernel<<<Qs, 256, sel_smem, st>>>(db->emb32, d, db->id_base, qs, cnt, cand, cand_v, cap, k, eps_rel,
+                                                     db->max_norm, db->qnorm.as<float>(), thr, dist + q0 * k,
+                                                     labels + q0 * k, flag);
         db->ctx->launches++;
         PF_CUDA(cudaGetLastError());
         return PFANN_OK;
     };
-    // Every group runs once without any host synchronisation; the (rare) groups whose candidate lists overflowed
-    // are found with ONE read-back of the per-group flags and redone with tightened thresholds.
+    // Every super-group runs once without any host synchronisation; the (rare) ones with an overflowed candidate
+    // list are found with ONE read-back of the flags and redone with tightened thresholds.
     int *flags = db->flags.as<int>();
     PF_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)(ngroups + 4), st));
     for (int64_t g = 0; g < ngroups; g++) {
-        const int64_t q0 = g * group;
-        const int Qg = (int)((Q - q0) < group ? (Q - q0) : group);
-        PF_TRY(prepass(q + q0 * d, Qg));
-        PF_TRY(filtered(q + q0 * d, Qg, q0, flags + g));
+        const int64_t q0 = g * sgroup;
+        const int Qs = (int)((Q - q0) < sgroup ? (Q - q0) : sgroup);
+        PF_TRY(prepass(q + q0 * d, Qs));
+        PF_TRY(filtered(q + q0 * d, Qs, q0, flags + g));
     }
     std::vector<int> hflags((size_t)ngroups);
     PF_CUDA(cudaMemcpyAsync(hflags.data(), flags, sizeof(int) * (size_t)ngroups, cudaMemcpyDeviceToHost, st));
     PF_CUDA(cudaStreamSynchronize(st));
     for (int64_t g = 0; g < ngroups; g++) {
         if (hflags[g] == 0) continue;
-        const int64_t q0 = g * group;
-        const int Qg = (int)((Q - q0) < group ? (Q - q0) : group);
-        const float *qg = q + q0 * d;
-        PF_TRY(prepass(qg, Qg));
+        const int64_t q0 = g * sgroup;
+        const int Qs = (int)((Q - q0) < sgroup ? (Q - q0) : sgroup);
+        const float *qs = q + q0 * d;
+        PF_TRY(prepass(qs, Qs));
         bool done = false;
         for (int iter = 0; iter < 5 && !done; iter++) {  // iteration 0 repeats the overflow and tightens the thresholds
             PF_CUDA(cudaMemsetAsync(flags + g, 0, sizeof(int), st));
-            PF_TRY(filtered(qg, Qg, q0, flags + g));
+            PF_TRY(filtered(qs, Qs, q0, flags + g));
             int overflow = 0;
             PF_CUDA(cudaMemcpyAsync(&overflow, flags + g, sizeof(int), cudaMemcpyDeviceToHost, st));
             PF_CUDA(cudaStreamSynchronize(st));
             done = (overflow == 0);
         }
         if (!done) {
-            // degenerate score distribution (e.g. massive exact ties): exact brute force for this group
+            // degenerate score distribution (e.g. massive exact ties): exact brute force for this super-group
             const size_t smem = (size_t)(k + 256) * 8 + (size_t)d * 4;
             PF_CUDA(cudaFuncSetAttribute(knn_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            knn_exact_kernel<<<Qg, 256, smem, st>>>(db->emb32, db->n, d, db->id_base, qg, k, dist + q0 * k,
+            knn_exact_kernel<<<Qs, 256, smem, st>>>(db->emb32, db->n, d, db->id_base, qs, k, dist + q0 * k,
                                                     labels + q0 * k);
             db->ctx->launches++;
             PF_CUDA(cudaGetLastError());
