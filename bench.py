@@ -265,7 +265,7 @@ def main():
 
     # Dominant kernel: conv_ln_tc_kernel, the fused conv + LayerNorm + ReLU of convolutions 1-7 (7 launches per
     # chunk).  Its big layers move 1.5 MB of activations per segment for 0.2 GFLOP: HBM-bound (ncu: DRAM 78 %,
-    # tensor pipe 32 %, profiles/r01/v4).  Algorithmic bytes = every input and output activation once (bf16).
+    # tensor pipe 32 %, profiles/r01/v5).  Algorithmic bytes = every input and output activation once (bf16).
     fused_ms = sum(detail.get('conv%d' % i, (0.0, 0))[0] for i in range(1, 8))
     fused_n = sum(detail.get('conv%d' % i, (0.0, 0))[1] for i in range(1, 8))
     conv_ms, conv_n = prof['conv_tc']
@@ -278,7 +278,7 @@ def main():
                 'frac': achieved / pk['hbm_gbs'],
                 'traffic': CONVLN_NCU_TRAFFIC_PER_SEG * n_seg * args.steps / max(fused_n, 1),
                 'traffic_source': 'ncu dram__bytes_read+write of the 7 launches of one 4096-segment chunk, per segment '
-                                  '(profiles/r01/v4/ncu_convln.csv), scaled to the average launch of this run',
+                                  '(profiles/r01/v5/ncu_convln.csv), scaled to the average launch of this run',
                 'algorithmic_bytes_per_launch': bytes_alg / max(fused_n, 1),
                 'peak_source': pk['source'],
                 'launches': fused_n, 'avg_launch_ms': fused_ms / max(fused_n, 1),
