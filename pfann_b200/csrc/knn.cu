@@ -432,8 +432,10 @@ int db_search_dev(Db *db, const float *q, int64_t Q, int k, float *dist, int64_t
     const float eps_rel = (tc ? 4.0e-3f : 0.f) + fmaxf(1.0e-5f, 1.2e-7f * (float)d);
     const int cap = db->cand_cap;
     const int group = tc ? (d <= 128 ? 256 : 128) : QG * 4;  // queries per database pass
-    // sample size: aim at ~1024 rows above the threshold (k * n / S ~ 1024), within [sample_rows, 256 Ki]
-    int64_t want = (int64_t)k * db->n / 1024;
+    // sample size: aim at ~256 rows above the threshold (k * n / S ~ 256), within [sample_rows, 256 Ki].  Every
+    // survivor costs ~100 instructions on the filter's hit path (measured: 360 k survivors per 256-query pass doubled
+    // the scan time of a 1.25 M-row shard), a sampled row costs one more tile of the cheap pre-pass.
+    int64_t want = (int64_t)k * db->n / 256;
     if (want < db->sample_rows) want = db->sample_rows;
     if (want > 262144) want = 262144;
     const int chunk = 8192;  // one kth-select CTA sorts this many sample scores in shared memory

@@ -20,7 +20,7 @@ db = Database.from_arrays(emb, key, {'top_k': 20}, 0.5, device=0)
 del emb
 prof = torch.zeros((148, 8), dtype=torch.int64, device=dev)
 os.environ['PFANN_KNN_PROF_PTR'] = str(prof.data_ptr())
-for Q in (19, 128):
+for Q in (19, 256):
     q = torch.randn((Q, 128), device=dev)
     q /= q.norm(dim=1, keepdim=True)
     D = torch.empty((Q, 20), device=dev)
