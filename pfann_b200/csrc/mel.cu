@@ -183,11 +183,16 @@ __global__ void __launch_bounds__(NTHREADS, 2) mel_kernel(const MelArgs a) {
     float2 twl[16];  // W_512^(lane * k1) for the register holding k1 = bitrev4(i)
 #pragma unroll
     for (int i = 0; i < 16; i++) twl[i] = __ldg(a.tw + ((2 * lane * bitrev4(i)) & (NFFT - 1)));
-    float2 wst[5];   // cross-lane stage twiddles W_(2 half)^(lane & (half-1)), half = 16,8,4,2,1
+    // cross-lane stage twiddles W_(2 half)^(lane & (half-1)), half = 16,8,4,2,1 -- for the lanes that keep the
+    // difference; the lanes that keep the sum multiply by 1, so one code path serves both (sgn = -1 / +1)
+    float2 wst[5];
+    float sgn[5];
 #pragma unroll
     for (int s = 0; s < 5; s++) {
         const int half = 16 >> s;
-        wst[s] = __ldg(a.tw + (lane & (half - 1)) * (NFFT / (2 * half)));
+        const bool upper = (lane & half) != 0;
+        wst[s] = upper ? __ldg(a.tw + (lane & (half - 1)) * (NFFT / (2 * half))) : make_float2(1.f, 0.f);
+        sgn[s] = upper ? -1.f : 1.f;
     }
     const int k2 = (int)(__brev((unsigned)lane) >> 27);
     float2 *zw = zbuf + warp * ZBUF_F2;
@@ -211,15 +216,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) mel_kernel(const MelArgs a) {
 #pragma unroll
         for (int s = 0; s < 5; s++) {
             const int half = 16 >> s;
-            const bool upper = (lane & half) != 0;
 #pragma unroll
             for (int i = 0; i < 16; i++) {
                 float2 p;
                 p.x = __shfl_xor_sync(0xffffffffu, v[i].x, half);
                 p.y = __shfl_xor_sync(0xffffffffu, v[i].y, half);
-                const float2 sum = cadd(v[i], p);
-                const float2 dif = cmul(csub(p, v[i]), wst[s]);
-                v[i] = upper ? dif : sum;
+                // lower lane: (p + v) * 1, upper lane: (p - v) * w -- the same values as computing both and
+                // selecting (x * 1 - y * 0 == x), at half the arithmetic
+                const float2 t = make_float2(fmaf(sgn[s], v[i].x, p.x), fmaf(sgn[s], v[i].y, p.y));
+                v[i] = cmul(t, wst[s]);
             }
         }
         // Z[k1 + 16 k2] with k1 = bitrev4(i), k2 = bitrev5(lane)
