@@ -38,23 +38,19 @@ def merge_topk(dists, labels, k):
 def combine_best(scores, songs, times):
     """[G][nq] raw per-shard winners -> global winner per query: score desc, then lower song id; then the
     reference's zero floor (it reads the answer out of the zero-initialised table, database.py:176,190)."""
-    scores, songs, times = np.asarray(scores), np.asarray(songs), np.asarray(times)
+    scores, songs, times = np.asarray(scores, np.float32), np.asarray(songs, np.int64), np.asarray(times, np.float32)
     nq = scores.shape[1]
-    out_s = np.zeros(nq, np.float32)
-    out_g = np.full(nq, -1, np.int32)
-    out_t = np.zeros(nq, np.float32)
-    for q in range(nq):
-        best = -1
-        for g in range(scores.shape[0]):
-            if songs[g, q] < 0:
-                continue
-            if best < 0 or scores[g, q] > scores[best, q] or (scores[g, q] == scores[best, q]
-                                                               and songs[g, q] < songs[best, q]):
-                best = g
-        if best >= 0:
-            out_g[q] = songs[best, q]
-            if scores[best, q] > 0:
-                out_s[q], out_t[q] = scores[best, q], times[best, q]
+    valid = songs >= 0
+    has = valid.any(axis=0)
+    sc = np.where(valid, scores, -np.inf).astype(np.float64)
+    top = sc.max(axis=0)                                            # best score among the shards that have a candidate
+    tied = valid & (sc == top[None, :])
+    best = np.where(tied, songs, np.iinfo(np.int64).max).argmin(axis=0)   # lowest song id among the tied shards
+    cols = np.arange(nq)
+    out_g = np.where(has, songs[best, cols], -1).astype(np.int32)
+    pos = has & (scores[best, cols] > 0)
+    out_s = np.where(pos, scores[best, cols], 0).astype(np.float32)
+    out_t = np.where(pos, times[best, cols], 0).astype(np.float32)
     return out_s, out_g, out_t
 
 
