@@ -104,9 +104,10 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_scan_tc_kernel(const __gri
         const int kb = ch >> 3, c = ch & 7;
         uint4 pk = make_uint4(0u, 0u, 0u, 0u);
         if (n < a.Qg) {
-            const float *src = a.q + (long long)n * a.d + ch * 8;
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(src[0], src[1]), p1 = __floats2bfloat162_rn(src[2], src[3]);
-            __nv_bfloat162 p2 = __floats2bfloat162_rn(src[4], src[5]), p3 = __floats2bfloat162_rn(src[6], src[7]);
+            const float4 *src = reinterpret_cast<const float4 *>(a.q + (long long)n * a.d + ch * 8);  // d % 64 == 0
+            const float4 lo = __ldg(src), hi = __ldg(src + 1);
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(lo.x, lo.y), p1 = __floats2bfloat162_rn(lo.z, lo.w);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(hi.x, hi.y), p3 = __floats2bfloat162_rn(hi.z, hi.w);
             pk.x = *reinterpret_cast<uint32_t *>(&p0);
             pk.y = *reinterpret_cast<uint32_t *>(&p1);
             pk.z = *reinterpret_cast<uint32_t *>(&p2);
