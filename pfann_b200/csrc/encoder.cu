@@ -268,7 +268,11 @@ __global__ void __launch_bounds__(256) l0_moments_kernel(const L0Args a, const M
     __shared__ double red[8];
     const float *m = a.mel + (long long)blockIdx.x * a.F * a.T;
     const int P = a.F * a.To;
-    double S[3] = {0, 0, 0}, R[6] = {0, 0, 0, 0, 0, 0};  // R: 00 01 02 11 12 22
+    // Same arithmetic as the moments block at the end of mel_kernel (mel.cu), so that the fused extract path and
+    // mel -> model give identical statistics: fp32 partial sums over 16 positions per thread, double across threads.
+    float Sf[3] = {0.f, 0.f, 0.f}, Rf[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // R: 00 01 02 11 12 22
+    double S[3] = {0, 0, 0}, R[6] = {0, 0, 0, 0, 0, 0};
+    int cnt = 0;
     for (int p = threadIdx.x; p < P; p += blockDim.x) {
         const int f = p / a.To, to = p - f * a.To;
         float v[3] = {0.f, 0.f, 0.f};
@@ -276,10 +280,17 @@ __global__ void __launch_bounds__(256) l0_moments_kernel(const L0Args a, const M
             const int t = 2 * to + a.off[j];
             if (t >= 0 && t < a.T) v[j] = m[f * a.T + t];
         }
-        S[0] += v[0]; S[1] += v[1]; S[2] += v[2];
-        R[0] += (double)v[0] * v[0]; R[1] += (double)v[0] * v[1]; R[2] += (double)v[0] * v[2];
-        R[3] += (double)v[1] * v[1]; R[4] += (double)v[1] * v[2]; R[5] += (double)v[2] * v[2];
+        Sf[0] += v[0]; Sf[1] += v[1]; Sf[2] += v[2];
+        Rf[0] = fmaf(v[0], v[0], Rf[0]); Rf[1] = fmaf(v[0], v[1], Rf[1]); Rf[2] = fmaf(v[0], v[2], Rf[2]);
+        Rf[3] = fmaf(v[1], v[1], Rf[3]); Rf[4] = fmaf(v[1], v[2], Rf[4]); Rf[5] = fmaf(v[2], v[2], Rf[5]);
+        if (++cnt == 16) {
+            for (int i = 0; i < 3; i++) S[i] += (double)Sf[i], Sf[i] = 0.f;
+            for (int i = 0; i < 6; i++) R[i] += (double)Rf[i], Rf[i] = 0.f;
+            cnt = 0;
+        }
     }
+    for (int i = 0; i < 3; i++) S[i] += (double)Sf[i];
+    for (int i = 0; i < 6; i++) R[i] += (double)Rf[i];
     for (int i = 0; i < 3; i++) S[i] = block_sum_d(S[i], red);
     for (int i = 0; i < 6; i++) R[i] = block_sum_d(R[i], red);
     if (threadIdx.x == 0) {
@@ -296,6 +307,28 @@ __global__ void __launch_bounds__(256) l0_moments_kernel(const L0Args a, const M
         if (var < 0.0) var = 0.0;
         stats[blockIdx.x] = make_float2((float)mean, (float)(1.0 / sqrt(var + 1e-5)));
     }
+}
+
+// Same statistics from moments the mel kernel already reduced while the tile was in its shared memory (fused
+// extract path): one thread per sample.
+__global__ void l0_stats_kernel(const double *moments /*[nb][9]*/, const Model::L0Consts k, double P, double C,
+                                float2 *stats, int nb) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    const double *mo = moments + (long long)b * 9;
+    const double S[3] = {mo[0], mo[1], mo[2]};
+    const double Rm[3][3] = {{mo[3], mo[4], mo[5]}, {mo[4], mo[6], mo[7]}, {mo[5], mo[7], mo[8]}};
+    double s1 = P * k.Bsum, s2 = P * k.B2;
+    for (int j = 0; j < 3; j++) {
+        s1 += k.A[j] * S[j];
+        s2 += 2.0 * k.H[j] * S[j];
+        for (int jj = 0; jj < 3; jj++) s2 += k.G[j][jj] * Rm[j][jj];
+    }
+    const double N = P * C;
+    const double mean = s1 / N;
+    double var = s2 / N - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[b] = make_float2((float)mean, (float)(1.0 / sqrt(var + 1e-5)));
 }
 
 // thread = (PP consecutive output positions along time, group of 8 channels); it loops over the samples of its
@@ -762,7 +795,11 @@ int launch_l0_fused(Model *m, const float *mel, ActT *X, int nb) {
     a.mel = mel; a.F = g.Fi; a.T = g.Ti; a.To = g.To; a.ntaps = g.ntaps; a.C = g.Co;
     for (int j = 0; j < 3; j++) a.off[j] = g.tap_off[j];
     cudaStream_t st = m->ctx->stream;
-    {
+    if (m->cur_moments != nullptr) {
+        ProfScope ps(m->ctx, K_LN, 34);
+        l0_stats_kernel<<<cdiv(nb, 256), 256, 0, st>>>(m->cur_moments, m->l0c, (double)g.Fi * g.To, (double)g.Co,
+                                                        m->cur_stats, nb);
+    } else {
         ProfScope ps(m->ctx, K_LN, 34);
         l0_moments_kernel<<<nb, 256, 0, st>>>(a, m->l0c, m->cur_stats);
     }
@@ -915,12 +952,14 @@ namespace {
 namespace pfann {
 
 // device-pointer forward used by the C-ABI wrappers and by extract.cu
-int model_forward_dev(Model *m, const float *mel, int64_t B, int norm, float *z) {
+// `moments` (optional, [B][9] doubles from the mel kernel) replaces the layer-0 moments pass
+int model_forward_dev(Model *m, const float *mel, int64_t B, int norm, float *z, const double *moments) {
     PF_CHECK(m->precision >= 0, PFANN_ERR_STATE, "pfann_model_forward: call pfann_model_finalize first");
     PF_TRY(plan_workspace(m));
     const long long mel_per = (long long)m->F * m->T;
     for (int64_t b0 = 0; b0 < B; b0 += m->chunk) {
         const int nb = (int)((B - b0) < m->chunk ? (B - b0) : m->chunk);
+        m->cur_moments = (moments != nullptr && m->l0_fused) ? moments + b0 * 9 : nullptr;
         if (m->precision == PFANN_PRECISION_BF16)
             PF_TRY(forward_chunk<__nv_bfloat16>(m, mel + b0 * mel_per, nb, norm, z + b0 * m->d));
         else
@@ -962,6 +1001,7 @@ void pfann_model_destroy(pfann_model *hm) {
     cudaFree(m->l0_gb16); cudaFree(m->l0_btile);
     m->ybuf.release(); m->xa.release(); m->xb.release(); m->stats.release(); m->partials.release();
     m->tapbuf.release(); m->melbuf.release(); m->zbuf.release(); m->ln_part.release(); m->ln_err.release();
+    m->mombuf.release();
     delete m;
 }
 
@@ -1125,7 +1165,7 @@ int pfann_model_forward(pfann_model *hm, const float *mel, int64_t B, int norm, 
     void *zd;
     PF_TRY(stage_input(m->ctx, 0, mel, in_b, &xd));
     PF_TRY(stage_output(m->ctx, 0, z, out_b, &zd));
-    PF_TRY(model_forward_dev(m, (const float *)xd, B, norm, (float *)zd));
+    PF_TRY(model_forward_dev(m, (const float *)xd, B, norm, (float *)zd, nullptr));
     PF_TRY(finish_output(m->ctx, 0, z, out_b));
     return is_device_ptr(z) ? PFANN_OK : tc_ln_check(m);
 }

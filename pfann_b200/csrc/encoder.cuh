@@ -62,6 +62,8 @@ struct Model {
     DevBuf ybuf, xa, xb, stats, partials, tapbuf, melbuf, zbuf;   // chunk-sized workspace ("tail" phase)
     DevBuf ln_part, ln_err;  // fused conv+LayerNorm: statistics exchange table, time-out flag
     float2 *cur_stats = nullptr, *cur_partials = nullptr;  // statistics buffers of the phase being executed
+    const double *cur_moments = nullptr;  // layer-0 moments of the chunk being executed when the mel kernel made them
+    DevBuf mombuf;                        // [chunk][9] doubles (fused extract path)
     int prof_idx = 0;      // convolution being executed (detail slot of the optional event profile)
     int tap_layer = -1;
     long long tap_numel = 0;

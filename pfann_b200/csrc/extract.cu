@@ -1,18 +1,22 @@
 // extract.cu -- stages 1+2 back to back on the device: the builder / matcher inner loop
 // (builder.py:88-99, matcher.py:110-127) and the segmenter tail that feeds it (musicdata.py:82-88).
 // The log-mel tile of a chunk never leaves HBM-resident scratch; only PCM goes in and z comes out.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "encoder.cuh"
 #include "pfann_b200.h"
 
 namespace pfann {
-int mel_forward_dev(pfann_mel *h, const float *x_dev, int64_t B, float *out_dev);
+int mel_forward_dev(pfann_mel *h, const float *x_dev, int64_t B, float *out_dev, double *moments, int m_ntaps,
+                    const int *m_off);
 int mel_forward_pcm_dev(pfann_mel *h, const int16_t *pcm_dev, int64_t n_samples, const int64_t *start_dev,
-                        const int32_t *valid_dev, int64_t B, float *out_dev);
+                        const int32_t *valid_dev, int64_t B, float *out_dev, double *moments, int m_ntaps,
+                        const int *m_off);
 Ctx *mel_ctx(pfann_mel *h);
 void mel_dims(pfann_mel *h, int *seg_len, int *n_mels, int *T);
-int model_forward_dev(Model *m, const float *mel, int64_t B, int norm, float *z);
+int model_forward_dev(Model *m, const float *mel, int64_t B, int norm, float *z, const double *moments);
 }  // namespace pfann
 
 using namespace pfann;
@@ -54,10 +58,18 @@ int pfann_extract_segments(pfann_mel *mel, pfann_model *hm, const float *x, int6
     PF_TRY(stage_output(m->ctx, 0, z, out_b, &zd));
     const size_t mel_per = (size_t)m->F * m->T;
     PF_TRY(m->melbuf.ensure(mel_per * 4 * (size_t)m->chunk));
+    // the mel kernel also reduces the 9 moments the first LayerNorm needs (taps of layer-0 conv1) while the tile is
+    // in its shared memory
+    const ConvGeom &g0 = m->conv[0].g;
+    double *mom = nullptr;
+    if (m->l0_fused && getenv("PFANN_B200_NO_MEL_MOMENTS") == nullptr) {
+        PF_TRY(m->mombuf.ensure(sizeof(double) * 9 * (size_t)m->chunk));
+        mom = m->mombuf.as<double>();
+    }
     for (int64_t b0 = 0; b0 < B; b0 += m->chunk) {
         const int64_t nb = (B - b0) < m->chunk ? (B - b0) : m->chunk;
-        PF_TRY(mel_forward_dev(mel, (const float *)xd + b0 * seg_len, nb, m->melbuf.as<float>()));
-        PF_TRY(model_forward_dev(m, m->melbuf.as<float>(), nb, norm, (float *)zd + b0 * m->d));
+        PF_TRY(mel_forward_dev(mel, (const float *)xd + b0 * seg_len, nb, m->melbuf.as<float>(), mom, g0.ntaps, g0.tap_off));
+        PF_TRY(model_forward_dev(m, m->melbuf.as<float>(), nb, norm, (float *)zd + b0 * m->d, mom));
     }
     PF_TRY(finish_output(m->ctx, 0, z, out_b));
     return is_device_ptr(z) ? PFANN_OK : tc_ln_check(m);
@@ -136,6 +148,14 @@ int pfann_extract_pcm16(pfann_mel *mel, pfann_model *hm, const int16_t *pcm, con
     }
     const size_t mel_per = (size_t)m->F * m->T;
     PF_TRY(m->melbuf.ensure(mel_per * 4 * (size_t)m->chunk));
+    // the mel kernel also reduces the 9 moments the first LayerNorm needs (taps of layer-0 conv1) while the tile is
+    // in its shared memory
+    const ConvGeom &g0 = m->conv[0].g;
+    double *mom = nullptr;
+    if (m->l0_fused && getenv("PFANN_B200_NO_MEL_MOMENTS") == nullptr) {
+        PF_TRY(m->mombuf.ensure(sizeof(double) * 9 * (size_t)m->chunk));
+        mom = m->mombuf.as<double>();
+    }
     for (int64_t b0 = 0, k = 0; b0 < B; b0 += m->chunk, k++) {
         const int64_t nb = (B - b0) < m->chunk ? (B - b0) : m->chunk;
         if (pipe_in) {
@@ -143,8 +163,8 @@ int pfann_extract_pcm16(pfann_mel *mel, pfann_model *hm, const int16_t *pcm, con
             PF_CUDA(cudaStreamWaitEvent(ctx->stream, ev_in[k], 0));
         }
         PF_TRY(mel_forward_pcm_dev(mel, (const int16_t *)pd, n_samples, (const int64_t *)sd + b0,
-                                   (const int32_t *)vd + b0, nb, m->melbuf.as<float>()));
-        PF_TRY(model_forward_dev(m, m->melbuf.as<float>(), nb, norm, (float *)zd + b0 * m->d));
+                                   (const int32_t *)vd + b0, nb, m->melbuf.as<float>(), mom, g0.ntaps, g0.tap_off));
+        PF_TRY(model_forward_dev(m, m->melbuf.as<float>(), nb, norm, (float *)zd + b0 * m->d, mom));
         if (pipe_out) {
             PF_CUDA(cudaEventRecord(ev_done[k], ctx->stream));
             PF_CUDA(cudaStreamWaitEvent(ctx->copy_out, ev_done[k], 0));

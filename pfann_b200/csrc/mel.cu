@@ -58,6 +58,10 @@ struct MelArgs {
     const float *win;
     const int *fb_start, *fb_cnt;
     const float *fb_w;
+    // optional (fused extract path): 9 moments of the log-mel tile under the taps of layer-0 conv1, so that the
+    // encoder needs no second pass over the tile for its first LayerNorm (see encoder.cu: l0_stats_kernel)
+    double *moments;         // [B][9]: S0 S1 S2 R00 R01 R02 R11 R12 R22, or nullptr
+    int m_ntaps, m_off[3];
 };
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
@@ -267,6 +271,53 @@ __global__ void __launch_bounds__(NTHREADS, 2) mel_kernel(const MelArgs a) {
         __syncwarp();
     }
     __syncthreads();
+    if (a.moments != nullptr) {
+        // per thread: fp32 partial sums over its positions (f, to), stride-2 taps along time; across threads: double
+        const int To = (a.T + 1) / 2, P = a.n_mels * To;
+        float Sf[3] = {0.f, 0.f, 0.f}, Rf[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        int cnt = 0;
+        for (int p = tid; p < P; p += NTHREADS) {
+            const int f = p / To, to = p - f * To;
+            float v[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const int t = 2 * to + a.m_off[j];
+                if (j < a.m_ntaps && t >= 0 && t < a.T) v[j] = tile[f * Tp + t];
+            }
+            Sf[0] += v[0]; Sf[1] += v[1]; Sf[2] += v[2];
+            Rf[0] = fmaf(v[0], v[0], Rf[0]); Rf[1] = fmaf(v[0], v[1], Rf[1]); Rf[2] = fmaf(v[0], v[2], Rf[2]);
+            Rf[3] = fmaf(v[1], v[1], Rf[3]); Rf[4] = fmaf(v[1], v[2], Rf[4]); Rf[5] = fmaf(v[2], v[2], Rf[5]);
+            if (++cnt == 16) {
+#pragma unroll
+                for (int i = 0; i < 3; i++) acc[i] += (double)Sf[i], Sf[i] = 0.f;
+#pragma unroll
+                for (int i = 0; i < 6; i++) acc[3 + i] += (double)Rf[i], Rf[i] = 0.f;
+                cnt = 0;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 3; i++) acc[i] += (double)Sf[i];
+#pragma unroll
+        for (int i = 0; i < 6; i++) acc[3 + i] += (double)Rf[i];
+        double *wred = reinterpret_cast<double *>(zbuf);  // [NWARPS][9]: the FFT scratch is free by now
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 9; i++) wred[warp * 9 + i] = acc[i];
+        }
+        __syncthreads();
+        if (tid < 9) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < NWARPS; w++) t += wred[w * 9 + tid];  // fixed order: deterministic
+            a.moments[b * 9 + tid] = t;
+        }
+    }
     float *o = a.out + b * (int64_t)a.n_mels * a.T;
     const int tot = a.n_mels * a.T;
     for (int i = tid; i < tot; i += NTHREADS) {
@@ -315,15 +366,20 @@ MelArgs base_args(MelPlan *p) {
 
 namespace pfann {
 // used by extract.cu: run stage 1 on device-resident inputs into a device buffer
-int mel_forward_dev(pfann_mel *h, const float *x_dev, int64_t B, float *out_dev) {
+int mel_forward_dev(pfann_mel *h, const float *x_dev, int64_t B, float *out_dev, double *moments, int m_ntaps,
+                    const int *m_off) {
     MelPlan *p = reinterpret_cast<MelPlan *>(h);
     MelArgs a = base_args(p);
     a.x = x_dev;
     a.out = out_dev;
+    a.moments = moments;
+    a.m_ntaps = m_ntaps;
+    for (int j = 0; j < 3; j++) a.m_off[j] = (moments && j < m_ntaps) ? m_off[j] : 0;
     return launch_mel(p, a, B, false);
 }
 int mel_forward_pcm_dev(pfann_mel *h, const int16_t *pcm_dev, int64_t n_samples, const int64_t *start_dev,
-                        const int32_t *valid_dev, int64_t B, float *out_dev) {
+                        const int32_t *valid_dev, int64_t B, float *out_dev, double *moments, int m_ntaps,
+                        const int *m_off) {
     MelPlan *p = reinterpret_cast<MelPlan *>(h);
     MelArgs a = base_args(p);
     a.pcm = pcm_dev;
@@ -331,6 +387,9 @@ int mel_forward_pcm_dev(pfann_mel *h, const int16_t *pcm_dev, int64_t n_samples,
     a.seg_start = start_dev;
     a.seg_valid = valid_dev;
     a.out = out_dev;
+    a.moments = moments;
+    a.m_ntaps = m_ntaps;
+    for (int j = 0; j < 3; j++) a.m_off[j] = (moments && j < m_ntaps) ? m_off[j] : 0;
     return launch_mel(p, a, B, true);
 }
 Ctx *mel_ctx(pfann_mel *h) { return reinterpret_cast<MelPlan *>(h)->ctx; }
@@ -456,7 +515,7 @@ int pfann_mel_forward(pfann_mel *h, const float *x, int64_t B, float *out) {
     void *od;
     PF_TRY(stage_input(p->ctx, 0, x, in_b, &xd));
     PF_TRY(stage_output(p->ctx, 0, out, out_b, &od));
-    PF_TRY(mel_forward_dev(h, (const float *)xd, B, (float *)od));
+    PF_TRY(mel_forward_dev(h, (const float *)xd, B, (float *)od, nullptr, 0, nullptr));
     return finish_output(p->ctx, 0, out, out_b);
 }
 
@@ -475,7 +534,7 @@ int pfann_mel_forward_pcm16(pfann_mel *h, const int16_t *pcm, int64_t n_samples,
     PF_TRY(stage_input(p->ctx, 2, seg_valid, (size_t)B * 4, &vd));
     PF_TRY(stage_output(p->ctx, 0, out, out_b, &od));
     PF_TRY(mel_forward_pcm_dev(h, (const int16_t *)pd, n_samples, (const int64_t *)sd, (const int32_t *)vd, B,
-                               (float *)od));
+                               (float *)od, nullptr, 0, nullptr));
     return finish_output(p->ctx, 0, out, out_b);
 }
 
