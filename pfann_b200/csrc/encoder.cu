@@ -265,14 +265,11 @@ struct L0Args {
 };
 
 __global__ void __launch_bounds__(256) l0_moments_kernel(const L0Args a, const Model::L0Consts k, float2 *stats) {
-    __shared__ double red[8];
     const float *m = a.mel + (long long)blockIdx.x * a.F * a.T;
     const int P = a.F * a.To;
     // Same arithmetic as the moments block at the end of mel_kernel (mel.cu), so that the fused extract path and
-    // mel -> model give identical statistics: fp32 partial sums over 16 positions per thread, double across threads.
-    float Sf[3] = {0.f, 0.f, 0.f}, Rf[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // R: 00 01 02 11 12 22
-    double S[3] = {0, 0, 0}, R[6] = {0, 0, 0, 0, 0, 0};
-    int cnt = 0;
+    // mel -> model give identical statistics: fp32 within a thread and a warp, double across the warps.
+    float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // S0 S1 S2 R00 R01 R02 R11 R12 R22
     for (int p = threadIdx.x; p < P; p += blockDim.x) {
         const int f = p / a.To, to = p - f * a.To;
         float v[3] = {0.f, 0.f, 0.f};
@@ -280,19 +277,30 @@ __global__ void __launch_bounds__(256) l0_moments_kernel(const L0Args a, const M
             const int t = 2 * to + a.off[j];
             if (t >= 0 && t < a.T) v[j] = m[f * a.T + t];
         }
-        Sf[0] += v[0]; Sf[1] += v[1]; Sf[2] += v[2];
-        Rf[0] = fmaf(v[0], v[0], Rf[0]); Rf[1] = fmaf(v[0], v[1], Rf[1]); Rf[2] = fmaf(v[0], v[2], Rf[2]);
-        Rf[3] = fmaf(v[1], v[1], Rf[3]); Rf[4] = fmaf(v[1], v[2], Rf[4]); Rf[5] = fmaf(v[2], v[2], Rf[5]);
-        if (++cnt == 16) {
-            for (int i = 0; i < 3; i++) S[i] += (double)Sf[i], Sf[i] = 0.f;
-            for (int i = 0; i < 6; i++) R[i] += (double)Rf[i], Rf[i] = 0.f;
-            cnt = 0;
+        acc[0] += v[0]; acc[1] += v[1]; acc[2] += v[2];
+        acc[3] = fmaf(v[0], v[0], acc[3]); acc[4] = fmaf(v[0], v[1], acc[4]); acc[5] = fmaf(v[0], v[2], acc[5]);
+        acc[6] = fmaf(v[1], v[1], acc[6]); acc[7] = fmaf(v[1], v[2], acc[7]); acc[8] = fmaf(v[2], v[2], acc[8]);
+    }
+    __shared__ double wred[8][9];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) wred[warp][i] = (double)acc[i];
+    }
+    __syncthreads();
+    double S[3], R[6];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 9; i++) {
+            double t = 0.0;
+            for (int w = 0; w < 8; w++) t += wred[w][i];
+            if (i < 3) S[i] = t; else R[i - 3] = t;
         }
     }
-    for (int i = 0; i < 3; i++) S[i] += (double)Sf[i];
-    for (int i = 0; i < 6; i++) R[i] += (double)Rf[i];
-    for (int i = 0; i < 3; i++) S[i] = block_sum_d(S[i], red);
-    for (int i = 0; i < 6; i++) R[i] = block_sum_d(R[i], red);
     if (threadIdx.x == 0) {
         const double Rm[3][3] = {{R[0], R[1], R[2]}, {R[1], R[3], R[4]}, {R[2], R[4], R[5]}};
         double s1 = (double)P * k.Bsum, s2 = (double)P * k.B2;

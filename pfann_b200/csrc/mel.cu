@@ -274,9 +274,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) mel_kernel(const MelArgs a) {
     if (a.moments != nullptr) {
         // per thread: fp32 partial sums over its positions (f, to), stride-2 taps along time; across threads: double
         const int To = (a.T + 1) / 2, P = a.n_mels * To;
-        float Sf[3] = {0.f, 0.f, 0.f}, Rf[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        int cnt = 0;
+        // fp32 within a thread and within a warp (512 products), double across the warps: fp64 runs at 1/64 rate
+        float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // S0 S1 S2 R00 R01 R02 R11 R12 R22
         for (int p = tid; p < P; p += NTHREADS) {
             const int f = p / To, to = p - f * To;
             float v[3] = {0.f, 0.f, 0.f};
@@ -285,21 +284,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) mel_kernel(const MelArgs a) {
                 const int t = 2 * to + a.m_off[j];
                 if (j < a.m_ntaps && t >= 0 && t < a.T) v[j] = tile[f * Tp + t];
             }
-            Sf[0] += v[0]; Sf[1] += v[1]; Sf[2] += v[2];
-            Rf[0] = fmaf(v[0], v[0], Rf[0]); Rf[1] = fmaf(v[0], v[1], Rf[1]); Rf[2] = fmaf(v[0], v[2], Rf[2]);
-            Rf[3] = fmaf(v[1], v[1], Rf[3]); Rf[4] = fmaf(v[1], v[2], Rf[4]); Rf[5] = fmaf(v[2], v[2], Rf[5]);
-            if (++cnt == 16) {
-#pragma unroll
-                for (int i = 0; i < 3; i++) acc[i] += (double)Sf[i], Sf[i] = 0.f;
-#pragma unroll
-                for (int i = 0; i < 6; i++) acc[3 + i] += (double)Rf[i], Rf[i] = 0.f;
-                cnt = 0;
-            }
+            acc[0] += v[0]; acc[1] += v[1]; acc[2] += v[2];
+            acc[3] = fmaf(v[0], v[0], acc[3]); acc[4] = fmaf(v[0], v[1], acc[4]); acc[5] = fmaf(v[0], v[2], acc[5]);
+            acc[6] = fmaf(v[1], v[1], acc[6]); acc[7] = fmaf(v[1], v[2], acc[7]); acc[8] = fmaf(v[2], v[2], acc[8]);
         }
-#pragma unroll
-        for (int i = 0; i < 3; i++) acc[i] += (double)Sf[i];
-#pragma unroll
-        for (int i = 0; i < 6; i++) acc[3 + i] += (double)Rf[i];
         double *wred = reinterpret_cast<double *>(zbuf);  // [NWARPS][9]: the FFT scratch is free by now
 #pragma unroll
         for (int i = 0; i < 9; i++) {
@@ -308,7 +296,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) mel_kernel(const MelArgs a) {
         }
         if (lane == 0) {
 #pragma unroll
-            for (int i = 0; i < 9; i++) wred[warp * 9 + i] = acc[i];
+            for (int i = 0; i < 9; i++) wred[warp * 9 + i] = (double)acc[i];
         }
         __syncthreads();
         if (tid < 9) {
