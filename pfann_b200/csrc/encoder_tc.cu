@@ -16,8 +16,13 @@
 //    tile i (tcgen05.ld, + bias, raw output staged through swizzled smem into coalesced 16-byte stores,
 //    per-sample LayerNorm partial sums into fixed slots -- no atomics, bit-reproducible) while the tensor
 //    core already accumulates tile i + 1.
-// LayerNorm itself (global over (C,F,T) of a sample) is finished by ln_finalize_kernel and applied by
-// ln_apply_kernel in encoder.cu.
+// Three kernels live here:
+//   conv_gemm_tc_kernel   the plain implicit GEMM described above (raw output + LayerNorm partial sums; LayerNorm is
+//                         finished by ln_finalize_kernel and applied by ln_apply_kernel in encoder.cu) -- used for the
+//                         eight small tail convolutions;
+//   conv_ln_tc_kernel     convolutions 1-7 with LayerNorm + ReLU inside the epilogue (statistics exchanged between
+//                         CTAs through an L2 table), no raw output at all;
+//   l0_tc_kernel          layer-0 conv1 (C_in = 1) + ln1 + ReLU as one K = 16 hi/lo-split MMA per 128 positions.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <stdlib.h>
@@ -63,10 +68,6 @@ struct TcArgs {
     int n_stages, b_res;  // smem ring depth; 1 = the whole weight matrix stays resident in shared memory
 };
 
-template <int BN>
-__host__ __device__ constexpr int tc_stages() {
-    return BN >= 256 ? 4 : 6;
-}
 
 // Persistent: grid = #SMs, every CTA walks tiles t = blockIdx.x, +gridDim.x, ... of the (m_tile, n_tile) space.
 //   warp 0      TMA producer  -- runs ahead of the MMAs by up to STAGES K-blocks, across tile boundaries
