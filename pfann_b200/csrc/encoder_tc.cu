@@ -422,13 +422,16 @@ __global__ void __launch_bounds__(LN_THREADS, 1) conv_ln_tc_kernel(const __grid_
             }
             int s = 0;
             uint32_t round = 0;
+            long long prod_wait = 0;
             for (int i = 0; i < nt_cta; i++) {
                 const long long m0 = (long long)(lane_id + i * a.L) * GR + (long long)rb * BM;
                 const int f0 = (int)((m0 / a.To) % a.fdim);
                 const int b0 = (int)(m0 / ((long long)a.To * a.fdim));
                 int tap = 0, kbt = 0;
                 for (int kb = 0; kb < KB; kb++) {
+                    const long long c0 = PROF ? clock64() : 0;
                     if (round > 0) ptx::mbar_wait(&empty_bar[s], (round - 1) & 1);
+                    if (PROF) prod_wait += clock64() - c0;
                     unsigned char *sa = sbase + (size_t)s * STAGE_BYTES;
                     ptx::mbar_expect_tx(&full_bar[s], STAGE_BYTES);
                     const CUtensorMap *mA = tap == 0 ? &mapA0 : (tap == 1 ? &mapA1 : &mapA2);
@@ -438,6 +441,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) conv_ln_tc_kernel(const __grid_
                     if (++s == STAGES) s = 0, round++;
                 }
             }
+            if (PROF && a.prof) a.prof[(size_t)blockIdx.x * 8 + 7] = (unsigned long long)prod_wait;
         }
     } else if (warp == 1) {
         if (lane == 0) {
@@ -446,9 +450,12 @@ __global__ void __launch_bounds__(LN_THREADS, 1) conv_ln_tc_kernel(const __grid_
             int s = 0;
             uint32_t round = 0;
             if (a.b_res) ptx::mbar_wait(&bres_bar, 0);
+            long long mw_empty = 0, mw_full = 0;
             for (int i = 0; i < nt_cta; i++) {
                 const int slot = i & 3;
+                const long long c0 = PROF ? clock64() : 0;
                 if (i >= 4) ptx::mbar_wait(&tempty_bar[slot], (uint32_t)((i >> 2) - 1) & 1);
+                if (PROF) mw_empty += clock64() - c0;
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(slot * BN);
                 {   // accumulator := bias (ones x bias rows)
@@ -456,7 +463,9 @@ __global__ void __launch_bounds__(LN_THREADS, 1) conv_ln_tc_kernel(const __grid_
                     ptx::umma_f16(d_tmem, dc, dc + 2, idesc, 0);
                 }
                 for (int kb = 0; kb < KB; kb++) {
+                    const long long c1 = PROF ? clock64() : 0;
                     ptx::mbar_wait(&full_bar[s], round & 1);
+                    if (PROF) mw_full += clock64() - c1;
                     ptx::tc_fence_after();
                     const uint32_t sa = ptx::smem_u32(sbase + (size_t)s * STAGE_BYTES);
                     const uint64_t da = ptx::umma_desc_k_sw128(sa);
@@ -468,6 +477,10 @@ __global__ void __launch_bounds__(LN_THREADS, 1) conv_ln_tc_kernel(const __grid_
                     if (++s == STAGES) s = 0, round++;
                 }
                 ptx::umma_commit(&tfull_bar[slot]);
+            }
+            if (PROF && a.prof) {
+                a.prof[(size_t)blockIdx.x * 8 + 5] = (unsigned long long)mw_empty;
+                a.prof[(size_t)blockIdx.x * 8 + 6] = (unsigned long long)mw_full;
             }
         }
     } else if (warp < 2 + LN_EPI_WARPS) {

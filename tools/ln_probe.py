@@ -24,10 +24,11 @@ ex.extract_pcm16(pcm, off)
 p = _lib.profile_read(0)
 print({k: round(v[0], 3) for k, v in p.items() if v[1]})
 pr = prof.cpu().numpy().astype(np.float64)
-names = ['wait MMA', 'pass1', 'wait stats', 'pass2']
+names = ['wait MMA', 'pass1', 'wait stats', 'pass2', '| MMA: wait slot', 'wait TMA', '| TMA: wait stage']
 for idx in range(1, 15):
     g = pr[idx, :, 4].sum() / 1.0
     if g == 0:
         continue
-    per = [pr[idx, :, j].sum() / 8.0 / g for j in range(4)]   # cycles per tile per CTA (avg of 8 warps)
+    per = [pr[idx, :, j].sum() / 16.0 / g for j in range(4)]   # cycles per tile per CTA (avg of 16 warps)
+    per += [pr[idx, :, j].sum() / g for j in (5, 6, 7)]          # single-thread roles
     print('conv %2d: tiles/CTA %.0f | cycles per tile: %s' % (idx, g / 148, ', '.join('%s %.0f' % (n, v) for n, v in zip(names, per))))
