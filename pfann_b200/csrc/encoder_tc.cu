@@ -361,7 +361,6 @@ __global__ void __launch_bounds__(LN_THREADS, 1) conv_ln_tc_kernel(const __grid_
     // B = columns 16-31, initialises the accumulator with the bias -- the epilogue never touches it (bias reads
     // from shared memory used to cost more L1 data-pipe cycles than the tensor core's own operand reads).
     unsigned char *cb_s = sBres + (a.b_res ? (size_t)KB * B_BYTES : 0);
-    unsigned char *stage_out = cb_s + 16384;                                      // 16 warps x 1 KB store staging
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], bres_bar;
     __shared__ __align__(8) uint64_t tfull_bar[4], tempty_bar[4], sready_bar[4];
     __shared__ float2 stat_s[4][4];                                               // [slot][sample of the tile] (mean, rstd)
@@ -489,7 +488,6 @@ __global__ void __launch_bounds__(LN_THREADS, 1) conv_ln_tc_kernel(const __grid_
         const int cc = wc * 32;                         // first column of this warp inside the CTA's 128-channel slice
         const int pub = wc * 4 + quarter;               // index of this warp's word in the exchange table
         const int sgq = quarter >> (2 - a.sg_shift);    // which sample of the tile this warp's 32 rows belong to
-        uint4 *stg = reinterpret_cast<uint4 *>(stage_out + (size_t)ew * 1024);
         // gamma/beta of (row = this lane, this warp's 32 columns) never change for a CTA position: 32 registers,
         // loaded once ([position][chunk][quarter][8 x 16 B][lane]: one 512-byte request per warp load)
         uint4 gq[4], bq[4];
@@ -555,7 +553,6 @@ __global__ void __launch_bounds__(LN_THREADS, 1) conv_ln_tc_kernel(const __grid_
                 const float rstd = st.y, nmr = -st.x * st.y;
                 const long long mrow0 = (long long)(lane_id + j * a.L) * GR + (long long)rb * BM + quarter * 32;
                 const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
-                const int sw = (lane >> 2) & 1;
                 uint32_t va[16], vb[16];
                 ptx::tmem_ld_32x32b_x16(t_lane + (uint32_t)(slot * BN), va);
                 ptx::tmem_ld_32x32b_x16(t_lane + (uint32_t)(slot * BN + 16), vb);
@@ -566,8 +563,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) conv_ln_tc_kernel(const __grid_
                 if (lane == 0) ptx::mbar_arrive(&tempty_bar[slot]);
 #pragma unroll
                 for (int hh = 0; hh < 2; hh++) {
-                    // 16 columns: normalise, affine (packed bf16 FMA), ReLU; registers (row = lane) -> swizzled 1 KB
-                    // staging (32 rows x 32 B) -> sector-complete 32-byte row pieces
+                    // 16 columns: normalise, affine (packed bf16 FMA), ReLU
                     uint32_t pk[8];
 #pragma unroll
                     for (int q = 0; q < 2; q++) {
@@ -587,18 +583,11 @@ __global__ void __launch_bounds__(LN_THREADS, 1) conv_ln_tc_kernel(const __grid_
                             pk[4 * q + e] = *reinterpret_cast<const uint32_t *>(&y2);
                         }
                     }
-                    stg[lane * 2 + (0 ^ sw)] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    stg[lane * 2 + (1 ^ sw)] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                    __syncwarp();
-#pragma unroll
-                    for (int r0 = 0; r0 < 32; r0 += 16) {
-                        const int r = r0 + (lane >> 1), ch = lane & 1;
-                        const uint4 val = stg[r * 2 + (ch ^ ((r >> 2) & 1))];
-                        if (mrow0 + r < a.M)
-                            *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(a.X) +
-                                                       ((mrow0 + r) * a.Co + n0 + cc + hh * 16) * 2 + ch * 16) = val;
-                    }
-                    __syncwarp();
+                    // one full 32-byte sector per thread (STG.256), straight from registers: staging the rows through
+                    // shared memory for wider row pieces cost more L1-data-pipe wavefronts and two warp barriers
+                    if (mrow0 + lane < a.M)
+                        ptx::st_global_v8(reinterpret_cast<unsigned char *>(a.X) +
+                                              ((mrow0 + lane) * a.Co + n0 + cc + hh * 16) * 2, pk);
                 }
                 if (PROF) pc[2] += t0 - tw, pc[3] += clock64() - t0;
             }
@@ -700,6 +689,7 @@ struct L0TcArgs {
     __nv_bfloat16 *X;          // [nb][P][128]
     int nb, F, T, To, ntaps, off[3];
     int PB;                    // position blocks per sample (P / 128)
+    int direct_store;          // 1 (default): 32-byte stores straight from registers; 0: staged 64-byte row pieces
 };
 constexpr int L0_BUILD_WARPS = 2;
 constexpr int L0_THREADS = 32 * (L0_BUILD_WARPS + 1 + 16);
@@ -856,6 +846,7 @@ __global__ void __launch_bounds__(L0_THREADS, 1) l0_tc_kernel(const L0TcArgs a) 
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tempty_bar[slot]);
+            uint32_t pd[8];
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 const uint4 g4 = gq[q], b4 = bq[q];
@@ -872,7 +863,18 @@ __global__ void __launch_bounds__(L0_THREADS, 1) l0_tc_kernel(const L0TcArgs a) 
                     y2 = __hmax2(y2, zero2);
                     pk[e] = *reinterpret_cast<const uint32_t *>(&y2);
                 }
-                stg[lane * 4 + (q ^ sw)] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                if (a.direct_store) {
+#pragma unroll
+                    for (int e = 0; e < 4; e++) pd[4 * (q & 1) + e] = pk[e];
+                    if (q & 1)
+                        ptx::st_global_v8(reinterpret_cast<unsigned char *>(a.X) + ((mrow0 + lane) * 128 + cc + (q >> 1) * 16) * 2, pd);
+                } else {
+                    stg[lane * 4 + (q ^ sw)] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+            }
+            if (a.direct_store) {
+                pb = pbn; s = sn;
+                continue;
             }
             __syncwarp();
 #pragma unroll
@@ -980,9 +982,9 @@ int launch_tc(Model *m, const TcConv &tc, const TcArgs &args_in) {
 
 int launch_tc_ln(Model *m, const TcConv &tc, const LnGeom &lg, const TcLnArgs &args_in) {
     TcLnArgs args = args_in;
-    // shared-memory plan: 16 KB bias tile + 16 KB store staging are fixed; the weight slice stays resident
+    // shared-memory plan: the 16 KB bias tile is fixed; the weight slice stays resident
     // when that leaves room for >= 3 activation stages, otherwise weights stream through the ring next to them
-    const size_t budget = 225 * 1024, fixed = 16384 + LN_EPI_WARPS * 1024;
+    const size_t budget = 225 * 1024, fixed = 16384;
     const size_t A = (size_t)BM * BK * 2, B = (size_t)LN_BN * BK * 2;
     const size_t bres = (size_t)args.kb_per_tap * args.ntaps * B;
     static const char *env_bres = getenv("PFANN_B200_LN_BRES");
@@ -1212,6 +1214,8 @@ int tc_l0(Model *m, const float *mel, const float2 *stats, __nv_bfloat16 *X, int
     a.nb = nb; a.F = g.Fi; a.T = g.Ti; a.To = g.To; a.ntaps = g.ntaps;
     for (int j = 0; j < 3; j++) a.off[j] = j < g.ntaps ? g.tap_off[j] : 0;
     a.PB = g.Fo * g.To / 128;
+    static const char *env_ds = getenv("PFANN_B200_L0_DIRECT_STORE");
+    a.direct_store = env_ds ? atoi(env_ds) : 1;  // measured 2 % faster than the staged 64-byte row pieces
     const size_t smem = (size_t)L0_STAGES * 16384 + 16384 + 16 * 2048 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
