@@ -95,3 +95,27 @@ def test_extract_slice_properties():
     same = (z[0:58] * z[1:59]).sum(1).mean()
     other = (z[0:58] * z[59:117]).sum(1).mean()
     assert same > other
+
+
+def test_extract_large_chunk_equals_small_chunk():
+    """The bench configuration (chunk = 16384 segments: hundreds of tiles per CTA position in the fused conv+LayerNorm
+    kernel, statistics exchanged between up to 16 CTAs per sample) gives bit for bit the fingerprints of a small-chunk
+    run: per-sample statistics are summed in a fixed order, independent of how segments are batched."""
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from pfann_b200.extract import Extractor
+    params = synth.read_config('default')
+    sd = synth.make_state_dict(params, seed=11)
+    big = Extractor(params, sd, device=0, precision='bf16', chunk=16384)
+    small = Extractor(params, sd, device=0, precision='bf16', chunk=96)
+    clip, n_clips = 240000, 290                                   # 17110 segments: one full chunk + a ragged one
+    g = torch.Generator(device='cuda')
+    g.manual_seed(5)
+    pcm = (torch.randn(n_clips * clip, generator=g, device='cuda') * 4000).to(torch.int16)
+    off = np.arange(n_clips + 1, dtype=np.int64) * clip
+    z, counts = big.extract_pcm16(pcm, off)
+    assert z.shape == (n_clips * 59, 128) and (counts == 59).all()
+    torch.testing.assert_close(z.norm(dim=1), torch.ones(z.shape[0], device='cuda'), atol=1e-5, rtol=0)
+    for c0 in (0, 137, 277, 286):                                 # first chunk, middle, chunk boundary, ragged tail
+        zs, _ = small.extract_pcm16(pcm[c0 * clip:(c0 + 4) * clip], off[c0:c0 + 5] - off[c0])
+        assert torch.equal(zs, z[c0 * 59:(c0 + 4) * 59]), c0
