@@ -843,6 +843,12 @@ int launch_l0_fused(Model *m, const float *mel, ActT *X, int nb) {
     return PFANN_OK;
 }
 
+// largest dynamic shared-memory size the head kernels have been opted in to (shared by all callers)
+size_t &head_smem_attr() {
+    static size_t attr = 0;
+    return attr;
+}
+
 // one chunk of nb <= m->chunk samples through the 8 layers + head
 template <typename ActT>
 int forward_chunk(Model *m, const float *mel, int nb, int norm, float *z) {
@@ -901,13 +907,16 @@ int forward_chunk(Model *m, const float *mel, int nb, int norm, float *z) {
         PF_TRY((launch_ln_apply<float, ActT>(m, last, Y, xb, nb)));
         PF_TRY(save_tap<ActT>(m, 7, xb, nb));
     }
+    PF_CUDA(cudaGetLastError());  // anything left over from the layer loop is not the head's
     const int threads = ((m->d + 31) / 32) * 32;
     ProfScope ps(m->ctx, K_HEAD, 33);
     const int v = m->h / m->d;
     const size_t smem_fast =
         ((size_t)m->u * v * threads + 2 * (size_t)m->u * threads + (size_t)HEAD_HG * HEAD_HS * (threads / 32)) * 4;
     if ((v == 8 || v == 16) && threads * HEAD_HG <= 256 && smem_fast <= 200 * 1024) {
-        static size_t attr = 0;
+        // one cache for both instantiations of this template: a per-instantiation static once LOWERED the limit the
+        // other instantiation had raised (fp32 n640d64 after bf16 default) and the next default launch failed
+        size_t &attr = head_smem_attr();
         if (smem_fast > attr) {
             PF_CUDA(cudaFuncSetAttribute(head_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
             PF_CUDA(cudaFuncSetAttribute(head_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
@@ -926,7 +935,18 @@ int forward_chunk(Model *m, const float *mel, int nb, int norm, float *z) {
             Y, m->cur_stats, last.gamma, last.beta, m->w1, m->b1, m->w2, m->b2, z, m->d, m->h, m->u, norm);
     }
     m->ctx->launches++;
-    PF_CUDA(cudaGetLastError());
+    {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            cudaFuncAttributes fa8, fa16;
+            cudaFuncGetAttributes(&fa8, head_kernel<8>);
+            cudaFuncGetAttributes(&fa16, head_kernel<16>);
+            set_error("head kernel launch failed: %s (d=%d h=%d u=%d v=%d threads=%d nb=%d smem=%zu; max dynamic smem <8> %d <16> %d)",
+                      cudaGetErrorString(e), m->d, m->h, m->u, v, threads, nb, smem_fast, fa8.maxDynamicSharedSizeBytes,
+                      fa16.maxDynamicSharedSizeBytes);
+            return PFANN_ERR_CUDA;
+        }
+    }
     return PFANN_OK;
 }
 

@@ -38,6 +38,7 @@ struct MelPlan {
     Ctx *ctx;
     int sample_rate, n_fft, hop, n_mels, seg_len, T;
     int fb_stride;
+    int k_lo = 0;             // smallest spectrum bin with a non-zero mel weight (bins below are never formed)
     float2 *d_tw = nullptr;   // W_1024^k = exp(-2 pi i k / 1024), k in [0, 1024)
     float *d_win = nullptr;   // periodic Hann, 1024
     int *d_fb_start = nullptr, *d_fb_cnt = nullptr;
@@ -53,7 +54,7 @@ struct MelArgs {
     const int64_t *seg_start;
     const int32_t *seg_valid;
     float *out;              // [B][n_mels][T]
-    int n, hop, T, n_mels, fb_stride;
+    int n, hop, T, n_mels, fb_stride, k_lo;
     const float2 *tw;
     const float *win;
     const int *fb_start, *fb_cnt;
@@ -241,6 +242,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) mel_kernel(const MelArgs a) {
         for (int it = 0; it < 17; it++) {
             const int k = lane + 32 * it;
             P[it] = 0.f;
+            if (32 * it + 31 < a.k_lo) continue;  // warp-uniform: no mel filter reaches these bins (f_min)
             if (k <= NFFT / 2) {
                 const int ka = k & 511, kb = (512 - k) & 511;
                 const float2 A = zw[(ka >> 4) * ZSTRIDE + (ka & 15)];
@@ -266,7 +268,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) mel_kernel(const MelArgs a) {
             const float *w = a.fb_w + (size_t)m * a.fb_stride;
             float acc = 0.f;
             for (int j = 0; j < c; j++) acc = fmaf(__ldg(w + j), pw[s0 + j], acc);
-            tile[m * Tp + t] = logf(acc + 1e-8f);
+            tile[m * Tp + t] = __logf(acc + 1e-8f);  // MUFU.LG2 path: |error| ~1e-6 in the log domain
         }
         __syncwarp();
     }
@@ -342,6 +344,7 @@ MelArgs base_args(MelPlan *p) {
     a.T = p->T;
     a.n_mels = p->n_mels;
     a.fb_stride = p->fb_stride;
+    a.k_lo = p->k_lo;
     a.tw = p->d_tw;
     a.win = p->d_win;
     a.fb_start = p->d_fb_start;
@@ -456,6 +459,9 @@ int pfann_mel_create(pfann_ctx *hctx, int sample_rate, int n_fft, int hop, doubl
         if (cnt[m] > stride) stride = cnt[m];
     }
     p->fb_stride = stride;
+    p->k_lo = n_freqs;
+    for (int m = 0; m < n_mels; m++)
+        if (cnt[m] > 0 && start[m] < p->k_lo) p->k_lo = start[m];
     std::vector<float> fbw((size_t)n_mels * stride, 0.f);
     for (int m = 0; m < n_mels; m++)
         for (int j = 0; j < cnt[m]; j++) fbw[(size_t)m * stride + j] = rows[m][j];

@@ -224,6 +224,22 @@ def test_extract_host_buffers_pipeline_equals_device_buffers(dev):
     assert np.array_equal(out.numpy(), z_host)
 
 
+def test_models_of_different_configs_and_precisions_interleave(dev):
+    """Regression: launch-attribute caches are per process -- a small fp32 model used after a large bf16 model once
+    lowered the head kernel's shared-memory opt-in and the next large launch failed with 'invalid argument'."""
+    big, params, _ = _net('default', 'bf16', dev, 3)
+    x = torch.from_numpy(orc.melspec(synth.synth_segments(3, seed=1), params)).to(dev)
+    z0 = big(x).cpu().numpy()
+    small32, _, _ = _net('n640d64', 'fp32', dev, 3)
+    small16, _, _ = _net('n640d64', 'bf16', dev, 3)
+    assert small32(x).shape == (3, 64) and small16(x).shape == (3, 64)
+    big32, _, _ = _net('default', 'fp32', dev, 3)
+    z1 = big(x).cpu().numpy()
+    z2 = big32(x).cpu().numpy()
+    assert np.array_equal(z0, z1)
+    assert (1 - (z1 * z2).sum(1)).max() < EMB_BF16_COS
+
+
 def test_extract_pcm16_equals_mel_plus_model(dev):
     """builder.py:88-99 fused: PCM in, fingerprints out == framing -> mel -> model done step by step."""
     import ctypes
