@@ -17,3 +17,14 @@ def pytest_configure(config):
 @pytest.fixture(scope='session')
 def golden_dir():
     return GOLDEN
+
+
+def pytest_collection_modifyitems(config, items):
+    """PFANN_TEST_ORDER=reverse | shuffle:<seed> runs the tests in another order: the library keeps per-process
+    caches (kernel attributes, workspaces), so order dependence is a real failure mode worth checking."""
+    order = os.environ.get('PFANN_TEST_ORDER', '')
+    if order == 'reverse':
+        items.reverse()
+    elif order.startswith('shuffle'):
+        import random
+        random.Random(int(order.split(':')[1]) if ':' in order else 0).shuffle(items)
