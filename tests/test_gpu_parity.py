@@ -62,6 +62,22 @@ def test_mel_many_segments_vs_oracle(dev):
     assert err.max() < MEL_MAX_TOL and err.mean() < MEL_MEAN_TOL, (err.max(), err.mean())
 
 
+def test_mel_plans_of_different_segment_lengths_coexist(dev):
+    """The layer takes any segment length like the reference module; plans of different lengths (different
+    shared-memory sizes) live side by side: long, short, long again."""
+    from pfann_b200.datautil.melspec import build_mel_spec_layer
+    params = synth.read_config('default')
+    mel = build_mel_spec_layer(params).to(dev)
+    x = synth.synth_segments(3, seed=8)
+    for n in (8000, 4096, 12000, 8000):
+        xi = np.ascontiguousarray(np.tile(x, (1, 2))[:, :n])
+        y = mel(torch.from_numpy(xi).to(dev)).cpu().numpy()
+        ref = orc.melspec(xi, params)
+        assert y.shape == ref.shape == (3, 256, 1 + n // 256)
+        err = np.abs(y - ref)
+        assert err.max() < MEL_MAX_TOL and err.mean() < MEL_MEAN_TOL, (n, err.max(), err.mean())
+
+
 def test_mel_pcm16_framing_vs_oracle(dev):
     """musicdata.py:48,82-88 folded into the kernel: ragged clips incl. one shorter than a segment."""
     import ctypes
