@@ -301,7 +301,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
 // Four 128 x 128 fp32 accumulators rotate through TMEM.  Per tile i the sixteen epilogue warps run
 //   pass 1 (tile i)     tcgen05.ld, + bias, per-warp (sum, sum of squares); each warp publishes its pair as ONE
 //                       64-bit word into a global exchange table (all-ones = not written yet);
-//   pass 2 (tile i - 3) tcgen05.ld again, normalise with the sample statistics, affine, ReLU, bf16, coalesced store;
+//   pass 2 (tile i - 3) tcgen05.ld again, normalise with the sample statistics, affine, ReLU, bf16, one 32-byte
+//                       sector store per thread and 16 columns (STG.256);
 // one more "statistics" warp polls the table until the P * 16 words of a sample group are there, adds them in a fixed
 // order (double) and hands (mean, rstd) to pass 2 through shared memory.  The exchange latency (a few microseconds
 // through L2) is hidden behind three tiles of work, the tensor core runs one tile ahead of the epilogue, and no
