@@ -33,12 +33,46 @@ import numpy as np
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
+METRIC = 'fingerprints/s (builder) and queries/s vs 10M\u00d7d128 DB at 1/2/4/8 B200'   # BASELINE.json, both arms
 FLOP_PER_SEG = 0.533e9        # algorithmic FLOPs/segment, default.json, zero-pad taps excluded
-# conv_ln_tc_kernel (convolutions 1-7 of default.json): input + output activations per segment, bf16
-CONVLN_BYTES_PER_SEG = 2 * sum(i + o for i, o in [(524288, 262144), (262144, 131072), (131072, 65536), (65536, 65536),
-                                                  (65536, 32768), (32768, 16384), (16384, 8192)])
-CONVLN_NCU_TRAFFIC_PER_SEG = 13.529e9 / 4096   # ncu dram__bytes_read+write.sum of the 7 launches of a 4096-segment chunk
+ALG_BYTES_PER_SEG = 32768 + 512   # SURVEY 8d stage 2: fp32 log-mel tile in, d=128 fp32 fingerprint out (weights amortised)
 SEG_BYTES_MEL = 64768         # stage-1 algorithmic bytes per segment (fp32 entry point)
+# ncu dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel family (convolutions 0-7: the fused
+# layer-0 + conv kernel and the fused conv + LayerNorm kernels) for one 4096-segment chunk, per segment; see
+# profiles/r02/README.md for the capture this number comes from
+DOMINANT_NCU_TRAFFIC_PER_SEG = None
+
+
+def workload_name(clips, clip_seconds, n_seg):
+    return ('builder: %d x %d s synthetic 8 kHz mono int16 per GPU -> %d segments -> d=128 embeddings, '
+            'configs/default.json, seeded random weights' % (clips, clip_seconds, n_seg))
+
+
+def conv_alg_flops(params):
+    """Algorithmic FLOPs per segment of each of the 16 convolutions: 2 * Ci * Co per (output
+    position, kernel tap) pair whose tap reads a real input element -- taps that only see the TF-"same" zero
+    padding of model.py:18-19,24-25 are not counted.  Sums to 0.533 GFLOP for configs/default.json."""
+    m = params['model']
+    d, h = m['d'], m['h']
+    F = params['n_mels']
+    T = int(params['segment_size'] * params['sample_rate']) // params['stft_hop'] + 1   # melspec.py: 1 + seg_len / hop
+    ch = [1, d, d, 2 * d, 2 * d, 4 * d, 4 * d, h, h]
+
+    def live(n):          # (output position, tap) pairs inside the input, k = 3, stride 2, TF-same padding
+        no = (n - 1) // 2 + 1
+        padl = ((n - 1) // 2 * 2 + 3 - n) // 2
+        return sum(1 for o in range(no) for j in range(3) if 0 <= 2 * o + j - padl < n), no
+    out = []
+    for l in range(8):
+        lt, To = live(T)
+        out.append(2.0 * ch[l] * ch[l + 1] * F * lt)          # conv1: 1x3 along time
+        lf, Fo = live(F)
+        if m.get('fuller', False):
+            out.append(2.0 * ch[l + 1] * ch[l + 1] * To * lf)  # conv2: 3x1 along frequency, dense
+        else:
+            out.append(2.0 * ch[l + 1] * To * lf)              # depthwise
+        F, T = Fo, To
+    return out
 
 
 def peaks():
@@ -163,10 +197,11 @@ def run_reference(args):
     v = float(np.mean(rates))
     sample = '%d segments per step (of 590000), batch 32, torch %s CPU' % (n_seg, torch.__version__)
     print(json.dumps({
-        'impl': 'reference', 'metric': 'fingerprints/s (builder)', 'value': v, 'unit': 'fingerprints/s',
+        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'fingerprints/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000.0 * n_seg / v,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'builder: 10k x 30 s synthetic 8 kHz mono -> d=128 embeddings (configs/default.json)',
+        'config': {'workload': workload_name(args.clips, args.clip_seconds,
+                                             args.clips * ((args.clip_seconds * 8000 - 8000) // 4000 + 1)),
                    'note': 'CPU port timed on a bounded sample of the workload'},
         'cpu_baseline': {'value': v, 'unit': 'fingerprints/s', 'cores': threads, 'kind': 'port', 'sample': sample},
         'e2e': {'value': v, 'unit': 'fingerprints/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -263,28 +298,45 @@ def main():
     assert abs(float(np.linalg.norm(z_host[:16].numpy(), axis=1).mean()) - 1.0) < 1e-3
     del pcm_host
 
-    # Dominant kernel: conv_ln_tc_kernel, the fused conv + LayerNorm + ReLU of convolutions 1-7 (7 launches per
-    # chunk).  Its big layers move 1.5 MB of activations per segment for 0.2 GFLOP: HBM-bound (ncu: DRAM 78 %,
-    # tensor pipe 32 %, profiles/r01/v5).  Algorithmic bytes = every input and output activation once (bf16).
-    fused_ms = sum(detail.get('conv%d' % i, (0.0, 0))[0] for i in range(1, 8))
-    fused_n = sum(detail.get('conv%d' % i, (0.0, 0))[1] for i in range(1, 8))
+    # Dominant kernel family: the tcgen05 convolution kernels with LayerNorm + ReLU fused into the epilogue
+    # (convolutions 0-7: the fused layer-0 + conv kernel and conv_ln_tc_kernel).  SURVEY 8d: stage 2 is a dense
+    # contraction, bound = tensor; achieved = ALGORITHMIC FLOPs (zero-pad taps excluded) / CUDA-event time of exactly
+    # those launches on the launching stream; peak = measured sustained dense bf16 (kernel timed inside a long step).
+    alg = conv_alg_flops(params)
+    dom = [i for i in range(8) if detail.get('conv%d' % i, (0.0, 0))[1]]
+    fused_ms = sum(detail['conv%d' % i][0] for i in dom)
+    fused_n = sum(detail['conv%d' % i][1] for i in dom)
     conv_ms, conv_n = prof['conv_tc']
-    bytes_alg = CONVLN_BYTES_PER_SEG * n_seg * args.steps
-    achieved = bytes_alg / (fused_ms / 1000.0) / 1e9 if fused_ms > 0 else 0.0
-    flops = FLOP_PER_SEG * n_seg * args.steps
-    tens = flops / (conv_ms / 1000.0) / 1e12 if conv_ms > 0 else 0.0
-    roofline = {'bound': 'hbm', 'kernel': 'conv_ln_tc_kernel (tcgen05 implicit-GEMM convolutions 1-7 fused with LayerNorm + ReLU)',
-                'achieved': achieved, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
-                'frac': achieved / pk['hbm_gbs'],
-                'traffic': CONVLN_NCU_TRAFFIC_PER_SEG * n_seg * args.steps / max(fused_n, 1),
-                'traffic_source': 'ncu dram__bytes_read+write of the 7 launches of one 4096-segment chunk, per segment '
-                                  '(profiles/r01/v5/ncu_convln.csv), scaled to the average launch of this run',
-                'algorithmic_bytes_per_launch': bytes_alg / max(fused_n, 1),
-                'peak_source': pk['source'],
+    dom_flops = sum(alg[:8]) * n_seg * args.steps          # a fused kernel covers every convolution up to its own
+    achieved = dom_flops / (fused_ms / 1000.0) / 1e12 if fused_ms > 0 else 0.0
+    tens = FLOP_PER_SEG * n_seg * args.steps / (conv_ms / 1000.0) / 1e12 if conv_ms > 0 else 0.0
+    outs = [524288, 262144, 131072, 65536, 65536, 32768, 16384, 8192]   # elements per segment after convolutions 0-7
+    front_fused = 'conv0' not in detail                                  # layer-0 conv1 produced inside conv 1's pipeline
+    act_bytes = 2 * sum(outs[i - 1] + outs[i] for i in range(2, 8)) + 2 * outs[1] + \
+        (32768 if front_fused else 32768 + 4 * outs[0])                  # bf16 activations that touch HBM, in + out
+    traffic = DOMINANT_NCU_TRAFFIC_PER_SEG * n_seg * args.steps / max(fused_n, 1) if DOMINANT_NCU_TRAFFIC_PER_SEG else None
+    roofline = {'bound': 'tensor',
+                'kernel': 'fused tcgen05 convolution + LayerNorm + ReLU kernels, convolutions 0-7 '
+                          '(front_tc_kernel + conv_ln_tc_kernel)',
+                'achieved': achieved, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s',
+                'frac': achieved / pk['tf_sustained'], 'traffic': traffic,
+                'traffic_source': 'ncu dram__bytes_read+write of these launches for one 4096-segment chunk, per segment '
+                                  '(profiles/r02), scaled to the average launch of this run',
+                'algorithmic_flops_per_launch': dom_flops / max(fused_n, 1),
+                'algorithmic_bytes_per_segment': ALG_BYTES_PER_SEG,
+                'traffic_over_algorithmic_bytes': (DOMINANT_NCU_TRAFFIC_PER_SEG / ALG_BYTES_PER_SEG
+                                                   if DOMINANT_NCU_TRAFFIC_PER_SEG else None),
+                'peak_source': pk['source'] + ' (bf16_tflops_sustained)',
                 'launches': fused_n, 'avg_launch_ms': fused_ms / max(fused_n, 1),
                 'share_of_step': fused_ms / (t_dev * 1000.0),
+                # SURVEY 8d stage-2 figure over the whole step (mel, head, tail convolutions included in the time)
+                'stage2_whole_step': {'tflops': value / world * FLOP_PER_SEG / 1e12,
+                                      'frac_of_bf16_sustained': value / world * FLOP_PER_SEG / 1e12 / pk['tf_sustained']},
                 'all_tensor_core_kernels': {'tflops': tens, 'frac_of_bf16_sustained': tens / pk['tf_sustained'],
                                             'ms_per_step': conv_ms / args.steps, 'launches': conv_n},
+                # secondary view: the same launches against the HBM roofline (bf16 activations in + out, once each)
+                'hbm_view': {'gbs': act_bytes * n_seg * args.steps / (fused_ms / 1000.0) / 1e9 if fused_ms > 0 else 0.0,
+                             'peak_gbs': pk['hbm_gbs'], 'note': 'inter-layer activations that still touch HBM'},
                 'classes_ms_per_step': {k: round(v[0] / args.steps, 3) for k, v in prof.items() if v[1]},
                 'kernels_ms_per_step': {k: round(v[0] / args.steps, 3) for k, v in detail.items()}}
     mel_ms, _ = prof['mel']
@@ -292,12 +344,11 @@ def main():
         roofline['mel_hbm_frac'] = (SEG_BYTES_MEL * n_seg * args.steps / (mel_ms / 1000.0) / 1e9) / pk['hbm_gbs']
 
     out = {
-        'metric': 'fingerprints/s (builder) and queries/s vs 10Mxd128 DB', 'value': value,
+        'metric': METRIC, 'value': value,
         'unit': 'fingerprints/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1000.0 * t_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
-        'config': {'workload': 'builder: %d x %d s synthetic 8 kHz mono int16 per GPU -> %d segments -> d=128 '
-                               'embeddings, configs/default.json, seeded random weights' % (args.clips, args.clip_seconds, n_seg),
+        'config': {'workload': workload_name(args.clips, args.clip_seconds, n_seg),
                    'chunk': args.chunk, 'l2': 'inputs (%.1f GB PCM per GPU) larger than L2' % (pcm.numel() * 2 / 1e9),
                    'embedding_norm_check': znorm},
         'e2e': {'value': e2e, 'unit': 'fingerprints/s', 'h2d_bytes_per_step': int(pcm.numel() * 2),
@@ -343,20 +394,23 @@ def bench_match(torch, args, world, rank, local, device, barrier, max_over_ranks
     emb = emb / emb.norm(dim=1, keepdim=True)
     db = Database.from_arrays(emb, key, {'top_k': k, 'frame_shift_mul': 1}, 0.5, device=local, songs=(s0, s1),
                               emb_is_shard=True)
-    # queries: every rank needs the same set; plant them in rank 0's shard and broadcast
+    # queries: planted uniformly over the whole database (every shard owns its share of the true diagonals); each
+    # rank contributes the rows it owns, a sum assembles them, rank 0 adds the noise and broadcasts
     nq = args.queries
     gq = torch.Generator(device=device)
     gq.manual_seed(5)
-    rows0 = int(pos[shard_songs(pos, world)[0][1]])
-    qsong = torch.randint(0, max(1, rows0 // song_len - 1), (nq,), generator=gq, device=device)
+    qsong = torch.randint(0, max(1, n_songs - 1), (nq,), generator=gq, device=device)
     qoff = torch.randint(0, song_len - q_len + 1, (nq,), generator=gq, device=device)
-    idx = (qsong * song_len + qoff)[:, None] + torch.arange(q_len, device=device)[None, :]
+    idx = ((qsong * song_len + qoff)[:, None] + torch.arange(q_len, device=device)[None, :]).reshape(-1)
+    mine = (idx >= r0) & (idx < r1)
+    q = torch.zeros((nq * q_len, d), device=device)
+    q[mine] = emb[idx[mine] - r0]
+    if world > 1:
+        torch.distributed.all_reduce(q)
     if rank == 0:
-        q = emb[idx.reshape(-1)].reshape(nq, q_len, d)
+        q = q.reshape(nq, q_len, d)
         q = q + torch.randn(q.shape, generator=gq, device=device) * (1.0 / d ** 0.5)
         q = (q / q.norm(dim=2, keepdim=True)).reshape(-1, d).contiguous()
-    else:
-        q = torch.empty((nq * q_len, d), device=device)
     if world > 1:
         torch.distributed.broadcast(q, 0)
     emb_host = emb.cpu() if (world == 1 and not args.no_cpu) else None   # for the CPU baseline of this leg
@@ -379,12 +433,17 @@ def bench_match(torch, args, world, rank, local, device, barrier, max_over_ranks
             times.append(t)
         res['song'], res['time'] = np.concatenate(songs), np.concatenate(times)
 
+    msteps = max(1, args.steps)
+    timed(torch, step, 0, max(1, min(args.warmup, 2)), barrier)       # warm-up OUTSIDE the profiled window
+    t_plain = max_over_ranks(timed(torch, step, msteps, 0, barrier))  # the reported value: no per-launch event pairs
     l0 = _lib.launches(local)
     _lib.profile(local, True)
-    t = max_over_ranks(timed(torch, step, 1, 1, barrier))
+    timed(torch, step, 1, 0, barrier)                                 # one more pass only for the per-kernel breakdown
     prof = _lib.profile_read(local)
     detail = _lib.profile_detail(local)
     _lib.profile(local, False)
+    launches_per_step = int(_lib.launches(local) - l0)
+    t = t_plain / msteps
     acc = float(np.mean((res['song'] == qsong.cpu().numpy()) & (res['time'] == qoff.cpu().numpy() * 0.5)))
     # per-file regime (matcher.py:136 issues one search per query file: 19 vectors per database pass): the scan is
     # HBM-bound there -- report it against the measured copy bandwidth (north_star: >= 70 % of the HBM roofline)
@@ -402,18 +461,45 @@ def bench_match(torch, args, world, rank, local, device, barrier, max_over_ranks
     per_file = {'queries_per_pass': q_len, 'scan_ms': pf_ms, 'search_ms_all_kernels': pf_all,
                 'scan_gbs': (r1 - r0) * d * 2 / (pf_ms / 1e3) / 1e9 if pf_ms else None,
                 'frac_of_hbm_peak': ((r1 - r0) * d * 2 / (pf_ms / 1e3) / 1e9) / pk['hbm_gbs'] if pf_ms else None}
-    # the same through the single-call host API with host buffers (only meaningful at world == 1)
-    e2e = None
-    if world == 1:
-        qh = q.cpu().numpy()
-        db.query_batch(qh[:B * q_len], qi[:B])
-        t0 = time.perf_counter()
+    # end to end through the host API with HOST buffers (queries from pinned host memory, answers back as numpy),
+    # batched regime: the same sharded call, at every N
+    qh = torch.empty(q.shape, dtype=torch.float32, pin_memory=True)
+    qh.copy_(q)
+    torch.cuda.synchronize()
+    qhn = qh.numpy()
+
+    def step_e2e():
         for b0 in range(0, nq, B):
             b1 = min(nq, b0 + B)
             qii = qi[b0:b1].copy()
             qii[:, 0] -= b0 * q_len
-            db.query_batch(qh[b0 * q_len:b1 * q_len], qii)
-        e2e = nq / (time.perf_counter() - t0)
+            sdb.query_batch(qhn[b0 * q_len:b1 * q_len], qii)
+
+    step_e2e()
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    step_e2e()
+    torch.cuda.synchronize()
+    barrier()
+    e2e = nq / max_over_ranks(time.perf_counter() - t0)
+    # per-file regime end to end: one call per query file, the reference's own pattern (matcher.py:136)
+    nf = min(nq, 200)
+    one = np.array([[0, q_len]], np.int64)
+    for i in range(3):
+        sdb.query_batch(qhn[i * q_len:(i + 1) * q_len], one)
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ok_pf = 0
+    for i in range(nf):
+        _, g1, t1 = sdb.query_batch(qhn[i * q_len:(i + 1) * q_len], one)
+        ok_pf += int(g1[0] == res['song'][i] and t1[0] == res['time'][i])
+    torch.cuda.synchronize()
+    barrier()
+    per_file['e2e_queries_per_s'] = nf / max_over_ranks(time.perf_counter() - t0)
+    per_file['e2e_files'] = nf
+    per_file['e2e_equals_batched'] = ok_pf == nf
     cpu = None
     if emb_host is not None:
         # reference path on the host cores: exact inner-product top-k (torch-CPU matmul + topk standing in for
@@ -436,19 +522,22 @@ def bench_match(torch, args, world, rank, local, device, barrier, max_over_ranks
                          'IndexFlatIP, rerank = C restatement of cpp/seqscore.cpp' % (ncpu, nq, n),
                'answers_equal_gpu': ok == ncpu}
         del emb_host, dbn
-    scan_ms, scan_n = prof['knn_scan']
+    scan_ms, scan_n = detail.get('knn_scan_full', (0.0, 0))     # filtered scans of ONE profiled step (pre-pass excluded)
     rows_local = r1 - r0
-    passes = scan_n  # each launch streams (a sample of, or all of) the shard once
-    return {'metric': 'queries/s', 'value': nq / t, 'unit': 'queries/s', 'e2e': e2e, 'db_rows': n, 'queries': nq,
+    passes = scan_n  # each launch streams the shard once against up to 256 resident queries
+    scan_flops = 2.0 * nq * q_len * rows_local * d
+    return {'metric': 'queries/s', 'value': nq / t, 'unit': 'queries/s',
+            'e2e': {'value': e2e, 'unit': 'queries/s', 'h2d_bytes_per_step': int(nq * q_len * d * 4), 'd2h_bytes_per_step': int(nq * 12)}, 'db_rows': n, 'queries': nq,
             'vectors_per_query': q_len, 'top_k': k, 'shard_rows': rows_local, 'accuracy_vs_planted': acc,
             'query_files_per_db_pass': B, 'regime': 'batched: 256 query vectors per database pass (TMEM-read-bound epilogue, see DESIGN.md)',
             'classes_ms': {kk: round(v[0], 3) for kk, v in prof.items() if v[1]},
             'kernels_ms': {kk: [round(v[0], 3), v[1]] for kk, v in detail.items()},
             'knn_scan': {'launches': passes, 'ms': scan_ms,
-                         'tflops': (2.0 * nq * q_len * rows_local * d) / (scan_ms / 1000.0) / 1e12 if scan_ms else None,
-                         'frac_of_bf16_peak': ((2.0 * nq * q_len * rows_local * d) / (scan_ms / 1000.0) / 1e12) / pk['tf_sustained'] if scan_ms else None},
+                         'tflops': scan_flops / (scan_ms / 1000.0) / 1e12 if scan_ms else None,
+                         'frac_of_bf16_sustained': scan_flops / (scan_ms / 1000.0) / 1e12 / pk['tf_sustained'] if scan_ms else None,
+                         'gbs': passes * rows_local * d * 2 / (scan_ms / 1000.0) / 1e9 if scan_ms else None},
             'per_file_regime': per_file,
-            'gpu_launches': int(_lib.launches(local) - l0), 'cpu_baseline': cpu}
+            'steps': msteps, 'ms_per_step': 1000.0 * t, 'gpu_launches': launches_per_step, 'cpu_baseline': cpu}
 
 
 if __name__ == '__main__':

@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from . import synth
-from .database import Database, read_file_list, write_flat_ip_index
+from .database import Database, read_file_list, write_flat_ip_index_from_file
 from .datautil import musicdata
 from .extract import Extractor
 
@@ -41,38 +41,60 @@ def _load_state(model_dir):
     return {k: v.float() for k, v in sd.items()}
 
 
-def extract_files(ex, files, frame_shift_mul, log=None):
-    """Fingerprints of every file, concatenated in list order, + segments per file (0 = unreadable,
-    builder.py:82-86).  Mono 16-bit files at the model rate take the fused PCM path in ONE batched call."""
+# Files are processed in bounded batches (the reference streams file by file, builder.py:75-103): a 10 M-row
+# database is ~80 GB of int16 PCM, which must never sit in host memory at once.
+BATCH_PCM_BYTES = 1 << 30      # ~1 GB of decoded PCM per GPU call
+BATCH_FILES = 4096
+
+
+def iter_extract(ex, files, frame_shift_mul, max_bytes=None, max_files=None):
+    """Yields (first file index, emb [n, d] fp32, counts [n_files_in_batch]) for consecutive batches of `files`.
+    Fingerprints are in list order; a count of 0 = unreadable file (builder.py:82-86).  Mono 16-bit files at the
+    model rate take the fused PCM path, one batched GPU call per batch."""
     sr = ex.params['sample_rate']
-    kinds, datas = [], []
-    for f in files:
-        try:
-            kind, data = musicdata.read_wav_pcm16(f, sr)
-        except Exception as e:  # noqa: BLE001  (musicdata.py:95-101: log and yield zero segments)
-            print('load %s error! %s' % (f, e))
-            kind, data = 'error', None
-        kinds.append(kind)
-        datas.append(data)
-    counts = np.zeros(len(files), np.int64)
-    parts = [None] * len(files)
-    pcm_ids = [i for i, k in enumerate(kinds) if k == 'pcm16']
-    if pcm_ids:
-        off = np.concatenate([[0], np.cumsum([len(datas[i]) for i in pcm_ids])]).astype(np.int64)
-        pcm = np.concatenate([datas[i] for i in pcm_ids]) if off[-1] else np.zeros(0, np.int16)
-        z, cnt = ex.extract_pcm16(pcm, off, frame_shift_mul=frame_shift_mul)
-        pos = np.concatenate([[0], np.cumsum(cnt)])
-        for j, i in enumerate(pcm_ids):
-            parts[i] = z[pos[j]:pos[j + 1]]
-            counts[i] = cnt[j]
-    for i, k in enumerate(kinds):
-        if k == 'float':
-            rows = musicdata.frame_float(datas[i], ex.seg_len, ex.hop // frame_shift_mul)
-            parts[i] = ex.extract_segments(rows)
-            counts[i] = rows.shape[0]
-    emb = [p for p in parts if p is not None and len(p)]
-    emb = np.concatenate(emb) if emb else np.zeros((0, ex.d), np.float32)
-    return emb, counts
+    max_bytes = BATCH_PCM_BYTES if max_bytes is None else max_bytes
+    max_files = BATCH_FILES if max_files is None else max_files
+    i = 0
+    while i < len(files):
+        i0, kinds, datas, nbytes = i, [], [], 0
+        while i < len(files) and len(kinds) < max_files and (nbytes < max_bytes or not kinds):
+            try:
+                kind, data = musicdata.read_wav_pcm16(files[i], sr)
+                nbytes += data.nbytes
+            except Exception as e:  # noqa: BLE001  (musicdata.py:95-101: log and yield zero segments)
+                print('load %s error! %s' % (files[i], e))
+                kind, data = 'error', None
+            kinds.append(kind)
+            datas.append(data)
+            i += 1
+        counts = np.zeros(len(kinds), np.int64)
+        parts = [None] * len(kinds)
+        pcm_ids = [j for j, k in enumerate(kinds) if k == 'pcm16']
+        if pcm_ids:
+            off = np.concatenate([[0], np.cumsum([len(datas[j]) for j in pcm_ids])]).astype(np.int64)
+            pcm = np.concatenate([datas[j] for j in pcm_ids]) if off[-1] else np.zeros(0, np.int16)
+            z, cnt = ex.extract_pcm16(pcm, off, frame_shift_mul=frame_shift_mul)
+            pos = np.concatenate([[0], np.cumsum(cnt)])
+            for jj, j in enumerate(pcm_ids):
+                parts[j] = z[pos[jj]:pos[jj + 1]]
+                counts[j] = cnt[jj]
+        for j, k in enumerate(kinds):
+            if k == 'float':
+                rows = musicdata.frame_float(datas[j], ex.seg_len, ex.hop // frame_shift_mul)
+                parts[j] = ex.extract_segments(rows)
+                counts[j] = rows.shape[0]
+        emb = [q for q in parts if q is not None and len(q)]
+        yield i0, (np.concatenate(emb) if emb else np.zeros((0, ex.d), np.float32)), counts
+
+
+def extract_files(ex, files, frame_shift_mul, log=None):
+    """All fingerprints at once (small lists / tests); the command lines stream through iter_extract."""
+    embs, counts = [], []
+    for _, e, c in iter_extract(ex, files, frame_shift_mul):
+        embs.append(e)
+        counts.append(c)
+    emb = np.concatenate(embs) if embs else np.zeros((0, ex.d), np.float32)
+    return emb, (np.concatenate(counts) if counts else np.zeros(0, np.int64))
 
 
 def builder_main(argv):
@@ -86,14 +108,25 @@ def builder_main(argv):
     print('model loaded')
     files = read_file_list(file_list_for_db)
     os.makedirs(dir_for_db, exist_ok=True)
+    factory = params.get('indexer', {}).get('index_factory', 'Flat')
+    if factory != 'Flat':
+        # builder.py:111-130 trains a faiss index of this type; this build searches exactly (BASELINE configs 3/4)
+        print('warning: index_factory %r is not built here; landmarkValue is written as an exact inner-product '
+              'index (IndexFlatIP) and searched by brute force' % factory)
     t0 = time.time()
-    emb, counts = extract_files(ex, files, 1)          # builder.py:64: the database is always built at fsm = 1
-    print('total', emb.shape[0], 'embeddings (%.3fs)' % (time.time() - t0))
-    if emb.shape[0] == 0:
+    total, counts = 0, []
+    with open(os.path.join(dir_for_db, 'embeddings'), 'wb') as femb:            # builder.py:71,99: appended per batch
+        for _, emb, cnt in iter_extract(ex, files, 1):                          # builder.py:64: always fsm = 1
+            femb.write(np.ascontiguousarray(emb, dtype=np.float32).tobytes())
+            total += emb.shape[0]
+            counts.append(cnt)
+    counts = np.concatenate(counts) if counts else np.zeros(0, np.int64)
+    print('total', total, 'embeddings (%.3fs)' % (time.time() - t0))
+    if total == 0:
         print('The database is empty!')
-    emb.astype(np.float32).tofile(os.path.join(dir_for_db, 'embeddings'))           # builder.py:99
     print('writing database')
-    write_flat_ip_index(os.path.join(dir_for_db, 'landmarkValue'), emb)             # builder.py:135-136
+    write_flat_ip_index_from_file(os.path.join(dir_for_db, 'landmarkValue'), os.path.join(dir_for_db, 'embeddings'),
+                                  total, ex.d)                                  # builder.py:135-136
     counts.astype(np.int32).tofile(os.path.join(dir_for_db, 'landmarkKey'))         # builder.py:138-139
     shutil.copyfile(file_list_for_db, os.path.join(dir_for_db, 'songList.txt'))     # builder.py:141
     shutil.copyfile(cfg_path, os.path.join(dir_for_db, 'configs.json'))             # builder.py:144
@@ -101,39 +134,55 @@ def builder_main(argv):
     return 0
 
 
-def _write_results(result_file, names, db, scores, songs, times, song_scores):
-    result_file2 = os.path.splitext(result_file)[0] + '_detail.csv'
-    with open(result_file, 'w', encoding='utf8', newline='\n') as fout, \
-            open(result_file2, 'w', encoding='utf8', newline='\n') as fout2, \
-            open(result_file + '.bin', 'wb') as fbin:
-        w = csv.writer(fout2)
-        w.writerow(['query', 'answer', 'score', 'time', 'part_scores'])              # matcher.py:84
-        n_songs = len(db.songList)
-        for i, name in enumerate(names):
-            if songs[i] is None:                                                     # matcher.py:94-107
-                fout.write('%s\t%s\n' % (name, 'error'))
-                w.writerow([name, 'error', -1e999, 0])
-                fbin.write(np.zeros([n_songs, 2], dtype=np.float32).tobytes())
-                continue
-            ans = db.songList[songs[i]]                                              # matcher.py:138 (-1 -> last)
-            fout.write('%s\t%s\n' % (name, ans))
-            w.writerow([name, ans, scores[i], times[i]])
-            fbin.write(song_scores[i].astype(np.float32).tobytes())
+class _ResultWriter:
+    """matcher.py:40-42,80-84,157-166: the three result files, written row by row as batches finish (the .bin
+    grows by n_songs * 8 bytes per query and is never held in memory)."""
+
+    def __init__(self, result_file, db):
+        self.db = db
+        self.fout = open(result_file, 'w', encoding='utf8', newline='\n')
+        self.fout2 = open(os.path.splitext(result_file)[0] + '_detail.csv', 'w', encoding='utf8', newline='\n')
+        self.fbin = open(result_file + '.bin', 'wb')
+        self.w = csv.writer(self.fout2)
+        self.w.writerow(['query', 'answer', 'score', 'time', 'part_scores'])         # matcher.py:84
+        self.n_songs = len(db.songList)
+
+    def error(self, name):                                                           # matcher.py:94-107
+        self.fout.write('%s\t%s\n' % (name, 'error'))
+        self.w.writerow([name, 'error', -1e999, 0])
+        self.fbin.write(np.zeros([self.n_songs, 2], dtype=np.float32).tobytes())
+
+    def row(self, name, score, song, tim, song_scores):
+        ans = self.db.songList[song]                                                 # matcher.py:138 (-1 -> last)
+        self.fout.write('%s\t%s\n' % (name, ans))
+        self.w.writerow([name, ans, score, tim])
+        self.fbin.write(np.ascontiguousarray(song_scores, dtype=np.float32).tobytes())
+
+    def close(self):
+        for f in (self.fout, self.fout2, self.fbin):
+            f.close()
 
 
-def _match(db, names, emb, counts, result_file, batch=256):
+def _match(db, names, emb, counts, out, batch=256):
+    """Search + sequence score for the query files `names` (fingerprints `emb`, `counts[i]` rows each); rows go
+    to the writer `out` in list order."""
     pos = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
-    scores, songs, times, sscores = [None] * len(names), [None] * len(names), [None] * len(names), [None] * len(names)
-    ok = [i for i in range(len(names)) if counts[i] > 0]
-    for b0 in range(0, len(ok), batch):
-        ids = ok[b0:b0 + batch]
-        q = np.concatenate([emb[pos[i]:pos[i + 1]] for i in ids])
-        lens = np.array([counts[i] for i in ids], np.int64)
+    i = 0
+    while i < len(names):
+        if counts[i] <= 0:
+            out.error(names[i])
+            i += 1
+            continue
+        ids = []
+        while i < len(names) and counts[i] > 0 and len(ids) < batch:
+            ids.append(i)
+            i += 1
+        q = np.concatenate([emb[pos[j]:pos[j + 1]] for j in ids])
+        lens = np.array([counts[j] for j in ids], np.int64)
         qi = np.stack([np.concatenate([[0], np.cumsum(lens)[:-1]]), lens], axis=1)
         s, g, t, ss = db.query_batch(q, qi, want_song_scores=True)
-        for j, i in enumerate(ids):
-            scores[i], songs[i], times[i], sscores[i] = float(s[j]), int(g[j]), float(t[j]), ss[j]
-    _write_results(result_file, names, db, scores, songs, times, sscores)
+        for jj, j in enumerate(ids):
+            out.row(names[j], float(s[jj]), int(g[jj]), float(t[jj]), ss[jj])
 
 
 def matcher_main(argv):
@@ -151,8 +200,12 @@ def matcher_main(argv):
     print('database loaded')
     names = read_file_list(file_list_for_query)
     t0 = time.time()
-    emb, counts = extract_files(ex, names, fsm)
-    _match(db, names, emb, counts, result_file)
+    out = _ResultWriter(result_file, db)
+    try:
+        for i0, emb, counts in iter_extract(ex, names, fsm):
+            _match(db, names[i0:i0 + len(counts)], emb, counts, out)
+    finally:
+        out.close()
     print('total query time %.6fs' % (time.time() - t0))
     return 0
 
@@ -167,12 +220,17 @@ def extractemb_main(argv):
     fsm = params['indexer'].get('frame_shift_mul', 1)
     ex = Extractor(params, _load_state(dir_for_db))
     names = read_file_list(file_list_for_query)
-    emb, counts = extract_files(ex, names, fsm)
     os.makedirs(out_dir, exist_ok=True)
-    emb.astype(np.float32).tofile(os.path.join(out_dir, 'query_embeddings'))        # extractemb.py:83
+    total, counts = 0, []
+    with open(os.path.join(out_dir, 'query_embeddings'), 'wb') as femb:             # extractemb.py:83
+        for _, emb, cnt in iter_extract(ex, names, fsm):
+            femb.write(np.ascontiguousarray(emb, dtype=np.float32).tobytes())
+            total += emb.shape[0]
+            counts.append(cnt)
+    counts = np.concatenate(counts) if counts else np.zeros(0, np.int64)
     pos = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
     np.stack([pos[:-1], counts.astype(np.int64)], axis=1).tofile(os.path.join(out_dir, 'query_index'))  # :85
-    print('total', emb.shape[0], 'embeddings')
+    print('total', total, 'embeddings')
     shutil.copyfile(file_list_for_query, os.path.join(out_dir, 'queryList.txt'))    # extractemb.py:90
     shutil.copyfile(cfg, os.path.join(out_dir, 'configs.json'))
     return 0
@@ -187,9 +245,18 @@ def matchemb_main(argv):
     names = read_file_list(os.path.join(dir_for_query, 'queryList.txt'))
     d = params['model']['d']
     db = Database(dir_for_db, params['indexer'], params['hop_size'])
-    emb = np.fromfile(os.path.join(dir_for_query, 'query_embeddings'), dtype=np.float32).reshape([-1, d])
+    emb = np.memmap(os.path.join(dir_for_query, 'query_embeddings'), dtype=np.float32, mode='r').reshape([-1, d]) \
+        if os.path.getsize(os.path.join(dir_for_query, 'query_embeddings')) else np.zeros((0, d), np.float32)
     qidx = np.fromfile(os.path.join(dir_for_query, 'query_index'), dtype=np.int64).reshape([-1, 2])
-    # matchemb.py:63-65 slices [start, start+len) per file; files that failed to load have len 0
-    flat = np.concatenate([emb[s:s + l] for s, l in qidx]) if len(qidx) else emb[:0]
-    _match(db, names, flat, qidx[:, 1], result_file)
+    # matchemb.py:63-65 slices [start, start+len) per file; files that failed to load have len 0.  The embedding
+    # file is memory-mapped and walked in batches of query files.
+    out = _ResultWriter(result_file, db)
+    try:
+        step = 4096
+        for i0 in range(0, len(names), step):
+            part = qidx[i0:i0 + step]
+            flat = np.concatenate([emb[s:s + l] for s, l in part]) if len(part) else emb[:0]
+            _match(db, names[i0:i0 + step], flat, part[:, 1], out)
+    finally:
+        out.close()
     return 0

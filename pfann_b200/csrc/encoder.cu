@@ -843,12 +843,6 @@ int launch_l0_fused(Model *m, const float *mel, ActT *X, int nb) {
     return PFANN_OK;
 }
 
-// largest dynamic shared-memory size the head kernels have been opted in to (shared by all callers)
-size_t &head_smem_attr() {
-    static size_t attr = 0;
-    return attr;
-}
-
 // one chunk of nb <= m->chunk samples through the 8 layers + head
 template <typename ActT>
 int forward_chunk(Model *m, const float *mel, int nb, int norm, float *z) {
@@ -914,14 +908,11 @@ int forward_chunk(Model *m, const float *mel, int nb, int norm, float *z) {
     const size_t smem_fast =
         ((size_t)m->u * v * threads + 2 * (size_t)m->u * threads + (size_t)HEAD_HG * HEAD_HS * (threads / 32)) * 4;
     if ((v == 8 || v == 16) && threads * HEAD_HG <= 256 && smem_fast <= 200 * 1024) {
-        // one cache for both instantiations of this template: a per-instantiation static once LOWERED the limit the
-        // other instantiation had raised (fp32 n640d64 after bf16 default) and the next default launch failed
-        size_t &attr = head_smem_attr();
-        if (smem_fast > attr) {
+        // the opt-in is per device/context and per function: set it for the instantiation being launched
+        if (v == 8)
             PF_CUDA(cudaFuncSetAttribute(head_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
+        else
             PF_CUDA(cudaFuncSetAttribute(head_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
-            attr = smem_fast;
-        }
         const int want = (nb + HEAD_HG * HEAD_HS - 1) / (HEAD_HG * HEAD_HS);
         const int grid = want < m->ctx->sm_count ? want : m->ctx->sm_count;
         if (v == 8)
@@ -1028,7 +1019,8 @@ void pfann_model_destroy(pfann_model *hm) {
     cudaFree(m->w1); cudaFree(m->b1); cudaFree(m->w2); cudaFree(m->b2); cudaFree(m->l0_w);
     cudaFree(m->l0_gb16); cudaFree(m->l0_btile);
     m->ybuf.release(); m->xa.release(); m->xb.release(); m->stats.release(); m->partials.release();
-    m->tapbuf.release(); m->melbuf.release(); m->zbuf.release(); m->ln_part.release(); m->ln_err.release();
+    m->tapbuf.release(); m->melbuf.release(); m->zbuf.release(); m->ln_part.release();
+    if (m->ln_err_host) cudaFreeHost(m->ln_err_host);
     m->mombuf.release();
     delete m;
 }
@@ -1195,7 +1187,7 @@ int pfann_model_forward(pfann_model *hm, const float *mel, int64_t B, int norm, 
     PF_TRY(stage_output(m->ctx, 0, z, out_b, &zd));
     PF_TRY(model_forward_dev(m, (const float *)xd, B, norm, (float *)zd, nullptr));
     PF_TRY(finish_output(m->ctx, 0, z, out_b));
-    return is_device_ptr(z) ? PFANN_OK : tc_ln_check(m);
+    return tc_ln_check(m, !is_device_ptr(z));
 }
 
 int pfann_model_get_activation(pfann_model *hm, int layer, float *out, int64_t numel) {

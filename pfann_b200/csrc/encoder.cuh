@@ -60,7 +60,8 @@ struct Model {
     bool l0_fused = false;
     bool y_bf16 = true;     // tensor-core convs write their raw output in bf16 (statistics stay fp32)
     DevBuf ybuf, xa, xb, stats, partials, tapbuf, melbuf, zbuf;   // chunk-sized workspace ("tail" phase)
-    DevBuf ln_part, ln_err;  // fused conv+LayerNorm: statistics exchange table, time-out flag
+    DevBuf ln_part;          // fused conv+LayerNorm: statistics exchange table
+    int *ln_err_host = nullptr, *ln_err_dev = nullptr;  // its time-out flag: pinned, mapped (readable without a sync)
     float2 *cur_stats = nullptr, *cur_partials = nullptr;  // statistics buffers of the phase being executed
     const double *cur_moments = nullptr;  // layer-0 moments of the chunk being executed when the mel kernel made them
     DevBuf mombuf;                        // [chunk][9] doubles (fused extract path)
@@ -86,7 +87,10 @@ struct LnGeom {
 };
 LnGeom ln_geom(const ConvGeom &g);
 bool tc_ln_supported(Model *m, int idx);
-int tc_ln_check(Model *m);
+// Reports (and clears) a timed-out statistics exchange.  sync = true waits for the stream first (calls whose results
+// are complete on return); sync = false only looks at the flag as it is now, i.e. reports a time-out of EARLIER
+// stream-ordered work (device-pointer calls must not block).
+int tc_ln_check(Model *m, bool sync = true);
 // layer-0 conv1 + ln1 + ReLU as one K = 16 MMA per 128 positions (statistics from the moments kernel)
 bool tc_l0_supported(Model *m);
 int tc_l0(Model *m, const float *mel, const float2 *stats, __nv_bfloat16 *X, int nb);

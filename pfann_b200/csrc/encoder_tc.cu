@@ -963,12 +963,8 @@ int launch_tc(Model *m, const TcConv &tc, const TcArgs &args_in) {
     size_t smem = 0;
     plan_ring(BN, args.kb_per_tap * args.ntaps, args.NT, 4 * 4096 + (size_t)args.Co * 4, &args.n_stages, &args.b_res, &smem);
     PF_CHECK(args.n_stages >= 2, PFANN_ERR_UNSUPPORTED, "conv GEMM: no room for a shared-memory ring");
-    static size_t attr_smem = 0;  // per instantiation: raise the opt-in limit only when a launch needs more
-    if (smem > attr_smem) {
-        PF_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, YT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem));
-        attr_smem = smem;
-    }
+    // the opt-in is per device/context: set it on every launch (a process-wide cache skipped it on a second GPU)
+    PF_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, YT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long ntiles = (long long)args.m_tiles * args.NT;
     long long grid = m->ctx->sm_count;
     if (grid > ntiles) grid = ntiles;
@@ -1006,22 +1002,21 @@ int launch_tc_ln(Model *m, const TcConv &tc, const LnGeom &lg, const TcLnArgs &a
     PF_CHECK(st >= 2, PFANN_ERR_UNSUPPORTED, "fused conv+LN: no room for a shared-memory ring");
     args.n_stages = (int)st;
     const size_t smem = st * (A + (args.b_res ? 0 : B)) + (args.b_res ? bres : 0) + fixed + 1024;
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-        PF_CUDA(cudaFuncSetAttribute(conv_ln_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (args.prof)
         PF_CUDA(cudaFuncSetAttribute(conv_ln_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
-    }
+    else
+        PF_CUDA(cudaFuncSetAttribute(conv_ln_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // exchange table: all-ones = "not written"
     const size_t part_bytes = (size_t)args.n_groups * lg.P * LN_EPI_WARPS * sizeof(unsigned long long);
     PF_TRY(m->ln_part.ensure(part_bytes));
-    if (m->ln_err.p == nullptr) {
-        PF_TRY(m->ln_err.ensure(sizeof(int)));
-        PF_CUDA(cudaMemsetAsync(m->ln_err.p, 0, sizeof(int), m->ctx->stream));
+    if (m->ln_err_host == nullptr) {
+        PF_CUDA(cudaHostAlloc(&m->ln_err_host, sizeof(int), cudaHostAllocMapped));
+        *m->ln_err_host = 0;
+        PF_CUDA(cudaHostGetDevicePointer(&m->ln_err_dev, m->ln_err_host, 0));
     }
     PF_CUDA(cudaMemsetAsync(m->ln_part.p, 0xFF, part_bytes, m->ctx->stream));
     args.part = m->ln_part.as<unsigned long long>();
-    args.err = m->ln_err.as<int>();
+    args.err = m->ln_err_dev;
     int L = m->ctx->sm_count / lg.P;
     if (L > args.n_groups) L = args.n_groups;
     PF_CHECK(L >= 1, PFANN_ERR_UNSUPPORTED, "fused conv+LN: %d positions do not fit %d SMs", lg.P, m->ctx->sm_count);
@@ -1218,11 +1213,7 @@ int tc_l0(Model *m, const float *mel, const float2 *stats, __nv_bfloat16 *X, int
     static const char *env_ds = getenv("PFANN_B200_L0_DIRECT_STORE");
     a.direct_store = env_ds ? atoi(env_ds) : 1;  // measured 2 % faster than the staged 64-byte row pieces
     const size_t smem = (size_t)L0_STAGES * 16384 + 16384 + 16 * 2048 + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-        PF_CUDA(cudaFuncSetAttribute(l0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    PF_CUDA(cudaFuncSetAttribute(l0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long grid = m->ctx->sm_count;
     const long long tiles = (long long)a.PB * nb;
     if (grid > tiles) grid = tiles;
@@ -1233,13 +1224,16 @@ int tc_l0(Model *m, const float *mel, const float2 *stats, __nv_bfloat16 *X, int
     return PFANN_OK;
 }
 
-// 1 when a statistics exchange of the fused conv+LayerNorm kernel ever timed out (synchronises the stream)
-int tc_ln_check(Model *m) {
-    if (m->ln_err.p == nullptr) return PFANN_OK;
-    int flag = 0;
-    PF_CUDA(cudaMemcpyAsync(&flag, m->ln_err.p, sizeof(int), cudaMemcpyDeviceToHost, m->ctx->stream));
-    PF_CUDA(cudaStreamSynchronize(m->ctx->stream));
-    PF_CHECK(flag == 0, PFANN_ERR_STATE, "fused conv+LayerNorm: statistics exchange timed out (CTAs not co-resident?)");
+int tc_ln_check(Model *m, bool sync) {
+    if (m->ln_err_host == nullptr) return PFANN_OK;
+    if (sync) PF_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    const int flag = *reinterpret_cast<volatile int *>(m->ln_err_host);
+    if (flag != 0) {
+        *m->ln_err_host = 0;  // reported once; later calls start clean
+        set_error("fused conv+LayerNorm: statistics exchange timed out (CTAs not co-resident?); the embeddings of "
+                  "the affected call are invalid");
+        return PFANN_ERR_STATE;
+    }
     return PFANN_OK;
 }
 

@@ -72,7 +72,7 @@ int pfann_extract_segments(pfann_mel *mel, pfann_model *hm, const float *x, int6
         PF_TRY(model_forward_dev(m, m->melbuf.as<float>(), nb, norm, (float *)zd + b0 * m->d, mom));
     }
     PF_TRY(finish_output(m->ctx, 0, z, out_b));
-    return is_device_ptr(z) ? PFANN_OK : tc_ln_check(m);
+    return tc_ln_check(m, !is_device_ptr(z));
 }
 
 int pfann_extract_pcm16(pfann_mel *mel, pfann_model *hm, const int16_t *pcm, const int64_t *clip_off, int n_clips,

@@ -420,6 +420,10 @@ namespace pfann {
 int db_search_dev(Db *db, const float *q, int64_t Q, int k, float *dist, int64_t *labels) {
     cudaStream_t st = db->ctx->stream;
     if (Q == 0) return PFANN_OK;
+    // every caller (pfann_db_search / _query / _rerank) ends up here: the candidate lists and the k-th selection
+    // are sized for k <= cand_cap and k <= 2048
+    PF_CHECK(k > 0 && k <= db->cand_cap && k <= 2048, PFANN_ERR_UNSUPPORTED, "database search: k=%d too large (max %d)", k,
+             db->cand_cap < 2048 ? db->cand_cap : 2048);
     if (db->n == 0) {
         fill_empty_kernel<<<cdiv(Q * k, 256), 256, 0, st>>>(dist, labels, Q * k);
         db->ctx->launches++;
@@ -544,6 +548,10 @@ int db_search_dev(Db *db, const float *q, int64_t Q, int k, float *dist, int64_t
 
 }  // namespace pfann
 
+namespace {
+int db_fill(Db *db, const float *emb, const int32_t *landmark_key);  // device allocations + copies of pfann_db_open
+}
+
 extern "C" {
 
 int pfann_db_open(pfann_ctx *hctx, const float *emb, int64_t n, int d, const int32_t *landmark_key, int n_songs,
@@ -559,6 +567,22 @@ int pfann_db_open(pfann_ctx *hctx, const float *emb, int64_t n, int d, const int
     Db *db = new Db();
     db->ctx = ctx;
     db->n = n; db->d = d; db->n_songs = n_songs; db->id_base = id_base; db->song_base = song_base;
+    const int rc_fill = db_fill(db, emb, landmark_key);
+    if (rc_fill != PFANN_OK) {  // nothing of a half-built shard survives an error
+        pfann_db_close(reinterpret_cast<pfann_db *>(db));
+        return rc_fill;
+    }
+    *out = reinterpret_cast<pfann_db *>(db);
+    return PFANN_OK;
+}
+
+}  // extern "C"
+
+namespace {
+int db_fill(Db *db, const float *emb, const int32_t *landmark_key) {
+    Ctx *ctx = db->ctx;
+    const int64_t n = db->n, id_base = db->id_base;
+    const int d = db->d, n_songs = db->n_songs;
     db->song_pos_host.resize((size_t)n_songs + 1);
     db->song_pos_host[0] = id_base;
     for (int i = 0; i < n_songs; i++) {  // database.py:83-86: cumulative sum with a leading zero
@@ -575,7 +599,8 @@ int pfann_db_open(pfann_ctx *hctx, const float *emb, int64_t n, int d, const int
     PF_CUDA(cudaMalloc(&db->emb32, sizeof(float) * (ne ? ne : 1)));
     PF_CUDA(cudaMalloc(&db->emb16, sizeof(__nv_bfloat16) * (ne ? ne : 1)));
     if (n > 0) {
-        PF_CUDA(cudaMemcpy(db->emb32, emb, sizeof(float) * ne, cudaMemcpyDefault));
+        // on the context's stream: a device-resident `emb` produced by stream-ordered work is read in order
+        PF_CUDA(cudaMemcpyAsync(db->emb32, emb, sizeof(float) * ne, cudaMemcpyDefault, ctx->stream));
         to_bf16_kernel<<<cdiv((long long)ne, 256), 256, 0, ctx->stream>>>(db->emb32, db->emb16, (int64_t)ne);
         unsigned int *dmax;
         PF_CUDA(cudaMalloc(&dmax, sizeof(unsigned int)));
@@ -584,18 +609,16 @@ int pfann_db_open(pfann_ctx *hctx, const float *emb, int64_t n, int d, const int
         ctx->launches += 2;
         unsigned int hm = 0;
         PF_CUDA(cudaMemcpyAsync(&hm, dmax, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
-        PF_CUDA(cudaStreamSynchronize(ctx->stream));
-        PF_CUDA(cudaFree(dmax));
+        const cudaError_t e_sync = cudaStreamSynchronize(ctx->stream);
+        cudaFree(dmax);
+        PF_CUDA(e_sync);
         memcpy(&db->max_norm, &hm, sizeof(float));
     }
-    int rc = knn_tc_prepare(db);
-    if (rc != PFANN_OK) {
-        pfann_db_close(reinterpret_cast<pfann_db *>(db));
-        return rc;
-    }
-    *out = reinterpret_cast<pfann_db *>(db);
-    return PFANN_OK;
+    return knn_tc_prepare(db);
 }
+}  // namespace
+
+extern "C" {
 
 void pfann_db_close(pfann_db *h) {
     Db *db = reinterpret_cast<Db *>(h);
@@ -605,7 +628,7 @@ void pfann_db_close(pfann_db *h) {
     cudaFree(db->emb32);
     cudaFree(db->emb16);
     cudaFree(db->song_pos);
-    DevBuf *bufs[] = {&db->qbuf, &db->qnorm, &db->thr, &db->cnt, &db->cand, &db->sample, &db->flags, &db->dist,
+    DevBuf *bufs[] = {&db->qbuf, &db->qnorm, &db->thr, &db->cnt, &db->cand, &db->cand_v, &db->sample, &db->flags, &db->dist,
                       &db->labels, &db->rr_keys, &db->rr_scores, &db->rr_out, &db->lab_stage};
     for (DevBuf *b : bufs) b->release();
     delete db;

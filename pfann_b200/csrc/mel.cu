@@ -327,13 +327,11 @@ size_t mel_smem_bytes(int n, int n_mels, int T) {
 int launch_mel(MelPlan *p, const MelArgs &a, int64_t B, bool pcm) {
     if (B == 0) return PFANN_OK;
     PF_CHECK(B <= 0x7fffffffLL, PFANN_ERR_ARG, "mel: too many segments in one call (%lld)", (long long)B);
-    // opt-in limit: raised when a plan needs more, never lowered (plans with different segment lengths coexist)
-    static size_t attr = 0;
-    if (p->smem_bytes > attr) {
+    // opt-in limit: per device/context, so it is set for the instantiation being launched on every call
+    if (pcm)
         PF_CUDA(cudaFuncSetAttribute(mel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
+    else
         PF_CUDA(cudaFuncSetAttribute(mel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
-        attr = p->smem_bytes;
-    }
     ProfScope ps(p->ctx, K_MEL, 32);
     if (pcm)
         mel_kernel<true><<<(unsigned)B, NTHREADS, p->smem_bytes, p->ctx->stream>>>(a);

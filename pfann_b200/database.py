@@ -50,12 +50,31 @@ def write_flat_ip_index(path, emb):
         f.write(emb.tobytes())
 
 
+def write_flat_ip_index_from_file(path, emb_path, n, d, block=1 << 26):
+    """Same file as write_flat_ip_index, with the rows streamed from the raw `embeddings` file (builder.py:99)
+    instead of an in-memory array."""
+    with open(path, 'wb') as f, open(emb_path, 'rb') as src:
+        f.write(b'IxFI')
+        f.write(struct.pack('<iqqqBi', d, n, 1 << 20, 1 << 20, 1, 0))
+        f.write(struct.pack('<Q', n * d))
+        left = n * d * 4
+        while left > 0:
+            buf = src.read(min(block, left))
+            if not buf:
+                raise IOError('%s is shorter than %d x %d fp32 rows' % (emb_path, n, d))
+            f.write(buf)
+            left -= len(buf)
+
+
 def read_flat_index(path):
     """Rows of a faiss IndexFlat file, or None if `path` holds another index type."""
     with open(path, 'rb') as f:
         cc = f.read(4)
         if cc not in (b'IxFI', b'IxF2', b'IxFl'):
             return None
+        if cc == b'IxF2':
+            # an L2 flat index: for unit-norm fingerprints the ranking equals inner product, the distances differ
+            print('warning: %s is an L2 flat index (IxF2); it is searched by inner product here' % path)
         d, n, _, _, _, metric = struct.unpack('<iqqqBi', f.read(4 + 8 * 3 + 1 + 4))
         if metric > 1:
             f.read(4)
@@ -79,6 +98,10 @@ class Database:
         if os.path.exists(idx_path):
             emb = read_flat_index(idx_path)
         if emb is None:
+            if os.path.exists(idx_path):
+                # e.g. the reference's default IVF200,PQ64x8np (builder.py:114): NOT what is searched here
+                print('warning: %s is not a flat index; searching the raw `embeddings` exactly (brute-force inner '
+                      'product) -- results are those of IndexFlatIP, not of the approximate index' % idx_path)
             emb = np.fromfile(emb_path, dtype=np.float32)
             ntotal = int(key.sum())
             emb = emb.reshape([ntotal, -1]) if ntotal else emb.reshape([0, indexer_params.get('d', 128)])

@@ -442,3 +442,25 @@ def test_query_edge_cases(dev, tmp_path):
     assert (I == -1).all()
     sco, (sid, tim), ss = dbo.query_embeddings(np.ones((3, 128), np.float32))
     assert sid == -1 and sco == 0.0 and tim == 0.0 and not ss.any()
+
+
+def test_two_devices_in_one_process(dev):
+    """The shared-memory opt-in of every kernel is per device: a second GPU used from the same process must work
+    (a process-wide cache of cudaFuncSetAttribute once skipped it there) and give the same fingerprints."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two CUDA devices')
+    from pfann_b200.extract import Extractor
+    params = synth.read_config('default')
+    sd = synth.make_state_dict(params, seed=3)
+    lens = [20000, 8000, 12000]
+    pcm = np.concatenate([synth.synth_pcm(70 + i, n) for i, n in enumerate(lens)])
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    z0, _ = Extractor(params, sd, device=0, precision='bf16', chunk=16).extract_pcm16(pcm, off)
+    z1, _ = Extractor(params, sd, device=1, precision='bf16', chunk=16).extract_pcm16(pcm, off)
+    assert np.array_equal(z0, z1)
+    db, key = synth.synth_db(5000, d=128, seed=4)
+    from pfann_b200.database import Database
+    a = Database.from_arrays(db, key, {'top_k': 10, 'frame_shift_mul': 1}, 0.5, device=0)
+    b = Database.from_arrays(db, key, {'top_k': 10, 'frame_shift_mul': 1}, 0.5, device=1)
+    q = db[100:119]
+    assert a.query_embeddings(q)[:2] == b.query_embeddings(q)[:2]
