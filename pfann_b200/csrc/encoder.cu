@@ -795,27 +795,38 @@ int save_tap(Model *m, int l, const ActT *X, int nb, int total_nb = -1, int s0 =
     return PFANN_OK;
 }
 
+L0Args l0_args(Model *m, const float *mel) {
+    const ConvGeom &g = m->conv[0].g;
+    L0Args a;
+    a.mel = mel; a.F = g.Fi; a.T = g.Ti; a.To = g.To; a.ntaps = g.ntaps; a.C = g.Co;
+    for (int j = 0; j < 3; j++) a.off[j] = g.tap_off[j];
+    return a;
+}
+
+// ln1 statistics of layer 0 from the 9 moments of the mel tile -> m->cur_stats (one launch)
+int launch_l0_stats(Model *m, const float *mel, int nb) {
+    const ConvGeom &g = m->conv[0].g;
+    cudaStream_t st = m->ctx->stream;
+    ProfScope ps(m->ctx, K_LN, 34);
+    if (m->cur_moments != nullptr)
+        l0_stats_kernel<<<cdiv(nb, 256), 256, 0, st>>>(m->cur_moments, m->l0c, (double)g.Fi * g.To, (double)g.Co,
+                                                        m->cur_stats, nb);
+    else
+        l0_moments_kernel<<<nb, 256, 0, st>>>(l0_args(m, mel), m->l0c, m->cur_stats);
+    m->ctx->launches++;
+    PF_CUDA(cudaGetLastError());
+    return PFANN_OK;
+}
+
 template <typename ActT>
 int launch_l0_fused(Model *m, const float *mel, ActT *X, int nb) {
     const ConvWeights &cw = m->conv[0];
     const ConvGeom &g = cw.g;
-    L0Args a;
-    a.mel = mel; a.F = g.Fi; a.T = g.Ti; a.To = g.To; a.ntaps = g.ntaps; a.C = g.Co;
-    for (int j = 0; j < 3; j++) a.off[j] = g.tap_off[j];
+    const L0Args a = l0_args(m, mel);
     cudaStream_t st = m->ctx->stream;
-    if (m->cur_moments != nullptr) {
-        ProfScope ps(m->ctx, K_LN, 34);
-        l0_stats_kernel<<<cdiv(nb, 256), 256, 0, st>>>(m->cur_moments, m->l0c, (double)g.Fi * g.To, (double)g.Co,
-                                                        m->cur_stats, nb);
-    } else {
-        ProfScope ps(m->ctx, K_LN, 34);
-        l0_moments_kernel<<<nb, 256, 0, st>>>(a, m->l0c, m->cur_stats);
-    }
-    if (sizeof(ActT) == 2 && tc_l0_supported(m)) {
-        m->ctx->launches++;
-        PF_CUDA(cudaGetLastError());
+    PF_TRY(launch_l0_stats(m, mel, nb));
+    if (sizeof(ActT) == 2 && tc_l0_supported(m))
         return tc_l0(m, mel, m->cur_stats, reinterpret_cast<__nv_bfloat16 *>(X), nb);
-    }
     const int cgroups = g.Co / 8, ppb = 256 / cgroups, P = g.Fi * g.To;
     const int group = 32;
     // the 4-positions-per-thread variant needs the three taps to be the contiguous run {o, o+1, o+2}
@@ -838,7 +849,7 @@ int launch_l0_fused(Model *m, const float *mel, ActT *X, int nb) {
                                                              m->cur_stats, X, nb, group);
         }
     }
-    m->ctx->launches += 2;
+    m->ctx->launches++;
     PF_CUDA(cudaGetLastError());
     return PFANN_OK;
 }
@@ -859,6 +870,14 @@ int forward_chunk(Model *m, const float *mel, int nb, int norm, float *z) {
             const bool first = (l == 0 && which == 0);
             const bool last = (l == 7 && which == 1);
             bool stats_done = false, ybf = false;
+            if (first && tc && tc_front_supported(m)) {
+                // the whole first SeparableConv2d in one kernel: log-mel in, X1 out, X0 never touches HBM
+                PF_TRY(launch_l0_stats(m, mel, nb));
+                m->prof_idx = 1;
+                PF_TRY(tc_front(m, mel, m->cur_stats, reinterpret_cast<__nv_bfloat16 *>(xb), nb));
+                PF_TRY(save_tap<ActT>(m, 0, xb, nb));
+                break;
+            }
             if (first && m->l0_fused) {
                 // conv1 + ln1 + ReLU in one pass, statistics from the mel moments: nothing else to do
                 PF_TRY(launch_l0_fused<ActT>(m, mel, xa, nb));

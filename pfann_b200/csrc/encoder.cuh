@@ -95,6 +95,10 @@ int tc_ln_check(Model *m, bool sync = true);
 bool tc_l0_supported(Model *m);
 int tc_l0(Model *m, const float *mel, const float2 *stats, __nv_bfloat16 *X, int nb);
 int tc_conv_ln(Model *m, int idx, const __nv_bfloat16 *X, __nv_bfloat16 *Xout, int nb);
+int tc_ln_err_ptr(Model *m, int **dev_flag);   // device address of the (lazily created) time-out flag
+// front_tc.cu: layer-0 conv1 + ln1 + ReLU + conv2 + ln2 + ReLU in one kernel (log-mel in, X1 out; X0 never stored)
+bool tc_front_supported(Model *m);
+int tc_front(Model *m, const float *mel, const float2 *stats0, __nv_bfloat16 *Xout, int nb);
 // encoder.cu: size the chunk workspace (needs the conv geometries)
 int plan_workspace(Model *m);
 

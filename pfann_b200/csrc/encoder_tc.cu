@@ -1009,14 +1009,9 @@ int launch_tc_ln(Model *m, const TcConv &tc, const LnGeom &lg, const TcLnArgs &a
     // exchange table: all-ones = "not written"
     const size_t part_bytes = (size_t)args.n_groups * lg.P * LN_EPI_WARPS * sizeof(unsigned long long);
     PF_TRY(m->ln_part.ensure(part_bytes));
-    if (m->ln_err_host == nullptr) {
-        PF_CUDA(cudaHostAlloc(&m->ln_err_host, sizeof(int), cudaHostAllocMapped));
-        *m->ln_err_host = 0;
-        PF_CUDA(cudaHostGetDevicePointer(&m->ln_err_dev, m->ln_err_host, 0));
-    }
+    PF_TRY(tc_ln_err_ptr(m, &args.err));
     PF_CUDA(cudaMemsetAsync(m->ln_part.p, 0xFF, part_bytes, m->ctx->stream));
     args.part = m->ln_part.as<unsigned long long>();
-    args.err = m->ln_err_dev;
     int L = m->ctx->sm_count / lg.P;
     if (L > args.n_groups) L = args.n_groups;
     PF_CHECK(L >= 1, PFANN_ERR_UNSUPPORTED, "fused conv+LN: %d positions do not fit %d SMs", lg.P, m->ctx->sm_count);
@@ -1222,6 +1217,21 @@ int tc_l0(Model *m, const float *mel, const float2 *stats, __nv_bfloat16 *X, int
     m->ctx->launches++;
     PF_CUDA(cudaGetLastError());
     return PFANN_OK;
+}
+
+int tc_ln_err_ptr(Model *m, int **dev_flag) {
+    if (m->ln_err_host == nullptr) {
+        PF_CUDA(cudaHostAlloc(&m->ln_err_host, sizeof(int), cudaHostAllocMapped));
+        *m->ln_err_host = 0;
+        PF_CUDA(cudaHostGetDevicePointer(&m->ln_err_dev, m->ln_err_host, 0));
+    }
+    *dev_flag = m->ln_err_dev;
+    return PFANN_OK;
+}
+
+const CUtensorMap *tc_weight_map128(Model *m, int idx) {
+    TcState *st = reinterpret_cast<TcState *>(m->tc_state);
+    return (st != nullptr && st->conv[idx].supported) ? &st->conv[idx].mapB128 : nullptr;
 }
 
 int tc_ln_check(Model *m, bool sync) {

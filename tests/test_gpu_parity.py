@@ -210,6 +210,28 @@ def test_fused_conv_layernorm_matches_unfused(dev, monkeypatch):
     assert np.array_equal(net(x).cpu().numpy(), zf)     # and the fused path is bit-reproducible
 
 
+def test_front_kernel_matches_two_kernel_layer0(dev, monkeypatch):
+    """front_tc_kernel (layer-0 conv1 + ln1 + ReLU produced inside conv2's operand pipeline, X0 never stored) against
+    the round-1 pair l0_tc_kernel -> conv_ln_tc_kernel that materialises X0: same layer-0 output up to bf16 rounding
+    of X0, for a batch that is not a multiple of the 8 segments of a tile, over several chunks, bit-reproducible."""
+    net, params, sd = _net('default', 'bf16', dev, 5)
+    x = torch.from_numpy(orc.melspec(synth.synth_segments(43, seed=21), params)).to(dev)
+    a0 = net.layer_output(x, 0).numpy()
+    za = net(x).cpu().numpy()
+    net.chunk = 16
+    assert np.array_equal(net(x).cpu().numpy(), za)               # independent of the grouping into tiles / chunks
+    assert np.array_equal(net.layer_output(x[:16], 0).numpy(), a0[:16])
+    monkeypatch.setenv('PFANN_B200_NO_FRONT', '1')
+    b0 = net.layer_output(x[:16], 0).numpy()
+    zb = net(x).cpu().numpy()
+    rel = np.linalg.norm(a0[:16] - b0) / np.linalg.norm(b0)
+    assert rel < 5e-3, rel
+    assert (1 - (za * zb).sum(1)).max() < 1e-4
+    monkeypatch.delenv('PFANN_B200_NO_FRONT')
+    ref = orc.fpnetwork_forward(sd, x[:3].cpu().numpy(), params)
+    assert (1 - (za[:3] * ref).sum(1)).max() < EMB_BF16_COS
+
+
 def test_layer0_tensor_core_matches_cuda_core(dev, monkeypatch):
     """l0_tc_kernel (conv1 of layer 0 as one K = 16 bf16 hi/lo split MMA per 128 positions) against the CUDA-core
     fp32 formulation: same statistics, same bf16 output up to rounding."""
