@@ -161,6 +161,36 @@ int pfann_db_rerank(pfann_db *db, const float *queries, const int64_t *query_ind
                     const int64_t *labels, int top_k, int frame_shift_mul, float score_alpha,
                     float *best_score, int32_t *best_song, float *best_time);
 
+/* The same exchange for many GPUs without a host round trip per batch (pfann_b200/dist.py).  All data pointers
+ * are DEVICE pointers and every call is stream-ordered; nothing is read back.
+ *   1. pfann_db_search_thresholds: thr[Q] = a lower bound of this shard's k-th best score per query (sample
+ *      pre-pass).  The caller takes the element-wise MAXIMUM over the shards (one all-reduce of Q floats): still a
+ *      lower bound of the GLOBAL k-th best, provided all shards use one error bound (pfann_db_set_max_norm with the
+ *      maximum of pfann_db_max_norm over the shards).
+ *   2. pfann_db_search_filtered: exact top-k of the rows that reach thr, as sortable 64-bit keys
+ *      (order-preserving fp32 score bits << 32 | 0xFFFFFFFF - global row id; 0 = empty) -> ONE all-gather of
+ *      [Q][k] keys per batch, as BASELINE.json's north_star asks.  A candidate list that overflows its 4096
+ *      slots is redone with tighter thresholds: immediately (one read-back of a flag per call) or, with
+ *      defer_overflow_check, counted for pfann_db_take_overflow so that a stream of batches never waits for the host.
+ *   3. pfann_topk_merge_keys: [G][Q][k] gathered keys -> global top-k labels (and distances) per query.
+ *   4. pfann_db_rerank_packed: sequence score over the candidates whose songs this shard owns -> [nq][4] fp32
+ *      (score, song id bits, time in frames, 0); one all-gather of these tiny records, then
+ *   5. pfann_best_combine: [G][nq][4] -> the winner per query file (score desc, lower song id, zero floor of
+ *      database.py:176,190), same record layout. */
+int pfann_db_search_thresholds(pfann_db *db, const float *q, int64_t Q, int k, float *thr);
+int pfann_db_search_filtered(pfann_db *db, const float *q, int64_t Q, int k, float *thr, uint64_t *keys,
+                             int defer_overflow_check);
+/* Candidate lists that overflowed in calls made with defer_overflow_check = 1 since the last call of this function
+ * (read after synchronising the stream); non-zero: repeat those calls with defer_overflow_check = 0. */
+int pfann_db_take_overflow(pfann_db *db);
+int pfann_topk_merge_keys(pfann_ctx *ctx, const uint64_t *keys_g, int G, int64_t Q, int k, float *dist,
+                          int64_t *labels);
+int pfann_db_rerank_packed(pfann_db *db, const float *queries, const int64_t *query_index, int nq, int max_len,
+                           const int64_t *labels, int top_k, int frame_shift_mul, float score_alpha, float *packed);
+int pfann_best_combine(pfann_ctx *ctx, const float *packed_g, int G, int nq, float *packed_out);
+float pfann_db_max_norm(pfann_db *db);
+int pfann_db_set_max_norm(pfann_db *db, float max_norm);
+
 /* ---- reference-compatible symbols ------------------------------------------------------------- */
 
 /* Bit-compatible with cpp/seqscore.cpp:27-43 so that database.py:15-32 can load this library in place of

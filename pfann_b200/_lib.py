@@ -74,6 +74,15 @@ def _declare(L):
                                  POINTER(c_int32), POINTER(c_float), POINTER(c_float), c_int64]
     L.pfann_topk_merge.argtypes = [vp, vp, vp, c_int, c_int64, c_int, vp, vp]
     L.pfann_db_rerank.argtypes = [vp, vp, vp, c_int, vp, c_int, c_int, c_float, vp, vp, vp]
+    L.pfann_db_search_thresholds.argtypes = [vp, vp, c_int64, c_int, vp]
+    L.pfann_db_search_filtered.argtypes = [vp, vp, c_int64, c_int, vp, vp, c_int]
+    L.pfann_db_take_overflow.argtypes = [vp]
+    L.pfann_topk_merge_keys.argtypes = [vp, vp, c_int, c_int64, c_int, vp, vp]
+    L.pfann_db_rerank_packed.argtypes = [vp, vp, vp, c_int, c_int, vp, c_int, c_int, c_float, vp]
+    L.pfann_best_combine.argtypes = [vp, vp, c_int, c_int, vp]
+    L.pfann_db_max_norm.argtypes = [vp]
+    L.pfann_db_max_norm.restype = c_float
+    L.pfann_db_set_max_norm.argtypes = [vp, c_float]
     # reference-compatible pair, prototypes exactly as database.py:16-29
     L.seq_score.argtypes = [c_void_p, POINTER(c_int64), c_int, POINTER(c_float), c_int, POINTER(c_int64), c_int,
                             POINTER(c_float), c_int, c_float]

@@ -25,6 +25,7 @@ struct Db {
     // scratch
     DevBuf qbuf, qnorm, thr, cnt, cand, cand_v, sample, flags, dist, labels, rr_keys, rr_scores, rr_out, lab_stage;
     void *tc_state = nullptr;
+    int *ovf_host = nullptr, *ovf_dev = nullptr;  // deferred overflow count of the sharded search (pinned, mapped)
 };
 
 // exact canonical inner product shared with the oracle (oracle/pfann_oracle.c dot_fma_seq):
@@ -95,13 +96,16 @@ __device__ void bitonic_sort(K *keys, int n) {
 // knn.cu: device-pointer search (q, dist, labels all on the device, stream-ordered except for the
 // overflow check which synchronises once per query group)
 int db_search_dev(Db *db, const float *q, int64_t Q, int k, float *dist, int64_t *labels);
+int db_search_thresholds_dev(Db *db, const float *q, int64_t Q, int k, float *thr);
+int db_search_filtered_dev(Db *db, const float *q, int64_t Q, int k, float *thr, unsigned long long *keys, bool defer);
 // knn_tc.cu
 int knn_tc_prepare(Db *db);
-int64_t knn_tc_sample_slots(Db *db, int64_t r0, int64_t r1);
+int64_t knn_tc_sample_slots(Db *db, int64_t r0, int64_t r1, int ngroups);
 void knn_tc_release(Db *db);
-// approximate scan of rows [r0, r1) against Qg <= 128 queries; mode 0: store all scores to
-// sample[q][row - r0] (ld = sample_ld); mode 1: push row ids with score >= thr[q] into cand/cnt
-int knn_tc_scan(Db *db, const float *q, int Qg, int64_t r0, int64_t r1, int mode, float *sample, int64_t sample_ld,
-                const float *thr, int *cnt, uint32_t *cand, uint32_t *cand_v, int cap);
+// approximate scan of rows [r0, r1) against Qtot queries in groups of `group` <= 256 (one database pass per group,
+// all groups in ONE launch); mode 0: per-thread maxima of the scores to sample[q][slot] (ld = sample_ld);
+// mode 1: push row ids with score >= thr[q] into cand/cnt
+int knn_tc_scan(Db *db, const float *q, int Qtot, int group, int64_t r0, int64_t r1, int mode, float *sample,
+                int64_t sample_ld, const float *thr, int *cnt, uint32_t *cand, uint32_t *cand_v, int cap);
 
 }  // namespace pfann

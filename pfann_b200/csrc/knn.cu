@@ -393,15 +393,16 @@ __global__ void topk_merge_kernel(const float *dist_g, const int64_t *labels_g, 
     }
 }
 
-int scan(Db *db, bool tc, const float *q, int Qg, int64_t r0, int64_t r1, int mode, float *sample, int64_t sample_ld,
-         const float *thr, int *cnt, uint32_t *cand, uint32_t *cand_v, int cap) {
-    if (tc) return knn_tc_scan(db, q, Qg, r0, r1, mode, sample, sample_ld, thr, cnt, cand, cand_v, cap);
+// one launch for up to SG database passes (tensor-core scan) or one launch per QG-query slice (fp32 CUDA-core scan)
+int scan(Db *db, bool tc, const float *q, int Qs, int group, int64_t r0, int64_t r1, int mode, float *sample,
+         int64_t sample_ld, const float *thr, int *cnt, uint32_t *cand, uint32_t *cand_v, int cap) {
+    if (tc) return knn_tc_scan(db, q, Qs, group, r0, r1, mode, sample, sample_ld, thr, cnt, cand, cand_v, cap);
     const int64_t ntiles = (r1 - r0 + SCAN_ROWS - 1) / SCAN_ROWS;
     int64_t grid = (int64_t)db->ctx->sm_count * 4;
     if (grid > ntiles) grid = ntiles;
     const size_t smem = (size_t)(QG * db->d + SCAN_ROWS * (db->d + 4)) * 4;
-    for (int q0 = 0; q0 < Qg; q0 += QG) {
-        const int qn = (Qg - q0) < QG ? (Qg - q0) : QG;
+    for (int q0 = 0; q0 < Qs; q0 += QG) {
+        const int qn = (Qs - q0) < QG ? (Qs - q0) : QG;
         ProfScope ps(db->ctx, K_KNN_SCAN, mode == 0 ? 35 : 36);
         knn_scan_fp32_kernel<<<(unsigned)grid, SCAN_THREADS, smem, db->ctx->stream>>>(
             db->emb32, r0, r1, db->d, q + (int64_t)q0 * db->d, qn, mode, sample ? sample + q0 * sample_ld : nullptr,
@@ -413,121 +414,183 @@ int scan(Db *db, bool tc, const float *q, int Qg, int64_t r0, int64_t r1, int mo
     return PFANN_OK;
 }
 
-}  // namespace
+// deferred overflow check: add the per-super-group overflow flags of one call to a host-visible counter (launches of
+// one stream are serialised: a plain read-modify-write by one thread is enough)
+__global__ void accumulate_flags_kernel(const int *flags, int n, volatile int *total) {
+    int s = 0;
+    for (int i = 0; i < n; i++) s += flags[i];
+    if (s) *total = *total + s;
+}
 
-namespace pfann {
+__global__ void fill_f32_kernel(float *dst, float v, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = v;
+}
 
-int db_search_dev(Db *db, const float *q, int64_t Q, int k, float *dist, int64_t *labels) {
-    cudaStream_t st = db->ctx->stream;
-    if (Q == 0) return PFANN_OK;
-    // every caller (pfann_db_search / _query / _rerank) ends up here: the candidate lists and the k-th selection
-    // are sized for k <= cand_cap and k <= 2048
+// (dist, labels) -> one sortable 64-bit key per entry: flipped fp32 score in the high word, 0xFFFFFFFF - global id in
+// the low word (descending key = score descending, id ascending); empty slots (-1) become 0.
+__global__ void pack_keys_kernel(const float *dist, const int64_t *labels, int64_t n, unsigned long long *keys) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t id = labels[i];
+    keys[i] = id < 0 ? 0ull
+                     : (((unsigned long long)flipf(dist[i]) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)id));
+}
+
+// merge G gathered key lists [G][Q][k] -> global top-k per query: dist/labels [Q][k] (-FLT_MAX / -1 padding)
+__global__ void merge_keys_kernel(const unsigned long long *keys_g, int G, int64_t Q, int k, int P, float *dist,
+                                  int64_t *labels) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smraw);
+    const int64_t qi = blockIdx.x;
+    const int n = G * k;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const int g = i / k, j = i - g * k;
+        keys[i] = i < n ? keys_g[((int64_t)g * Q + qi) * k + j] : 0ull;
+    }
+    bitonic_sort<unsigned long long, true>(keys, P);
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        const unsigned long long key = keys[j];
+        if (key != 0ull) {
+            if (dist) dist[qi * k + j] = unflipf((uint32_t)(key >> 32));
+            labels[qi * k + j] = (int64_t)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
+        } else {
+            if (dist) dist[qi * k + j] = -FLT_MAX;
+            labels[qi * k + j] = -1;
+        }
+    }
+}
+
+// per-shard winners [G][nq] x (score, song, time) -> global winner per query file: score desc, then lower song id
+// (cpp/seqscore.cpp:121), then the reference's zero floor (database.py:176,190).  out: [nq] x (score, song bits, time, 0)
+__global__ void combine_best_kernel(const float4 *packed_g, int G, int nq, float4 *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    float bs = 0.f, bt = 0.f;
+    int bg = -1;
+    for (int g = 0; g < G; g++) {
+        const float4 v = packed_g[(size_t)g * nq + i];
+        const int song = __float_as_int(v.y);
+        if (song < 0) continue;
+        if (bg < 0 || v.x > bs || (v.x == bs && song < bg)) {
+            bs = v.x; bg = song; bt = v.z;
+        }
+    }
+    if (!(bg >= 0 && bs > 0.f)) bs = 0.f, bt = 0.f;   // nothing above the zero-initialised table
+    out[i] = make_float4(bs, __int_as_float(bg), bt, 0.f);
+}
+
+struct SearchPlan {
+    bool tc;
+    float eps_rel;
+    int cap, group, sgroup, S, chunk;
+    int64_t ngroups;
+};
+
+int plan_search(Db *db, int64_t Q, int k, SearchPlan *p) {
     PF_CHECK(k > 0 && k <= db->cand_cap && k <= 2048, PFANN_ERR_UNSUPPORTED, "database search: k=%d too large (max %d)", k,
              db->cand_cap < 2048 ? db->cand_cap : 2048);
-    if (db->n == 0) {
-        fill_empty_kernel<<<cdiv(Q * k, 256), 256, 0, st>>>(dist, labels, Q * k);
-        db->ctx->launches++;
-        PF_CUDA(cudaGetLastError());
-        return PFANN_OK;
-    }
     const int d = db->d;
-    const bool tc = db->use_tc && db->tc_state != nullptr;
+    p->tc = db->use_tc && db->tc_state != nullptr;
     // |scan score - exact score| <= eps_rel * |q| * |x|: bf16 operand rounding 2^-8 (+ fp32 accumulation order)
-    const float eps_rel = (tc ? 4.0e-3f : 0.f) + fmaxf(1.0e-5f, 1.2e-7f * (float)d);
-    const int cap = db->cand_cap;
-    const int group = tc ? (d <= 128 ? 256 : 128) : QG * 4;  // queries per database pass
+    p->eps_rel = (p->tc ? 4.0e-3f : 0.f) + fmaxf(1.0e-5f, 1.2e-7f * (float)d);
+    p->cap = db->cand_cap;
+    p->group = p->tc ? (d <= 128 ? 256 : 128) : QG * 4;  // queries per database pass
     // sample size: aim at ~256 rows above the threshold (k * n / S ~ 256), within [sample_rows, 256 Ki].  Every
     // survivor costs ~100 instructions on the filter's hit path (measured: 360 k survivors per 256-query pass doubled
     // the scan time of a 1.25 M-row shard), a sampled row costs one more tile of the cheap pre-pass.
     int64_t want = (int64_t)k * db->n / 256;
     if (want < db->sample_rows) want = db->sample_rows;
     if (want > 262144) want = 262144;
-    const int chunk = 8192;  // one kth-select CTA sorts this many sample scores in shared memory
+    p->chunk = 8192;  // one kth-select CTA sorts this many sample scores in shared memory
     int64_t max_chunks = 8192 / k;  // stage 2 sorts nchunks * k keys in shared memory
-    if (want > max_chunks * chunk) want = max_chunks * chunk;
-    const int S = (int)(db->n < want ? db->n : want);
-    // the tensor-core pre-pass leaves per-thread maxima (one per CTA and accumulator row) instead of every score
-    const int S_keys = tc ? (int)knn_tc_sample_slots(db, 0, S) : S;
-    const int nchunks = (S_keys + chunk - 1) / chunk;
-    int cpad = 1;
-    while (cpad < (S_keys < chunk ? S_keys : chunk)) cpad <<= 1;
-    int P2 = 1;
-    while (P2 < nchunks * k) P2 <<= 1;
-    // A "super-group" = up to SG database passes (SG * group queries) that share ONE launch of each small kernel
-    // (k-th selection of the sample, candidate ranking + exact rescoring): on a shard of a million rows a pass is
-    // ~90 us and the launch gaps of the small kernels would otherwise cost as much again.
-    const int SG = 4, sgroup = SG * group;
-    const int64_t ngroups = (Q + sgroup - 1) / sgroup;
-    PF_TRY(db->thr.ensure(sizeof(float) * sgroup));
-    PF_TRY(db->qnorm.ensure(sizeof(float) * sgroup));
-    PF_TRY(db->cnt.ensure(sizeof(int) * sgroup));
-    PF_TRY(db->cand.ensure(sizeof(uint32_t) * (size_t)sgroup * cap));
-    PF_TRY(db->cand_v.ensure(sizeof(uint32_t) * (size_t)sgroup * cap));
-    PF_TRY(db->sample.ensure(sizeof(float) * (size_t)sgroup * S_keys));
-    PF_TRY(db->rr_keys.ensure(sizeof(uint32_t) * (size_t)sgroup * nchunks * k));
-    PF_TRY(db->flags.ensure(sizeof(int) * (size_t)(ngroups + 4)));
-    const size_t sel_smem = (size_t)cap * 8 + (size_t)d * 4;
+    if (want > max_chunks * p->chunk) want = max_chunks * p->chunk;
+    p->S = (int)(db->n < want ? db->n : want);
+    // A "super-group" = up to SG database passes (SG * group queries) that share ONE launch of every kernel (scans
+    // included: the CTAs are split between the passes): on a shard of a million rows a pass is ~75 us and launch gaps,
+    // prologues and tails would otherwise cost as much again.
+    const int SG = 4;
+    p->sgroup = SG * p->group;
+    p->ngroups = (Q + p->sgroup - 1) / p->sgroup;
+    PF_TRY(db->thr.ensure(sizeof(float) * (size_t)p->sgroup));
+    PF_TRY(db->qnorm.ensure(sizeof(float) * (size_t)(Q > p->sgroup ? Q : p->sgroup)));
+    PF_TRY(db->cnt.ensure(sizeof(int) * p->sgroup));
+    PF_TRY(db->cand.ensure(sizeof(uint32_t) * (size_t)p->sgroup * p->cap));
+    PF_TRY(db->cand_v.ensure(sizeof(uint32_t) * (size_t)p->sgroup * p->cap));
+    PF_TRY(db->flags.ensure(sizeof(int) * (size_t)(p->ngroups + 4)));
+    const size_t sel_smem = (size_t)p->cap * 8 + (size_t)d * 4;
     PF_CUDA(cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
     PF_CUDA(cudaFuncSetAttribute(knn_scan_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)((QG * d + SCAN_ROWS * (d + 4)) * 4)));
-    float *thr = db->thr.as<float>();
+    return PFANN_OK;
+}
+
+// 1. threshold pre-pass on the first S rows for Qs <= sgroup queries: thr[q] = a lower bound of the k-th best scan
+// score of this shard (minus the scan's error bound), qnorm[q] = |q|
+int prepass(Db *db, const SearchPlan &p, const float *qs, int Qs, int k, float *thr, float *qnorm) {
+    cudaStream_t st = db->ctx->stream;
+    const int d = db->d;
+    const int ng = (Qs + p.group - 1) / p.group;
+    // the tensor-core pre-pass leaves per-thread maxima (one per CTA and accumulator row) instead of every score
+    const int S_keys = p.tc ? (int)knn_tc_sample_slots(db, 0, p.S, ng) : p.S;
+    const int nchunks = (S_keys + p.chunk - 1) / p.chunk;
+    int cpad = 1;
+    while (cpad < (S_keys < p.chunk ? S_keys : p.chunk)) cpad <<= 1;
+    int P2 = 1;
+    while (P2 < nchunks * k) P2 <<= 1;
+    PF_TRY(db->sample.ensure(sizeof(float) * (size_t)Qs * S_keys));
+    PF_TRY(db->rr_keys.ensure(sizeof(uint32_t) * (size_t)Qs * nchunks * k));
+    PF_TRY(scan(db, p.tc, qs, Qs, p.group, 0, p.S, 0, db->sample.as<float>(), S_keys, nullptr, nullptr, nullptr, nullptr, 0));
+    ProfScope ps(db->ctx, K_KNN_SELECT, 37);
+    knn_kth_chunk_kernel<<<dim3(Qs, nchunks), 256, (size_t)(cpad > 256 ? cpad : 256) * 4, st>>>(
+        db->sample.as<float>(), S_keys, S_keys, p.chunk, cpad, k, db->rr_keys.as<uint32_t>());
+    knn_kth_merge_kernel<<<Qs, 256, (size_t)P2 * 4, st>>>(db->rr_keys.as<uint32_t>(), nchunks * k, P2, S_keys, qs, d, k,
+                                                         p.eps_rel, db->max_norm, thr, qnorm);
+    db->ctx->launches += 2;
+    PF_CUDA(cudaGetLastError());
+    return PFANN_OK;
+}
+
+// 2. filtered scan of the whole shard, 3. ranking + exact rescoring; *flag += 1 per overflowed query
+int filtered(Db *db, const SearchPlan &p, const float *qs, int Qs, int k, float *thr, const float *qnorm, float *dist,
+             int64_t *labels, int *flag) {
+    cudaStream_t st = db->ctx->stream;
     int *cnt = db->cnt.as<int>();
     uint32_t *cand = db->cand.as<uint32_t>(), *cand_v = db->cand_v.as<uint32_t>();
-    // 1. threshold pre-pass on the first S rows (one scan per `group` queries, one k-th selection for all)
-    auto prepass = [&](const float *qs, int Qs) -> int {
-        for (int g0 = 0; g0 < Qs; g0 += group) {
-            const int Qg = (Qs - g0) < group ? (Qs - g0) : group;
-            PF_TRY(scan(db, tc, qs + (int64_t)g0 * d, Qg, 0, S, 0, db->sample.as<float>() + (size_t)g0 * S_keys, S_keys,
-                        nullptr, nullptr, nullptr, nullptr, 0));
-        }
-        ProfScope ps(db->ctx, K_KNN_SELECT, 37);
-        knn_kth_chunk_kernel<<<dim3(Qs, nchunks), 256, (size_t)(cpad > 256 ? cpad : 256) * 4, st>>>(
-            db->sample.as<float>(), S_keys, S_keys, chunk, cpad, k, db->rr_keys.as<uint32_t>());
-        knn_kth_merge_kernel<<<Qs, 256, (size_t)P2 * 4, st>>>(db->rr_keys.as<uint32_t>(), nchunks * k, P2, S_keys, qs, d, k,
-                                                             eps_rel, db->max_norm, thr, db->qnorm.as<float>());
-        db->ctx->launches += 2;
-        PF_CUDA(cudaGetLastError());
-        return PFANN_OK;
-    };
-    // 2. filtered scans of the whole shard, 3. ranking + exact rescoring; *flag += 1 per overflowed query
-    auto filtered = [&](const float *qs, int Qs, int64_t q0, int *flag) -> int {
-        PF_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * Qs, st));
-        for (int g0 = 0; g0 < Qs; g0 += group) {
-            const int Qg = (Qs - g0) < group ? (Qs - g0) : group;
-            PF_TRY(scan(db, tc, qs + (int64_t)g0 * d, Qg, 0, db->n, 1, nullptr, 0, thr + g0, cnt + g0,
-                        cand + (size_t)g0 * cap, cand_v + (size_t)g0 * cap, cap));
-        }
-        ProfScope ps(db->ctx, K_KNN_SELECT, 38);
-        knn_select_kernel<<<Qs, 256, sel_smem, st>>>(db->emb32, d, db->id_base, qs, cnt, cand, cand_v, cap, k, eps_rel,
-                                                     db->max_norm, db->qnorm.as<float>(), thr, dist + q0 * k,
-                                                     labels + q0 * k, flag);
-        db->ctx->launches++;
-        PF_CUDA(cudaGetLastError());
-        return PFANN_OK;
-    };
-    // Every super-group runs once without any host synchronisation; the (rare) ones with an overflowed candidate
-    // list are found with ONE read-back of the flags and redone with tightened thresholds.
+    PF_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * Qs, st));
+    PF_TRY(scan(db, p.tc, qs, Qs, p.group, 0, db->n, 1, nullptr, 0, thr, cnt, cand, cand_v, p.cap));
+    ProfScope ps(db->ctx, K_KNN_SELECT, 38);
+    const size_t sel_smem = (size_t)p.cap * 8 + (size_t)db->d * 4;
+    knn_select_kernel<<<Qs, 256, sel_smem, st>>>(db->emb32, db->d, db->id_base, qs, cnt, cand, cand_v, p.cap, k, p.eps_rel,
+                                                 db->max_norm, qnorm, thr, dist, labels, flag);
+    db->ctx->launches++;
+    PF_CUDA(cudaGetLastError());
+    return PFANN_OK;
+}
+
+// Every super-group has run once without any host synchronisation; the (rare) ones with an overflowed candidate
+// list are found with ONE read-back of the flags and redone with tightened thresholds.  `thr_all` (optional, [Q])
+// holds externally supplied thresholds (sharded search); otherwise the shard's own pre-pass is repeated.
+int redo_overflowed(Db *db, const SearchPlan &p, const float *q, int64_t Q, int k, float *thr_all, float *dist,
+                    int64_t *labels) {
+    cudaStream_t st = db->ctx->stream;
+    const int d = db->d;
     int *flags = db->flags.as<int>();
-    PF_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)(ngroups + 4), st));
-    for (int64_t g = 0; g < ngroups; g++) {
-        const int64_t q0 = g * sgroup;
-        const int Qs = (int)((Q - q0) < sgroup ? (Q - q0) : sgroup);
-        PF_TRY(prepass(q + q0 * d, Qs));
-        PF_TRY(filtered(q + q0 * d, Qs, q0, flags + g));
-    }
-    std::vector<int> hflags((size_t)ngroups);
-    PF_CUDA(cudaMemcpyAsync(hflags.data(), flags, sizeof(int) * (size_t)ngroups, cudaMemcpyDeviceToHost, st));
+    std::vector<int> hflags((size_t)p.ngroups);
+    PF_CUDA(cudaMemcpyAsync(hflags.data(), flags, sizeof(int) * (size_t)p.ngroups, cudaMemcpyDeviceToHost, st));
     PF_CUDA(cudaStreamSynchronize(st));
-    for (int64_t g = 0; g < ngroups; g++) {
+    for (int64_t g = 0; g < p.ngroups; g++) {
         if (hflags[g] == 0) continue;
-        const int64_t q0 = g * sgroup;
-        const int Qs = (int)((Q - q0) < sgroup ? (Q - q0) : sgroup);
+        const int64_t q0 = g * p.sgroup;
+        const int Qs = (int)((Q - q0) < p.sgroup ? (Q - q0) : p.sgroup);
         const float *qs = q + q0 * d;
-        PF_TRY(prepass(qs, Qs));
+        float *thr = thr_all ? thr_all + q0 : db->thr.as<float>();
+        float *qn = db->qnorm.as<float>() + (thr_all ? q0 : 0);
+        if (!thr_all) PF_TRY(prepass(db, p, qs, Qs, k, thr, qn));
         bool done = false;
-        for (int iter = 0; iter < 5 && !done; iter++) {  // iteration 0 repeats the overflow and tightens the thresholds
+        for (int iter = 0; iter < 5 && !done; iter++) {  // without external thresholds iteration 0 repeats the overflow
             PF_CUDA(cudaMemsetAsync(flags + g, 0, sizeof(int), st));
-            PF_TRY(filtered(qs, Qs, q0, flags + g));
+            PF_TRY(filtered(db, p, qs, Qs, k, thr, qn, dist + q0 * k, labels + q0 * k, flags + g));
             int overflow = 0;
             PF_CUDA(cudaMemcpyAsync(&overflow, flags + g, sizeof(int), cudaMemcpyDeviceToHost, st));
             PF_CUDA(cudaStreamSynchronize(st));
@@ -543,6 +606,97 @@ int db_search_dev(Db *db, const float *q, int64_t Q, int k, float *dist, int64_t
             PF_CUDA(cudaGetLastError());
         }
     }
+    return PFANN_OK;
+}
+
+}  // namespace
+
+namespace pfann {
+
+int db_search_dev(Db *db, const float *q, int64_t Q, int k, float *dist, int64_t *labels) {
+    cudaStream_t st = db->ctx->stream;
+    if (Q == 0) return PFANN_OK;
+    SearchPlan p;
+    PF_TRY(plan_search(db, Q, k, &p));   // every caller (pfann_db_search / _query / _rerank) ends up here: k is checked
+    if (db->n == 0) {
+        fill_empty_kernel<<<cdiv(Q * k, 256), 256, 0, st>>>(dist, labels, Q * k);
+        db->ctx->launches++;
+        PF_CUDA(cudaGetLastError());
+        return PFANN_OK;
+    }
+    int *flags = db->flags.as<int>();
+    PF_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)(p.ngroups + 4), st));
+    for (int64_t g = 0; g < p.ngroups; g++) {
+        const int64_t q0 = g * p.sgroup;
+        const int Qs = (int)((Q - q0) < p.sgroup ? (Q - q0) : p.sgroup);
+        PF_TRY(prepass(db, p, q + q0 * db->d, Qs, k, db->thr.as<float>(), db->qnorm.as<float>()));
+        PF_TRY(filtered(db, p, q + q0 * db->d, Qs, k, db->thr.as<float>(), db->qnorm.as<float>(), dist + q0 * k,
+                        labels + q0 * k, flags + g));
+    }
+    return redo_overflowed(db, p, q, Q, k, nullptr, dist, labels);
+}
+
+// Sharded search, phase 1 (device pointers): per-query thresholds of THIS shard for all Q queries.  A caller that
+// searches several shards takes the element-wise maximum over the shards (each is a lower bound of the GLOBAL k-th
+// best score, provided every shard uses the same error bound: pfann_db_set_max_norm) and hands it to phase 2.
+int db_search_thresholds_dev(Db *db, const float *q, int64_t Q, int k, float *thr) {
+    if (Q == 0) return PFANN_OK;
+    SearchPlan p;
+    PF_TRY(plan_search(db, Q, k, &p));
+    if (db->n == 0) {
+        fill_f32_kernel<<<cdiv(Q, 256), 256, 0, db->ctx->stream>>>(thr, -INFINITY, Q);   // an empty shard bounds nothing
+        db->ctx->launches++;
+        PF_CUDA(cudaGetLastError());
+        return PFANN_OK;
+    }
+    for (int64_t g = 0; g < p.ngroups; g++) {
+        const int64_t q0 = g * p.sgroup;
+        const int Qs = (int)((Q - q0) < p.sgroup ? (Q - q0) : p.sgroup);
+        PF_TRY(prepass(db, p, q + q0 * db->d, Qs, k, thr + q0, db->qnorm.as<float>() + q0));
+    }
+    return PFANN_OK;
+}
+
+// phase 2: filtered scans with the given thresholds (modified in place when a candidate list overflows) -> exact
+// top-k of the rows that pass, as sortable keys.  Shards whose rows do not reach the global thresholds return fewer
+// than k entries (0 keys) -- the merge only needs every member of the GLOBAL top-k, and those always pass.
+int db_search_filtered_dev(Db *db, const float *q, int64_t Q, int k, float *thr, unsigned long long *keys, bool defer) {
+    cudaStream_t st = db->ctx->stream;
+    if (Q == 0) return PFANN_OK;
+    SearchPlan p;
+    PF_TRY(plan_search(db, Q, k, &p));
+    PF_TRY(db->dist.ensure((size_t)Q * k * 4));
+    PF_TRY(db->labels.ensure((size_t)Q * k * 8));
+    float *dist = db->dist.as<float>();
+    int64_t *labels = db->labels.as<int64_t>();
+    if (db->n == 0) {
+        PF_CUDA(cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * (size_t)Q * k, st));
+        return PFANN_OK;
+    }
+    int *flags = db->flags.as<int>();
+    PF_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)(p.ngroups + 4), st));
+    for (int64_t g = 0; g < p.ngroups; g++) {
+        const int64_t q0 = g * p.sgroup;
+        const int Qs = (int)((Q - q0) < p.sgroup ? (Q - q0) : p.sgroup);
+        PF_TRY(filtered(db, p, q + q0 * db->d, Qs, k, thr + q0, db->qnorm.as<float>() + q0, dist + q0 * k, labels + q0 * k,
+                        flags + g));
+    }
+    if (defer) {
+        // no read-back here: the caller asks pfann_db_take_overflow() once after many calls and repeats them in the
+        // checked mode if any candidate list overflowed (rare: thresholds are sized for ~256 survivors of 4096 slots)
+        if (db->ovf_host == nullptr) {
+            PF_CUDA(cudaHostAlloc(&db->ovf_host, sizeof(int), cudaHostAllocMapped));
+            *db->ovf_host = 0;
+            PF_CUDA(cudaHostGetDevicePointer(&db->ovf_dev, db->ovf_host, 0));
+        }
+        accumulate_flags_kernel<<<1, 1, 0, st>>>(flags, (int)p.ngroups, db->ovf_dev);
+        db->ctx->launches++;
+    } else {
+        PF_TRY(redo_overflowed(db, p, q, Q, k, thr, dist, labels));
+    }
+    pack_keys_kernel<<<cdiv(Q * k, 256), 256, 0, st>>>(dist, labels, Q * k, keys);
+    db->ctx->launches++;
+    PF_CUDA(cudaGetLastError());
     return PFANN_OK;
 }
 
@@ -631,6 +785,7 @@ void pfann_db_close(pfann_db *h) {
     DevBuf *bufs[] = {&db->qbuf, &db->qnorm, &db->thr, &db->cnt, &db->cand, &db->cand_v, &db->sample, &db->flags, &db->dist,
                       &db->labels, &db->rr_keys, &db->rr_scores, &db->rr_out, &db->lab_stage};
     for (DevBuf *b : bufs) b->release();
+    if (db->ovf_host) cudaFreeHost(db->ovf_host);
     delete db;
 }
 
@@ -690,6 +845,78 @@ int pfann_topk_merge(pfann_ctx *hctx, const float *dist_g, const int64_t *labels
     PF_CUDA(cudaGetLastError());
     PF_TRY(finish_output(ctx, 0, dist, (size_t)Q * k * 4));
     return finish_output(ctx, 1, labels, (size_t)Q * k * 8);
+}
+
+/* ---- sharded search in two phases + key merge (pfann_b200/dist.py); DEVICE pointers, stream-ordered ---- */
+int pfann_db_search_thresholds(pfann_db *h, const float *q, int64_t Q, int k, float *thr) {
+    PF_CHECK(h && Q >= 0 && k > 0 && (Q == 0 || (q && thr)), PFANN_ERR_ARG, "pfann_db_search_thresholds: bad argument");
+    Db *db = reinterpret_cast<Db *>(h);
+    PF_CHECK(Q == 0 || (is_device_ptr(q) && is_device_ptr(thr)), PFANN_ERR_ARG,
+             "pfann_db_search_thresholds: q and thr must be device pointers");
+    PF_CUDA(cudaSetDevice(db->ctx->device));
+    return db_search_thresholds_dev(db, q, Q, k, thr);
+}
+
+int pfann_db_search_filtered(pfann_db *h, const float *q, int64_t Q, int k, float *thr, uint64_t *keys, int defer_overflow_check) {
+    PF_CHECK(h && Q >= 0 && k > 0 && (Q == 0 || (q && thr && keys)), PFANN_ERR_ARG, "pfann_db_search_filtered: bad argument");
+    Db *db = reinterpret_cast<Db *>(h);
+    PF_CHECK(Q == 0 || (is_device_ptr(q) && is_device_ptr(thr) && is_device_ptr(keys)), PFANN_ERR_ARG,
+             "pfann_db_search_filtered: q, thr and keys must be device pointers");
+    PF_CHECK(db->id_base + db->n <= 0xFFFFFFFFLL, PFANN_ERR_UNSUPPORTED,
+             "pfann_db_search_filtered: global row ids beyond 2^32 do not fit the packed keys");
+    PF_CUDA(cudaSetDevice(db->ctx->device));
+    return db_search_filtered_dev(db, q, Q, k, thr, reinterpret_cast<unsigned long long *>(keys), defer_overflow_check != 0);
+}
+
+int pfann_db_take_overflow(pfann_db *h) {
+    Db *db = reinterpret_cast<Db *>(h);
+    if (!db || !db->ovf_host) return 0;
+    const int v = *reinterpret_cast<volatile int *>(db->ovf_host);
+    *db->ovf_host = 0;
+    return v;
+}
+
+int pfann_topk_merge_keys(pfann_ctx *hctx, const uint64_t *keys_g, int G, int64_t Q, int k, float *dist, int64_t *labels) {
+    PF_CHECK(hctx && G > 0 && Q >= 0 && k > 0 && (Q == 0 || (keys_g && labels)), PFANN_ERR_ARG,
+             "pfann_topk_merge_keys: bad argument");
+    Ctx *ctx = reinterpret_cast<Ctx *>(hctx);
+    if (Q == 0) return PFANN_OK;
+    PF_CHECK(is_device_ptr(keys_g) && is_device_ptr(labels) && (!dist || is_device_ptr(dist)), PFANN_ERR_ARG,
+             "pfann_topk_merge_keys: device pointers only");
+    PF_CUDA(cudaSetDevice(ctx->device));
+    int P = 1;
+    while (P < G * k) P <<= 1;
+    PF_CHECK(P <= 8192, PFANN_ERR_UNSUPPORTED, "pfann_topk_merge_keys: G*k too large");
+    PF_CUDA(cudaFuncSetAttribute(merge_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P * 8));
+    merge_keys_kernel<<<(unsigned)Q, P >= 512 ? 256 : 64, (size_t)P * 8, ctx->stream>>>(
+        reinterpret_cast<const unsigned long long *>(keys_g), G, Q, k, P, dist, labels);
+    ctx->launches++;
+    PF_CUDA(cudaGetLastError());
+    return PFANN_OK;
+}
+
+int pfann_best_combine(pfann_ctx *hctx, const float *packed_g, int G, int nq, float *packed_out) {
+    PF_CHECK(hctx && G > 0 && nq >= 0 && (nq == 0 || (packed_g && packed_out)), PFANN_ERR_ARG, "pfann_best_combine: bad argument");
+    Ctx *ctx = reinterpret_cast<Ctx *>(hctx);
+    if (nq == 0) return PFANN_OK;
+    PF_CHECK(is_device_ptr(packed_g) && is_device_ptr(packed_out), PFANN_ERR_ARG, "pfann_best_combine: device pointers only");
+    PF_CUDA(cudaSetDevice(ctx->device));
+    combine_best_kernel<<<cdiv(nq, 256), 256, 0, ctx->stream>>>(reinterpret_cast<const float4 *>(packed_g), G, nq,
+                                                                reinterpret_cast<float4 *>(packed_out));
+    ctx->launches++;
+    PF_CUDA(cudaGetLastError());
+    return PFANN_OK;
+}
+
+float pfann_db_max_norm(pfann_db *h) { return h ? reinterpret_cast<Db *>(h)->max_norm : 0.f; }
+
+int pfann_db_set_max_norm(pfann_db *h, float max_norm) {
+    PF_CHECK(h && max_norm >= 0.f, PFANN_ERR_ARG, "pfann_db_set_max_norm: bad argument");
+    Db *db = reinterpret_cast<Db *>(h);
+    PF_CHECK(max_norm >= db->max_norm, PFANN_ERR_ARG, "pfann_db_set_max_norm: %g is below this shard's own maximum %g",
+             (double)max_norm, (double)db->max_norm);
+    db->max_norm = max_norm;
+    return PFANN_OK;
 }
 
 }  // extern "C"

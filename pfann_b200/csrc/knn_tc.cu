@@ -31,8 +31,9 @@ struct KnnTcState {
 };
 
 struct ScanArgs {
-    const float *q;      // [Qg][d] fp32
-    int Qg, d;
+    const float *q;      // [Qtot][d] fp32; CTA row blockIdx.y serves queries [group * y, group * y + Qg)
+    int Qtot, group;     // queries of the launch, queries per group (= per database pass)
+    int Qg, d;           // queries of this CTA's group (set inside the kernel)
     long long r0, r1;    // row range
     int mode;
     float *sample;       // mode 0: [Qg][sample_ld]
@@ -54,9 +55,23 @@ template <int N> struct ScanCfg {
     static constexpr int TROWS = N > 128 ? N : 128;      // rows of the threshold tile
 };
 
+// gridDim.y query groups share one launch: group y is scanned by the gridDim.x CTAs of its row, so the launch
+// gaps, kernel prologues (query staging, TMEM allocation) and tails of up to four database passes are paid once.
 template <int N, bool SAMPLE>
 __global__ void __launch_bounds__(KNN_THREADS, 1) knn_scan_tc_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                                     const ScanArgs a) {
+                                                                     const ScanArgs a_in) {
+    ScanArgs a = a_in;
+    {
+        const long long g0 = (long long)blockIdx.y * a.group;
+        a.Qg = (int)((a.Qtot - g0) < a.group ? (a.Qtot - g0) : a.group);
+        a.q += g0 * a.d;
+        if (a.sample) a.sample += g0 * a.sample_ld;
+        if (a.thr) a.thr += g0;
+        if (a.cnt) a.cnt += g0;
+        if (a.cand) a.cand += g0 * a.cap;
+        if (a.cand_v) a.cand_v += g0 * a.cap;
+        if (a.prof) a.prof += (size_t)blockIdx.y * gridDim.x * 8;
+    }
     constexpr int STAGES = ScanCfg<N>::STAGES, QCAP = ScanCfg<N>::QCAP, TROWS = ScanCfg<N>::TROWS;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *sbase = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -324,11 +339,12 @@ int launch_scan(Db *db, KnnTcState *st, const ScanArgs &a) {
                         (size_t)ScanCfg<N>::QCAP * 12 + (size_t)ScanCfg<N>::TROWS * 128;
     PF_CUDA(cudaFuncSetAttribute(knn_scan_tc_kernel<N, SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long ntiles = (a.r1 - a.r0 + BM - 1) / BM;
-    long long grid = db->ctx->sm_count;
+    const int ngroups = (a.Qtot + a.group - 1) / a.group;
+    long long grid = db->ctx->sm_count / ngroups;
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) return PFANN_OK;
     ProfScope ps(db->ctx, K_KNN_SCAN, a.mode == 0 ? 35 : 36);
-    knn_scan_tc_kernel<N, SAMPLE><<<(unsigned)grid, KNN_THREADS, smem, db->ctx->stream>>>(st->mapA, a);
+    knn_scan_tc_kernel<N, SAMPLE><<<dim3((unsigned)grid, (unsigned)ngroups), KNN_THREADS, smem, db->ctx->stream>>>(st->mapA, a);
     db->ctx->launches++;
     PF_CUDA(cudaGetLastError());
     return PFANN_OK;
@@ -370,20 +386,22 @@ void knn_tc_release(Db *db) {
 }
 
 // sample pre-pass (mode 0): number of per-thread maxima written per query for a row range
-int64_t knn_tc_sample_slots(Db *db, int64_t r0, int64_t r1) {
+int64_t knn_tc_sample_slots(Db *db, int64_t r0, int64_t r1, int ngroups) {
     const long long ntiles = (r1 - r0 + BM - 1) / BM;
-    long long grid = db->ctx->sm_count;
+    long long grid = db->ctx->sm_count / (ngroups > 0 ? ngroups : 1);
     if (grid > ntiles) grid = ntiles;
     return grid * BM;
 }
 
-int knn_tc_scan(Db *db, const float *q, int Qg, int64_t r0, int64_t r1, int mode, float *sample, int64_t sample_ld,
-                const float *thr, int *cnt, uint32_t *cand, uint32_t *cand_v, int cap) {
+int knn_tc_scan(Db *db, const float *q, int Qtot, int group, int64_t r0, int64_t r1, int mode, float *sample,
+                int64_t sample_ld, const float *thr, int *cnt, uint32_t *cand, uint32_t *cand_v, int cap) {
     KnnTcState *st = reinterpret_cast<KnnTcState *>(db->tc_state);
     PF_CHECK(st != nullptr, PFANN_ERR_STATE, "knn_tc_scan: tensor-core state missing");
-    PF_CHECK(Qg >= 1 && Qg <= 256, PFANN_ERR_ARG, "knn_tc_scan: 1..256 queries per pass");
+    PF_CHECK(group >= 1 && group <= 256 && Qtot >= 1 && (Qtot + group - 1) / group <= 8, PFANN_ERR_ARG,
+             "knn_tc_scan: 1..256 queries per pass, at most 8 passes per launch");
+    const int Qg = Qtot < group ? Qtot : group;   // widest group of the launch picks the instantiation
     ScanArgs a;
-    a.q = q; a.Qg = Qg; a.d = db->d; a.r0 = r0; a.r1 = r1; a.mode = mode;
+    a.q = q; a.Qtot = Qtot; a.group = group; a.Qg = Qg; a.d = db->d; a.r0 = r0; a.r1 = r1; a.mode = mode;
     a.sample = sample; a.sample_ld = sample_ld; a.thr = thr; a.cnt = cnt; a.cand = cand; a.cand_v = cand_v; a.cap = cap;
     const char *dbg = getenv("PFANN_KNN_DEBUG");
     a.debug = dbg ? atoi(dbg) : 0;

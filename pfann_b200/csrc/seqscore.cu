@@ -297,6 +297,11 @@ int rerank_dev(Db *db, const float *queries, const int64_t *query_index, int nq,
     return PFANN_OK;
 }
 
+__global__ void pack_best_kernel(const float *score, const int *song, const float *time, int nq, float4 *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq) out[i] = make_float4(score[i], __int_as_float(song[i]), time[i], 0.f);
+}
+
 int check_rerank_args(Db *db, int top_k, int fsm) {
     PF_CHECK(top_k > 0, PFANN_ERR_ARG, "rerank: top_k must be positive");
     PF_CHECK(fsm >= 1 && fsm <= 255, PFANN_ERR_ARG, "rerank: frame_shift_mul must be in 1..255");
@@ -353,6 +358,30 @@ int pfann_db_rerank(pfann_db *h, const float *queries, const int64_t *query_inde
     PF_TRY(finish_output(db->ctx, 0, best_score, (size_t)nq * 4));
     PF_TRY(finish_output(db->ctx, 1, best_song, (size_t)nq * 4));
     return finish_output(db->ctx, 2, best_time, (size_t)nq * 4);
+}
+
+/* all-device form for the sharded search: nothing is read back, the winners come out as one [nq][4] fp32 record
+ * (score, song id bits, time in frames, 0) ready for a single all-gather */
+int pfann_db_rerank_packed(pfann_db *h, const float *queries, const int64_t *query_index, int nq, int max_len,
+                           const int64_t *labels, int top_k, int fsm, float alpha, float *packed) {
+    PF_CHECK(h && nq >= 0 && max_len >= 0 && max_len < (1 << 20), PFANN_ERR_ARG, "pfann_db_rerank_packed: bad argument");
+    Db *db = reinterpret_cast<Db *>(h);
+    PF_TRY(check_rerank_args(db, top_k, fsm));
+    if (nq == 0) return PFANN_OK;
+    PF_CHECK(queries && query_index && labels && packed, PFANN_ERR_ARG, "pfann_db_rerank_packed: NULL argument");
+    PF_CHECK(is_device_ptr(queries) && is_device_ptr(query_index) && is_device_ptr(labels) && is_device_ptr(packed),
+             PFANN_ERR_ARG, "pfann_db_rerank_packed: device pointers only");
+    PF_CUDA(cudaSetDevice(db->ctx->device));
+    PF_TRY(db->rr_out.ensure((size_t)nq * 12));
+    float *bs = db->rr_out.as<float>();
+    int *bg = reinterpret_cast<int *>(bs + nq);
+    float *bt = reinterpret_cast<float *>(bg + nq);
+    PF_TRY(rerank_dev(db, queries, query_index, nq, max_len, labels, top_k, fsm, alpha, bs, bg, bt, nullptr, nullptr,
+                      nullptr, nullptr));
+    pack_best_kernel<<<cdiv(nq, 256), 256, 0, db->ctx->stream>>>(bs, bg, bt, nq, reinterpret_cast<float4 *>(packed));
+    db->ctx->launches++;
+    PF_CUDA(cudaGetLastError());
+    return PFANN_OK;
 }
 
 int pfann_db_seq_score(pfann_db *h, const int64_t *song_pos, int n_songs, const float *query, int query_len,

@@ -1,14 +1,18 @@
 """Row-sharded database search across GPUs: one process per GPU, the database cut at song
-boundaries into contiguous shards, queries replicated.  Per batch of query files there are exactly two
-exchanges, both tiny next to the HBM stream of the scan:
+boundaries into contiguous shards, queries replicated.  Per batch of query files:
 
-  1. all-gather of the per-shard top-k  [Q, k] x (fp32 score, int64 global row id), merged identically on
-     every rank into the global top-k (score desc, id asc);
-  2. all-gather of one (score, song, time) triple per query file per rank after each rank has run the
-     sequence score over the candidates whose songs it owns; arg-max with the reference's tie rule
-     (higher score, then lower song id, cpp/seqscore.cpp:121).
+  1. every rank runs its sample pre-pass and the per-query filter thresholds are combined with ONE all-reduce(max)
+     of Q floats: each shard's value is a lower bound of the GLOBAL k-th best score, so the maximum is the tightest
+     bound anybody found -- shards then keep far fewer rows than their own top-k would need;
+  2. filtered scan + exact rescoring per shard, then the ONE all-gather of per-shard top-k the north_star asks
+     for: [Q, k] sortable 64-bit keys (score bits << 32 | 0xFFFFFFFF - global row id), merged identically on every
+     rank into the global top-k (score desc, id asc);
+  3. every rank runs the sequence score over the candidates whose songs it owns; one all-gather of a 16-byte
+     (score, song, time) record per query file, arg-max with the reference's tie rule (higher score, then lower
+     song id, cpp/seqscore.cpp:121) on the device.
 
-With world size 1 both collectives vanish and this is exactly ``Database.query_batch``.
+Nothing is read back to the host between batches: ``query_batches`` enqueues everything and reads the answers once.
+With world size 1 the collectives vanish and the result is exactly ``Database.query_batch``.
 The reference has no multi-GPU search (its faiss hook clones replicas, database.py:101-104).
 """
 import numpy as np
@@ -27,12 +31,31 @@ def shard_songs(song_pos, world):
 
 
 def merge_topk(dists, labels, k):
-    """numpy statement of pfann_topk_merge: lists [G][Q][k] -> [Q][k], (valid, score desc, id asc)."""
+    """numpy statement of the top-k merge: lists [G][Q][k] -> [Q][k], (valid, score desc, id asc)."""
     D = np.concatenate(list(dists), axis=1)
     I = np.concatenate(list(labels), axis=1)
     invalid = I < 0
     order = np.lexsort((I, -D.astype(np.float64), invalid), axis=1)[:, :k]
     return np.take_along_axis(D, order, 1), np.take_along_axis(I, order, 1)
+
+
+def pack_keys(D, I):
+    """numpy statement of the key packing of pfann_db_search_filtered: order-preserving fp32 bits << 32 |
+    (0xFFFFFFFF - id); empty slots (id < 0) -> 0.  Descending key order = score desc, id asc."""
+    u = np.ascontiguousarray(D, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    flip = np.where(u >> np.uint64(31), u ^ np.uint64(0xFFFFFFFF), u ^ np.uint64(0x80000000))
+    key = (flip << np.uint64(32)) | (np.uint64(0xFFFFFFFF) - np.asarray(I).astype(np.uint64) % np.uint64(1 << 32))
+    return np.where(np.asarray(I) < 0, np.uint64(0), key)
+
+
+def unpack_keys(keys):
+    keys = np.asarray(keys, dtype=np.uint64)
+    hi = (keys >> np.uint64(32)).astype(np.uint32)
+    u = np.where(hi >> np.uint32(31), hi ^ np.uint32(0x80000000), hi ^ np.uint32(0xFFFFFFFF)).astype(np.uint32)
+    D = u.view(np.float32)
+    I = (np.uint64(0xFFFFFFFF) - (keys & np.uint64(0xFFFFFFFF))).astype(np.int64)
+    empty = keys == 0
+    return np.where(empty, np.float32(-3.4028235e38), D), np.where(empty, -1, I)
 
 
 def combine_best(scores, songs, times):
@@ -56,15 +79,31 @@ def combine_best(scores, songs, times):
 
 class ShardedDatabase:
     """Sharded brute-force search + sequence score.  ``backend`` is the per-shard engine; by default the
-    libpfann_b200 handle of this rank's shard (``pfann_b200.database.Database(..., songs=range)``)."""
+    libpfann_b200 handle of this rank's shard (``GpuShard(pfann_b200.database.Database(..., songs=range))``).
+
+    Backend contract (tensors live on the backend's device):
+      max_norm() / set_max_norm(v)               error bound of the approximate scan, made common to all shards
+      thresholds(q, k) -> [Q] fp32                lower bound of the shard's k-th best score per query
+      filtered_keys(q, k, thr, defer) -> [Q, k] int64  packed keys of the exact top-k among rows reaching thr
+      take_overflow() -> int                       overflowed candidate lists since the last call (deferred mode)
+      merge_keys(keys_g [G, Q, k]) -> [Q, k] int64 labels
+      rerank_packed(q, query_index, labels, k, fsm, alpha) -> [nq, 4] fp32 (score, song bits, frames, 0)
+      combine(packed_g [G, nq, 4]) -> [nq, 4] fp32
+    """
 
     def __init__(self, backend, top_k, frame_shift_mul=1, hop_size=0.5, score_alpha=0.0, group=None):
         self.backend = backend
         self.top_k, self.fsm, self.hop_size, self.alpha = top_k, frame_shift_mul, hop_size, float(score_alpha)
         self.group = group
+        import torch
         import torch.distributed as dist
         self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
         self.world = self.dist.get_world_size(group) if self.dist else 1
+        if self.world > 1:
+            # one error bound for every shard, so that the maximum of the per-shard thresholds stays a lower bound
+            m = torch.tensor([backend.max_norm()], dtype=torch.float32, device=backend.torch_device())
+            self.dist.all_reduce(m, op=self.dist.ReduceOp.MAX, group=group)
+            backend.set_max_norm(float(m.item()))
 
     def _all_gather(self, t):
         import torch
@@ -74,61 +113,135 @@ class ShardedDatabase:
         self.dist.all_gather(list(out.unbind(0)), t.contiguous(), group=self.group)   # nccl and gloo alike
         return out
 
+    def search(self, queries, defer=False):
+        """Global top-k labels [Q, k] (int64, on the backend's device) of replicated queries."""
+        b = self.backend
+        q = b.to_device(queries)
+        thr = b.thresholds(q, self.top_k)
+        if self.world > 1:
+            self.dist.all_reduce(thr, op=self.dist.ReduceOp.MAX, group=self.group)    # Q floats
+        keys = b.filtered_keys(q, self.top_k, thr, defer)
+        return q, b.merge_keys(self._all_gather(keys), self.top_k)                    # THE all-gather: [G, Q, k] keys
+
+    def _query_dev(self, queries, query_index, defer=False):
+        q, labels = self.search(queries, defer)
+        packed = self.backend.rerank_packed(q, query_index, labels, self.top_k, self.fsm, self.alpha)
+        return self.backend.combine(self._all_gather(packed))                         # [nq, 4], identical on every rank
+
+    def _to_host(self, packed):
+        p = packed.cpu().numpy()
+        score = np.ascontiguousarray(p[:, 0])
+        song = np.ascontiguousarray(p[:, 1]).view(np.int32)
+        tim = p[:, 2].astype(np.float64) * self.hop_size / self.fsm                   # database.py:191
+        return score, song, tim
+
     def query_batch(self, queries, query_index):
         """queries [sum len, d], query_index [nq, 2] (start, len), both replicated on every rank.
         Returns (score[nq], song[nq], time_s[nq]) identical on every rank."""
-        d_l, i_l = self.backend.search_local(queries, self.top_k)             # tensors on the backend's device
-        dg, ig = self._all_gather(d_l), self._all_gather(i_l)                 # exchange 1: [G, Q, k]
-        D, I = self.backend.merge(dg, ig, self.top_k) if self.world > 1 else (d_l, i_l)
-        s, g, t = self.backend.rerank_local(queries, query_index, I, self.top_k, self.fsm, self.alpha)
+        return self._to_host(self._query_dev(queries, query_index))
+
+    def query_batches(self, queries, query_index, batch):
+        """The same for many files, `batch` query files per database pass group; all batches are enqueued before
+        the single read-back, so exchanges and small kernels of one batch overlap the host work of the next."""
         import torch
-        pack = torch.stack([s.double(), g.double(), t.double()], dim=1)       # exchange 2: [G, nq, 3]
-        allp = self._all_gather(pack).cpu().numpy()
-        score, song, tim = combine_best(allp[:, :, 0].astype(np.float32), allp[:, :, 1].astype(np.int64),
-                                        allp[:, :, 2].astype(np.float32))
-        return score, song, tim.astype(np.float64) * self.hop_size / self.fsm               # database.py:191
+        query_index = np.asarray(query_index, dtype=np.int64).reshape(-1, 2)
+        if len(query_index) == 0:
+            return np.zeros(0, np.float32), np.zeros(0, np.int32), np.zeros(0, np.float64)
+
+        def run(defer):
+            outs = []
+            for b0 in range(0, len(query_index), batch):
+                qi = query_index[b0:b0 + batch]
+                lo, hi = int(qi[:, 0].min()), int((qi[:, 0] + qi[:, 1]).max())
+                qi = qi.copy()
+                qi[:, 0] -= lo
+                outs.append(self._query_dev(queries[lo:hi], qi, defer))
+            return self._to_host(torch.cat(outs, dim=0))                              # the one synchronisation
+
+        res = run(True)
+        # a candidate list that overflowed somewhere (rare) is only counted in the deferred mode: every rank must
+        # take the same decision, then the batches are repeated with the immediate check
+        ovf = torch.tensor([self.backend.take_overflow()], dtype=torch.int32, device=self.backend.torch_device())
+        if self.world > 1:
+            self.dist.all_reduce(ovf, op=self.dist.ReduceOp.MAX, group=self.group)
+        return run(False) if int(ovf.item()) else res
 
 
 class GpuShard:
-    """Per-rank engine over libpfann_b200: device-resident search / merge / rerank (all stream-ordered)."""
+    """Per-rank engine over libpfann_b200: device-resident, stream-ordered, no host read-backs."""
 
     def __init__(self, db):
         self.db = db          # pfann_b200.database.Database restricted to this rank's songs
 
-    def search_local(self, queries, k):
+    def torch_device(self):
+        import torch
+        return torch.device('cuda', self.db.device)
+
+    def to_device(self, queries):
+        import torch
+        return torch.as_tensor(queries, dtype=torch.float32).to(self.torch_device(), non_blocking=True).contiguous()
+
+    def max_norm(self):
+        from . import _lib
+        return float(_lib.lib().pfann_db_max_norm(self.db.handle))
+
+    def set_max_norm(self, v):
+        from . import _lib
+        _lib.check(_lib.lib().pfann_db_set_max_norm(self.db.handle, float(v)), 'pfann_db_set_max_norm')
+
+    def thresholds(self, q, k):
         import torch
         from . import _lib
-        dev = torch.device('cuda', self.db.device)
-        q = torch.as_tensor(queries, dtype=torch.float32).to(dev).contiguous()
-        D = torch.empty((q.shape[0], k), dtype=torch.float32, device=dev)
-        I = torch.empty((q.shape[0], k), dtype=torch.int64, device=dev)
+        thr = torch.empty(q.shape[0], dtype=torch.float32, device=q.device)
         _lib.use_torch_stream(self.db.device)
-        _lib.check(_lib.lib().pfann_db_search(self.db.handle, _lib.ptr(q), q.shape[0], k, _lib.ptr(D), _lib.ptr(I)),
-                   'pfann_db_search')
-        self._q = q
-        return D, I
+        _lib.check(_lib.lib().pfann_db_search_thresholds(self.db.handle, _lib.ptr(q), q.shape[0], k, _lib.ptr(thr)),
+                   'pfann_db_search_thresholds')
+        return thr
 
-    def merge(self, dg, ig, k):
+    def filtered_keys(self, q, k, thr, defer=False):
         import torch
         from . import _lib
-        G, Q = dg.shape[0], dg.shape[1]
-        D = torch.empty((Q, k), dtype=torch.float32, device=dg.device)
-        I = torch.empty((Q, k), dtype=torch.int64, device=dg.device)
-        _lib.check(_lib.lib().pfann_topk_merge(_lib.ctx(self.db.device), _lib.ptr(dg.contiguous()),
-                                               _lib.ptr(ig.contiguous()), G, Q, k, _lib.ptr(D), _lib.ptr(I)),
-                   'pfann_topk_merge')
-        return D, I
+        keys = torch.empty((q.shape[0], k), dtype=torch.int64, device=q.device)
+        _lib.use_torch_stream(self.db.device)
+        _lib.check(_lib.lib().pfann_db_search_filtered(self.db.handle, _lib.ptr(q), q.shape[0], k, _lib.ptr(thr),
+                                                       _lib.ptr(keys), int(bool(defer))), 'pfann_db_search_filtered')
+        return keys
 
-    def rerank_local(self, queries, query_index, labels, k, fsm, alpha):
+    def take_overflow(self):
+        from . import _lib
+        return int(_lib.lib().pfann_db_take_overflow(self.db.handle))
+
+    def merge_keys(self, keys_g, k, want_dist=False):
         import torch
         from . import _lib
-        dev = labels.device
-        qi = torch.as_tensor(np.ascontiguousarray(query_index, dtype=np.int64)).to(dev)
-        nq = qi.shape[0]
-        s = torch.empty(nq, dtype=torch.float32, device=dev)
-        g = torch.empty(nq, dtype=torch.int32, device=dev)
-        t = torch.empty(nq, dtype=torch.float32, device=dev)
-        _lib.check(_lib.lib().pfann_db_rerank(self.db.handle, _lib.ptr(self._q), _lib.ptr(qi), nq,
-                                              _lib.ptr(labels.contiguous()), k, fsm, float(alpha), _lib.ptr(s),
-                                              _lib.ptr(g), _lib.ptr(t)), 'pfann_db_rerank')
-        return s, g, t
+        G, Q = keys_g.shape[0], keys_g.shape[1]
+        labels = torch.empty((Q, k), dtype=torch.int64, device=keys_g.device)
+        dist = torch.empty((Q, k), dtype=torch.float32, device=keys_g.device) if want_dist else None
+        _lib.use_torch_stream(self.db.device)
+        _lib.check(_lib.lib().pfann_topk_merge_keys(_lib.ctx(self.db.device), _lib.ptr(keys_g.contiguous()), G, Q, k,
+                                                    _lib.ptr(dist), _lib.ptr(labels)), 'pfann_topk_merge_keys')
+        return (dist, labels) if want_dist else labels
+
+    def rerank_packed(self, q, query_index, labels, k, fsm, alpha):
+        import torch
+        from . import _lib
+        qi_host = np.ascontiguousarray(query_index, dtype=np.int64).reshape(-1, 2)
+        nq = qi_host.shape[0]
+        max_len = int(qi_host[:, 1].max()) if nq else 0
+        qi = torch.from_numpy(qi_host).to(q.device, non_blocking=True)
+        packed = torch.empty((nq, 4), dtype=torch.float32, device=q.device)
+        _lib.use_torch_stream(self.db.device)
+        _lib.check(_lib.lib().pfann_db_rerank_packed(self.db.handle, _lib.ptr(q), _lib.ptr(qi), nq, max_len,
+                                                     _lib.ptr(labels.contiguous()), k, fsm, float(alpha),
+                                                     _lib.ptr(packed)), 'pfann_db_rerank_packed')
+        return packed
+
+    def combine(self, packed_g):
+        import torch
+        from . import _lib
+        G, nq = packed_g.shape[0], packed_g.shape[1]
+        out = torch.empty((nq, 4), dtype=torch.float32, device=packed_g.device)
+        _lib.use_torch_stream(self.db.device)
+        _lib.check(_lib.lib().pfann_best_combine(_lib.ctx(self.db.device), _lib.ptr(packed_g.contiguous()), G, nq,
+                                                 _lib.ptr(out)), 'pfann_best_combine')
+        return out

@@ -11,7 +11,7 @@ import torch.multiprocessing as mp
 
 from oracle import pfann_oracle as orc
 from pfann_b200 import synth
-from pfann_b200.dist import ShardedDatabase, combine_best, merge_topk, shard_songs
+from pfann_b200.dist import ShardedDatabase, combine_best, merge_topk, pack_keys, shard_songs, unpack_keys
 
 
 class OracleShard:
@@ -21,32 +21,65 @@ class OracleShard:
         self.db, self.pos = db, pos
         self.s0, self.s1 = songs
         self.r0, self.r1 = int(pos[self.s0]), int(pos[self.s1])
+        self._norm = float(np.linalg.norm(db[self.r0:self.r1], axis=1).max()) if self.r1 > self.r0 else 0.0
 
-    def search_local(self, queries, k):
-        D, I = orc.flat_ip_search(self.db[self.r0:self.r1], np.asarray(queries), k)
-        I = np.where(I >= 0, I + self.r0, -1)
-        self._q = np.asarray(queries)
-        return torch.from_numpy(D), torch.from_numpy(I)
+    def torch_device(self):
+        return torch.device('cpu')
 
-    def merge(self, dg, ig, k):
-        D, I = merge_topk(list(dg.numpy()), list(ig.numpy()), k)
-        return torch.from_numpy(D), torch.from_numpy(I)
+    def to_device(self, queries):
+        return torch.as_tensor(np.asarray(queries), dtype=torch.float32)
 
-    def rerank_local(self, queries, query_index, labels, k, fsm, alpha):
-        labels = labels.numpy()
+    def max_norm(self):
+        return self._norm
+
+    def set_max_norm(self, v):
+        assert v >= self._norm
+        self._norm = v
+
+    def thresholds(self, q, k):
+        # like the GPU pre-pass: the k-th best score of a SAMPLE of the shard (a lower bound of its k-th best)
+        rows = self.db[self.r0:self.r1][::3]
+        sc = np.sort(q.numpy() @ rows.T, axis=1)[:, ::-1]
+        thr = sc[:, k - 1] if rows.shape[0] >= k else np.full(q.shape[0], -np.inf, np.float32)
+        return torch.from_numpy(np.ascontiguousarray(thr, dtype=np.float32))
+
+    def take_overflow(self):
+        return 0
+
+    def filtered_keys(self, q, k, thr, defer=False):
+        D, I = orc.flat_ip_search(self.db[self.r0:self.r1], q.numpy(), k)
+        keep = (I >= 0) & (D >= thr.numpy()[:, None])              # rows below the (global) threshold are dropped
+        I = np.where(keep, I + self.r0, -1)
+        return torch.from_numpy(pack_keys(D, I).view(np.int64))
+
+    def merge_keys(self, keys_g, k):
+        allk = np.concatenate(list(keys_g.numpy().view(np.uint64)), axis=1)
+        srt = np.sort(allk, axis=1)[:, ::-1][:, :k]                 # descending unsigned keys = score desc, id asc
+        return torch.from_numpy(np.ascontiguousarray(unpack_keys(srt)[1]))
+
+    def rerank_packed(self, q, query_index, labels, k, fsm, alpha):
+        labels, qn = labels.numpy(), q.numpy()
         nq = len(query_index)
-        s = np.full(nq, -np.inf, np.float32)
-        g = np.full(nq, -1, np.int32)
-        t = np.zeros(nq, np.float32)
+        out = np.zeros((nq, 4), np.float32)
+        song = np.full(nq, -1, np.int32)
+        out[:, 0] = -np.inf
         for i, (st, ln) in enumerate(query_index):
             lab = labels[st:st + ln].copy()
             lab[(lab < self.r0) | (lab >= self.r1)] = -1        # a shard scores only the songs it owns
-            best, ss = orc.seq_score(self.db, self.pos, self._q[st:st + ln], lab, fsm, alpha)
+            best, ss = orc.seq_score(self.db, self.pos, qn[st:st + ln], lab, fsm, alpha)
             if best >= 0:
                 # raw winner (no zero floor): highest per-song score, ties -> lower id
                 cand = np.nonzero(ss[:, 0] > 0)[0]
-                s[i], g[i], t[i] = (ss[best, 0], best, ss[best, 1]) if len(cand) else (0.0, best, 0.0)
-        return torch.from_numpy(s), torch.from_numpy(g), torch.from_numpy(t)
+                out[i, 0], song[i], out[i, 2] = (ss[best, 0], best, ss[best, 1]) if len(cand) else (0.0, best, 0.0)
+        out[:, 1] = song.view(np.float32)
+        return torch.from_numpy(out)
+
+    def combine(self, packed_g):
+        p = packed_g.numpy()
+        s, g, t = combine_best(p[:, :, 0], np.ascontiguousarray(p[:, :, 1]).view(np.int32), p[:, :, 2])
+        out = np.zeros((p.shape[1], 4), np.float32)
+        out[:, 0], out[:, 1], out[:, 2] = s, g.astype(np.int32).view(np.float32), t
+        return torch.from_numpy(out)
 
 
 def _worker(rank, world, port, ret):
@@ -60,6 +93,8 @@ def _worker(rank, world, port, ret):
     shard = OracleShard(db, pos, shard_songs(pos, world)[rank])
     sdb = ShardedDatabase(shard, 10, 1, 0.5)
     score, song, tim = sdb.query_batch(q, qi)
+    s2, g2, t2 = sdb.query_batches(q, qi, 4)                      # two batches, one read-back: same answers
+    assert np.array_equal(score, s2) and np.array_equal(song, g2) and np.array_equal(tim, t2)
     if rank == 0:
         ret['score'], ret['song'], ret['time'] = score, song, tim
     dist.destroy_process_group()
@@ -105,3 +140,15 @@ def test_merge_topk_and_combine_best_rules():
     assert list(g) == [3, 2, -1] and list(s) == [0.5, 0.0, 0.0] and list(t) == [4.0, 0.0, 0.0]
     s, g, t = combine_best([[0.5], [0.5]], [[9], [4]], [[1.0], [2.0]])
     assert g[0] == 4 and t[0] == 2.0                          # tie -> lower song id (seqscore.cpp:121)
+
+
+def test_key_packing_orders_like_score_desc_id_asc():
+    D = np.array([[0.5, -0.25, 0.5, 0.0, -0.0, 1e-30]], np.float32)
+    I = np.array([[9, 4, 3, 7, 8, -1]], np.int64)
+    keys = pack_keys(D, I)
+    order = np.argsort(keys[0], kind='stable')[::-1]                 # unsigned integer order, descending
+    assert list(I[0][order]) == [3, 9, 7, 8, 4, -1]                  # +0.0 sorts above -0.0 (distinct bit patterns)
+    srt = np.sort(keys, axis=1)[:, ::-1]
+    d2, i2 = unpack_keys(srt)
+    assert list(i2[0][:2]) == [3, 9] and i2[0][-1] == -1 and d2[0][0] == np.float32(0.5)
+    assert np.array_equal(unpack_keys(keys)[0][0][:5].view(np.uint32), D[0][:5].view(np.uint32))   # bit-exact scores

@@ -486,3 +486,50 @@ def test_two_devices_in_one_process(dev):
     b = Database.from_arrays(db, key, {'top_k': 10, 'frame_shift_mul': 1}, 0.5, device=1)
     q = db[100:119]
     assert a.query_embeddings(q)[:2] == b.query_embeddings(q)[:2]
+
+
+def test_sharded_search_phases_three_shards_one_gpu(dev):
+    """The multi-GPU exchange (pfann_b200/dist.py) with its collectives done by hand on one GPU: three shards cut at
+    song boundaries (one of them empty), thresholds combined with an element-wise maximum, ONE list of packed keys per
+    shard, merge, shard-local sequence score, winner combination == the unsharded database, bit for bit.  The global
+    thresholds leave shards with fewer than k survivors, and the deferred overflow check stays at zero."""
+    from pfann_b200.database import Database
+    from pfann_b200.dist import GpuShard, ShardedDatabase, shard_songs
+    db, key = synth.synth_db(60000, d=128, seed=4, song_len=59)
+    key = np.concatenate([key, np.zeros(3, np.int32)])             # trailing empty songs -> an empty last shard
+    pos = synth.song_pos_from_key(key)
+    qs, songs, offs = synth.synth_queries(db, key[:-3], 70, q_len=19, seed=8)
+    q_flat = qs.reshape(-1, 128)
+    qi = np.stack([np.arange(70) * 19, np.full(70, 19)], 1).astype(np.int64)
+    k = 20
+    params = {'top_k': k, 'frame_shift_mul': 1}
+    full = Database.from_arrays(db, key, params, 0.5, device=0)
+    cuts = shard_songs(pos, 2) + [(len(key), len(key))]
+    shards = [GpuShard(Database.from_arrays(db, key, params, 0.5, device=0, songs=c)) for c in cuts]
+    m = max(s.max_norm() for s in shards)
+    for s in shards:
+        s.set_max_norm(m)
+    q = shards[0].to_device(q_flat)
+    thr = torch.stack([s.thresholds(q, k) for s in shards]).amax(dim=0)
+    assert torch.isinf(shards[2].thresholds(q, k)).all()            # an empty shard bounds nothing
+    keys = torch.stack([s.filtered_keys(q, k, thr.clone(), True) for s in shards])
+    assert (keys[2] == 0).all() and (keys[:2] == 0).any()           # empty shard; some lists shorter than k
+    D, I = shards[0].merge_keys(keys, k, want_dist=True)
+    D0, I0 = full.search(q_flat, k)
+    assert np.array_equal(I.cpu().numpy(), I0) and np.array_equal(D.cpu().numpy().view(np.uint32), D0.view(np.uint32))
+    packed = torch.stack([s.rerank_packed(q, qi, I, k, 1, 0.0) for s in shards])
+    out = shards[1].combine(packed).cpu().numpy()
+    rs, rg, rt, _ = full.query_batch(q_flat, qi)
+    assert np.array_equal(out[:, 0], rs) and np.array_equal(np.ascontiguousarray(out[:, 1]).view(np.int32), rg)
+    assert np.array_equal(out[:, 2].astype(np.float64) * 0.5, rt)
+    assert np.array_equal(rg, songs) and np.array_equal(rt, offs * 0.5)
+    torch.cuda.synchronize()
+    assert all(s.take_overflow() == 0 for s in shards)
+    # the single-process wrapper (world size 1: no collectives) gives the same answers, batched or not
+    sdb = ShardedDatabase(GpuShard(full), k, 1, 0.5)
+    for res in (sdb.query_batch(q_flat, qi), sdb.query_batches(q_flat, qi, 32)):
+        assert np.array_equal(res[0], rs) and np.array_equal(res[1], rg) and np.array_equal(res[2], rt)
+    # a tiny candidate capacity forces overflows: counted in the deferred mode, repaired by the checked rerun
+    _lib.check(_lib.lib().pfann_db_set_tuning(full.handle, 32, -1, -1))
+    res = sdb.query_batches(q_flat, qi, 32)
+    assert np.array_equal(res[0], rs) and np.array_equal(res[1], rg) and np.array_equal(res[2], rt)

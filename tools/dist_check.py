@@ -28,16 +28,21 @@ for (n, k, fsm) in ((200_000, 20, 1), (50_000, 100, 2)):
                                  songs=shard_songs(pos, world)[rank])
     sdb = ShardedDatabase(GpuShard(shard), k, fsm, 0.5)
     score, song, tim = sdb.query_batch(q, qi)
+    s2, g2, t2 = sdb.query_batches(q, qi, 24)          # three batches, one read-back
     full = Database.from_arrays(db, key, {'top_k': k, 'frame_shift_mul': fsm}, 0.5, device=local)
     rs, rg, rt, _ = full.query_batch(q, qi)
     same = np.array_equal(song, rg) and np.array_equal(tim, rt) and np.array_equal(score, rs)
+    same = same and np.array_equal(song, g2) and np.array_equal(tim, t2) and np.array_equal(score, s2)
     if fsm == 1:
         same = same and np.array_equal(song, songs) and np.array_equal(tim, offs * 0.5)
     # the merged top-k equals the unsharded top-k bit for bit
     D, I = full.search(q[:57], k)
-    d_l, i_l = sdb.backend.search_local(q[:57], k)
-    dg, ig = sdb._all_gather(d_l), sdb._all_gather(i_l)
-    Dm, Im = sdb.backend.merge(dg, ig, k) if world > 1 else (d_l, i_l)
+    b = sdb.backend
+    qd = b.to_device(q[:57])
+    thr = b.thresholds(qd, k)
+    if world > 1:
+        dist.all_reduce(thr, op=dist.ReduceOp.MAX)
+    Dm, Im = b.merge_keys(sdb._all_gather(b.filtered_keys(qd, k, thr, False)), k, want_dist=True)
     same = same and np.array_equal(Im.cpu().numpy(), I) and np.array_equal(Dm.cpu().numpy().view(np.uint32), D.view(np.uint32))
     t = torch.tensor([int(same)], device='cuda')
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
