@@ -36,16 +36,35 @@
 
 /* torchaudio.functional.melscale_fbanks(n_freqs, f_min, f_max, n_mels, sample_rate,
  * norm=None, mel_scale='htk') as used by melspec.py:19-31.  fb is [n_freqs][n_mels]. */
-int orc_mel_fbanks(int n_freqs, double f_min, double f_max, int n_mels, int sample_rate,
-                   float *fb)
+/* torchaudio's two mel scales (functional._hz_to_mel / _mel_to_hz): 'htk' and 'slaney' (linear below 1 kHz,
+ * logarithmic above; melspec.py:30 selects slaney in naf_mode) */
+static double hz_to_mel(double f, int slaney)
+{
+    if (!slaney) return 2595.0 * log10(1.0 + f / 700.0);
+    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = 1000.0 / (200.0 / 3.0);
+    const double logstep = log(6.4) / 27.0;
+    return f >= min_log_hz ? min_log_mel + log(f / min_log_hz) / logstep : f / f_sp;
+}
+static double mel_to_hz(double m, int slaney)
+{
+    if (!slaney) return 700.0 * (pow(10.0, m / 2595.0) - 1.0);
+    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = 1000.0 / (200.0 / 3.0);
+    const double logstep = log(6.4) / 27.0;
+    return m >= min_log_mel ? min_log_hz * exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+
+/* slaney != 0: mel_scale='slaney' AND norm='slaney' (area normalisation 2 / (f[m+2] - f[m])), the pair
+ * melspec.py:29-30 selects in naf_mode */
+int orc_mel_fbanks_ex(int n_freqs, double f_min, double f_max, int n_mels, int sample_rate, int slaney,
+                      float *fb)
 {
     double *f_pts = (double *)malloc(sizeof(double) * (n_mels + 2));
     if (!f_pts) return -1;
-    double m_min = 2595.0 * log10(1.0 + f_min / 700.0);
-    double m_max = 2595.0 * log10(1.0 + f_max / 700.0);
+    double m_min = hz_to_mel(f_min, slaney);
+    double m_max = hz_to_mel(f_max, slaney);
     for (int i = 0; i < n_mels + 2; i++) {
         double m = m_min + (m_max - m_min) * (double)i / (double)(n_mels + 1);
-        f_pts[i] = 700.0 * (pow(10.0, m / 2595.0) - 1.0);
+        f_pts[i] = mel_to_hz(m, slaney);
     }
     double nyq = (double)(sample_rate / 2);
     for (int k = 0; k < n_freqs; k++) {
@@ -54,11 +73,19 @@ int orc_mel_fbanks(int n_freqs, double f_min, double f_max, int n_mels, int samp
             double down = (f - f_pts[m]) / (f_pts[m + 1] - f_pts[m]);
             double up = (f_pts[m + 2] - f) / (f_pts[m + 2] - f_pts[m + 1]);
             double v = down < up ? down : up;
-            fb[(size_t)k * n_mels + m] = (float)(v > 0.0 ? v : 0.0);
+            if (v < 0.0) v = 0.0;
+            if (slaney) v *= 2.0 / (f_pts[m + 2] - f_pts[m]);
+            fb[(size_t)k * n_mels + m] = (float)v;
         }
     }
     free(f_pts);
     return 0;
+}
+
+int orc_mel_fbanks(int n_freqs, double f_min, double f_max, int n_mels, int sample_rate,
+                   float *fb)
+{
+    return orc_mel_fbanks_ex(n_freqs, f_min, f_max, n_mels, sample_rate, 0, fb);
 }
 
 /* in-place iterative radix-2 complex FFT, n a power of two, double precision */
@@ -94,8 +121,22 @@ static void fft_c2c(double *re, double *im, int n)
  *   reflect-pad n_fft/2, Hann(periodic), rFFT, |.|^2     melspec.py:19-31 (torch.stft)
  *   HTK triangular mel (norm=None)           melspec.py:28-30
  *   + 1e-8, natural log                      melspec.py:41,46                          */
+int orc_melspec_ex(const float *x, int B, int n, int sample_rate, int n_fft, int hop,
+                   double f_min, double f_max, int n_mels, int naf_mode, int mel_log, int norm_max, float *out);
+
 int orc_melspec(const float *x, int B, int n, int sample_rate, int n_fft, int hop,
                 double f_min, double f_max, int n_mels, float *out)
+{
+    return orc_melspec_ex(x, B, n, sample_rate, n_fft, hop, f_min, f_max, n_mels, 0, 1, 0, out);
+}
+
+/* All options of MelSpec (melspec.py:4-50):
+ *   naf_mode   power = 1 (magnitude), zero padding instead of reflect, slaney mel scale + norm, + 0.06 instead of + 1e-8
+ *   mel_log    0 = none, 1 = natural log, 2 = log10              (melspec.py:43-46)
+ *   norm_max   spec_norm == 'max': normalise the waveform by max |x| (F.normalize p = inf) and subtract the
+ *              maximum of the (log-)mel tile afterwards           (melspec.py:35,48-49)  */
+int orc_melspec_ex(const float *x, int B, int n, int sample_rate, int n_fft, int hop,
+                   double f_min, double f_max, int n_mels, int naf_mode, int mel_log, int norm_max, float *out)
 {
     if (n_fft & (n_fft - 1)) return -2;
     if (n <= n_fft / 2) return -3; /* reflect pad needs pad < n */
@@ -105,7 +146,7 @@ int orc_melspec(const float *x, int B, int n, int sample_rate, int n_fft, int ho
     float *fb = (float *)malloc(sizeof(float) * (size_t)n_freqs * n_mels);
     double *win = (double *)malloc(sizeof(double) * n_fft);
     if (!fb || !win) return -1;
-    orc_mel_fbanks(n_freqs, f_min, f_max, n_mels, sample_rate, fb);
+    orc_mel_fbanks_ex(n_freqs, f_min, f_max, n_mels, sample_rate, naf_mode, fb);
     for (int i = 0; i < n_fft; i++) win[i] = 0.5 - 0.5 * cos(2.0 * M_PI * i / n_fft);
     int rc = 0;
 #pragma omp parallel
@@ -117,31 +158,52 @@ int orc_melspec(const float *x, int B, int n, int sample_rate, int n_fft, int ho
 #pragma omp for
         for (int b = 0; b < B; b++) {
             const float *xb = x + (size_t)b * n;
-            double ss = 0.0;
-            for (int i = 0; i < n; i++) ss += (double)xb[i] * xb[i];
-            double nrm = sqrt(ss);
+            double ss = 0.0, mx = 0.0;
+            for (int i = 0; i < n; i++) {
+                ss += (double)xb[i] * xb[i];
+                if (fabs((double)xb[i]) > mx) mx = fabs((double)xb[i]);
+            }
+            double nrm = norm_max ? mx : sqrt(ss);
             if (nrm < 1e-12) nrm = 1e-12;
             for (int i = 0; i < n + 2 * pad; i++) {
                 int j = i - pad;
+                if (naf_mode) {                      /* pad_mode='constant' */
+                    xp[i] = (j < 0 || j >= n) ? 0.0 : (double)xb[j] / nrm;
+                    continue;
+                }
                 if (j < 0) j = -j;
                 if (j >= n) j = 2 * (n - 1) - j;
                 xp[i] = (double)xb[j] / nrm;
             }
+            double tile_max = -1e300;
             for (int t = 0; t < T; t++) {
                 for (int i = 0; i < n_fft; i++) {
                     re[i] = xp[(size_t)t * hop + i] * win[i];
                     im[i] = 0.0;
                 }
                 fft_c2c(re, im, n_fft);
-                for (int k = 0; k < n_freqs; k++) pw[k] = re[k] * re[k] + im[k] * im[k];
+                for (int k = 0; k < n_freqs; k++) {
+                    pw[k] = re[k] * re[k] + im[k] * im[k];
+                    if (naf_mode) pw[k] = sqrt(pw[k]);   /* power = 1 */
+                }
                 for (int m = 0; m < n_mels; m++) {
                     double acc = 0.0;
                     for (int k = 0; k < n_freqs; k++) {
                         float w = fb[(size_t)k * n_mels + m];
                         if (w != 0.0f) acc += pw[k] * (double)w;
                     }
-                    out[((size_t)b * n_mels + m) * T + t] = (float)log(acc + 1e-8);
+                    double v = acc + (naf_mode ? 0.06 : 1e-8);
+                    if (mel_log == 1) v = log(v);
+                    else if (mel_log == 2) v = log10(v);
+                    if (v > tile_max) tile_max = v;
+                    out[((size_t)b * n_mels + m) * T + t] = (float)v;
                 }
+            }
+            if (norm_max) {   /* the reference subtracts the fp32 maximum of the fp32 tile (melspec.py:49) */
+                float fmx = -3.4e38f;
+                for (size_t i = 0; i < (size_t)n_mels * T; i++)
+                    if (out[(size_t)b * n_mels * T + i] > fmx) fmx = out[(size_t)b * n_mels * T + i];
+                for (size_t i = 0; i < (size_t)n_mels * T; i++) out[(size_t)b * n_mels * T + i] -= fmx;
             }
         }
         free(xp); free(re); free(im); free(pw);
@@ -176,6 +238,30 @@ int64_t orc_frame_pcm16(const int16_t *pcm, int64_t n, int seg, int hop, float *
  * Stage 2: encoder
  * ---------------------------------------------------------------------------------------- */
 
+static double act_fn(double y, int act)
+{
+    if (act == 1) return y > 0.0 ? y : expm1(y);   /* ELU(alpha = 1), model.py:10-11 */
+    return y > 0.0 ? y : 0.0;
+}
+
+/* the two orders of model.py:58-72: relu_after_bn ? act(LN(v)) : LN(act(v)) */
+static void layer_norm_act(double *v, size_t n, const float *g, const float *be, int act, int relu_after_bn)
+{
+    if (!relu_after_bn)
+        for (size_t i = 0; i < n; i++) v[i] = act_fn(v[i], act);
+    double mean = 0.0;
+    for (size_t i = 0; i < n; i++) mean += v[i];
+    mean /= (double)n;
+    double var = 0.0;
+    for (size_t i = 0; i < n; i++) { double d = v[i] - mean; var += d * d; }
+    var /= (double)n;
+    double rstd = 1.0 / sqrt(var + 1e-5);
+    for (size_t i = 0; i < n; i++) {
+        double y = (v[i] - mean) * rstd * (double)g[i] + (double)be[i];
+        v[i] = relu_after_bn ? act_fn(y, act) : y;
+    }
+}
+
 static void layer_norm_relu(double *v, size_t n, const float *g, const float *be)
 {
     /* torch.nn.LayerNorm over the whole (C,F,T) volume, eps=1e-5, biased variance,
@@ -200,15 +286,30 @@ static void layer_norm_relu(double *v, size_t n, const float *g, const float *be
  *   w2  fuller ? [Cout][Cout][3][1] : [Cout][1][3][1]  conv2 along freq (model.py:24-29)
  *   g2/be2 [Cout][F2][T2]
  *   y   [B][Cout][F2][T2];  mid (optional) [B][Cout][F][T2] = relu(ln1(conv1))          */
+int orc_sepconv_ex(const float *x, int B, int Cin, int Cout, int F, int T,
+                   const float *w1, const float *b1, const float *g1, const float *be1,
+                   const float *w2, const float *b2, const float *g2, const float *be2,
+                   int fuller, int s_t, int s_f, int act, int relu_after_bn, float *y, float *mid);
+
 int orc_sepconv(const float *x, int B, int Cin, int Cout, int F, int T,
                 const float *w1, const float *b1, const float *g1, const float *be1,
                 const float *w2, const float *b2, const float *g2, const float *be2,
                 int fuller, float *y, float *mid)
 {
-    const int k = 3, s = 2;
-    const int T2 = (T - 1) / s + 1, F2 = (F - 1) / s + 1;
-    const int padT = (T - 1) / s * s + k - T, padTl = padT / 2;
-    const int padF = (F - 1) / s * s + k - F, padFl = padF / 2;
+    return orc_sepconv_ex(x, B, Cin, Cout, F, T, w1, b1, g1, be1, w2, b2, g2, be2, fuller, 2, 2, 0, 1, y, mid);
+}
+
+/* the same with the options of model.py:15,58-72,84-85: time stride of conv1 / frequency stride of conv2
+ * (params['strides']), activation (0 ReLU, 1 ELU), relu_after_bn */
+int orc_sepconv_ex(const float *x, int B, int Cin, int Cout, int F, int T,
+                   const float *w1, const float *b1, const float *g1, const float *be1,
+                   const float *w2, const float *b2, const float *g2, const float *be2,
+                   int fuller, int s_t, int s_f, int act, int relu_after_bn, float *y, float *mid)
+{
+    const int k = 3;
+    const int T2 = (T - 1) / s_t + 1, F2 = (F - 1) / s_f + 1;
+    const int padT = (T - 1) / s_t * s_t + k - T, padTl = padT / 2;
+    const int padF = (F - 1) / s_f * s_f + k - F, padFl = padF / 2;
     const size_t n1 = (size_t)Cout * F * T2, n2 = (size_t)Cout * F2 * T2;
     int rc = 0;
 #pragma omp parallel for
@@ -223,21 +324,21 @@ int orc_sepconv(const float *x, int B, int Cin, int Cout, int F, int T,
                     double acc = b1[o];
                     for (int i = 0; i < Cin; i++)
                         for (int j = 0; j < k; j++) {
-                            int tt = t * s + j - padTl;
+                            int tt = t * s_t + j - padTl;
                             if (tt < 0 || tt >= T) continue;
                             acc += (double)w1[((size_t)o * Cin + i) * k + j] *
                                    (double)xb[((size_t)i * F + f) * T + tt];
                         }
                     a1[((size_t)o * F + f) * T2 + t] = acc;
                 }
-        layer_norm_relu(a1, n1, g1, be1);
+        layer_norm_act(a1, n1, g1, be1, act, relu_after_bn);
         if (mid) for (size_t i = 0; i < n1; i++) mid[(size_t)b * n1 + i] = (float)a1[i];
         for (int o = 0; o < Cout; o++)
             for (int f = 0; f < F2; f++)
                 for (int t = 0; t < T2; t++) {
                     double acc = b2[o];
                     for (int j = 0; j < k; j++) {
-                        int ff = f * s + j - padFl;
+                        int ff = f * s_f + j - padFl;
                         if (ff < 0 || ff >= F) continue;
                         if (fuller) {
                             for (int i = 0; i < Cout; i++)
@@ -249,7 +350,7 @@ int orc_sepconv(const float *x, int B, int Cin, int Cout, int F, int T,
                     }
                     a2[((size_t)o * F2 + f) * T2 + t] = acc;
                 }
-        layer_norm_relu(a2, n2, g2, be2);
+        layer_norm_act(a2, n2, g2, be2, act, relu_after_bn);
         for (size_t i = 0; i < n2; i++) y[(size_t)b * n2 + i] = (float)a2[i];
         free(a1); free(a2);
     }

@@ -42,6 +42,11 @@ def lib():
         L = ctypes.CDLL(build())
         L.orc_version.restype = ctypes.c_longlong
         L.orc_mel_fbanks.argtypes = [c_int, c_double, c_double, c_int, c_int, POINTER(c_float)]
+        L.orc_mel_fbanks_ex.argtypes = [c_int, c_double, c_double, c_int, c_int, c_int, POINTER(c_float)]
+        L.orc_melspec_ex.argtypes = [POINTER(c_float), c_int, c_int, c_int, c_int, c_int, c_double, c_double, c_int,
+                                     c_int, c_int, c_int, POINTER(c_float)]
+        L.orc_sepconv_ex.argtypes = [POINTER(c_float)] + [c_int] * 5 + [POINTER(c_float)] * 8 + [c_int] * 5 + \
+            [POINTER(c_float)] * 2
         L.orc_melspec.argtypes = [POINTER(c_float), c_int, c_int, c_int, c_int, c_int, c_double,
                                   c_double, c_int, POINTER(c_float)]
         L.orc_frame_pcm16.argtypes = [POINTER(c_int16), c_int64, c_int, c_int, POINTER(c_float), c_int64]
@@ -86,20 +91,25 @@ def ref_lib():
 def mel_fbanks(params):
     n_freqs = params['stft_n'] // 2 + 1
     fb = np.empty((n_freqs, params['n_mels']), np.float32)
-    lib().orc_mel_fbanks(n_freqs, params['f_min'], params['f_max'], params['n_mels'],
-                         params['sample_rate'], _p(fb, c_float))
+    lib().orc_mel_fbanks_ex(n_freqs, params['f_min'], params['f_max'], params['n_mels'],
+                            params['sample_rate'], int(bool(params.get('naf_mode', False))), _p(fb, c_float))
     return fb
 
 
+MEL_LOG = {None: 0, 'none': 0, 'log': 1, 'log10': 2}
+
+
 def melspec(x, params):
-    """MelSpec.forward (datautil/melspec.py:33-50), default options."""
+    """MelSpec.forward (datautil/melspec.py:33-50) with the options build_mel_spec_layer reads from the config
+    (melspec.py:60-62): naf_mode, mel_log ('log' | 'log10' | anything else = no logarithm), spec_norm ('l2' | 'max')."""
     x = _f32(x)
     B, n = x.shape
     T = 1 + n // params['stft_hop']
     out = np.empty((B, params['n_mels'], T), np.float32)
-    rc = lib().orc_melspec(_p(x, c_float), B, n, params['sample_rate'], params['stft_n'],
-                           params['stft_hop'], params['f_min'], params['f_max'], params['n_mels'],
-                           _p(out, c_float))
+    rc = lib().orc_melspec_ex(_p(x, c_float), B, n, params['sample_rate'], params['stft_n'],
+                              params['stft_hop'], params['f_min'], params['f_max'], params['n_mels'],
+                              int(bool(params.get('naf_mode', False))), MEL_LOG.get(params.get('mel_log', 'log'), 0),
+                              int(params.get('spec_norm', 'l2') == 'max'), _p(out, c_float))
     assert rc == 0, rc
     return out
 
@@ -116,16 +126,24 @@ def frame_pcm16(pcm, seg, hop):
 
 
 # ---------------------------------------------------------------- stage 2
+def layer_strides(params):
+    """(time stride of conv1, frequency stride of conv2) per layer: model.py:82-85."""
+    st = params['model'].get('strides')
+    if st is None:
+        return [(2, 2)] * 8
+    return [(int(st[i][0][1]), int(st[i][1][0])) for i in range(8)]
+
+
 def layer_shapes(params, F, T):
     """(Cin, Cout, F, T) of every SeparableConv2d, as MyF.__init__ builds them (model.py:79-93)."""
     m = params['model']
     d, h = m['d'], m['h']
     ch = [1, d, d, 2 * d, 2 * d, 4 * d, 4 * d, h, h]
     out = []
-    for i in range(8):
+    for i, (st, sf) in enumerate(layer_strides(params)):
         out.append((ch[i], ch[i + 1], F, T))
-        F = (F - 1) // 2 + 1
-        T = (T - 1) // 2 + 1
+        F = (F - 1) // sf + 1
+        T = (T - 1) // st + 1
     assert F == 1 and T == 1, 'output must be 1x1'  # model.py:94
     return out
 
@@ -137,18 +155,22 @@ def fpnetwork_forward(sd, x, params, norm=True, return_layers=False):
     B, F, T = x.shape
     m = params['model']
     fuller = int(bool(m.get('fuller', False)))
+    act = {'ReLU': 0, 'ELU': 1}[m.get('conv_activation', 'ReLU')]
+    after = int(bool(m.get('relu_after_bn', True)))
+    strides = layer_strides(params)
     cur = x.reshape(B, 1, F, T)
     layers = []
     for l, (ci, co, f, t) in enumerate(layer_shapes(params, F, T)):
         g = lambda k: _f32(sd['f.convs.%d.%s' % (l, k)])
-        f2, t2 = (f - 1) // 2 + 1, (t - 1) // 2 + 1
+        s_t, s_f = strides[l]
+        f2, t2 = (f - 1) // s_f + 1, (t - 1) // s_t + 1
         y = np.empty((B, co, f2, t2), np.float32)
         mid = np.empty((B, co, f, t2), np.float32)
         arrs = [g('conv1.weight'), g('conv1.bias'), g('ln1.weight'), g('ln1.bias'),
                 g('conv2.weight'), g('conv2.bias'), g('ln2.weight'), g('ln2.bias')]
         cur = _f32(cur)
-        rc = L.orc_sepconv(_p(cur, c_float), B, ci, co, f, t, *[_p(a, c_float) for a in arrs],
-                           fuller, _p(y, c_float), _p(mid, c_float))
+        rc = L.orc_sepconv_ex(_p(cur, c_float), B, ci, co, f, t, *[_p(a, c_float) for a in arrs],
+                              fuller, s_t, s_f, act, after, _p(y, c_float), _p(mid, c_float))
         assert rc == 0
         layers.append((mid, y))
         cur = y

@@ -35,13 +35,21 @@ def layer_shapes(params):
     d, h, u, F, T = model_dims(params)
     ch = [1, d, d, 2 * d, 2 * d, 4 * d, 4 * d, h, h]
     out = []
-    for i in range(8):
+    for i, (st, sf) in enumerate(layer_strides(params)):
         out.append((ch[i], ch[i + 1], F, T))
-        F = (F - 1) // 2 + 1
-        T = (T - 1) // 2 + 1
+        F = (F - 1) // sf + 1
+        T = (T - 1) // st + 1
     if F != 1 or T != 1:
         raise ValueError('output must be 1x1')  # model.py:94
     return out
+
+
+def layer_strides(params):
+    """(time stride of conv1, frequency stride of conv2) per SeparableConv2d (model.py:82-85)."""
+    st = params['model'].get('strides')
+    if st is None:
+        return [(2, 2)] * 8
+    return [(int(st[i][0][1]), int(st[i][1][0])) for i in range(8)]
 
 
 def make_state_dict(params, seed=0):
@@ -59,8 +67,9 @@ def make_state_dict(params, seed=0):
     def nrm(shape, std):
         return (rng.standard_normal(shape, dtype=np.float32) * np.float32(std)).astype(np.float32)
 
+    strides = layer_strides(params)
     for l, (ci, co, f, t) in enumerate(layer_shapes(params)):
-        f2, t2 = (f - 1) // 2 + 1, (t - 1) // 2 + 1
+        f2, t2 = (f - 1) // strides[l][1] + 1, (t - 1) // strides[l][0] + 1
         p = 'f.convs.%d.' % l
         sd[p + 'conv1.weight'] = nrm((co, ci, 1, 3), (1.0 / (3 * ci)) ** 0.5)
         sd[p + 'conv1.bias'] = nrm((co,), 0.1)

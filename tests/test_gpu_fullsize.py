@@ -119,3 +119,79 @@ def test_extract_large_chunk_equals_small_chunk():
     for c0 in (0, 137, 277, 286):                                 # first chunk, middle, chunk boundary, ragged tail
         zs, _ = small.extract_pcm16(pcm[c0 * clip:(c0 + 4) * clip], off[c0:c0 + 5] - off[c0])
         assert torch.equal(zs, z[c0 * 59:(c0 + 4) * 59]), c0
+
+
+def test_end_to_end_noisy_pcm_queries_bf16_equals_fp32_reference_path():
+    """north_star: "song-id / segment-offset pairs are bit-exact on the same inputs".  From PCM to the answer:
+    1 700 clips x 30 s -> a 100 300-row database; 240 query files = 10 s excerpts with additive noise (10 dB SNR),
+    re-quantised to int16.  Product path: bf16 tensor-core fingerprints -> GPU search + sequence score.  Reference
+    path: fp32 fingerprints (the validation-grade CUDA-core path, itself tied to the double-precision oracle here
+    on two query files) -> exact CPU inner-product top-k -> the oracle's seq_score (restatement of cpp/seqscore.cpp).
+    Both must name the same (song, offset) for every query, and that must be the excerpt's true position."""
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from oracle import pfann_oracle as orc          # checker only
+    from pfann_b200.database import Database
+    from pfann_b200.extract import Extractor
+    params = synth.read_config('default')
+    sd = synth.make_state_dict(params, seed=11)
+    n_clips, clip, hop, q_samples, k = 1700, 240000, 4000, 80000, 20
+    g = torch.Generator(device='cuda')
+    g.manual_seed(2026)
+    t = torch.arange(clip, device='cuda', dtype=torch.float32) / 8000.0
+    pcm = torch.empty(n_clips * clip, dtype=torch.int16, device='cuda')
+    for c0 in range(0, n_clips, 100):
+        w = torch.randn((100, clip + 1), generator=g, device='cuda')
+        x = 0.6 * w[:, 1:] + 0.4 * w[:, :-1]
+        for _ in range(3):
+            f = 300.0 + 3600.0 * torch.rand((100, 1), generator=g, device='cuda')
+            a = 0.3 + 0.7 * torch.rand((100, 1), generator=g, device='cuda')
+            ph = 6.2831853 * torch.rand((100, 1), generator=g, device='cuda')
+            x = x + a * torch.sin(6.2831853 * f * t[None, :] + ph)
+        x = x * (0.5 / x.abs().amax(dim=1, keepdim=True))
+        pcm[c0 * clip:(c0 + 100) * clip] = torch.round(x * 32767.0).to(torch.int16).reshape(-1)
+    off = np.arange(n_clips + 1, dtype=np.int64) * clip
+    ex16 = Extractor(params, sd, device=0, precision='bf16', chunk=8192)
+    ex32 = Extractor(params, sd, device=0, precision='fp32', chunk=512)
+    db16, counts = ex16.extract_pcm16(pcm, off)
+    db32, _ = ex32.extract_pcm16(pcm, off)
+    assert db16.shape[0] == n_clips * 59 >= 100_000 and (counts == 59).all()
+    # queries: noisy excerpts
+    rng = np.random.Generator(np.random.PCG64(99))
+    nq = 240
+    songs = rng.integers(0, n_clips, nq)
+    offs = rng.integers(0, (clip - q_samples) // hop + 1, nq)
+    qpcm = torch.empty(nq * q_samples, dtype=torch.int16, device='cuda')
+    for i in range(nq):
+        s0 = int(songs[i]) * clip + int(offs[i]) * hop
+        x = pcm[s0:s0 + q_samples].float()
+        noise = torch.randn(q_samples, generator=g, device='cuda') * (x.std() * 10 ** (-10 / 20))
+        qpcm[i * q_samples:(i + 1) * q_samples] = torch.clamp(torch.round(0.7 * (x + noise)), -32768, 32767).to(torch.int16)
+    qoff = np.arange(nq + 1, dtype=np.int64) * q_samples
+    q16, qc = ex16.extract_pcm16(qpcm, qoff)
+    q32, _ = ex32.extract_pcm16(qpcm, qoff)
+    assert (qc == 19).all()
+    cos = (q16 * q32).sum(1)
+    assert float((1 - cos).max()) < 1e-3                                         # bf16 vs fp32 fingerprints
+    # the fp32 path is anchored to the double-precision oracle on two query files (38 segments)
+    rows = np.concatenate([orc.frame_pcm16(qpcm[i * q_samples:(i + 1) * q_samples].cpu().numpy(), 8000, hop) for i in (0, 1)])
+    zo = orc.fpnetwork_forward(sd, orc.melspec(rows, params), params)
+    assert (1 - (zo * q32[:38].cpu().numpy()).sum(1)).max() < 2e-5
+    # product path
+    key = counts.astype(np.int32)
+    dbo = Database.from_arrays(db16, key, {'top_k': k, 'frame_shift_mul': 1}, 0.5, device=0)
+    qi = np.stack([np.arange(nq) * 19, np.full(nq, 19)], 1).astype(np.int64)
+    score, song, tim, _ = dbo.query_batch(q16.cpu().numpy(), qi)
+    # reference path on the CPU
+    pos = synth.song_pos_from_key(key)
+    dbn, qn = db32.cpu().numpy(), q32.cpu().numpy()
+    ref_song, ref_time = np.empty(nq, np.int64), np.empty(nq, np.float64)
+    for i in range(nq):
+        qq = qn[i * 19:(i + 1) * 19]
+        sc = qq @ dbn.T
+        lab = np.argsort(-sc, axis=1, kind='stable')[:, :k].astype(np.int64)
+        best, ss = orc.seq_score(dbn, pos, qq, lab, 1, 0.0)
+        ref_song[i], ref_time[i] = best, ss[best, 1] * 0.5
+    assert np.array_equal(song, ref_song) and np.array_equal(tim, ref_time)
+    assert np.array_equal(ref_song, songs) and np.array_equal(ref_time, offs * 0.5)
+    assert float(score.min()) > 0.2 and float(score.max()) < 0.999                 # the noise is felt

@@ -11,8 +11,20 @@ from pfann_b200 import _lib, synth  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
-MEL_MAX_TOL = 3e-3     # log domain; the reference itself (fp32) differs from the double oracle by 1.4e-3
+MEL_MAX_TOL = 3e-3     # log domain, bins near the 1e-8 floor: the reference itself (fp32) differs from the double oracle by 1.4e-3 there
 MEL_MEAN_TOL = 3e-5
+MEL_TOL_ABOVE_FLOOR = 1e-4   # max-abs in the log domain away from the floor (power > 1e-6 of the frame maximum)
+
+
+def _mel_check(y, ref):
+    """SURVEY 8c tolerance: 1e-4 in the log domain for every mel bin whose power exceeds 1e-6 of its frame's maximum
+    (cancellation in fp32 only matters below that), 3e-3 for the rest, 3e-5 on average."""
+    err = np.abs(y - ref)
+    strong = ref > ref.max(axis=-2, keepdims=True) + np.log(1e-6)
+    assert strong.mean() > 0.5
+    assert err[strong].max() < MEL_TOL_ABOVE_FLOOR, err[strong].max()
+    assert err.max() < MEL_MAX_TOL, err.max()
+    assert err.mean() < MEL_MEAN_TOL, err.mean()
 EMB_FP32_TOL = 1e-4    # abs, unit-norm embeddings, fp32 CUDA-core path
 EMB_BF16_COS = 1e-3    # 1 - cos, bf16 tensor-core path (bf16 operands, fp32 accumulate + LayerNorm)
 
@@ -41,6 +53,7 @@ def test_mel_vs_golden_and_oracle(dev, golden_dir):
         err = np.abs(y[:3] - ref[:3])
         assert err.max() < MEL_MAX_TOL, err.max()
         assert err.mean() < MEL_MEAN_TOL, err.mean()
+    _mel_check(y[:3], orc.melspec(x, params)[:3])
     np.testing.assert_allclose(y[3], np.log(np.float32(1e-8)), atol=1e-6)      # all-zero segment
     # host pointers go through the same kernel (staged inside the C-ABI call) and give identical bits
     y2 = mel(torch.from_numpy(x)).numpy()
@@ -57,9 +70,7 @@ def test_mel_many_segments_vs_oracle(dev):
     mel = build_mel_spec_layer(params).to(dev)
     x = synth.synth_segments(300, seed=3)
     y = mel(torch.from_numpy(x).to(dev)).cpu().numpy()
-    ref = orc.melspec(x, params)
-    err = np.abs(y - ref)
-    assert err.max() < MEL_MAX_TOL and err.mean() < MEL_MEAN_TOL, (err.max(), err.mean())
+    _mel_check(y, orc.melspec(x, params))
 
 
 def test_mel_plans_of_different_segment_lengths_coexist(dev):

@@ -49,6 +49,48 @@ def test_encoder_vs_reference_golden(golden_dir, name):
     np.testing.assert_allclose(np.linalg.norm(z, axis=1), 1.0, atol=1e-6)
 
 
+MEL_VARIANTS = {     # tools/gen_golden.py MEL_VARIANTS: option sets of melspec.py:27-49 beyond the default
+    'naf': {'naf_mode': True, 'mel_log': 'log10', 'spec_norm': 'max'},
+    'log10': {'mel_log': 'log10'},
+    'max': {'spec_norm': 'max'},
+    'nolog_naf': {'naf_mode': True, 'mel_log': 'none'},
+}
+MODEL_VARIANTS = {   # tools/gen_golden.py MODEL_VARIANTS: options of model.py:58-72,84-85 on configs/tiny.json
+    'elu': {'conv_activation': 'ELU'},
+    'act_first': {'relu_after_bn': False},
+    'elu_act_first': {'conv_activation': 'ELU', 'relu_after_bn': False},
+    'strides': {'strides': [[[1, 2], [2, 1]], [[1, 2], [2, 1]], [[1, 2], [2, 1]], [[1, 2], [2, 1]],
+                            [[1, 1], [2, 1]], [[1, 2], [2, 1]], [[1, 1], [2, 1]], [[1, 1], [2, 1]]]},
+}
+
+
+@pytest.mark.parametrize('name', sorted(MEL_VARIANTS))
+def test_melspec_variants_vs_reference_golden(golden_dir, name):
+    """naf_mode (magnitude, zero padding, slaney scale + norm, + 0.06), log10 / no log, spec_norm = max."""
+    g = np.load(os.path.join(golden_dir, 'mel_variants.npz'))[name]
+    params = dict(synth.read_config('default'), **MEL_VARIANTS[name])
+    y = orc.melspec(_mel_inputs(), params)
+    assert y.shape == g.shape == (4, 256, 32)
+    err = np.abs(y - g)
+    # the all-zero row included: x / max(|x|, 1e-12) = 0 -> the additive constant alone
+    tol = 2e-3 if not params.get("naf_mode") else 1e-4      # + 0.06 keeps naf_mode far from the cancellation floor
+    assert err.max() < tol, (name, err.max())
+    assert err.mean() < 2e-5, (name, err.mean())
+
+
+@pytest.mark.parametrize('name', sorted(MODEL_VARIANTS))
+def test_encoder_variants_vs_reference_golden(golden_dir, name):
+    base = synth.read_config('tiny')
+    params = dict(base, model=dict(base['model'], **MODEL_VARIANTS[name]))
+    g = np.load(os.path.join(golden_dir, 'enc_variants.npz'))
+    mel = np.load(os.path.join(golden_dir, 'mel_default.npz'))['mel']
+    sd = synth.make_state_dict(params, seed=21)
+    z, layers = orc.fpnetwork_forward(sd, mel, params, norm=True, return_layers=True)
+    np.testing.assert_allclose(layers[0][1], g['l0_' + name], rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(layers[-1][1].reshape(4, -1), g['enc_' + name], rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(z, g['z_' + name], rtol=0, atol=2e-5)
+
+
 def test_frame_pcm16_vs_reference_golden(golden_dir):
     g = np.load(os.path.join(golden_dir, 'musicdata.npz'))
     for fsm in (1, 2):

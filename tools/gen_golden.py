@@ -106,6 +106,58 @@ def golden_mel(params):
     return y
 
 
+# option sets of MelSpec beyond the default (melspec.py:27-49): NAF-converted models use naf_mode + log10 + max
+MEL_VARIANTS = {
+    'naf': {'naf_mode': True, 'mel_log': 'log10', 'spec_norm': 'max'},
+    'log10': {'mel_log': 'log10'},
+    'max': {'spec_norm': 'max'},
+    'nolog_naf': {'naf_mode': True, 'mel_log': 'none'},
+}
+# option sets of FpNetwork beyond the default (model.py:58-72,84-85), on the tiny config (d=8, h=32) and a
+# NAF-style stride schedule for F=256, T=32
+MODEL_VARIANTS = {
+    'elu': {'conv_activation': 'ELU'},
+    'act_first': {'relu_after_bn': False},
+    'elu_act_first': {'conv_activation': 'ELU', 'relu_after_bn': False},
+    'strides': {'strides': [[[1, 2], [2, 1]], [[1, 2], [2, 1]], [[1, 2], [2, 1]], [[1, 2], [2, 1]],
+                            [[1, 1], [2, 1]], [[1, 2], [2, 1]], [[1, 1], [2, 1]], [[1, 1], [2, 1]]]},
+}
+
+
+def golden_mel_variants(params):
+    from datautil.melspec import build_mel_spec_layer
+    x = np.concatenate([synth.synth_segments(3, seed=1), np.zeros((1, 8000), np.float32)])
+    out = {}
+    for name, opt in MEL_VARIANTS.items():
+        p = dict(params, **opt)
+        mel = build_mel_spec_layer(p).eval()
+        with torch.no_grad():
+            out[name] = mel(torch.from_numpy(x)).numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, 'mel_variants.npz'), **out)
+
+
+def golden_model_variants(mel):
+    from model import FpNetwork
+    base = synth.read_config('tiny')
+    out = {}
+    for name, opt in MODEL_VARIANTS.items():
+        params = dict(base, model=dict(base['model'], **opt))
+        d, h, u, F, T = synth.model_dims(params)
+        sd = synth.make_state_dict(params, seed=21)
+        net = FpNetwork(d, h, u, F, T, params['model']).eval()
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        with torch.no_grad():
+            x = torch.from_numpy(mel)
+            out['z_' + name] = net(x, norm=True).numpy()
+            cur = x.unsqueeze(1)
+            for i, conv in enumerate(net.f.convs):
+                cur = conv(cur)
+                if i == 0:
+                    out['l0_' + name] = cur.numpy().astype(np.float32)
+            out['enc_' + name] = cur.reshape(cur.shape[0], -1).numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, 'enc_variants.npz'), **out)
+
+
 def golden_encoder(name, params, mel, seed):
     from model import FpNetwork
     d, h, u, F, T = synth.model_dims(params)
@@ -214,6 +266,8 @@ def main():
     golden_encoder('default', default, mel, seed=11)
     golden_encoder('n640d64', synth.read_config('n640d64'), mel, seed=12)
     golden_encoder('tiny', synth.read_config('tiny'), mel, seed=13)
+    golden_mel_variants(default)
+    golden_model_variants(mel)
     golden_db(faiss)
     golden_musicdata(default)
     for f in sorted(os.listdir(OUT)):
