@@ -62,9 +62,21 @@ int pfann_ctx_profile_detail(pfann_ctx *ctx, double *ms, long long *count, int n
 /* ---- stage 1: log-mel front end -------------------------------------------------------------- */
 
 /* Replaces datautil/melspec.py:52-63 build_mel_spec_layer(params) for the default option set
- * (naf_mode=False, mel_log='log', spec_norm='l2').  n_fft must be 1024 (every shipped config). */
+ * (naf_mode=False, mel_log='log', spec_norm='l2'); pfann_mel_create_ex takes the other options.  n_fft must be
+ * 1024 (every shipped config). */
 int pfann_mel_create(pfann_ctx *ctx, int sample_rate, int n_fft, int hop, double f_min, double f_max,
                      int n_mels, int seg_len, pfann_mel **out);
+/* All options build_mel_spec_layer reads from the config (melspec.py:52-63):
+ *   naf_mode       != 0: magnitude instead of power, zero instead of reflect padding, slaney mel scale and
+ *                  normalisation, + 0.06 instead of + 1e-8                     (melspec.py:27-30,38-41)
+ *   mel_log        PFANN_MEL_LOG_NONE / _E / _10                               (melspec.py:43-46)
+ *   spec_norm_max  != 0: spec_norm == 'max' -- normalise the waveform by max |x| and subtract the maximum of
+ *                  the tile afterwards                                         (melspec.py:35,48-49)        */
+#define PFANN_MEL_LOG_NONE 0
+#define PFANN_MEL_LOG_E 1
+#define PFANN_MEL_LOG_10 2
+int pfann_mel_create_ex(pfann_ctx *ctx, int sample_rate, int n_fft, int hop, double f_min, double f_max,
+                        int n_mels, int seg_len, int naf_mode, int mel_log, int spec_norm_max, pfann_mel **out);
 void pfann_mel_destroy(pfann_mel *mel);
 /* Replaces MelSpec.forward (datautil/melspec.py:33-50): x[B][seg_len] fp32 -> out[B][n_mels][T] fp32,
  * T = 1 + seg_len / hop.  L2-normalise, reflect-pad STFT power, HTK mel, log(. + 1e-8). */
@@ -84,6 +96,14 @@ int pfann_mel_n_frames(pfann_mel *mel);
 /* Replaces FpNetwork(d, h, u, F, T, params) (model.py:132-146).  Supported option set: k=3, stride 2,
  * ReLU, relu_after_bn=True; `fuller` as in params['model'] (model.py:26-29). */
 int pfann_model_create(pfann_ctx *ctx, int d, int h, int u, int F, int T, int fuller, pfann_model **out);
+/* All options of FpNetwork's params (model.py:132-146): conv_activation (model.py:7-12), relu_after_bn
+ * (model.py:58-72: 0 = activation BEFORE each LayerNorm), strides (model.py:82-85: int[8][2] = time stride of
+ * conv1, frequency stride of conv2 per layer; NULL = all 2).  Anything but (ReLU, 1, all 2) runs on the CUDA-core
+ * fp32 kernels whatever precision pfann_model_finalize is given: the tcgen05 path serves the default option set. */
+#define PFANN_ACT_RELU 0
+#define PFANN_ACT_ELU 1
+int pfann_model_create_ex(pfann_ctx *ctx, int d, int h, int u, int F, int T, int fuller, int conv_activation,
+                          int relu_after_bn, const int *strides, pfann_model **out);
 void pfann_model_destroy(pfann_model *m);
 /* Replaces load_state_dict (builder.py:56): `name` is the reference state_dict key
  * ("f.convs.3.conv1.weight", "f.convs.0.ln2.bias", "g.linear1.weight", ...), `data` fp32 in the

@@ -43,12 +43,14 @@ def _declare(L):
     L.pfann_ctx_profile_read.argtypes = [vp, POINTER(c_double), POINTER(c_longlong), c_int]
     L.pfann_ctx_profile_detail.argtypes = [vp, POINTER(c_double), POINTER(c_longlong), c_int]
     L.pfann_mel_create.argtypes = [vp, c_int, c_int, c_int, c_double, c_double, c_int, c_int, POINTER(vp)]
+    L.pfann_mel_create_ex.argtypes = [vp, c_int, c_int, c_int, c_double, c_double, c_int, c_int, c_int, c_int, c_int, POINTER(vp)]
     L.pfann_mel_destroy.argtypes = [vp]
     L.pfann_mel_destroy.restype = None
     L.pfann_mel_forward.argtypes = [vp, vp, c_int64, vp]
     L.pfann_mel_forward_pcm16.argtypes = [vp, vp, c_int64, vp, vp, c_int64, vp]
     L.pfann_mel_n_frames.argtypes = [vp]
     L.pfann_model_create.argtypes = [vp, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(vp)]
+    L.pfann_model_create_ex.argtypes = [vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(vp)]
     L.pfann_model_destroy.argtypes = [vp]
     L.pfann_model_destroy.restype = None
     L.pfann_model_set_param.argtypes = [vp, c_char_p, vp, c_int64]

@@ -28,7 +28,7 @@ struct ConvArgs {
     const float *bias;  // [Co]
     float *Y;           // [nb][Fo][To][Co]
     long long M;        // nb * Fo * To
-    int Ci, Co, Fi, Ti, Fo, To, axis, ntaps, K;
+    int Ci, Co, Fi, Ti, Fo, To, axis, ntaps, K, stride;
     int off[3];
 };
 
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) conv_gemm_fp32_kernel(const ConvArgs<InT>
         const long long b = r / a.Fo;
         for (int j = 0; j < a.ntaps; j++) {
             int fi = fo, ti = to;
-            if (a.axis == 0) ti = 2 * to + a.off[j]; else fi = 2 * fo + a.off[j];
+            if (a.axis == 0) ti = a.stride * to + a.off[j]; else fi = a.stride * fo + a.off[j];
             if (fi >= 0 && fi < a.Fi && ti >= 0 && ti < a.Ti)
                 rowp[j] = a.X + ((b * a.Fi + fi) * a.Ti + ti) * (long long)a.Ci;
         }
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256) conv_gemm_fp32_kernel(const ConvArgs<InT>
 template <typename InT>
 __global__ void conv_dw_kernel(const InT *X, const float *W /*[Co][ntaps]*/, const float *bias, float *Y,
                                long long total, int C, int Fi, int Ti, int Fo, int To, int ntaps, int off0, int off1,
-                               int off2) {
+                               int off2, int stride) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int c = (int)(i % C);
@@ -155,7 +155,7 @@ __global__ void conv_dw_kernel(const InT *X, const float *W /*[Co][ntaps]*/, con
     const int offs[3] = {off0, off1, off2};
     float acc = __ldg(bias + c);
     for (int j = 0; j < ntaps; j++) {
-        const int fi = 2 * fo + offs[j];
+        const int fi = stride * fo + offs[j];
         if (fi < 0 || fi >= Fi) continue;
         acc = fmaf(__ldg(W + c * ntaps + j), (float)X[((b * Fi + fi) * Ti + to) * (long long)C + c], acc);
     }
@@ -177,16 +177,29 @@ __device__ __forceinline__ double block_sum_d(double v, double *red) {
     return t;
 }
 
-// two-pass statistics, one CTA per sample: stats[b] = (mean, 1/sqrt(var + eps))
-__global__ void __launch_bounds__(512) ln_stats_kernel(const float *Y, long long E, float2 *stats) {
+// conv_activation of model.py:7-12: 0 = ReLU, 1 = ELU(alpha = 1)
+__device__ __forceinline__ float act_fn(float v, int act) {
+    return act == 1 ? (v > 0.f ? v : expm1f(v)) : fmaxf(v, 0.f);
+}
+// the two orders of model.py:58-72.  mode bit 0-1 = activation, bit 2 = activation BEFORE the LayerNorm
+// (relu_after_bn == False): out = LN(act(y)); otherwise out = act(LN(y)).
+__device__ __forceinline__ float ln_act(float y, float2 st, float g, float b, int mode) {
+    if (mode & 4) return fmaf((act_fn(y, mode & 3) - st.x) * st.y, g, b);
+    return act_fn(fmaf((y - st.x) * st.y, g, b), mode & 3);
+}
+
+// two-pass statistics, one CTA per sample: stats[b] = (mean, 1/sqrt(var + eps)); with mode bit 2 the statistics are
+// those of act(y)
+__global__ void __launch_bounds__(512) ln_stats_kernel(const float *Y, long long E, float2 *stats, int mode) {
     __shared__ double red[16];
     const float *y = Y + (long long)blockIdx.x * E;
+    const bool pre = (mode & 4) != 0;
     double s = 0.0;
-    for (long long i = threadIdx.x; i < E; i += blockDim.x) s += (double)y[i];
+    for (long long i = threadIdx.x; i < E; i += blockDim.x) s += (double)(pre ? act_fn(y[i], mode & 3) : y[i]);
     const double mean = block_sum_d(s, red) / (double)E;
     double q = 0.0;
     for (long long i = threadIdx.x; i < E; i += blockDim.x) {
-        const double dlt = (double)y[i] - mean;
+        const double dlt = (double)(pre ? act_fn(y[i], mode & 3) : y[i]) - mean;
         q += dlt * dlt;
     }
     const double var = block_sum_d(q, red) / (double)E;
@@ -211,7 +224,8 @@ __device__ __forceinline__ float ld_y1(const __nv_bfloat16 *p) { return __bfloat
 
 template <typename YT, typename OutT>
 __global__ void __launch_bounds__(256) ln_apply_kernel(const YT *Y, const float2 *stats, const float *gamma,
-                                                       const float *beta, OutT *X, long long E, int nb, int group) {
+                                                       const float *beta, OutT *X, long long E, int nb, int group,
+                                                       int mode) {
     const long long e0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (e0 >= E) return;
     const int b0 = blockIdx.y * group;
@@ -222,10 +236,16 @@ __global__ void __launch_bounds__(256) ln_apply_kernel(const YT *Y, const float2
         for (int b = b0; b < b1; b++) {
             const float2 st = __ldg(stats + b);
             const float4 v = ld_y4(Y + (long long)b * E + e0);
-            const float o0 = fmaxf(fmaf((v.x - st.x) * st.y, g.x, be.x), 0.f);
-            const float o1 = fmaxf(fmaf((v.y - st.x) * st.y, g.y, be.y), 0.f);
-            const float o2 = fmaxf(fmaf((v.z - st.x) * st.y, g.z, be.z), 0.f);
-            const float o3 = fmaxf(fmaf((v.w - st.x) * st.y, g.w, be.w), 0.f);
+            float o0, o1, o2, o3;
+            if (mode == 0) {   // default option set: ReLU after the LayerNorm
+                o0 = fmaxf(fmaf((v.x - st.x) * st.y, g.x, be.x), 0.f);
+                o1 = fmaxf(fmaf((v.y - st.x) * st.y, g.y, be.y), 0.f);
+                o2 = fmaxf(fmaf((v.z - st.x) * st.y, g.z, be.z), 0.f);
+                o3 = fmaxf(fmaf((v.w - st.x) * st.y, g.w, be.w), 0.f);
+            } else {
+                o0 = ln_act(v.x, st, g.x, be.x, mode); o1 = ln_act(v.y, st, g.y, be.y, mode);
+                o2 = ln_act(v.z, st, g.z, be.z, mode); o3 = ln_act(v.w, st, g.w, be.w, mode);
+            }
             OutT *x = X + (long long)b * E + e0;
             if (sizeof(OutT) == 4) {
                 *reinterpret_cast<float4 *>(x) = make_float4(o0, o1, o2, o3);
@@ -242,8 +262,7 @@ __global__ void __launch_bounds__(256) ln_apply_kernel(const YT *Y, const float2
             const float2 st = __ldg(stats + b);
             for (int i = 0; i < 4 && e0 + i < E; i++)
                 store_out(X + (long long)b * E + e0 + i,
-                          fmaxf(fmaf((ld_y1(Y + (long long)b * E + e0 + i) - st.x) * st.y, __ldg(gamma + e0 + i),
-                                     __ldg(beta + e0 + i)), 0.f));
+                          ln_act(ld_y1(Y + (long long)b * E + e0 + i), st, __ldg(gamma + e0 + i), __ldg(beta + e0 + i), mode));
         }
     }
 }
@@ -566,13 +585,13 @@ __global__ void __launch_bounds__(256) head_kernel(const float *Y /*[nb][h]*/, c
 // generic fallback (v > 16 or weights too large for shared memory): one CTA per sample, weights from L2
 __global__ void head_kernel_generic(const float *Y, const float2 *stats, const float *gamma, const float *beta,
                                     const float *w1, const float *b1, const float *w2, const float *b2, float *z, int d,
-                                    int h, int u, int norm) {
+                                    int h, int u, int norm, int mode) {
     extern __shared__ float hs[];  // [h] + [32]
     float *red = hs + h;
     const long long b = blockIdx.x;
     const float2 st = stats[b];
     for (int i = threadIdx.x; i < h; i += blockDim.x)
-        hs[i] = fmaxf(fmaf((Y[b * h + i] - st.x) * st.y, __ldg(gamma + i), __ldg(beta + i)), 0.f);
+        hs[i] = ln_act(Y[b * h + i], st, __ldg(gamma + i), __ldg(beta + i), mode);
     __syncthreads();
     const int g = threadIdx.x, v = h / d;
     float out = 0.f;
@@ -626,9 +645,9 @@ void free_conv(ConvWeights &c) {
     c = ConvWeights();
 }
 
-// live taps of a k=3, stride-2 "same" convolution over an axis of length n (model.py:18-19)
-void live_taps(int n, int *ntaps, int *tap_k, int *tap_off) {
-    const int k = 3, s = 2;
+// live taps of a k=3, stride-s "same" convolution over an axis of length n (model.py:18-19)
+void live_taps(int n, int s, int *ntaps, int *tap_k, int *tap_off) {
+    const int k = 3;
     const int no = (n - 1) / s + 1;
     const int pad = (n - 1) / s * s + k - n, padl = pad / 2;
     *ntaps = 0;
@@ -741,13 +760,13 @@ int launch_conv_fp32(Model *m, const ConvWeights &cw, const InT *X, float *Y, in
         const long long total = (long long)nb * g.out_per_sample();
         conv_dw_kernel<InT><<<cdiv(total, 256), 256, 0, st>>>(X, cw.w_kn, cw.bias, Y, total, g.Co, g.Fi, g.Ti, g.Fo,
                                                                  g.To, g.ntaps, g.tap_off[0], g.tap_off[1],
-                                                                 g.tap_off[2]);
+                                                                 g.tap_off[2], g.stride);
     } else {
         ConvArgs<InT> a;
         a.X = X; a.W = cw.w_kn; a.bias = cw.bias; a.Y = Y;
         a.M = (long long)nb * g.rows_per_sample();
         a.Ci = g.Ci; a.Co = g.Co; a.Fi = g.Fi; a.Ti = g.Ti; a.Fo = g.Fo; a.To = g.To;
-        a.axis = g.axis; a.ntaps = g.ntaps; a.K = g.K();
+        a.axis = g.axis; a.ntaps = g.ntaps; a.K = g.K(); a.stride = g.stride;
         for (int j = 0; j < 3; j++) a.off[j] = g.tap_off[j];
         dim3 grid(cdiv(a.M, BM), cdiv(g.Co, BN));
         conv_gemm_fp32_kernel<InT><<<grid, 256, 0, st>>>(a);
@@ -766,7 +785,7 @@ int launch_ln_apply(Model *m, const ConvWeights &cw, const YT *Y, OutT *X, int n
     dim3 grid(cdiv(E, 1024), cdiv(nb, group));
     ProfScope ps(m->ctx, K_LN, 16 + m->prof_idx);
     ln_apply_kernel<YT, OutT><<<grid, 256, 0, m->ctx->stream>>>(Y, m->cur_stats, cw.gamma, cw.beta, X, E, nb,
-                                                                group);
+                                                                group, m->act | (m->act_first ? 4 : 0));
     m->ctx->launches++;
     PF_CUDA(cudaGetLastError());
     return PFANN_OK;
@@ -774,7 +793,8 @@ int launch_ln_apply(Model *m, const ConvWeights &cw, const YT *Y, OutT *X, int n
 
 int launch_stats(Model *m, const ConvWeights &cw, const float *Y, int nb) {
     ProfScope ps(m->ctx, K_LN, 16 + m->prof_idx);
-    ln_stats_kernel<<<nb, 512, 0, m->ctx->stream>>>(Y, cw.g.out_per_sample(), m->cur_stats);
+    ln_stats_kernel<<<nb, 512, 0, m->ctx->stream>>>(Y, cw.g.out_per_sample(), m->cur_stats,
+                                                    m->act | (m->act_first ? 4 : 0));
     m->ctx->launches++;
     PF_CUDA(cudaGetLastError());
     return PFANN_OK;
@@ -926,7 +946,7 @@ int forward_chunk(Model *m, const float *mel, int nb, int norm, float *z) {
     const int v = m->h / m->d;
     const size_t smem_fast =
         ((size_t)m->u * v * threads + 2 * (size_t)m->u * threads + (size_t)HEAD_HG * HEAD_HS * (threads / 32)) * 4;
-    if ((v == 8 || v == 16) && threads * HEAD_HG <= 256 && smem_fast <= 200 * 1024) {
+    if (!m->variant && (v == 8 || v == 16) && threads * HEAD_HG <= 256 && smem_fast <= 200 * 1024) {
         // the opt-in is per device/context and per function: set it for the instantiation being launched
         if (v == 8)
             PF_CUDA(cudaFuncSetAttribute(head_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
@@ -942,7 +962,8 @@ int forward_chunk(Model *m, const float *mel, int nb, int norm, float *z) {
                 Y, m->cur_stats, last.gamma, last.beta, m->w1, m->b1, m->w2, m->b2, z, nb, m->d, m->h, m->u, norm);
     } else {
         head_kernel_generic<<<nb, threads, (m->h + 32) * sizeof(float), m->ctx->stream>>>(
-            Y, m->cur_stats, last.gamma, last.beta, m->w1, m->b1, m->w2, m->b2, z, m->d, m->h, m->u, norm);
+            Y, m->cur_stats, last.gamma, last.beta, m->w1, m->b1, m->w2, m->b2, z, m->d, m->h, m->u, norm,
+            m->act | (m->act_first ? 4 : 0));
     }
     m->ctx->launches++;
     {
@@ -1011,19 +1032,37 @@ int model_forward_dev(Model *m, const float *mel, int64_t B, int norm, float *z,
 extern "C" {
 
 int pfann_model_create(pfann_ctx *hctx, int d, int h, int u, int F, int T, int fuller, pfann_model **out) {
+    return pfann_model_create_ex(hctx, d, h, u, F, T, fuller, PFANN_ACT_RELU, 1, nullptr, out);
+}
+
+int pfann_model_create_ex(pfann_ctx *hctx, int d, int h, int u, int F, int T, int fuller, int conv_activation,
+                          int relu_after_bn, const int *strides, pfann_model **out) {
     PF_CHECK(hctx && out, PFANN_ERR_ARG, "pfann_model_create: NULL argument");
     PF_CHECK(d > 0 && h > 0 && u > 0 && F > 0 && T > 0, PFANN_ERR_ARG, "pfann_model_create: bad dimensions");
     PF_CHECK(h % d == 0, PFANN_ERR_ARG, "h must be divisible by d");  // model.py:112
     PF_CHECK(d <= 1024, PFANN_ERR_UNSUPPORTED, "pfann_model_create: d > 1024 unsupported");
+    PF_CHECK(conv_activation == PFANN_ACT_RELU || conv_activation == PFANN_ACT_ELU, PFANN_ERR_ARG,
+             "pfann_model_create: conv_activation must be PFANN_ACT_RELU or PFANN_ACT_ELU");  // model.py:7-12
     int f = F, t = T;
+    bool custom = false;
     for (int i = 0; i < 8; i++) {
-        f = (f - 1) / 2 + 1;
-        t = (t - 1) / 2 + 1;
+        const int st = strides ? strides[2 * i] : 2, sf = strides ? strides[2 * i + 1] : 2;
+        PF_CHECK(st >= 1 && st <= 3 && sf >= 1 && sf <= 3, PFANN_ERR_ARG, "pfann_model_create: strides must be 1..3");
+        custom = custom || st != 2 || sf != 2;
+        f = (f - 1) / sf + 1;
+        t = (t - 1) / st + 1;
     }
     PF_CHECK(f == 1 && t == 1, PFANN_ERR_ARG, "output must be 1x1");  // model.py:94
     Model *m = new Model();
     m->ctx = reinterpret_cast<Ctx *>(hctx);
     m->d = d; m->h = h; m->u = u; m->F = F; m->T = T;
+    m->act = conv_activation;
+    m->act_first = relu_after_bn == 0;
+    for (int i = 0; i < 8; i++) {
+        m->st_t[i] = strides ? strides[2 * i] : 2;
+        m->st_f[i] = strides ? strides[2 * i + 1] : 2;
+    }
+    m->variant = custom || m->act != PFANN_ACT_RELU || m->act_first;
     m->fuller = fuller != 0;
     *out = reinterpret_cast<pfann_model *>(m);
     return PFANN_OK;
@@ -1066,19 +1105,22 @@ int pfann_model_finalize(pfann_model *hm, int precision) {
     Model *m = reinterpret_cast<Model *>(hm);
     PF_CUDA(cudaSetDevice(m->ctx->device));
     tc_release(m);
-    m->precision = precision;
+    // option variants have no tensor-core kernels: they run on the CUDA-core fp32 path (still on the GPU)
+    m->precision = m->variant ? PFANN_PRECISION_FP32 : precision;
     const int ch[9] = {1, m->d, m->d, 2 * m->d, 2 * m->d, 4 * m->d, 4 * m->d, m->h, m->h};
     int F = m->F, T = m->T;
     for (int l = 0; l < 8; l++) {
-        const int F2 = (F - 1) / 2 + 1, T2 = (T - 1) / 2 + 1;
+        const int F2 = (F - 1) / m->st_f[l] + 1, T2 = (T - 1) / m->st_t[l] + 1;
         ConvGeom g1 = {};
         g1.Ci = ch[l]; g1.Co = ch[l + 1]; g1.Fi = F; g1.Ti = T; g1.Fo = F; g1.To = T2; g1.axis = 0;
+        g1.stride = m->st_t[l];
         g1.depthwise = false;
-        live_taps(T, &g1.ntaps, g1.tap_k, g1.tap_off);
+        live_taps(T, g1.stride, &g1.ntaps, g1.tap_k, g1.tap_off);
         ConvGeom g2 = {};
         g2.Ci = ch[l + 1]; g2.Co = ch[l + 1]; g2.Fi = F; g2.Ti = T2; g2.Fo = F2; g2.To = T2; g2.axis = 1;
+        g2.stride = m->st_f[l];
         g2.depthwise = !m->fuller;
-        live_taps(F, &g2.ntaps, g2.tap_k, g2.tap_off);
+        live_taps(F, g2.stride, &g2.ntaps, g2.tap_k, g2.tap_off);
         int rc = finalize_conv(m, l, 0, g1);
         if (rc == PFANN_OK) rc = finalize_conv(m, l, 1, g2);
         if (rc != PFANN_OK) {
@@ -1110,7 +1152,7 @@ int pfann_model_finalize(pfann_model *hm, int precision) {
         PF_TRY(upload(wt, &m->l0_w));
         cudaFree(m->l0_gb16); cudaFree(m->l0_btile);
         m->l0_gb16 = nullptr; m->l0_btile = nullptr;
-        if (precision == PFANN_PRECISION_BF16 && g.Co == 128 && (g.Fo * g.To) % 128 == 0) {
+        if (m->precision == PFANN_PRECISION_BF16 && g.Co == 128 && (g.Fo * g.To) % 128 == 0) {
             // tensor-core layer-0 kernel: weight tile [128 channels][64 K] bf16 in the 128-byte-swizzled K-major
             // layout (only K columns 0-15 are read): [wh0 wh1 wh2 | wh0 wh1 wh2 | wl0 wl1 wl2 | bh bm bl 0 0 0 0]
             std::vector<__nv_bfloat16> bt(128 * 64, __float2bfloat16_rn(0.f));
@@ -1153,8 +1195,8 @@ int pfann_model_finalize(pfann_model *hm, int precision) {
         m->y_bf16 = getenv("PFANN_B200_Y_FP32") == nullptr;
         bool taps_run = true;  // the fused kernel reads the mel run off[0], off[0]+1, off[0]+2
         for (int j = 1; j < g.ntaps; j++) taps_run = taps_run && g.tap_off[j] == g.tap_off[0] + j;
-        m->l0_fused = taps_run && g.Ci == 1 && g.Co % 8 == 0 && (256 % (g.Co / 8)) == 0 && g.Co / 8 <= 256 &&
-                      getenv("PFANN_B200_NO_L0_FUSION") == nullptr;
+        m->l0_fused = !m->variant && taps_run && g.Ci == 1 && g.Co % 8 == 0 && (256 % (g.Co / 8)) == 0 &&
+                      g.Co / 8 <= 256 && getenv("PFANN_B200_NO_L0_FUSION") == nullptr;
     }
     const int v = m->h / m->d;
     const std::vector<float> *w1 = find_param(m, "g.linear1.weight", (size_t)m->d * m->u * v);
@@ -1170,7 +1212,7 @@ int pfann_model_finalize(pfann_model *hm, int precision) {
     PF_TRY(upload(*b1, &m->b1));
     PF_TRY(upload(*w2, &m->w2));
     PF_TRY(upload(*b2, &m->b2));
-    if (precision == PFANN_PRECISION_BF16) {
+    if (m->precision == PFANN_PRECISION_BF16) {
         int rc = tc_prepare(m);
         if (rc != PFANN_OK) {
             m->precision = -1;

@@ -21,6 +21,7 @@ struct ConvGeom {
     int Ci, Co;          // input / output channels
     int Fi, Ti, Fo, To;  // input / output spatial extent
     int axis;            // 0 = along T, 1 = along F
+    int stride = 2;      // along the convolved axis (model.py:84-85; 2 unless params['strides'] says otherwise)
     int ntaps;           // live taps
     int tap_k[3];        // original kernel index of live tap j
     int tap_off[3];      // input offset of live tap j
@@ -44,6 +45,11 @@ struct Model {
     Ctx *ctx;
     int d, h, u, F, T;
     bool fuller;
+    // option variants (model.py:58-72,84-85): served by the CUDA-core kernels, whatever precision was asked for
+    int act = 0;              // 0 ReLU, 1 ELU
+    bool act_first = false;   // relu_after_bn == False: activation BEFORE the LayerNorm
+    int st_t[8], st_f[8];     // time stride of conv1 / frequency stride of conv2 per layer
+    bool variant = false;
     int precision = -1;
     int chunk = 256;
     std::map<std::string, std::vector<float>> host;  // reference-keyed fp32 parameters (as given)

@@ -38,6 +38,7 @@ struct MelPlan {
     Ctx *ctx;
     int sample_rate, n_fft, hop, n_mels, seg_len, T;
     int fb_stride;
+    int naf_mode = 0, mel_log = 1, norm_max = 0;   // melspec.py:27-49 options (see pfann_mel_create_ex)
     int k_lo = 0;             // smallest spectrum bin with a non-zero mel weight (bins below are never formed)
     float2 *d_tw = nullptr;   // W_1024^k = exp(-2 pi i k / 1024), k in [0, 1024)
     float *d_win = nullptr;   // periodic Hann, 1024
@@ -55,6 +56,7 @@ struct MelArgs {
     const int32_t *seg_valid;
     float *out;              // [B][n_mels][T]
     int n, hop, T, n_mels, fb_stride, k_lo;
+    int naf_mode, mel_log, norm_max;
     const float2 *tw;
     const float *win;
     const int *fb_start, *fb_cnt;
@@ -106,6 +108,19 @@ __device__ __forceinline__ float block_sum(float v, float *red) {
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < NWARPS; i++) t += red[i];  // same order in every thread: deterministic
+    return t;
+}
+
+__device__ __forceinline__ float block_max(float v, float *red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    float t = red[0];
+#pragma unroll
+    for (int i = 1; i < NWARPS; i++) t = fmaxf(t, red[i]);
     return t;
 }
 
@@ -171,16 +186,23 @@ __global__ void __launch_bounds__(NTHREADS, 2) mel_kernel(const MelArgs a) {
         __syncthreads();
     }
 
-    // ---- L2 normalisation factor (melspec.py:35-36, eps 1e-12) -------------------------------
-    float part = 0.f;
-    for (int i = tid; i < n; i += NTHREADS) part = fmaf(x[i], x[i], part);
-    const float ss = block_sum(part, red);
-    const float scale = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    // ---- normalisation factor (melspec.py:35-36, F.normalize eps 1e-12): L2, or max |x| for spec_norm = 'max' ----
+    float scale;
+    if (a.norm_max) {
+        float part = 0.f;
+        for (int i = tid; i < n; i += NTHREADS) part = fmaxf(part, fabsf(x[i]));
+        scale = 1.0f / fmaxf(block_max(part, red), 1e-12f);
+    } else {
+        float part = 0.f;
+        for (int i = tid; i < n; i += NTHREADS) part = fmaf(x[i], x[i], part);
+        const float ss = block_sum(part, red);
+        scale = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    }
 
-    // ---- reflect padding (torch.stft center=True, pad_mode='reflect') -------------------------
+    // ---- padding of torch.stft(center=True): 'reflect', or zeros in naf_mode (melspec.py:28) ----
     for (int i = tid; i < pad; i += NTHREADS) {
-        xs[i] = xs[2 * pad - i];                        // padded[i] = x[pad - i]
-        xs[pad + n + i] = xs[pad + n - 2 - i];          // padded[pad+n+i] = x[n-2-i]
+        xs[i] = a.naf_mode ? 0.f : xs[2 * pad - i];                   // padded[i] = x[pad - i]
+        xs[pad + n + i] = a.naf_mode ? 0.f : xs[pad + n - 2 - i];     // padded[pad+n+i] = x[n-2-i]
     }
     __syncthreads();
 
@@ -253,6 +275,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) mel_kernel(const MelArgs a) {
                 const float2 O = make_float2(0.5f * D.y, -0.5f * D.x);
                 const float2 X = cadd(E, cmul(__ldg(a.tw + k), O));
                 P[it] = X.x * X.x + X.y * X.y;
+                if (a.naf_mode) P[it] = sqrtf(P[it]);   // power = 1 (melspec.py:27)
             }
         }
         __syncwarp();
@@ -268,11 +291,20 @@ __global__ void __launch_bounds__(NTHREADS, 2) mel_kernel(const MelArgs a) {
             const float *w = a.fb_w + (size_t)m * a.fb_stride;
             float acc = 0.f;
             for (int j = 0; j < c; j++) acc = fmaf(__ldg(w + j), pw[s0 + j], acc);
-            tile[m * Tp + t] = __logf(acc + 1e-8f);  // MUFU.LG2 path: |error| ~1e-6 in the log domain
+            const float v = acc + (a.naf_mode ? 0.06f : 1e-8f);              // melspec.py:39,41
+            // MUFU.LG2 path: |error| ~1e-6 in the log domain
+            tile[m * Tp + t] = a.mel_log == 1 ? __logf(v) : (a.mel_log == 2 ? __log10f(v) : v);
         }
         __syncwarp();
     }
     __syncthreads();
+    if (a.norm_max) {   // melspec.py:48-49: x - amax(x) over the (mel, time) tile
+        float part = -INFINITY;
+        for (int i = tid; i < a.n_mels * a.T; i += NTHREADS) part = fmaxf(part, tile[(i / a.T) * Tp + (i % a.T)]);
+        const float mx = block_max(part, red);
+        for (int i = tid; i < a.n_mels * a.T; i += NTHREADS) tile[(i / a.T) * Tp + (i % a.T)] -= mx;
+        __syncthreads();
+    }
     if (a.moments != nullptr) {
         // per thread: fp32 partial sums over its positions (f, to), stride-2 taps along time; across threads: double
         const int To = (a.T + 1) / 2, P = a.n_mels * To;
@@ -350,6 +382,7 @@ MelArgs base_args(MelPlan *p) {
     a.n_mels = p->n_mels;
     a.fb_stride = p->fb_stride;
     a.k_lo = p->k_lo;
+    a.naf_mode = p->naf_mode; a.mel_log = p->mel_log; a.norm_max = p->norm_max;
     a.tw = p->d_tw;
     a.win = p->d_win;
     a.fb_start = p->d_fb_start;
@@ -401,7 +434,14 @@ extern "C" {
 
 int pfann_mel_create(pfann_ctx *hctx, int sample_rate, int n_fft, int hop, double f_min, double f_max,
                      int n_mels, int seg_len, pfann_mel **out) {
+    return pfann_mel_create_ex(hctx, sample_rate, n_fft, hop, f_min, f_max, n_mels, seg_len, 0, PFANN_MEL_LOG_E, 0, out);
+}
+
+int pfann_mel_create_ex(pfann_ctx *hctx, int sample_rate, int n_fft, int hop, double f_min, double f_max,
+                        int n_mels, int seg_len, int naf_mode, int mel_log, int spec_norm_max, pfann_mel **out) {
     PF_CHECK(hctx && out, PFANN_ERR_ARG, "pfann_mel_create: NULL argument");
+    PF_CHECK(mel_log >= PFANN_MEL_LOG_NONE && mel_log <= PFANN_MEL_LOG_10, PFANN_ERR_ARG,
+             "pfann_mel_create: mel_log must be 0 (none), 1 (log) or 2 (log10)");
     PF_CHECK(n_fft == NFFT, PFANN_ERR_UNSUPPORTED, "pfann_mel_create: n_fft=%d unsupported (kernel is built for 1024)",
              n_fft);
     PF_CHECK(hop > 0 && (hop % 2) == 0, PFANN_ERR_UNSUPPORTED, "pfann_mel_create: hop must be even (got %d)", hop);
@@ -417,6 +457,7 @@ int pfann_mel_create(pfann_ctx *hctx, int sample_rate, int n_fft, int hop, doubl
     p->hop = hop;
     p->n_mels = n_mels;
     p->seg_len = seg_len;
+    p->naf_mode = naf_mode != 0; p->mel_log = mel_log; p->norm_max = spec_norm_max != 0;
     p->T = 1 + seg_len / hop;
     // the last frame must stay inside the padded signal
     PF_CHECK((p->T - 1) * hop + n_fft <= seg_len + n_fft, PFANN_ERR_ARG, "pfann_mel_create: bad framing");
@@ -434,12 +475,22 @@ int pfann_mel_create(pfann_ctx *hctx, int sample_rate, int n_fft, int hop, doubl
         tw[k].y = (float)(-sin(2.0 * PI * k / NFFT));
         win[k] = (float)(0.5 - 0.5 * cos(2.0 * PI * k / NFFT));  // torch.hann_window(periodic=True)
     }
-    // torchaudio.functional.melscale_fbanks(norm=None, mel_scale='htk') (melspec.py:19-31), kept sparse
+    // torchaudio.functional.melscale_fbanks (melspec.py:19-31), kept sparse: norm=None + mel_scale='htk', or the
+    // slaney scale (linear below 1 kHz, logarithmic above) with slaney area normalisation in naf_mode
     const int n_freqs = n_fft / 2 + 1;
     std::vector<double> f_pts(n_mels + 2);
-    const double m_min = 2595.0 * log10(1.0 + f_min / 700.0), m_max = 2595.0 * log10(1.0 + f_max / 700.0);
-    for (int i = 0; i < n_mels + 2; i++)
-        f_pts[i] = 700.0 * (pow(10.0, (m_min + (m_max - m_min) * i / (n_mels + 1)) / 2595.0) - 1.0);
+    const bool slaney = p->naf_mode != 0;
+    const double f_sp = 200.0 / 3.0, min_log_mel = 1000.0 / f_sp, logstep = log(6.4) / 27.0;
+    auto hz_to_mel = [&](double f) {
+        if (!slaney) return 2595.0 * log10(1.0 + f / 700.0);
+        return f >= 1000.0 ? min_log_mel + log(f / 1000.0) / logstep : f / f_sp;
+    };
+    auto mel_to_hz = [&](double m) {
+        if (!slaney) return 700.0 * (pow(10.0, m / 2595.0) - 1.0);
+        return m >= min_log_mel ? 1000.0 * exp(logstep * (m - min_log_mel)) : f_sp * m;
+    };
+    const double m_min = hz_to_mel(f_min), m_max = hz_to_mel(f_max);
+    for (int i = 0; i < n_mels + 2; i++) f_pts[i] = mel_to_hz(m_min + (m_max - m_min) * i / (n_mels + 1));
     std::vector<int> start(n_mels), cnt(n_mels);
     std::vector<std::vector<float>> rows(n_mels);
     int stride = 1;
@@ -453,6 +504,7 @@ int pfann_mel_create(pfann_ctx *hctx, int sample_rate, int n_fft, int hop, doubl
             double up = (f_pts[m + 2] - f) / (f_pts[m + 2] - f_pts[m + 1]);
             double v = down < up ? down : up;
             if (v > 0.0) {
+                if (slaney) v *= 2.0 / (f_pts[m + 2] - f_pts[m]);
                 w[k] = (float)v;
                 if (first < 0) first = k;
                 last = k;

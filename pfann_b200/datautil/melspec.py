@@ -12,16 +12,13 @@ from .. import _lib
 
 
 class MelSpec(torch.nn.Module):
-    """Mirror of MelSpec (datautil/melspec.py:4-50).  Only the default option set has a kernel
-    (naf_mode=False, mel_log='log', spec_norm='l2' -- what configs/default.json and n640d64.json use);
-    anything else raises instead of silently computing something different."""
+    """Mirror of MelSpec (datautil/melspec.py:4-50) with all of its options: naf_mode (magnitude spectrum, zero
+    padding, slaney mel scale + normalisation, + 0.06), mel_log ('log' | 'log10' | anything else = none, as
+    melspec.py:43-46 falls through) and spec_norm ('l2' | 'max')."""
 
     def __init__(self, sample_rate=8000, stft_n=1024, stft_hop=256, f_min=300, f_max=4000, n_mels=256,
                  naf_mode=False, mel_log='log', spec_norm='l2'):
         super(MelSpec, self).__init__()
-        if naf_mode or mel_log != 'log' or spec_norm != 'l2':
-            raise NotImplementedError('pfann_b200 MelSpec: only naf_mode=False, mel_log="log", spec_norm="l2" '
-                                      'have a B200 kernel (SURVEY.md 8f.4 lists the variants as next)')
         self.sample_rate, self.stft_n, self.stft_hop = sample_rate, stft_n, stft_hop
         self.f_min, self.f_max, self.n_mels = f_min, f_max, n_mels
         self.naf_mode, self.mel_log, self.spec_norm = naf_mode, mel_log, spec_norm
@@ -31,9 +28,12 @@ class MelSpec(torch.nn.Module):
         key = (device, seg_len)
         if key not in self._plans:
             h = ctypes.c_void_p()
-            _lib.check(_lib.lib().pfann_mel_create(_lib.ctx(device), self.sample_rate, self.stft_n, self.stft_hop,
-                                                   float(self.f_min), float(self.f_max), self.n_mels, seg_len,
-                                                   ctypes.byref(h)), 'pfann_mel_create')
+            log_mode = {'log': 1, 'log10': 2}.get(self.mel_log, 0)
+            _lib.check(_lib.lib().pfann_mel_create_ex(_lib.ctx(device), self.sample_rate, self.stft_n, self.stft_hop,
+                                                      float(self.f_min), float(self.f_max), self.n_mels, seg_len,
+                                                      int(bool(self.naf_mode)), log_mode,
+                                                      int(self.spec_norm == 'max'), ctypes.byref(h)),
+                       'pfann_mel_create_ex')
             self._plans[key] = h
         return self._plans[key]
 

@@ -28,12 +28,15 @@ def _precision(name):
 
 
 class SeparableConv2d(Module):
-    """Parameter container with the shapes of model.py:15-31 (k=3, stride (2,2))."""
+    """Parameter container with the shapes of model.py:15-31 (k = 3; s = (time stride of conv1, frequency stride
+    of conv2))."""
 
     def __init__(self, i, o, k, s, in_F, in_T, fuller=False, activation='ReLU', relu_after_bn=True):
         super(SeparableConv2d, self).__init__()
-        if activation != 'ReLU' or not relu_after_bn or k != 3 or tuple(s) != (2, 2):
-            raise NotImplementedError('pfann_b200: only ReLU, relu_after_bn=True, k=3, stride 2 have a B200 kernel')
+        if activation not in ('ReLU', 'ELU'):
+            raise KeyError(activation)                                   # model.py:12
+        if k != 3:
+            raise NotImplementedError('pfann_b200: kernel size 3 only (the reference never builds another, model.py:81)')
         self.conv1 = Conv2d(i, o, kernel_size=(1, k), stride=(1, s[0]))
         self.ln1 = LayerNorm((o, in_F, (in_T - 1) // s[0] + 1))
         if fuller:
@@ -46,15 +49,18 @@ class SeparableConv2d(Module):
 class MyF(Module):
     def __init__(self, d, h, u, in_F, in_T, fuller=False, activation='ReLU', strides=None, relu_after_bn=True):
         super(MyF, self).__init__()
-        if strides is not None:
-            raise NotImplementedError('pfann_b200: custom strides (NAF-converted models) are not supported yet')
         channels = [1, d, d, 2 * d, 2 * d, 4 * d, 4 * d, h, h]
         convs = []
+        self.strides = []
         for i in range(8):
-            convs.append(SeparableConv2d(channels[i], channels[i + 1], 3, (2, 2), in_F, in_T, fuller=fuller,
+            s = (2, 2)
+            if strides is not None:
+                s = strides[i][0][1], strides[i][1][0]                   # model.py:84-85
+            convs.append(SeparableConv2d(channels[i], channels[i + 1], 3, s, in_F, in_T, fuller=fuller,
                                          activation=activation, relu_after_bn=relu_after_bn))
-            in_F = (in_F - 1) // 2 + 1
-            in_T = (in_T - 1) // 2 + 1
+            self.strides.append((int(s[0]), int(s[1])))
+            in_F = (in_F - 1) // s[1] + 1
+            in_T = (in_T - 1) // s[0] + 1
         assert in_F == in_T == 1, 'output must be 1x1'
         self.convs = ModuleList(convs)
 
@@ -71,7 +77,9 @@ class MyG(Module):
 
 class FpNetwork(Module):
     """model.py:132-153.  ``params`` is ``params['model']`` of the JSON config; the extra optional key
-    ``b200_precision`` ('bf16' tensor-core path, default; 'fp32' CUDA-core validation path) picks the kernels."""
+    ``b200_precision`` ('bf16' tensor-core path, default; 'fp32' CUDA-core validation path) picks the kernels.
+    The option variants (conv_activation='ELU', relu_after_bn=False, custom strides -- NAF-converted models) run on
+    the CUDA-core kernels whatever precision is asked for: the tcgen05 path serves the default option set."""
 
     def __init__(self, d, h, u, F, T, params):
         super(FpNetwork, self).__init__()
@@ -83,6 +91,8 @@ class FpNetwork(Module):
         self.g = MyG(d, h, u)
         self.dims = (d, h, u, F, T)
         self.fuller = bool(params.get('fuller', False))
+        self.activation = params.get('conv_activation', 'ReLU')
+        self.relu_after_bn = bool(params.get('relu_after_bn', True))
         self.precision = _precision(params.get('b200_precision'))
         self.chunk = int(params.get('b200_chunk', 0))
         self._handles = {}     # device -> (handle, weights fingerprint)
@@ -101,8 +111,10 @@ class FpNetwork(Module):
         if ent is None:
             d, h, u, F, T = self.dims
             hnd = ctypes.c_void_p()
-            _lib.check(L.pfann_model_create(_lib.ctx(device), d, h, u, F, T, int(self.fuller), ctypes.byref(hnd)),
-                       'pfann_model_create')
+            st = (ctypes.c_int * 16)(*[v for pair in self.f.strides for v in pair])
+            _lib.check(L.pfann_model_create_ex(_lib.ctx(device), d, h, u, F, T, int(self.fuller),
+                                               {'ReLU': 0, 'ELU': 1}[self.activation], int(self.relu_after_bn), st,
+                                               ctypes.byref(hnd)), 'pfann_model_create_ex')
         else:
             hnd = ent[0]
         for name, p in self.state_dict().items():

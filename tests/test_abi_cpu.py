@@ -74,15 +74,23 @@ def test_model_mirror_has_reference_state_dict_keys():
         net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
 
 
-def test_unsupported_options_raise():
+def test_option_variants_construct_like_the_reference():
+    """Every option of melspec.py:4-31 / model.py:132-146 is accepted (they have kernels now); the state_dict of a
+    custom-stride network has the reference's shapes; an unknown activation fails like model.py:12."""
     from pfann_b200.datautil.melspec import MelSpec
     from pfann_b200.model import FpNetwork
-    with pytest.raises(NotImplementedError):
-        MelSpec(naf_mode=True)
-    with pytest.raises(NotImplementedError):
-        MelSpec(mel_log='log10')
-    with pytest.raises(NotImplementedError):
-        FpNetwork(128, 1024, 32, 256, 32, {'conv_activation': 'ELU'})
+    MelSpec(naf_mode=True, mel_log='log10', spec_norm='max')
+    FpNetwork(128, 1024, 32, 256, 32, {'conv_activation': 'ELU', 'relu_after_bn': False})
+    strides = [[[1, 2], [2, 1]]] * 4 + [[[1, 1], [2, 1]], [[1, 2], [2, 1]], [[1, 1], [2, 1]], [[1, 1], [2, 1]]]
+    params = dict(synth.read_config('tiny'))
+    params['model'] = dict(params['model'], strides=strides)
+    d, h, u, F, T = synth.model_dims(params)
+    net = FpNetwork(d, h, u, F, T, params['model'])
+    sd = synth.make_state_dict(params, seed=1)
+    assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == {k: tuple(v.shape) for k, v in sd.items()}
+    assert tuple(net.f.convs[4].ln1.normalized_shape) == (4 * d, 16, 2)       # time stride 1 in layer 4
+    with pytest.raises(KeyError):
+        FpNetwork(8, 32, 4, 256, 32, {'conv_activation': 'GELU'})
 
 
 def test_flat_index_file_roundtrip(tmp_path):

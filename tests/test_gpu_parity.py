@@ -73,6 +73,43 @@ def test_mel_many_segments_vs_oracle(dev):
     _mel_check(y, orc.melspec(x, params))
 
 
+MEL_VARIANTS = {     # tools/gen_golden.py MEL_VARIANTS: option sets of melspec.py:27-49 beyond the default
+    'naf': {'naf_mode': True, 'mel_log': 'log10', 'spec_norm': 'max'},
+    'log10': {'mel_log': 'log10'},
+    'max': {'spec_norm': 'max'},
+    'nolog_naf': {'naf_mode': True, 'mel_log': 'none'},
+}
+
+
+@pytest.mark.parametrize('name', sorted(MEL_VARIANTS))
+def test_mel_variants_vs_golden_and_oracle(dev, golden_dir, name):
+    """naf_mode (magnitude, zero padding, slaney scale + norm, + 0.06), log10 / no log, spec_norm = max: the kernel
+    against the reference's own output (golden) and the double-precision oracle."""
+    from pfann_b200.datautil.melspec import build_mel_spec_layer
+    params = dict(synth.read_config('default'), **MEL_VARIANTS[name])
+    mel = build_mel_spec_layer(params).to(dev)
+    x = _mel_inputs()
+    y = mel(torch.from_numpy(x).to(dev)).cpu().numpy()
+    g = np.load(os.path.join(golden_dir, 'mel_variants.npz'))[name]
+    ref = orc.melspec(x, params)
+    naf = bool(params.get('naf_mode'))
+    for want in (g, ref):
+        err = np.abs(y - want)
+        assert err.max() < (2e-4 if naf else MEL_MAX_TOL), (name, err.max())     # + 0.06 keeps naf_mode off the floor
+        assert err.mean() < MEL_MEAN_TOL, (name, err.mean())
+    # and through the fused PCM entry point (the matcher / builder path): same bits as rows -> mel
+    pcm = synth.synth_pcm(77, 12000)
+    rows = orc.frame_pcm16(pcm, 8000, 4000)
+    h = mel.plan_handle(0, 8000)
+    out = np.empty((rows.shape[0], 256, 32), np.float32)
+    st, va = np.array([0, 4000], np.int64), np.array([8000, 8000], np.int32)
+    _lib.use_torch_stream(0)
+    _lib.check(_lib.lib().pfann_mel_forward_pcm16(h, _lib.ptr(pcm), pcm.shape[0], _lib.ptr(st), _lib.ptr(va), 2,
+                                                  _lib.ptr(out)))
+    err = np.abs(out - orc.melspec(rows, params))
+    assert err.max() < (2e-4 if naf else MEL_MAX_TOL) and err.mean() < MEL_MEAN_TOL, (name, err.max(), err.mean())
+
+
 def test_mel_plans_of_different_segment_lengths_coexist(dev):
     """The layer takes any segment length like the reference module; plans of different lengths (different
     shared-memory sizes) live side by side: long, short, long again."""
@@ -170,6 +207,42 @@ def test_encoder_bf16_tensor_core_vs_golden(dev, golden_dir, name):
         b = ref.layer_output(x, l).numpy()
         rel = np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-12)
         assert rel < 3e-2, (l, rel)
+
+
+MODEL_VARIANTS = {   # tools/gen_golden.py MODEL_VARIANTS: options of model.py:58-72,84-85 on configs/tiny.json
+    'elu': {'conv_activation': 'ELU'},
+    'act_first': {'relu_after_bn': False},
+    'elu_act_first': {'conv_activation': 'ELU', 'relu_after_bn': False},
+    'strides': {'strides': [[[1, 2], [2, 1]], [[1, 2], [2, 1]], [[1, 2], [2, 1]], [[1, 2], [2, 1]],
+                            [[1, 1], [2, 1]], [[1, 2], [2, 1]], [[1, 1], [2, 1]], [[1, 1], [2, 1]]]},
+}
+
+
+@pytest.mark.parametrize('name', sorted(MODEL_VARIANTS))
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_encoder_variants_vs_golden_and_oracle(dev, golden_dir, name, precision):
+    """ELU, activation before the LayerNorm, NAF-style stride schedules: against the reference's own outputs
+    (goldens made by model.py) and the oracle.  These options run on the CUDA-core kernels whatever precision is
+    asked for, so both settings must give the fp32-grade answer."""
+    from pfann_b200.model import FpNetwork
+    base = synth.read_config('tiny')
+    params = dict(base, model=dict(base['model'], **MODEL_VARIANTS[name]))
+    d, h, u, F, T = synth.model_dims(params)
+    sd = synth.make_state_dict(params, seed=21)
+    net = FpNetwork(d, h, u, F, T, dict(params['model'], b200_precision=precision)).to(dev)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    net.eval()
+    g = np.load(os.path.join(golden_dir, 'enc_variants.npz'))
+    mel = np.load(os.path.join(golden_dir, 'mel_default.npz'))['mel']
+    x = torch.from_numpy(mel).to(dev)
+    z = net(x).cpu().numpy()
+    np.testing.assert_allclose(z, g['z_' + name], rtol=0, atol=EMB_FP32_TOL)
+    np.testing.assert_allclose(net.layer_output(x, 0).numpy(), g['l0_' + name], rtol=2e-3, atol=2e-4)
+    np.testing.assert_allclose(net.layer_output(x, 7).numpy().reshape(4, -1), g['enc_' + name], rtol=2e-3, atol=2e-4)
+    np.testing.assert_allclose(z, orc.fpnetwork_forward(sd, mel, params), rtol=0, atol=EMB_FP32_TOL)
+    # default-config extract path with a variant model: PCM in, fingerprints out
+    zr = net(x, norm=False).cpu().numpy()
+    np.testing.assert_allclose(zr / np.linalg.norm(zr, axis=1, keepdims=True), z, rtol=0, atol=1e-5)
 
 
 def test_encoder_bf16_is_deterministic_and_chunk_invariant(dev):
