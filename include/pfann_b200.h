@@ -133,6 +133,38 @@ int pfann_extract_segments(pfann_mel *mel, pfann_model *m, const float *x, int64
 int pfann_extract_pcm16(pfann_mel *mel, pfann_model *m, const int16_t *pcm, const int64_t *clip_off,
                         int n_clips, int hop_samples, int norm, float *z, int32_t *seg_counts);
 int64_t pfann_count_segments(const int64_t *clip_off, int n_clips, int seg_len, int hop_samples);
+/* The same for clips that went through the GPU ingest below (fp32 mono samples at the model rate). */
+int pfann_extract_f32(pfann_mel *mel, pfann_model *m, const float *wav, const int64_t *clip_off, int n_clips,
+                      int hop_samples, int norm, float *z, int32_t *seg_counts);
+
+/* ---- ingest: decoded PCM of any channel count / rate -> mono fp32 at the model rate (DEVICE pointers) ------- */
+
+/* Replaces musicdata.py:44-48: interleaved int16 frames -> planar fp32 [nch][n_frames], scaled by 1/32768. */
+int pfann_pcm16_to_planar(pfann_ctx *ctx, const int16_t *pcm, int64_t n_frames, int nch, float *out);
+/* Replaces julius.ResampleFrac(old_sr, new_sr) as called at musicdata.py:29,58,66 (third-party, unpinned, absent from
+ * the build container: restated from its published algorithm -- windowed sinc, zeros = 24, rolloff = 0.945, replicate
+ * padding -- and checked against oracle/pfann_oracle.py only).  x [nch][n] -> y [nch][pfann_resample_len(n, ..)].
+ * The reference resamples minute by minute and discards half a second at every seam (musicdata.py:50-66); away from
+ * the ends that equals resampling the whole clip at once, which is what this does. */
+int64_t pfann_resample_len(int64_t n, int old_sr, int new_sr);
+int pfann_resample_frac(pfann_ctx *ctx, const float *x, int nch, int64_t n, int old_sr, int new_sr, float *y);
+/* Replaces musicdata.py:72-80: mean over the channels; for two channels whose difference carries more than 1000x the
+ * power of their sum (fake stereo with opposite phase) channel 1 is negated first.  x [nch][n] -> mono [n]. */
+int pfann_mix_mono(pfann_ctx *ctx, const float *x, int nch, int64_t n, float *mono);
+
+/* ---- training-step pieces (train.py, datautil/specaug.py, datautil/noise.py; DEVICE pointers) -------------- */
+
+/* Replaces similarity_loss(y, tau) of train.py:41-52 (NT-Xent; rows 2i, 2i+1 are positive pairs) together with its
+ * backward: loss (one float) and, if dy != NULL, dL/dy [N][d].  fp32 throughout: logits are divided by tau = 0.05,
+ * bf16 products would be off by percents after exp(). */
+int pfann_ntxent(pfann_ctx *ctx, const float *y, int N, int d, float tau, float *loss, float *dy);
+/* Replaces SpecAugment.augment (datautil/specaug.py:40-42) for a batch: x[B][F][T] *= 1 - mask_b, mask_b = cutout
+ * rectangle + frequency band + time band given as rects[b] = {f0, f1, t0, t1, fb0, fb1, tb0, tb1} (half-open); the
+ * random draws stay on the host in the reference's order (specaug.py:13-38) so that seeds reproduce. */
+int pfann_specaug_apply(pfann_ctx *ctx, float *x, const int32_t *rects, int64_t B, int F, int T);
+/* Replaces NoiseData.add_noises arithmetic (datautil/noise.py:96-109): out[b] = x[b] + ratio_b * noise[b],
+ * ratio_b = rms(x[b]) / rms(noise[b]) * 10^(-snr_db[b] / 20), rms clamped at sqrt(1e-12). */
+int pfann_snr_mix(pfann_ctx *ctx, const float *x, const float *noise, const float *snr_db, int64_t B, int n, float *out);
 
 /* ---- stage 3: database search + sequence score ------------------------------------------------- */
 

@@ -272,3 +272,70 @@ def query_embeddings_base(db, song_pos, query, labels, frame_shift_mul, hop_size
                 best = sco
                 best_song_t = sid, real_time
     return best, best_song_t, song_score
+
+
+# ---------------------------------------------------------------- training-step pieces
+def similarity_loss(y, tau):
+    """train.py:41-52 in float64, with its analytic gradient: (loss, dL/dy)."""
+    y = np.asarray(y, np.float64)
+    N = y.shape[0]
+    a = y @ y.T / tau
+    np.fill_diagonal(a, -np.inf)                      # the row's own entry is left out (train.py:46)
+    m = a.max(axis=1, keepdims=True)
+    lse = m[:, 0] + np.log(np.exp(a - m).sum(axis=1))
+    p = np.arange(N) ^ 1                              # train.py:48: partner of row i
+    loss = -(a[np.arange(N), p] - lse).sum() / N
+    P = np.exp(a - lse[:, None])
+    G = P.copy()
+    G[np.arange(N), p] -= 1.0
+    dy = (G + G.T) @ y / (tau * N)
+    return loss, dy
+
+
+def add_noises(x, noise, snr_db):
+    """datautil/noise.py:96-109 given the noise rows and the SNRs."""
+    x, noise = np.asarray(x, np.float64), np.asarray(noise, np.float64)
+    vx = np.sqrt(np.maximum((x ** 2).mean(axis=1), 1e-12))
+    vn = np.sqrt(np.maximum((noise ** 2).mean(axis=1), 1e-12))
+    ratio = vx / vn * 10.0 ** (-np.asarray(snr_db, np.float64) / 20.0)
+    return x + ratio[:, None] * noise
+
+
+# ---------------------------------------------------------------- ingest (SURVEY 8f.2)
+def resample_frac(x, old_sr, new_sr, zeros=24, rolloff=0.945):
+    """julius.ResampleFrac(old_sr, new_sr)(x) for x[..., n] -- julius is a third-party dependency of the reference
+    (musicdata.py:1,29; unpinned, readme.md:20) that is absent here, so this restates its published algorithm and is
+    NOT pinned to julius itself ("parity unpinned"): windowed-sinc kernels per output phase, replicate padding,
+    output length int(new_sr * n / old_sr)."""
+    import math
+    x = np.asarray(x, np.float64)
+    g = math.gcd(old_sr, new_sr)
+    o, w = old_sr // g, new_sr // g
+    if o == w:
+        return x.copy()
+    sr = min(o, w) * rolloff
+    width = math.ceil(zeros * o / sr)
+    idx = np.arange(-width, width + o, dtype=np.float64)
+    kern = []
+    for i in range(w):
+        t = np.clip((-i / w + idx / o) * sr, -zeros, zeros) * math.pi
+        k = np.sinc(t / math.pi) * np.cos(t / zeros / 2) ** 2
+        kern.append(k / k.sum())
+    kern = np.stack(kern)                                          # [new, K]
+    n = x.shape[-1]
+    xp = np.concatenate([np.repeat(x[..., :1], width, -1), x, np.repeat(x[..., -1:], width + o, -1)], -1)
+    n_frames = (xp.shape[-1] - kern.shape[1]) // o + 1
+    win = np.lib.stride_tricks.sliding_window_view(xp, kern.shape[1], axis=-1)[..., ::o, :][..., :n_frames, :]
+    y = np.einsum('...mk,ik->...mi', win, kern).reshape(*x.shape[:-1], -1)
+    return y[..., :int(w * n / o)]
+
+
+def mix_mono(wav):
+    """musicdata.py:72-80: wav[nch, n] -> mono[n] with the fake-stereo rule (fp32 like the reference)."""
+    wav = np.array(wav, np.float32)
+    if wav.shape[0] == 2:
+        pow1 = ((wav[0] - wav[1]) ** 2).mean()
+        pow2 = ((wav[0] + wav[1]) ** 2).mean()
+        if pow1 > pow2 * 1000:
+            wav[1] *= -1
+    return wav.mean(axis=0, dtype=np.float32)

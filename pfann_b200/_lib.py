@@ -61,6 +61,15 @@ def _declare(L):
     L.pfann_model_get_activation.argtypes = [vp, c_int, vp, c_int64]
     L.pfann_extract_segments.argtypes = [vp, vp, vp, c_int64, c_int, vp]
     L.pfann_extract_pcm16.argtypes = [vp, vp, vp, POINTER(c_int64), c_int, c_int, c_int, vp, POINTER(c_int32)]
+    L.pfann_extract_f32.argtypes = [vp, vp, vp, POINTER(c_int64), c_int, c_int, c_int, vp, POINTER(c_int32)]
+    L.pfann_pcm16_to_planar.argtypes = [vp, vp, c_int64, c_int, vp]
+    L.pfann_resample_len.argtypes = [c_int64, c_int, c_int]
+    L.pfann_resample_len.restype = c_int64
+    L.pfann_resample_frac.argtypes = [vp, vp, c_int, c_int64, c_int, c_int, vp]
+    L.pfann_mix_mono.argtypes = [vp, vp, c_int, c_int64, vp]
+    L.pfann_ntxent.argtypes = [vp, vp, c_int, c_int, c_float, vp, vp]
+    L.pfann_specaug_apply.argtypes = [vp, vp, vp, c_int64, c_int, c_int]
+    L.pfann_snr_mix.argtypes = [vp, vp, vp, vp, c_int64, c_int, vp]
     L.pfann_count_segments.argtypes = [POINTER(c_int64), c_int, c_int, c_int]
     L.pfann_count_segments.restype = c_int64
     L.pfann_db_open.argtypes = [vp, vp, c_int64, c_int, POINTER(c_int32), c_int, c_int64, c_int64, POINTER(vp)]

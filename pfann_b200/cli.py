@@ -50,7 +50,8 @@ BATCH_FILES = 4096
 def iter_extract(ex, files, frame_shift_mul, max_bytes=None, max_files=None):
     """Yields (first file index, emb [n, d] fp32, counts [n_files_in_batch]) for consecutive batches of `files`.
     Fingerprints are in list order; a count of 0 = unreadable file (builder.py:82-86).  Mono 16-bit files at the
-    model rate take the fused PCM path, one batched GPU call per batch."""
+    model rate take the fused PCM path, everything else the GPU ingest (resample + mono mix); one batched GPU call
+    per kind and batch."""
     sr = ex.params['sample_rate']
     max_bytes = BATCH_PCM_BYTES if max_bytes is None else max_bytes
     max_files = BATCH_FILES if max_files is None else max_files
@@ -60,7 +61,7 @@ def iter_extract(ex, files, frame_shift_mul, max_bytes=None, max_files=None):
         while i < len(files) and len(kinds) < max_files and (nbytes < max_bytes or not kinds):
             try:
                 kind, data = musicdata.read_wav_pcm16(files[i], sr)
-                nbytes += data.nbytes
+                nbytes += data.nbytes if kind == 'pcm16' else data[0].nbytes
             except Exception as e:  # noqa: BLE001  (musicdata.py:95-101: log and yield zero segments)
                 print('load %s error! %s' % (files[i], e))
                 kind, data = 'error', None
@@ -78,11 +79,13 @@ def iter_extract(ex, files, frame_shift_mul, max_bytes=None, max_files=None):
             for jj, j in enumerate(pcm_ids):
                 parts[j] = z[pos[jj]:pos[jj + 1]]
                 counts[j] = cnt[jj]
-        for j, k in enumerate(kinds):
-            if k == 'float':
-                rows = musicdata.frame_float(datas[j], ex.seg_len, ex.hop // frame_shift_mul)
-                parts[j] = ex.extract_segments(rows)
-                counts[j] = rows.shape[0]
+        wav_ids = [j for j, k in enumerate(kinds) if k == 'wav']      # multi-channel / other rates: GPU ingest
+        if wav_ids:
+            z, cnt = ex.extract_wavs([datas[j] for j in wav_ids], frame_shift_mul=frame_shift_mul)
+            pos = np.concatenate([[0], np.cumsum(cnt)])
+            for jj, j in enumerate(wav_ids):
+                parts[j] = z[pos[jj]:pos[jj + 1]]
+                counts[j] = cnt[jj]
         emb = [q for q in parts if q is not None and len(q)]
         yield i0, (np.concatenate(emb) if emb else np.zeros((0, ex.d), np.float32)), counts
 

@@ -13,7 +13,7 @@ int mel_forward_dev(pfann_mel *h, const float *x_dev, int64_t B, float *out_dev,
                     const int *m_off);
 int mel_forward_pcm_dev(pfann_mel *h, const int16_t *pcm_dev, int64_t n_samples, const int64_t *start_dev,
                         const int32_t *valid_dev, int64_t B, float *out_dev, double *moments, int m_ntaps,
-                        const int *m_off);
+                        const int *m_off, const float *wavf_dev);
 Ctx *mel_ctx(pfann_mel *h);
 void mel_dims(pfann_mel *h, int *seg_len, int *n_mels, int *T);
 int model_forward_dev(Model *m, const float *mel, int64_t B, int norm, float *z, const double *moments);
@@ -75,8 +75,13 @@ int pfann_extract_segments(pfann_mel *mel, pfann_model *hm, const float *x, int6
     return tc_ln_check(m, !is_device_ptr(z));
 }
 
-int pfann_extract_pcm16(pfann_mel *mel, pfann_model *hm, const int16_t *pcm, const int64_t *clip_off, int n_clips,
-                        int hop, int norm, float *z, int32_t *seg_counts) {
+}  // extern "C"
+
+namespace {
+// clips stored back to back as mono samples (int16 PCM: esz = 2, or fp32 from the GPU ingest: esz = 4)
+int extract_clips(pfann_mel *mel, pfann_model *hm, const void *pcm_v, int esz, const int64_t *clip_off, int n_clips,
+                  int hop, int norm, float *z, int32_t *seg_counts) {
+    const unsigned char *pcm = reinterpret_cast<const unsigned char *>(pcm_v);
     PF_CHECK(mel && hm && clip_off && n_clips >= 0 && hop > 0, PFANN_ERR_ARG, "pfann_extract_pcm16: bad argument");
     Model *m = reinterpret_cast<Model *>(hm);
     int seg_len;
@@ -109,10 +114,10 @@ int pfann_extract_pcm16(pfann_mel *mel, pfann_model *hm, const int16_t *pcm, con
     const bool pipe_in = !is_device_ptr(pcm), pipe_out = !is_device_ptr(z);
     const int64_t n_chunks = (B + m->chunk - 1) / m->chunk;
     if (pipe_in) {
-        PF_TRY(ctx->stage_in[0].ensure((size_t)n_samples * 2));
+        PF_TRY(ctx->stage_in[0].ensure((size_t)n_samples * esz));
         pd = ctx->stage_in[0].p;
     } else {
-        pd = pcm + clip_off[0];
+        pd = pcm + clip_off[0] * esz;
     }
     PF_TRY(stage_input(ctx, 1, start.data(), (size_t)B * 8, &sd));
     PF_TRY(stage_input(ctx, 2, valid.data(), (size_t)B * 4, &vd));
@@ -130,8 +135,8 @@ int pfann_extract_pcm16(pfann_mel *mel, pfann_model *hm, const int16_t *pcm, con
         int64_t need = start[last] + seg_len;
         if (need > n_samples) need = n_samples;
         if (need > copied) {
-            PF_CUDA(cudaMemcpyAsync((int16_t *)ctx->stage_in[0].p + copied, pcm + clip_off[0] + copied,
-                                    (size_t)(need - copied) * 2, cudaMemcpyHostToDevice, ctx->copy_in));
+            PF_CUDA(cudaMemcpyAsync((unsigned char *)ctx->stage_in[0].p + copied * esz, pcm + (clip_off[0] + copied) * esz,
+                                    (size_t)(need - copied) * esz, cudaMemcpyHostToDevice, ctx->copy_in));
             copied = need;
         }
         PF_CUDA(cudaEventRecord(ev_in[k], ctx->copy_in));
@@ -162,8 +167,9 @@ int pfann_extract_pcm16(pfann_mel *mel, pfann_model *hm, const int16_t *pcm, con
             if (k + 1 < n_chunks) PF_TRY(upload_for_chunk(k + 1));
             PF_CUDA(cudaStreamWaitEvent(ctx->stream, ev_in[k], 0));
         }
-        PF_TRY(mel_forward_pcm_dev(mel, (const int16_t *)pd, n_samples, (const int64_t *)sd + b0,
-                                   (const int32_t *)vd + b0, nb, m->melbuf.as<float>(), mom, g0.ntaps, g0.tap_off));
+        PF_TRY(mel_forward_pcm_dev(mel, esz == 2 ? (const int16_t *)pd : nullptr, n_samples, (const int64_t *)sd + b0,
+                                   (const int32_t *)vd + b0, nb, m->melbuf.as<float>(), mom, g0.ntaps, g0.tap_off,
+                                   esz == 4 ? (const float *)pd : nullptr));
         PF_TRY(model_forward_dev(m, m->melbuf.as<float>(), nb, norm, (float *)zd + b0 * m->d, mom));
         if (pipe_out) {
             PF_CUDA(cudaEventRecord(ev_done[k], ctx->stream));
@@ -179,6 +185,19 @@ int pfann_extract_pcm16(pfann_mel *mel, pfann_model *hm, const int16_t *pcm, con
     for (auto &e : ev_in) cudaEventDestroy(e);
     for (auto &e : ev_done) cudaEventDestroy(e);
     return tc_ln_check(m);
+}
+}  // namespace
+
+extern "C" {
+
+int pfann_extract_pcm16(pfann_mel *mel, pfann_model *hm, const int16_t *pcm, const int64_t *clip_off, int n_clips,
+                        int hop, int norm, float *z, int32_t *seg_counts) {
+    return extract_clips(mel, hm, pcm, 2, clip_off, n_clips, hop, norm, z, seg_counts);
+}
+
+int pfann_extract_f32(pfann_mel *mel, pfann_model *hm, const float *wav, const int64_t *clip_off, int n_clips,
+                      int hop, int norm, float *z, int32_t *seg_counts) {
+    return extract_clips(mel, hm, wav, 4, clip_off, n_clips, hop, norm, z, seg_counts);
 }
 
 }  // extern "C"

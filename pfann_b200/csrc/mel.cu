@@ -51,6 +51,7 @@ struct MelPlan {
 struct MelArgs {
     const float *x;          // fp32 rows [B][n]           (x != nullptr)
     const int16_t *pcm;      // or int16 PCM + descriptors  (pcm != nullptr)
+    const float *wavf;       // or fp32 mono samples + the same descriptors (GPU ingest path, ingest.cu)
     int64_t pcm_len;
     const int64_t *seg_start;
     const int32_t *seg_valid;
@@ -161,25 +162,35 @@ __global__ void __launch_bounds__(NTHREADS, 2) mel_kernel(const MelArgs a) {
     } else {
         const int64_t start = a.seg_start[b];
         const int valid = a.seg_valid[b];
-        const int16_t *src = a.pcm + start;
-        int16_t *stg = reinterpret_cast<int16_t *>(tile);
-        const bool bulk = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((valid & 7) == 0) && valid > 0;
-        if (bulk) {
-            if (tid == 0) {
-                ptx::mbar_expect_tx(&bar, (uint32_t)valid * 2u);
-                ptx::bulk_g2s(stg, src, (uint32_t)valid * 2u, &bar);
-            }
-            ptx::mbar_wait(&bar, 0);
-        } else {
-            for (int i = tid; i < valid; i += NTHREADS) stg[i] = src[i];
-            __syncthreads();
-        }
-        // musicdata.py:48 (x 1/32768 in fp32), :82-84 (zero-pad), :88 (mean removal)
         float part = 0.f;
-        for (int i = tid; i < n; i += NTHREADS) {
-            float v = i < valid ? (float)stg[i] * (1.0f / 32768.0f) : 0.f;
-            x[i] = v;
-            part += v;
+        if (a.wavf != nullptr) {
+            // already scaled, resampled and mixed to mono on the GPU (ingest.cu): musicdata.py:82-84 (zero-pad)
+            const float *src = a.wavf + start;
+            for (int i = tid; i < n; i += NTHREADS) {
+                const float v = i < valid ? __ldg(src + i) : 0.f;
+                x[i] = v;
+                part += v;
+            }
+        } else {
+            const int16_t *src = a.pcm + start;
+            int16_t *stg = reinterpret_cast<int16_t *>(tile);
+            const bool bulk = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((valid & 7) == 0) && valid > 0;
+            if (bulk) {
+                if (tid == 0) {
+                    ptx::mbar_expect_tx(&bar, (uint32_t)valid * 2u);
+                    ptx::bulk_g2s(stg, src, (uint32_t)valid * 2u, &bar);
+                }
+                ptx::mbar_wait(&bar, 0);
+            } else {
+                for (int i = tid; i < valid; i += NTHREADS) stg[i] = src[i];
+                __syncthreads();
+            }
+            // musicdata.py:48 (x 1/32768 in fp32), :82-84 (zero-pad), :88 (mean removal)
+            for (int i = tid; i < n; i += NTHREADS) {
+                float v = i < valid ? (float)stg[i] * (1.0f / 32768.0f) : 0.f;
+                x[i] = v;
+                part += v;
+            }
         }
         const float mean = block_sum(part, red) / (float)n;
         for (int i = tid; i < n; i += NTHREADS) x[i] -= mean;
@@ -408,10 +419,11 @@ int mel_forward_dev(pfann_mel *h, const float *x_dev, int64_t B, float *out_dev,
 }
 int mel_forward_pcm_dev(pfann_mel *h, const int16_t *pcm_dev, int64_t n_samples, const int64_t *start_dev,
                         const int32_t *valid_dev, int64_t B, float *out_dev, double *moments, int m_ntaps,
-                        const int *m_off) {
+                        const int *m_off, const float *wavf_dev) {
     MelPlan *p = reinterpret_cast<MelPlan *>(h);
     MelArgs a = base_args(p);
     a.pcm = pcm_dev;
+    a.wavf = wavf_dev;
     a.pcm_len = n_samples;
     a.seg_start = start_dev;
     a.seg_valid = valid_dev;
@@ -583,7 +595,7 @@ int pfann_mel_forward_pcm16(pfann_mel *h, const int16_t *pcm, int64_t n_samples,
     PF_TRY(stage_input(p->ctx, 2, seg_valid, (size_t)B * 4, &vd));
     PF_TRY(stage_output(p->ctx, 0, out, out_b, &od));
     PF_TRY(mel_forward_pcm_dev(h, (const int16_t *)pd, n_samples, (const int64_t *)sd, (const int32_t *)vd, B,
-                               (float *)od, nullptr, 0, nullptr));
+                               (float *)od, nullptr, 0, nullptr, nullptr));
     return finish_output(p->ctx, 0, out, out_b);
 }
 

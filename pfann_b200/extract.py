@@ -65,6 +65,53 @@ class Extractor:
                    'pfann_extract_pcm16')
         return out, counts
 
+    def ingest_wav(self, pcm, rate):
+        """Decoded 16-bit PCM of any channel count and rate (int16 [n_frames, nch]) -> fp32 mono at the model rate
+        on the GPU: musicdata.py:44-80 (scale, julius-style fractional resampling, mono mix with the fake-stereo
+        rule).  Returns a 1-D CUDA tensor."""
+        L, dev = _lib.lib(), self.device.index
+        pcm = np.array(pcm, dtype=np.int16, order='C')           # own, writable copy (WAV readers hand out views)
+        if pcm.ndim == 1:
+            pcm = pcm[:, None]
+        n, nch = pcm.shape
+        h = _lib.use_torch_stream(dev)
+        src = torch.from_numpy(pcm).to(self.device)
+        planar = torch.empty((nch, n), dtype=torch.float32, device=self.device)
+        _lib.check(L.pfann_pcm16_to_planar(h, _lib.ptr(src), n, nch, _lib.ptr(planar)), 'pfann_pcm16_to_planar')
+        sr = self.params['sample_rate']
+        if rate != sr:
+            n_out = int(L.pfann_resample_len(n, int(rate), int(sr)))
+            res = torch.empty((nch, n_out), dtype=torch.float32, device=self.device)
+            _lib.check(L.pfann_resample_frac(h, _lib.ptr(planar), nch, n, int(rate), int(sr), _lib.ptr(res)),
+                       'pfann_resample_frac')
+            planar, n = res, n_out
+        mono = torch.empty(n, dtype=torch.float32, device=self.device)
+        _lib.check(L.pfann_mix_mono(h, _lib.ptr(planar), nch, n, _lib.ptr(mono)), 'pfann_mix_mono')
+        return mono
+
+    def extract_f32(self, wav, clip_off, frame_shift_mul=1, norm=True):
+        """wav: fp32 mono at the model rate, clips back to back, ON THE GPU (e.g. from ingest_wav); like extract_pcm16."""
+        clip_off = np.ascontiguousarray(clip_off, dtype=np.int64)
+        n_clips = len(clip_off) - 1
+        n_seg = self.count_segments(clip_off, frame_shift_mul)
+        out = torch.empty((n_seg, self.d), dtype=torch.float32, device=self.device)
+        counts = np.empty(n_clips, np.int32)
+        hm, hn, dev = self._handles()
+        _lib.use_torch_stream(dev)
+        _lib.check(_lib.lib().pfann_extract_f32(hm, hn, _lib.ptr(wav.contiguous()), clip_off.ctypes.data_as(POINTER(c_int64)),
+                                                n_clips, self.hop // frame_shift_mul, int(bool(norm)), _lib.ptr(out),
+                                                counts.ctypes.data_as(POINTER(c_int32))), 'pfann_extract_f32')
+        return out, counts
+
+    def extract_wavs(self, wavs, frame_shift_mul=1, norm=True):
+        """wavs: list of (int16 [n_frames, nch], rate) as read from WAV files -> (z numpy [n_seg, d], seg_counts):
+        GPU ingest of every clip, then ONE fused framing + mel + network call over all of them."""
+        monos = [self.ingest_wav(p, r) for p, r in wavs]
+        off = np.concatenate([[0], np.cumsum([m.shape[0] for m in monos])]).astype(np.int64)
+        wav = torch.cat(monos) if monos else torch.zeros(0, dtype=torch.float32, device=self.device)
+        z, counts = self.extract_f32(wav, off, frame_shift_mul, norm)
+        return z.cpu().numpy(), counts
+
     def extract_segments(self, rows, norm=True):
         """rows [B, seg_len] fp32 as MusicDataset yields them (musicdata.py:87-88) -> z [B, d]."""
         on_dev = isinstance(rows, torch.Tensor) and rows.is_cuda

@@ -158,6 +158,45 @@ def golden_model_variants(mel):
     np.savez_compressed(os.path.join(OUT, 'enc_variants.npz'), **out)
 
 
+def _reference_function(path, name):
+    """The named top-level function of a reference source file, executed as written (train.py imports tensorboardX and
+    torch_optimizer at module level, which are not installed: the function itself only needs torch)."""
+    import ast
+    src = open(os.path.join(REF, path)).read()
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name == name:
+            ns = {'torch': torch, 'np': np}
+            exec(compile(ast.Module(body=[node], type_ignores=[]), path, 'exec'), ns)
+            return ns[name]
+    raise KeyError(name)
+
+
+def golden_train():
+    """similarity_loss of train.py:41-52 (value + autograd gradient) and SpecAugment masks of specaug.py:13-38."""
+    loss_fn = _reference_function('train.py', 'similarity_loss')
+    out = {}
+    for tag, (N, d, seed) in {'n640d64': (640, 64, 5), 'n8d16': (8, 16, 6)}.items():
+        rng = np.random.Generator(np.random.PCG64(seed))
+        y = rng.standard_normal((N, d)).astype(np.float32)
+        y[1::2] = y[0::2] + 0.5 * y[1::2]                       # positive pairs are correlated
+        y /= np.linalg.norm(y, axis=1, keepdims=True)
+        for dt, sfx in ((torch.float32, ''), (torch.float64, '_f64')):
+            t = torch.from_numpy(y).to(dt).requires_grad_(True)
+            loss = loss_fn(t, 0.05)
+            loss.backward()
+            out['loss_%s%s' % (tag, sfx)] = np.float64(loss.item())
+            out['dy_%s%s' % (tag, sfx)] = t.grad.numpy().astype(np.float32)
+        out['seed_' + tag] = seed
+    from datautil.specaug import SpecAugment
+    sa = SpecAugment({'cutout_min': 0.1, 'cutout_max': 0.5})
+    torch.manual_seed(1234)
+    out['specaug_masks'] = np.stack([sa.get_mask(256, 32).numpy() for _ in range(6)]).astype(np.uint8)
+    torch.manual_seed(77)
+    x = torch.arange(2 * 256 * 32, dtype=torch.float32).reshape(2, 256, 32) + 1
+    out['specaug_x'] = sa.augment(x).numpy()
+    np.savez_compressed(os.path.join(OUT, 'train.npz'), **out)
+
+
 def golden_encoder(name, params, mel, seed):
     from model import FpNetwork
     d, h, u, F, T = synth.model_dims(params)
@@ -268,6 +307,7 @@ def main():
     golden_encoder('tiny', synth.read_config('tiny'), mel, seed=13)
     golden_mel_variants(default)
     golden_model_variants(mel)
+    golden_train()
     golden_db(faiss)
     golden_musicdata(default)
     for f in sorted(os.listdir(OUT)):
