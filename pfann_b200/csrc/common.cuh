@@ -67,6 +67,9 @@ struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;  // H2D / D2H pipelines of pfann_extract_pcm16 (host buffers)
+    // extraction overlap: the encoder of chunk k on a high-priority stream, the mel kernel of chunk k + 1 on a
+    // low-priority one (its CTAs fill the SMs the cooperative encoder kernels leave idle)
+    cudaStream_t enc_stream = nullptr, mel_stream = nullptr;
     int sm_count = 148;
     long long launches = 0;  // kernels of OURS launched through this context (bench: gpu_launches)
     DevBuf stage_in[4], stage_out[4];

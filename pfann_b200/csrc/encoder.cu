@@ -1079,7 +1079,7 @@ void pfann_model_destroy(pfann_model *hm) {
     m->ybuf.release(); m->xa.release(); m->xb.release(); m->stats.release(); m->partials.release();
     m->tapbuf.release(); m->melbuf.release(); m->zbuf.release(); m->ln_part.release();
     if (m->ln_err_host) cudaFreeHost(m->ln_err_host);
-    m->mombuf.release();
+    m->mombuf.release(); m->melbuf2.release(); m->mombuf2.release();
     delete m;
 }
 

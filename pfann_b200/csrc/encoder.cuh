@@ -71,6 +71,7 @@ struct Model {
     float2 *cur_stats = nullptr, *cur_partials = nullptr;  // statistics buffers of the phase being executed
     const double *cur_moments = nullptr;  // layer-0 moments of the chunk being executed when the mel kernel made them
     DevBuf mombuf;                        // [chunk][9] doubles (fused extract path)
+    DevBuf melbuf2, mombuf2;              // second set: mel of chunk k + 1 runs while chunk k is encoded
     int prof_idx = 0;      // convolution being executed (detail slot of the optional event profile)
     int tap_layer = -1;
     long long tap_numel = 0;

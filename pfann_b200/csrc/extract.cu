@@ -156,27 +156,101 @@ int extract_clips(pfann_mel *mel, pfann_model *hm, const void *pcm_v, int esz, c
     // the mel kernel also reduces the 9 moments the first LayerNorm needs (taps of layer-0 conv1) while the tile is
     // in its shared memory
     const ConvGeom &g0 = m->conv[0].g;
-    double *mom = nullptr;
-    if (m->l0_fused && getenv("PFANN_B200_NO_MEL_MOMENTS") == nullptr) {
-        PF_TRY(m->mombuf.ensure(sizeof(double) * 9 * (size_t)m->chunk));
-        mom = m->mombuf.as<double>();
+    const bool want_mom = m->l0_fused && getenv("PFANN_B200_NO_MEL_MOMENTS") == nullptr;
+    if (want_mom) PF_TRY(m->mombuf.ensure(sizeof(double) * 9 * (size_t)m->chunk));
+    // Overlap: the mel kernel of chunk k + 1 runs on a low-priority stream while chunk k is encoded on a high-priority
+    // one.  The cooperative encoder kernels leave SMs idle (the fused layer-0 kernel uses 128 of 148) and have gaps
+    // between launches; the short-lived mel CTAs fill them, and because the encoder's CTAs are scheduled first whenever
+    // an SM frees up they never wait long for co-residency.  Two mel / moment buffers alternate.
+    const bool overlap = n_chunks > 1 && getenv("PFANN_B200_NO_OVERLAP") == nullptr;
+    float *melb[2] = {m->melbuf.as<float>(), m->melbuf.as<float>()};
+    double *momb[2] = {want_mom ? m->mombuf.as<double>() : nullptr, want_mom ? m->mombuf.as<double>() : nullptr};
+    cudaStream_t user = ctx->stream;
+    std::vector<cudaEvent_t> ev_mel(overlap ? n_chunks : 0), ev_enc(overlap ? n_chunks : 0);
+    if (overlap) {
+        PF_TRY(m->melbuf2.ensure(mel_per * 4 * (size_t)m->chunk));
+        melb[1] = m->melbuf2.as<float>();
+        if (want_mom) {
+            PF_TRY(m->mombuf2.ensure(sizeof(double) * 9 * (size_t)m->chunk));
+            momb[1] = m->mombuf2.as<double>();
+        }
+        if (ctx->enc_stream == nullptr) {
+            int lo = 0, hi = 0;
+            PF_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // lo = least, hi = greatest priority
+            PF_CUDA(cudaStreamCreateWithPriority(&ctx->enc_stream, cudaStreamNonBlocking, hi));
+            PF_CUDA(cudaStreamCreateWithPriority(&ctx->mel_stream, cudaStreamNonBlocking, lo));
+        }
+        for (auto &e : ev_mel) PF_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto &e : ev_enc) PF_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        cudaEvent_t ev0;   // everything enqueued on the caller's stream so far (descriptors, earlier calls) comes first
+        PF_CUDA(cudaEventCreateWithFlags(&ev0, cudaEventDisableTiming));
+        PF_CUDA(cudaEventRecord(ev0, user));
+        PF_CUDA(cudaStreamWaitEvent(ctx->enc_stream, ev0, 0));
+        PF_CUDA(cudaStreamWaitEvent(ctx->mel_stream, ev0, 0));
+        PF_CUDA(cudaEventDestroy(ev0));
     }
-    for (int64_t b0 = 0, k = 0; b0 < B; b0 += m->chunk, k++) {
+    auto run_mel = [&](int64_t k) -> int {
+        const int64_t b0 = k * m->chunk;
         const int64_t nb = (B - b0) < m->chunk ? (B - b0) : m->chunk;
-        if (pipe_in) {
-            if (k + 1 < n_chunks) PF_TRY(upload_for_chunk(k + 1));
-            PF_CUDA(cudaStreamWaitEvent(ctx->stream, ev_in[k], 0));
+        return mel_forward_pcm_dev(mel, esz == 2 ? (const int16_t *)pd : nullptr, n_samples, (const int64_t *)sd + b0,
+                                   (const int32_t *)vd + b0, nb, melb[k & 1], momb[k & 1], g0.ntaps, g0.tap_off,
+                                   esz == 4 ? (const float *)pd : nullptr);
+    };
+    int rc = PFANN_OK;
+    if (overlap) {   // mel of chunk 0
+        ctx->stream = ctx->mel_stream;
+        if (pipe_in) rc = cudaStreamWaitEvent(ctx->mel_stream, ev_in[0], 0) == cudaSuccess ? PFANN_OK : PFANN_ERR_CUDA;
+        if (rc == PFANN_OK) rc = run_mel(0);
+        if (rc == PFANN_OK && cudaEventRecord(ev_mel[0], ctx->mel_stream) != cudaSuccess) rc = PFANN_ERR_CUDA;
+    }
+    for (int64_t b0 = 0, k = 0; b0 < B && rc == PFANN_OK; b0 += m->chunk, k++) {
+        const int64_t nb = (B - b0) < m->chunk ? (B - b0) : m->chunk;
+        if (pipe_in && k + 1 < n_chunks) rc = upload_for_chunk(k + 1);
+        if (rc != PFANN_OK) break;
+        if (overlap) {
+            if (k + 1 < n_chunks) {   // mel of the NEXT chunk first, so that it is in flight while this one is encoded
+                ctx->stream = ctx->mel_stream;
+                if (k >= 1) cudaStreamWaitEvent(ctx->mel_stream, ev_enc[k - 1], 0);   // its buffers were chunk k - 1's
+                if (pipe_in) cudaStreamWaitEvent(ctx->mel_stream, ev_in[k + 1], 0);
+                rc = run_mel(k + 1);
+                if (rc != PFANN_OK) break;
+                cudaEventRecord(ev_mel[k + 1], ctx->mel_stream);
+            }
+            ctx->stream = ctx->enc_stream;
+            cudaStreamWaitEvent(ctx->enc_stream, ev_mel[k], 0);
+            rc = model_forward_dev(m, melb[k & 1], nb, norm, (float *)zd + b0 * m->d, momb[k & 1]);
+            if (rc != PFANN_OK) break;
+            cudaEventRecord(ev_enc[k], ctx->enc_stream);
+            if (pipe_out) {
+                cudaStreamWaitEvent(ctx->copy_out, ev_enc[k], 0);
+                cudaMemcpyAsync(z + b0 * m->d, (float *)zd + b0 * m->d, (size_t)nb * m->d * 4, cudaMemcpyDeviceToHost,
+                                ctx->copy_out);
+            }
+        } else {
+            if (pipe_in) cudaStreamWaitEvent(ctx->stream, ev_in[k], 0);
+            rc = run_mel(k);
+            if (rc == PFANN_OK) rc = model_forward_dev(m, melb[k & 1], nb, norm, (float *)zd + b0 * m->d, momb[k & 1]);
+            if (rc == PFANN_OK && pipe_out) {
+                cudaEventRecord(ev_done[k], ctx->stream);
+                cudaStreamWaitEvent(ctx->copy_out, ev_done[k], 0);
+                cudaMemcpyAsync(z + b0 * m->d, (float *)zd + b0 * m->d, (size_t)nb * m->d * 4, cudaMemcpyDeviceToHost,
+                                ctx->copy_out);
+            }
         }
-        PF_TRY(mel_forward_pcm_dev(mel, esz == 2 ? (const int16_t *)pd : nullptr, n_samples, (const int64_t *)sd + b0,
-                                   (const int32_t *)vd + b0, nb, m->melbuf.as<float>(), mom, g0.ntaps, g0.tap_off,
-                                   esz == 4 ? (const float *)pd : nullptr));
-        PF_TRY(model_forward_dev(m, m->melbuf.as<float>(), nb, norm, (float *)zd + b0 * m->d, mom));
-        if (pipe_out) {
-            PF_CUDA(cudaEventRecord(ev_done[k], ctx->stream));
-            PF_CUDA(cudaStreamWaitEvent(ctx->copy_out, ev_done[k], 0));
-            PF_CUDA(cudaMemcpyAsync(z + b0 * m->d, (float *)zd + b0 * m->d, (size_t)nb * m->d * 4,
-                                    cudaMemcpyDeviceToHost, ctx->copy_out));
+    }
+    ctx->stream = user;
+    if (overlap) {
+        // the caller's stream continues after the last encoder chunk (and after the mel stream, which is idle by then)
+        if (rc == PFANN_OK) {
+            cudaStreamWaitEvent(user, ev_enc[n_chunks - 1], 0);
+        } else {
+            cudaStreamSynchronize(ctx->enc_stream);
+            cudaStreamSynchronize(ctx->mel_stream);
         }
+    }
+    if (cudaGetLastError() != cudaSuccess && rc == PFANN_OK) {
+        set_error("pfann_extract: stream / event plumbing failed");
+        rc = PFANN_ERR_CUDA;
     }
     // the descriptor vectors are host temporaries: make sure their H2D copies are done before they die
     PF_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -184,6 +258,9 @@ int extract_clips(pfann_mel *mel, pfann_model *hm, const void *pcm_v, int esz, c
     if (pipe_out) PF_CUDA(cudaStreamSynchronize(ctx->copy_out));
     for (auto &e : ev_in) cudaEventDestroy(e);
     for (auto &e : ev_done) cudaEventDestroy(e);
+    for (auto &e : ev_mel) cudaEventDestroy(e);
+    for (auto &e : ev_enc) cudaEventDestroy(e);
+    if (rc != PFANN_OK) return rc;
     return tc_ln_check(m);
 }
 }  // namespace
