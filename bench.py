@@ -40,7 +40,7 @@ SEG_BYTES_MEL = 64768         # stage-1 algorithmic bytes per segment
 # ncu dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel family (convolutions 0-7: the fused
 # layer-0 + conv kernel and the fused conv + LayerNorm kernels) for one 4096-segment chunk, per segment; see
 # profiles/r02/README.md for the capture this number comes from
-DOMINANT_NCU_TRAFFIC_PER_SEG = None
+DOMINANT_NCU_TRAFFIC_PER_SEG = (2.0956e9 + 0.1409e9 + 4.704e9 + 2.410e9) / 4096   # front_tc (r/w) + conv_ln_tc convs 2-7 (r/w)
 
 
 def workload_name(clips, clip_seconds, n_seg):
