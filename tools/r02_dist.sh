@@ -8,9 +8,9 @@ N=$(nvidia-smi -L | wc -l)
 if [ "$N" -ge 2 ]; then
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 tools/dist_check.py > $O/dist_check_n$N.log 2>&1; echo "dist_check exit $?" | tee -a $O/summary.txt
 tail -n 4 $O/dist_check_n$N.log
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --steps 2 --warmup 3 --clips 1000 > $O/bench_n$N.log 2>&1; echo "bench exit $?" | tee -a $O/summary.txt
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --steps 2 --warmup 3 > $O/bench_n$N.log 2>&1; echo "bench exit $?" | tee -a $O/summary.txt
 tail -n 1 $O/bench_n$N.log | python -c "import sys,json; j=json.loads(sys.stdin.read()); m=j['match']; print(j['value'], m['value'], m['e2e'], m['kernels_ms'], m['per_file_regime'])"
 else
-timeout 900 python bench.py --steps 2 --warmup 3 --clips 1000 --no-cpu > $O/bench_n1.log 2>&1; echo "bench exit $?" | tee -a $O/summary.txt
+timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu > $O/bench_n1.log 2>&1; echo "bench exit $?" | tee -a $O/summary.txt
 tail -n 1 $O/bench_n1.log | python -c "import sys,json; j=json.loads(sys.stdin.read()); m=j['match']; print(j['value'], m['value'], m['e2e'], m['kernels_ms'], m['per_file_regime'])"
 fi
