@@ -241,6 +241,9 @@ int pfann_db_rerank_packed(pfann_db *db, const float *queries, const int64_t *qu
                            const int64_t *labels, int top_k, int frame_shift_mul, float score_alpha, float *packed);
 int pfann_best_combine(pfann_ctx *ctx, const float *packed_g, int G, int nq, float *packed_out);
 float pfann_db_max_norm(pfann_db *db);
+/* Rows of the threshold pre-pass = max(floor, scale * k * n / 256): with G shards whose thresholds are max-reduced the
+ * union of the per-shard samples does the work, so each shard can sample less (dist.py uses 0.5 from 4 shards on). */
+int pfann_db_set_sample_scale(pfann_db *db, float scale);
 int pfann_db_set_max_norm(pfann_db *db, float max_norm);
 
 /* ---- reference-compatible symbols ------------------------------------------------------------- */

@@ -91,6 +91,7 @@ def _declare(L):
     L.pfann_topk_merge_keys.argtypes = [vp, vp, c_int, c_int64, c_int, vp, vp]
     L.pfann_db_rerank_packed.argtypes = [vp, vp, vp, c_int, c_int, vp, c_int, c_int, c_float, vp]
     L.pfann_best_combine.argtypes = [vp, vp, c_int, c_int, vp]
+    L.pfann_db_set_sample_scale.argtypes = [vp, c_float]
     L.pfann_db_max_norm.argtypes = [vp]
     L.pfann_db_max_norm.restype = c_float
     L.pfann_db_set_max_norm.argtypes = [vp, c_float]

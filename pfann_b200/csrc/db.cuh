@@ -20,7 +20,8 @@ struct Db {
     float max_norm = 0.f;            // max row L2 norm (error bound of the approximate scan)
     // tuning (tests shrink these to force the overflow / backstop paths)
     int cand_cap = 4096;             // candidate slots per query (power of two, <= 4096)
-    int sample_rows = 16384;         // rows scanned in the threshold pre-pass
+    int sample_rows = 16384;         // rows scanned in the threshold pre-pass (floor)
+    float sample_scale = 1.f;        // multiplier of the k * n / 256 target (sharded search: thresholds are max-reduced)
     int use_tc = 1;                  // tensor-core bf16 scan when available, else fp32 CUDA-core scan
     // scratch
     DevBuf qbuf, qnorm, thr, cnt, cand, cand_v, sample, flags, dist, labels, rr_keys, rr_scores, rr_out, lab_stage;

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(256) knn_kth_merge_kernel(const uint32_t *part
 // only that prefix of the ranking (a few dozen rows) is re-scored exactly in fp32 (gathering 512-byte rows of the
 // fp32 database is what used to dominate this kernel), sorted by (score desc, id asc) and emitted.
 // flags[0] += 1 for every query whose candidate list overflowed (its threshold is tightened in place).
-__global__ void __launch_bounds__(256) knn_select_kernel(const float *__restrict__ db, int d, int64_t id_base,
+__global__ void __launch_bounds__(256, 3) knn_select_kernel(const float *__restrict__ db, int d, int64_t id_base,
                                                          const float *__restrict__ q, const int *cnt,
                                                          const uint32_t *cand, const uint32_t *cand_v, int cap, int k,
                                                          float eps_rel, float max_norm, const float *qnorm, float *thr,
@@ -499,7 +499,7 @@ int plan_search(Db *db, int64_t Q, int k, SearchPlan *p) {
     // sample size: aim at ~256 rows above the threshold (k * n / S ~ 256), within [sample_rows, 256 Ki].  Every
     // survivor costs ~100 instructions on the filter's hit path (measured: 360 k survivors per 256-query pass doubled
     // the scan time of a 1.25 M-row shard), a sampled row costs one more tile of the cheap pre-pass.
-    int64_t want = (int64_t)k * db->n / 256;
+    int64_t want = (int64_t)((double)k * db->n / 256 * db->sample_scale);
     if (want < db->sample_rows) want = db->sample_rows;
     if (want > 262144) want = 262144;
     p->chunk = 8192;  // one kth-select CTA sorts this many sample scores in shared memory
@@ -905,6 +905,12 @@ int pfann_best_combine(pfann_ctx *hctx, const float *packed_g, int G, int nq, fl
                                                                 reinterpret_cast<float4 *>(packed_out));
     ctx->launches++;
     PF_CUDA(cudaGetLastError());
+    return PFANN_OK;
+}
+
+int pfann_db_set_sample_scale(pfann_db *h, float scale) {
+    PF_CHECK(h && scale > 0.f && scale <= 4.f, PFANN_ERR_ARG, "pfann_db_set_sample_scale: scale must be in (0, 4]");
+    reinterpret_cast<Db *>(h)->sample_scale = scale;
     return PFANN_OK;
 }
 

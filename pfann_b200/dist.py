@@ -104,6 +104,8 @@ class ShardedDatabase:
             m = torch.tensor([backend.max_norm()], dtype=torch.float32, device=backend.torch_device())
             self.dist.all_reduce(m, op=self.dist.ReduceOp.MAX, group=group)
             backend.set_max_norm(float(m.item()))
+            if self.world >= 4 and hasattr(backend, 'set_sample_scale'):
+                backend.set_sample_scale(0.5)      # the max-reduced thresholds see the union of all shards' samples
 
     def _all_gather(self, t):
         import torch
@@ -188,6 +190,10 @@ class GpuShard:
     def set_max_norm(self, v):
         from . import _lib
         _lib.check(_lib.lib().pfann_db_set_max_norm(self.db.handle, float(v)), 'pfann_db_set_max_norm')
+
+    def set_sample_scale(self, scale):
+        from . import _lib
+        _lib.check(_lib.lib().pfann_db_set_sample_scale(self.db.handle, float(scale)), 'pfann_db_set_sample_scale')
 
     def thresholds(self, q, k):
         import torch
