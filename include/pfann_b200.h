@@ -166,6 +166,17 @@ int pfann_specaug_apply(pfann_ctx *ctx, float *x, const int32_t *rects, int64_t 
  * ratio_b = rms(x[b]) / rms(noise[b]) * 10^(-snr_db[b] / 20), rms clamped at sqrt(1e-12). */
 int pfann_snr_mix(pfann_ctx *ctx, const float *x, const float *noise, const float *snr_db, int64_t B, int n, float *out);
 
+/* Replaces the forward/backward of `y = model(mel(x))` ... `loss.backward()` in the training loop (train.py:96-103,
+ * FpNetwork.forward model.py:148-153 under torch autograd), fp32.  train_forward computes z[B][d] from mel[B][F][T]
+ * like pfann_model_forward (norm: 0 skips the final L2 normalisation) and keeps every convolution's raw output,
+ * LayerNorm statistics and activations; train_backward takes dz = dL/dz [B][d] of the same batch and leaves the
+ * parameter gradients in the model; get_grad copies the gradient of the parameter with state_dict key `name`, in the
+ * reference's element order (host or device `out`).  Gradients are sums over the batch like torch's; they are
+ * overwritten, not accumulated, by the next backward.  ReLU + relu_after_bn only (PFANN_ERR_UNSUPPORTED otherwise). */
+int pfann_model_train_forward(pfann_model *m, const float *mel, int64_t B, int norm, float *z);
+int pfann_model_train_backward(pfann_model *m, const float *dz, int norm);
+int pfann_model_get_grad(pfann_model *m, const char *name, float *out, int64_t numel);
+
 /* ---- stage 3: database search + sequence score ------------------------------------------------- */
 
 /* Replaces Database.__init__ (database.py:74-99) for a Flat inner-product index: `emb` is the

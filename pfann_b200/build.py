@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 LIB = os.path.join(CSRC, 'libpfann_b200.so')
-SOURCES = ['ctx.cu', 'mel.cu', 'encoder.cu', 'encoder_tc.cu', 'front_tc.cu', 'extract.cu', 'knn.cu', 'knn_tc.cu', 'seqscore.cu', 'ingest.cu', 'train.cu']
+SOURCES = ['ctx.cu', 'mel.cu', 'encoder.cu', 'encoder_tc.cu', 'front_tc.cu', 'extract.cu', 'knn.cu', 'knn_tc.cu', 'seqscore.cu', 'ingest.cu', 'train.cu', 'encoder_train.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
          '-Xcompiler', '-fPIC', '-I', INCLUDE, '-I', CSRC]

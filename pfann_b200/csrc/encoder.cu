@@ -30,6 +30,7 @@ struct ConvArgs {
     long long M;        // nb * Fo * To
     int Ci, Co, Fi, Ti, Fo, To, axis, ntaps, K, stride;
     int off[3];
+    int trans;          // 1 = backward-data gather: output position p reads source (p - off[j]) / stride when that is integral
 };
 
 constexpr int BM = 64, BN = 64, BK = 16;
@@ -56,8 +57,15 @@ __global__ void __launch_bounds__(256) conv_gemm_fp32_kernel(const ConvArgs<InT>
         const long long b = r / a.Fo;
         for (int j = 0; j < a.ntaps; j++) {
             int fi = fo, ti = to;
-            if (a.axis == 0) ti = a.stride * to + a.off[j]; else fi = a.stride * fo + a.off[j];
-            if (fi >= 0 && fi < a.Fi && ti >= 0 && ti < a.Ti)
+            bool ok = true;
+            if (a.trans) {   // transposed convolution (training backward, encoder_train.cu): X is the gradient of the conv output
+                const int num = (a.axis == 0 ? to : fo) - a.off[j];
+                ok = num >= 0 && (num % a.stride) == 0;
+                if (a.axis == 0) ti = num / a.stride; else fi = num / a.stride;
+            } else {
+                if (a.axis == 0) ti = a.stride * to + a.off[j]; else fi = a.stride * fo + a.off[j];
+            }
+            if (ok && fi >= 0 && fi < a.Fi && ti >= 0 && ti < a.Ti)
                 rowp[j] = a.X + ((b * a.Fi + fi) * a.Ti + ti) * (long long)a.Ci;
         }
     }
@@ -134,7 +142,7 @@ __global__ void __launch_bounds__(256) conv_gemm_fp32_kernel(const ConvArgs<InT>
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int n = n0 + tx * 4 + j;
-            if (n < a.Co) a.Y[m * a.Co + n] = acc[i][j] + __ldg(a.bias + n);
+            if (n < a.Co) a.Y[m * a.Co + n] = acc[i][j] + (a.bias ? __ldg(a.bias + n) : 0.f);
         }
     }
 }
@@ -766,7 +774,7 @@ int launch_conv_fp32(Model *m, const ConvWeights &cw, const InT *X, float *Y, in
         a.X = X; a.W = cw.w_kn; a.bias = cw.bias; a.Y = Y;
         a.M = (long long)nb * g.rows_per_sample();
         a.Ci = g.Ci; a.Co = g.Co; a.Fi = g.Fi; a.Ti = g.Ti; a.Fo = g.Fo; a.To = g.To;
-        a.axis = g.axis; a.ntaps = g.ntaps; a.K = g.K(); a.stride = g.stride;
+        a.axis = g.axis; a.ntaps = g.ntaps; a.K = g.K(); a.stride = g.stride; a.trans = 0;
         for (int j = 0; j < 3; j++) a.off[j] = g.tap_off[j];
         dim3 grid(cdiv(a.M, BM), cdiv(g.Co, BN));
         conv_gemm_fp32_kernel<InT><<<grid, 256, 0, st>>>(a);
@@ -1027,6 +1035,40 @@ int model_forward_dev(Model *m, const float *mel, int64_t B, int norm, float *z,
     return PFANN_OK;
 }
 
+// ---- fp32 building blocks shared with the training path (encoder_train.cu) ----
+int enc_conv_f32(Model *m, const ConvWeights &cw, const float *X, float *Y, int nb) {
+    return launch_conv_fp32<float>(m, cw, X, Y, nb);
+}
+int enc_ln_stats_f32(Model *m, const ConvWeights &cw, const float *Y, int nb, float2 *stats) {
+    float2 *keep = m->cur_stats;
+    m->cur_stats = stats;
+    const int rc = launch_stats(m, cw, Y, nb);
+    m->cur_stats = keep;
+    return rc;
+}
+int enc_ln_apply_f32(Model *m, const ConvWeights &cw, const float *Y, const float2 *stats, float *X, int nb) {
+    float2 *keep = m->cur_stats;
+    m->cur_stats = const_cast<float2 *>(stats);
+    const int rc = launch_ln_apply<float, float>(m, cw, Y, X, nb);
+    m->cur_stats = keep;
+    return rc;
+}
+// dXin[nb][Fi][Ti][Ci] = transposed convolution of dY[nb][Fo][To][Co] with Wt[(tap, o)][c] (dense convs only)
+int enc_conv_bwd_data_f32(Model *m, const ConvGeom &g, const float *dY, const float *Wt, float *dX, int nb) {
+    ConvArgs<float> a;
+    a.X = dY; a.W = Wt; a.bias = nullptr; a.Y = dX;
+    a.M = (long long)nb * g.Fi * g.Ti;
+    a.Ci = g.Co; a.Co = g.Ci; a.Fi = g.Fo; a.Ti = g.To; a.Fo = g.Fi; a.To = g.Ti;
+    a.axis = g.axis; a.ntaps = g.ntaps; a.K = g.ntaps * g.Co; a.stride = g.stride; a.trans = 1;
+    for (int j = 0; j < 3; j++) a.off[j] = g.tap_off[j];
+    dim3 grid(cdiv(a.M, BM), cdiv(a.Co, BN));
+    ProfScope ps(m->ctx, K_CONV_CC, m->prof_idx);
+    conv_gemm_fp32_kernel<float><<<grid, 256, 0, m->ctx->stream>>>(a);
+    m->ctx->launches++;
+    PF_CUDA(cudaGetLastError());
+    return PFANN_OK;
+}
+
 }  // namespace pfann
 
 extern "C" {
@@ -1073,6 +1115,7 @@ void pfann_model_destroy(pfann_model *hm) {
     if (!m) return;
     cudaSetDevice(m->ctx->device);
     tc_release(m);
+    train_release(m);
     for (int i = 0; i < 16; i++) free_conv(m->conv[i]);
     cudaFree(m->w1); cudaFree(m->b1); cudaFree(m->w2); cudaFree(m->b2); cudaFree(m->l0_w);
     cudaFree(m->l0_gb16); cudaFree(m->l0_btile);
@@ -1105,6 +1148,7 @@ int pfann_model_finalize(pfann_model *hm, int precision) {
     Model *m = reinterpret_cast<Model *>(hm);
     PF_CUDA(cudaSetDevice(m->ctx->device));
     tc_release(m);
+    train_invalidate(m);   // saved activations and transposed weights belong to the previous parameters
     // option variants have no tensor-core kernels: they run on the CUDA-core fp32 path (still on the GPU)
     m->precision = m->variant ? PFANN_PRECISION_FP32 : precision;
     const int ch[9] = {1, m->d, m->d, 2 * m->d, 2 * m->d, 4 * m->d, 4 * m->d, m->h, m->h};

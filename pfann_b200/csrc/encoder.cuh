@@ -76,6 +76,7 @@ struct Model {
     int tap_layer = -1;
     long long tap_numel = 0;
     void *tc_state = nullptr;  // tensor maps etc., owned by encoder_tc.cu
+    void *train_state = nullptr;  // saved activations and gradients, owned by encoder_train.cu
 };
 
 // encoder_tc.cu
@@ -106,6 +107,9 @@ int tc_ln_err_ptr(Model *m, int **dev_flag);   // device address of the (lazily 
 // front_tc.cu: layer-0 conv1 + ln1 + ReLU + conv2 + ln2 + ReLU in one kernel (log-mel in, X1 out; X0 never stored)
 bool tc_front_supported(Model *m);
 int tc_front(Model *m, const float *mel, const float2 *stats0, __nv_bfloat16 *Xout, int nb);
+// encoder_train.cu
+void train_release(Model *m);
+void train_invalidate(Model *m);   // parameters changed: drop what was derived from them, keep the buffers
 // encoder.cu: size the chunk workspace (needs the conv geometries)
 int plan_workspace(Model *m);
 

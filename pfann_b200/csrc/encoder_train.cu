@@ -1,0 +1,639 @@
+// encoder_train.cu -- training step of the fingerprint network (BASELINE configs[4]): FpNetwork forward
+// with the activations kept (model.py:148-153) and its backward, i.e. what torch autograd does for the reference in
+// train.py:99-103.  fp32 CUDA-core kernels throughout (the reference trains in fp32 / AMP; gradients feed an optimizer, a
+// bf16 tensor-core backward is future work -- DESIGN.md section 8); activations are channels-last like the inference
+// path.  Supported option set: ReLU, relu_after_bn = True, any strides, dense or depthwise conv2.
+//
+// Per convolution i (conv -> LayerNorm over (C,F,T) with per-element affine -> ReLU), given dA = dL/d(output):
+//     dn   = dA * [A > 0]                                   ReLU'
+//     dgamma[e] += dn[b,e] * xhat[b,e],  dbeta[e] += dn[b,e]  xhat = (Y - mean_b) * rstd_b      (sum over the batch)
+//     g    = dn * gamma
+//     dY   = rstd_b * (g - mean_e(g) - xhat * mean_e(g * xhat))                                   LayerNorm backward
+//     dW[(j,c)][o] = sum_m X_in[m @ tap j][c] * dY[m][o],   db[o] = sum_m dY[m][o]                 weight gradient
+//     dX_in = transposed convolution of dY with W                                                 data gradient
+#include <math.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "encoder.cuh"
+#include "pfann_b200.h"
+
+using namespace pfann;
+
+namespace pfann {
+int enc_conv_f32(Model *m, const ConvWeights &cw, const float *X, float *Y, int nb);
+int enc_ln_stats_f32(Model *m, const ConvWeights &cw, const float *Y, int nb, float2 *stats);
+int enc_ln_apply_f32(Model *m, const ConvWeights &cw, const float *Y, const float2 *stats, float *X, int nb);
+int enc_conv_bwd_data_f32(Model *m, const ConvGeom &g, const float *dY, const float *Wt, float *dX, int nb);
+}  // namespace pfann
+
+namespace {
+
+struct TrainState {
+    int B = 0;
+    DevBuf Y[16], X[16], stats[16];        // raw conv outputs, post-activation outputs, (mean, rstd) per sample
+    DevBuf lnred;                          // [B] (mean g, mean g xhat) of the LayerNorm backward
+    DevBuf dA, dB;                         // gradient ping-pong buffers (largest activation)
+    DevBuf hp, hr, hdr;                    // head: pre-ELU [B][d u], pre-normalisation output [B][d], its gradient
+    DevBuf gW[16], gB[16], gG[16], gBe[16], gw1, gb1, gw2, gb2;   // parameter gradients (kernel layouts)
+    float *wt[16] = {};                    // transposed weights [(tap, o)][c] for the data gradient
+    const float *mel = nullptr;
+    bool have_grads = false;
+};
+
+__device__ __forceinline__ double block_sum_d(double v, double *red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int i = 0; i < nw; i++) t += red[i];
+    return t;
+}
+
+// ---- head (model.py:122-130), training forward: x = activated encoder output [B][h] ----
+__global__ void head_train_fwd_kernel(const float *x, const float *w1, const float *b1, const float *w2, const float *b2,
+                                      float *p, float *r, float *z, int d, int h, int u, int norm) {
+    extern __shared__ float red[];
+    const long long b = blockIdx.x;
+    const int g = threadIdx.x, v = h / d;
+    float out = 0.f;
+    if (g < d) {
+        out = b2[g];
+        for (int j = 0; j < u; j++) {
+            float acc = b1[g * u + j];
+            for (int i = 0; i < v; i++) acc = fmaf(w1[(size_t)(g * u + j) * v + i], x[b * h + g * v + i], acc);
+            p[(b * d + g) * u + j] = acc;
+            out = fmaf(w2[g * u + j], acc > 0.f ? acc : expm1f(acc), out);
+        }
+        r[b * d + g] = out;
+    }
+    float s = g < d ? out * out : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += red[i];
+    if (g < d) z[b * d + g] = norm ? out / fmaxf(sqrtf(t), 1e-12f) : out;
+}
+
+// dr = d(loss)/d(r) from dz: F.normalize backward  dr = (dz - z (z . dz)) / max(|r|, eps)   (identity when !norm)
+__global__ void normalize_bwd_kernel(const float *dz, const float *r, float *dr, int d, int norm) {
+    extern __shared__ float red[];
+    const long long b = blockIdx.x;
+    const int g = threadIdx.x;
+    const float rv = g < d ? r[b * d + g] : 0.f, gv = g < d ? dz[b * d + g] : 0.f;
+    if (!norm) {
+        if (g < d) dr[b * d + g] = gv;
+        return;
+    }
+    float s1 = rv * rv, s2 = rv * gv;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const int nw = blockDim.x >> 5;
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = s1; red[nw + (threadIdx.x >> 5)] = s2; }
+    __syncthreads();
+    float t1 = 0.f, t2 = 0.f;
+    for (int i = 0; i < nw; i++) { t1 += red[i]; t2 += red[nw + i]; }
+    const float nrm = fmaxf(sqrtf(t1), 1e-12f);
+    if (g < d) dr[b * d + g] = (gv - rv * (t2 / (nrm * nrm))) / nrm;
+}
+
+// one CTA per output dimension g, one thread per hidden unit j: sums over the batch in registers (no atomics);
+// dx[b][g v + i] = sum_j dp[b][g][j] w1[g][j][i] via a warp reduction
+__global__ void head_bwd_kernel(const float *x, const float *p, const float *dr, const float *w1, const float *w2, int B, int d,
+                                int h, int u, float *gw1, float *gb1, float *gw2, float *gb2, float *dx) {
+    const int g = blockIdx.x, j = threadIdx.x, v = h / d;   // blockDim.x = 32 >= u
+    float aw1[16], ab1 = 0.f, aw2 = 0.f, ab2 = 0.f, w1r[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        aw1[i] = 0.f;
+        w1r[i] = (j < u && i < v) ? w1[(size_t)(g * u + j) * v + i] : 0.f;
+    }
+    const float w2v = j < u ? w2[g * u + j] : 0.f;
+    for (int b = 0; b < B; b++) {
+        const float drv = dr[(size_t)b * d + g];
+        const float pv = j < u ? p[((size_t)b * d + g) * u + j] : 0.f;
+        const float e = pv > 0.f ? pv : expm1f(pv);
+        const float dp = j < u ? drv * w2v * (pv > 0.f ? 1.f : e + 1.f) : 0.f;   // ELU' = 1 or exp(p)
+        aw2 = fmaf(drv, e, aw2);
+        ab2 += drv;
+        ab1 += dp;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            if (i < v) {
+                const float xv = x[(size_t)b * h + g * v + i];
+                aw1[i] = fmaf(dp, xv, aw1[i]);
+                float c = dp * w1r[i];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                if (j == 0) dx[(size_t)b * h + g * v + i] = c;
+            }
+        }
+    }
+    if (j < u) {
+        for (int i = 0; i < v && i < 16; i++) gw1[(size_t)(g * u + j) * v + i] = aw1[i];
+        gb1[g * u + j] = ab1;
+        gw2[g * u + j] = aw2;
+    }
+    if (j == 0) gb2[g] = ab2;
+}
+
+// ---- LayerNorm + ReLU backward ----
+// red[b] = (mean_e g, mean_e g xhat), g = dA [A > 0] gamma
+__global__ void __launch_bounds__(512) ln_bwd_reduce_kernel(const float *dA, const float *A, const float *Y, const float2 *stats,
+                                                            const float *gamma, long long E, float2 *red) {
+    __shared__ double sh[16];
+    const long long b = blockIdx.x;
+    const float2 st = stats[b];
+    double s1 = 0.0, s2 = 0.0;
+    for (long long e = threadIdx.x; e < E; e += blockDim.x) {
+        const float a = A[b * E + e];
+        if (a > 0.f) {
+            const float g = dA[b * E + e] * gamma[e];
+            s1 += (double)g;
+            s2 += (double)g * (double)((Y[b * E + e] - st.x) * st.y);
+        }
+    }
+    const double t1 = block_sum_d(s1, sh), t2 = block_sum_d(s2, sh);
+    if (threadIdx.x == 0) red[b] = make_float2((float)(t1 / (double)E), (float)(t2 / (double)E));
+}
+
+// dY (in place over dA) and the affine gradients; a thread owns 4 consecutive elements and walks `group` samples
+__global__ void __launch_bounds__(256) ln_bwd_apply_kernel(float *dA, const float *A, const float *Y, const float2 *stats,
+                                                           const float2 *red, const float *gamma, long long E, int nb, int group,
+                                                           float *gG, float *gBe) {
+    const long long e0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (e0 >= E) return;
+    const int b0 = blockIdx.y * group, b1 = (b0 + group) < nb ? (b0 + group) : nb;
+    const int n = (int)((E - e0) < 4 ? (E - e0) : 4);
+    float gam[4], ag[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = 0; i < n; i++) gam[i] = gamma[e0 + i];
+    for (int b = b0; b < b1; b++) {
+        const float2 st = stats[b], rd = red[b];
+        for (int i = 0; i < n; i++) {
+            const long long idx = (long long)b * E + e0 + i;
+            const float dn = A[idx] > 0.f ? dA[idx] : 0.f;
+            const float xh = (Y[idx] - st.x) * st.y;
+            ag[i] = fmaf(dn, xh, ag[i]);
+            ab[i] += dn;
+            dA[idx] = st.y * (dn * gam[i] - rd.x - xh * rd.y);
+        }
+    }
+    for (int i = 0; i < n; i++) {
+        atomicAdd(gG + e0 + i, ag[i]);
+        atomicAdd(gBe + e0 + i, ab[i]);
+    }
+}
+
+// ---- dense convolution, weight gradient: dW[k][o] += sum_{m in slice} A[m][k] dY[m][o], k = (tap, c) ----
+struct BwdWArgs {
+    const float *X;     // conv input [nb][Fi][Ti][Ci]
+    const float *dY;    // [M][Co]
+    float *dW;          // [K][Co]
+    float *db;          // [Co]
+    long long M, m_per_split;
+    int Ci, Co, Fi, Ti, Fo, To, axis, ntaps, K, stride;
+    int off[3];
+};
+
+__global__ void __launch_bounds__(256) conv_bwd_w_kernel(const BwdWArgs a) {
+    __shared__ float As[16][64 + 4];   // [m][k]
+    __shared__ float Gs[16][64];       // [m][o]
+    const int tid = threadIdx.x;
+    const int k0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+    const long long m_begin = (long long)blockIdx.z * a.m_per_split;
+    long long m_end = m_begin + a.m_per_split;
+    if (m_end > a.M) m_end = a.M;
+    // loader roles: 16 rows x 16 threads, each 4 consecutive k (A) / 4 consecutive o (G)
+    const int lm = tid >> 4, lq = (tid & 15) * 4;
+    const int tx = tid & 15, ty = tid >> 4;   // compute: k = ty*4.., o = tx*4..
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+    float bsum = 0.f;   // bias gradient: k-tile 0 only, thread column o = n0 + tid (tid < 64)
+    for (long long m0 = m_begin; m0 < m_end; m0 += 16) {
+        const long long m = m0 + lm;
+        float av[4] = {0.f, 0.f, 0.f, 0.f}, gv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (m < m_end) {
+            const int to = (int)(m % a.To);
+            const long long r = m / a.To;
+            const int fo = (int)(r % a.Fo);
+            const long long b = r / a.Fo;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int k = k0 + lq + e;
+                if (k < a.K) {
+                    const int tap = k / a.Ci, c = k - tap * a.Ci;
+                    int fi = fo, ti = to;
+                    if (a.axis == 0) ti = a.stride * to + a.off[tap]; else fi = a.stride * fo + a.off[tap];
+                    if (fi >= 0 && fi < a.Fi && ti >= 0 && ti < a.Ti) av[e] = __ldg(a.X + ((b * a.Fi + fi) * a.Ti + ti) * (long long)a.Ci + c);
+                }
+                const int o = n0 + lq + e;
+                if (o < a.Co) gv[e] = __ldg(a.dY + m * a.Co + o);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            As[lm][lq + e] = av[e];
+            Gs[lm][lq + e] = gv[e];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int mm = 0; mm < 16; mm++) {
+            const float4 a4 = *reinterpret_cast<const float4 *>(&As[mm][ty * 4]);
+            const float4 g4 = *reinterpret_cast<const float4 *>(&Gs[mm][tx * 4]);
+            const float aa[4] = {a4.x, a4.y, a4.z, a4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(aa[i], gg[j], acc[i][j]);
+        }
+        if (blockIdx.x == 0 && tid < 64) {
+#pragma unroll
+            for (int mm = 0; mm < 16; mm++) bsum += Gs[mm][tid];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int k = k0 + ty * 4 + i;
+        if (k >= a.K) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int o = n0 + tx * 4 + j;
+            if (o < a.Co) atomicAdd(a.dW + (size_t)k * a.Co + o, acc[i][j]);
+        }
+    }
+    if (blockIdx.x == 0 && tid < 64 && n0 + tid < a.Co) atomicAdd(a.db + n0 + tid, bsum);
+}
+
+// ---- depthwise conv2 (fuller == false): data and weight gradients ----
+__global__ void dw_bwd_data_kernel(const float *dY, const float *W /*[C][ntaps]*/, float *dX, long long total, int C, int Fi,
+                                   int Ti, int Fo, int ntaps, int off0, int off1, int off2, int stride) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over dX [nb][Fi][Ti][C]
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const int t = (int)(r % Ti);
+    r /= Ti;
+    const int fi = (int)(r % Fi);
+    const long long b = r / Fi;
+    const int offs[3] = {off0, off1, off2};
+    float acc = 0.f;
+    for (int j = 0; j < ntaps; j++) {
+        const int num = fi - offs[j];
+        if (num < 0 || num % stride) continue;
+        const int fo = num / stride;
+        if (fo >= Fo) continue;
+        acc = fmaf(W[c * ntaps + j], dY[((b * Fo + fo) * Ti + t) * (long long)C + c], acc);
+    }
+    dX[i] = acc;
+}
+
+// thread = (channel c, slice of positions): partial sums over its slice, then atomics (C * ntaps addresses)
+__global__ void dw_bwd_w_kernel(const float *X, const float *dY, long long rows /*nb*Fo*To*/, int C, int Fi, int Ti, int Fo,
+                                int To, int ntaps, int off0, int off1, int off2, int stride, float *gW, float *gB) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const int offs[3] = {off0, off1, off2};
+    const long long per = (rows + gridDim.y - 1) / gridDim.y;
+    const long long r0 = (long long)blockIdx.y * per, r1 = (r0 + per) < rows ? (r0 + per) : rows;
+    float aw[3] = {0.f, 0.f, 0.f}, ab = 0.f;
+    for (long long m = r0; m < r1; m++) {
+        const int to = (int)(m % To);
+        const long long r = m / To;
+        const int fo = (int)(r % Fo);
+        const long long b = r / Fo;
+        const float g = dY[m * C + c];
+        ab += g;
+        for (int j = 0; j < ntaps; j++) {
+            const int fi = stride * fo + offs[j];
+            if (fi >= 0 && fi < Fi) aw[j] = fmaf(g, X[((b * Fi + fi) * Ti + to) * (long long)C + c], aw[j]);
+        }
+    }
+    for (int j = 0; j < ntaps; j++) atomicAdd(gW + c * ntaps + j, aw[j]);
+    atomicAdd(gB + c, ab);
+}
+
+// kernel layouts -> the reference's (PyTorch) element order, for device-side readers of the gradients
+// mode 0: dense conv [(j, c)][o] -> [o][c][3];  1: depthwise [o][ntaps] -> [o][1][3];  2: LayerNorm [f][t][o] -> [o][f][t]
+__global__ void grad_layout_kernel(const float *src, float *dst, long long total, int mode, int Ci, int Co, int ntaps, int k0,
+                                   int k1, int k2, int Fo, int To) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    if (mode == 2) {
+        const int t = (int)(i % To);
+        const long long r = i / To;
+        const int f = (int)(r % Fo), o = (int)(r / Fo);
+        dst[i] = src[((long long)f * To + t) * Co + o];
+        return;
+    }
+    const int k = (int)(i % 3);
+    const long long r = i / 3;
+    const int tk[3] = {k0, k1, k2};
+    int j = -1;
+    for (int q = 0; q < ntaps; q++)
+        if (tk[q] == k) j = q;
+    float v = 0.f;   // dead taps only ever multiply padding
+    if (j >= 0) {
+        if (mode == 1) v = src[r * ntaps + j];
+        else {
+            const int c = (int)(r % Ci), o = (int)(r / Ci);
+            v = src[((long long)j * Ci + c) * Co + o];
+        }
+    }
+    dst[i] = v;
+}
+
+TrainState *state(Model *m) {
+    if (m->train_state == nullptr) m->train_state = new TrainState();
+    return reinterpret_cast<TrainState *>(m->train_state);
+}
+
+int zero(Ctx *ctx, DevBuf &b, size_t bytes) {
+    PF_TRY(b.ensure(bytes));
+    PF_CUDA(cudaMemsetAsync(b.p, 0, bytes, ctx->stream));
+    return PFANN_OK;
+}
+
+}  // namespace
+
+namespace pfann {
+void train_invalidate(Model *m) {
+    TrainState *t = reinterpret_cast<TrainState *>(m->train_state);
+    if (!t) return;
+    for (int i = 0; i < 16; i++) {
+        cudaFree(t->wt[i]);
+        t->wt[i] = nullptr;
+    }
+    t->B = 0;
+    t->have_grads = false;
+}
+void train_release(Model *m) {
+    TrainState *t = reinterpret_cast<TrainState *>(m->train_state);
+    if (!t) return;
+    for (int i = 0; i < 16; i++) {
+        t->Y[i].release(); t->X[i].release(); t->stats[i].release();
+        t->gW[i].release(); t->gB[i].release(); t->gG[i].release(); t->gBe[i].release();
+        cudaFree(t->wt[i]);
+    }
+    t->lnred.release(); t->dA.release(); t->dB.release(); t->hp.release(); t->hr.release(); t->hdr.release();
+    t->gw1.release(); t->gb1.release(); t->gw2.release(); t->gb2.release();
+    delete t;
+    m->train_state = nullptr;
+}
+}  // namespace pfann
+
+extern "C" {
+
+int pfann_model_train_forward(pfann_model *hm, const float *mel, int64_t B, int norm, float *z) {
+    PF_CHECK(hm && mel && z && B > 0 && B <= 65535, PFANN_ERR_ARG, "pfann_model_train_forward: bad argument");
+    Model *m = reinterpret_cast<Model *>(hm);
+    PF_CHECK(m->precision >= 0, PFANN_ERR_STATE, "pfann_model_train_forward: call pfann_model_finalize first");
+    PF_CHECK(m->act == PFANN_ACT_RELU && !m->act_first, PFANN_ERR_UNSUPPORTED,
+             "pfann_model_train_forward: only ReLU with relu_after_bn = True has a backward");
+    PF_CHECK(is_device_ptr(mel) && is_device_ptr(z), PFANN_ERR_ARG, "pfann_model_train_forward: device pointers only");
+    PF_CHECK(m->h / m->d <= 16 && m->u <= 32 && m->d <= 1024, PFANN_ERR_UNSUPPORTED,
+             "pfann_model_train_forward: head needs h/d <= 16 and u <= 32");
+    PF_CUDA(cudaSetDevice(m->ctx->device));
+    TrainState *t = state(m);
+    t->B = (int)B;
+    t->mel = mel;
+    t->have_grads = false;
+    const float *in = mel;
+    for (int i = 0; i < 16; i++) {
+        const ConvWeights &cw = m->conv[i];
+        const size_t bytes = (size_t)B * cw.g.out_per_sample() * 4;
+        PF_TRY(t->Y[i].ensure(bytes));
+        PF_TRY(t->X[i].ensure(bytes));
+        PF_TRY(t->stats[i].ensure((size_t)B * sizeof(float2)));
+        m->prof_idx = i;
+        PF_TRY(enc_conv_f32(m, cw, in, t->Y[i].as<float>(), (int)B));
+        PF_TRY(enc_ln_stats_f32(m, cw, t->Y[i].as<float>(), (int)B, t->stats[i].as<float2>()));
+        PF_TRY(enc_ln_apply_f32(m, cw, t->Y[i].as<float>(), t->stats[i].as<float2>(), t->X[i].as<float>(), (int)B));
+        in = t->X[i].as<float>();
+    }
+    PF_TRY(t->hp.ensure((size_t)B * m->d * m->u * 4));
+    PF_TRY(t->hr.ensure((size_t)B * m->d * 4));
+    const int threads = ((m->d + 31) / 32) * 32;
+    ProfScope ps(m->ctx, K_HEAD, 33);
+    head_train_fwd_kernel<<<(unsigned)B, threads, 64 * sizeof(float), m->ctx->stream>>>(
+        in, m->w1, m->b1, m->w2, m->b2, t->hp.as<float>(), t->hr.as<float>(), z, m->d, m->h, m->u, norm);
+    m->ctx->launches++;
+    PF_CUDA(cudaGetLastError());
+    return PFANN_OK;
+}
+
+int pfann_model_train_backward(pfann_model *hm, const float *dz, int norm) {
+    PF_CHECK(hm && dz, PFANN_ERR_ARG, "pfann_model_train_backward: bad argument");
+    Model *m = reinterpret_cast<Model *>(hm);
+    TrainState *t = reinterpret_cast<TrainState *>(m->train_state);
+    PF_CHECK(t && t->B > 0, PFANN_ERR_STATE, "pfann_model_train_backward: no forward to differentiate");
+    PF_CHECK(is_device_ptr(dz), PFANN_ERR_ARG, "pfann_model_train_backward: device pointers only");
+    PF_CUDA(cudaSetDevice(m->ctx->device));
+    Ctx *ctx = m->ctx;
+    cudaStream_t st = ctx->stream;
+    const int B = t->B, d = m->d, h = m->h, u = m->u, v = h / d;
+    // ---- head ----
+    PF_TRY(t->hdr.ensure((size_t)B * d * 4));
+    PF_TRY(t->gw1.ensure((size_t)d * u * v * 4));
+    PF_TRY(t->gb1.ensure((size_t)d * u * 4));
+    PF_TRY(t->gw2.ensure((size_t)d * u * 4));
+    PF_TRY(t->gb2.ensure((size_t)d * 4));
+    size_t max_act = 0;
+    for (int i = 0; i < 16; i++)
+        if ((size_t)m->conv[i].g.out_per_sample() > max_act) max_act = (size_t)m->conv[i].g.out_per_sample();
+    PF_TRY(t->dA.ensure((size_t)B * max_act * 4));
+    PF_TRY(t->dB.ensure((size_t)B * max_act * 4));
+    const int threads = ((d + 31) / 32) * 32;
+    {
+        ProfScope ps(ctx, K_HEAD, 33);
+        normalize_bwd_kernel<<<B, threads, 64 * sizeof(float), st>>>(dz, t->hr.as<float>(), t->hdr.as<float>(), d, norm);
+        head_bwd_kernel<<<d, 32, 0, st>>>(t->X[15].as<float>(), t->hp.as<float>(), t->hdr.as<float>(), m->w1, m->w2, B, d, h, u,
+                                          t->gw1.as<float>(), t->gb1.as<float>(), t->gw2.as<float>(), t->gb2.as<float>(),
+                                          t->dA.as<float>());
+        ctx->launches += 2;
+        PF_CUDA(cudaGetLastError());
+    }
+    float *dcur = t->dA.as<float>(), *dnext = t->dB.as<float>();   // dcur = gradient w.r.t. X[i]
+    PF_TRY(t->lnred.ensure((size_t)B * sizeof(float2)));
+    for (int i = 15; i >= 0; i--) {
+        const ConvWeights &cw = m->conv[i];
+        const ConvGeom &g = cw.g;
+        const long long E = g.out_per_sample();
+        m->prof_idx = i;
+        PF_TRY(zero(ctx, t->gG[i], (size_t)E * 4));
+        PF_TRY(zero(ctx, t->gBe[i], (size_t)E * 4));
+        const size_t wbytes = (size_t)(g.depthwise ? g.Co * g.ntaps : g.K() * g.Co) * 4;
+        PF_TRY(zero(ctx, t->gW[i], wbytes));
+        PF_TRY(zero(ctx, t->gB[i], (size_t)g.Co * 4));
+        {   // LayerNorm + ReLU backward: dcur becomes dY in place
+            ProfScope ps(ctx, K_LN, 16 + i);
+            ln_bwd_reduce_kernel<<<B, 512, 0, st>>>(dcur, t->X[i].as<float>(), t->Y[i].as<float>(), t->stats[i].as<float2>(),
+                                                    cw.gamma, E, t->lnred.as<float2>());
+            int group = 16;
+            while (group > 1 && (long long)cdiv(E, 1024) * cdiv(B, group) < 2LL * ctx->sm_count) group >>= 1;
+            dim3 grid(cdiv(E, 1024), cdiv(B, group));
+            ln_bwd_apply_kernel<<<grid, 256, 0, st>>>(dcur, t->X[i].as<float>(), t->Y[i].as<float>(), t->stats[i].as<float2>(),
+                                                      t->lnred.as<float2>(), cw.gamma, E, B, group, t->gG[i].as<float>(),
+                                                      t->gBe[i].as<float>());
+            ctx->launches += 2;
+            PF_CUDA(cudaGetLastError());
+        }
+        const float *xin = i == 0 ? t->mel : t->X[i - 1].as<float>();
+        const long long rows = (long long)B * g.rows_per_sample();
+        ProfScope ps(ctx, K_CONV_CC, i);
+        if (g.depthwise) {
+            dim3 gw(cdiv(g.Co, 128), 64);
+            dw_bwd_w_kernel<<<gw, 128, 0, st>>>(xin, dcur, rows, g.Co, g.Fi, g.Ti, g.Fo, g.To, g.ntaps, g.tap_off[0], g.tap_off[1],
+                                                g.tap_off[2], g.stride, t->gW[i].as<float>(), t->gB[i].as<float>());
+            const long long total = (long long)B * g.Fi * g.Ti * g.Ci;
+            dw_bwd_data_kernel<<<cdiv(total, 256), 256, 0, st>>>(dcur, cw.w_kn, dnext, total, g.Co, g.Fi, g.Ti, g.Fo, g.ntaps,
+                                                                 g.tap_off[0], g.tap_off[1], g.tap_off[2], g.stride);
+            ctx->launches += 2;
+        } else {
+            BwdWArgs a;
+            a.X = xin; a.dY = dcur; a.dW = t->gW[i].as<float>(); a.db = t->gB[i].as<float>();
+            a.M = rows;
+            a.Ci = g.Ci; a.Co = g.Co; a.Fi = g.Fi; a.Ti = g.Ti; a.Fo = g.Fo; a.To = g.To; a.axis = g.axis; a.ntaps = g.ntaps;
+            a.K = g.K(); a.stride = g.stride;
+            for (int j = 0; j < 3; j++) a.off[j] = g.tap_off[j];
+            const int kt = (int)cdiv(a.K, 64), nt = (int)cdiv(a.Co, 64);
+            int splits = (4 * ctx->sm_count + kt * nt - 1) / (kt * nt);
+            if (splits > (int)cdiv(rows, 64)) splits = (int)cdiv(rows, 64);
+            if (splits < 1) splits = 1;
+            a.m_per_split = ((rows + splits - 1) / splits + 15) / 16 * 16;
+            splits = (int)cdiv(rows, a.m_per_split);
+            conv_bwd_w_kernel<<<dim3(kt, nt, splits), 256, 0, st>>>(a);
+            ctx->launches++;
+            if (i > 0) {
+                if (t->wt[i] == nullptr) {   // [(tap, o)][c] from w_kn [(tap, c)][o], once per finalize
+                    std::vector<float> hw((size_t)g.K() * g.Co), ht((size_t)g.ntaps * g.Co * g.Ci);
+                    PF_CUDA(cudaMemcpyAsync(hw.data(), cw.w_kn, hw.size() * 4, cudaMemcpyDeviceToHost, st));
+                    PF_CUDA(cudaStreamSynchronize(st));
+                    for (int j = 0; j < g.ntaps; j++)
+                        for (int c = 0; c < g.Ci; c++)
+                            for (int o = 0; o < g.Co; o++)
+                                ht[((size_t)j * g.Co + o) * g.Ci + c] = hw[((size_t)j * g.Ci + c) * g.Co + o];
+                    PF_CUDA(cudaMalloc(&t->wt[i], ht.size() * 4));
+                    PF_CUDA(cudaMemcpyAsync(t->wt[i], ht.data(), ht.size() * 4, cudaMemcpyHostToDevice, st));
+                    PF_CUDA(cudaStreamSynchronize(st));
+                }
+                PF_TRY(enc_conv_bwd_data_f32(m, g, dcur, t->wt[i], dnext, B));
+            }
+        }
+        PF_CUDA(cudaGetLastError());
+        float *tmp = dcur; dcur = dnext; dnext = tmp;
+    }
+    t->have_grads = true;
+    return PFANN_OK;
+}
+
+// gradient of the parameter with the reference's state_dict key `name`, in the reference's (PyTorch) element order
+int pfann_model_get_grad(pfann_model *hm, const char *name, float *out, int64_t numel) {
+    PF_CHECK(hm && name && out, PFANN_ERR_ARG, "pfann_model_get_grad: bad argument");
+    Model *m = reinterpret_cast<Model *>(hm);
+    TrainState *t = reinterpret_cast<TrainState *>(m->train_state);
+    PF_CHECK(t && t->have_grads, PFANN_ERR_STATE, "pfann_model_get_grad: call pfann_model_train_backward first");
+    PF_CUDA(cudaSetDevice(m->ctx->device));
+    cudaStream_t st = m->ctx->stream;
+    auto fetch = [&](const DevBuf &b, size_t n, std::vector<float> &h) -> int {
+        h.resize(n);
+        PF_CUDA(cudaMemcpyAsync(h.data(), b.p, n * 4, cudaMemcpyDeviceToHost, st));
+        PF_CUDA(cudaStreamSynchronize(st));
+        return PFANN_OK;
+    };
+    std::vector<float> hbuf, res;
+    const std::string key(name);
+    int l = -1;
+    char cn[16] = {0}, pn[16] = {0};
+    const bool conv_key = sscanf(name, "f.convs.%d.%15[a-z0-9].%15s", &l, cn, pn) == 3 && l >= 0 && l < 8;
+    if (is_device_ptr(out)) {   // stays on the device: one layout kernel or one copy on the context's stream
+        const DevBuf *src = nullptr;
+        long long total = 0;
+        int mode = -1;
+        const ConvGeom *g = nullptr;
+        if (conv_key) {
+            const std::string c(cn), p(pn);
+            const int i = 2 * l + ((c == "conv2" || c == "ln2") ? 1 : 0);
+            g = &m->conv[i].g;
+            if ((c == "conv1" || c == "conv2") && p == "weight") {
+                src = &t->gW[i]; mode = g->depthwise ? 1 : 0; total = (long long)g->Co * (g->depthwise ? 1 : g->Ci) * 3;
+            } else if ((c == "conv1" || c == "conv2") && p == "bias") {
+                src = &t->gB[i]; total = g->Co;
+            } else if ((c == "ln1" || c == "ln2") && (p == "weight" || p == "bias")) {
+                src = p == "weight" ? &t->gG[i] : &t->gBe[i]; mode = 2; total = g->out_per_sample();
+            }
+        } else if (key == "g.linear1.weight") { src = &t->gw1; total = (long long)m->d * m->u * (m->h / m->d);
+        } else if (key == "g.linear1.bias") { src = &t->gb1; total = (long long)m->d * m->u;
+        } else if (key == "g.linear2.weight") { src = &t->gw2; total = (long long)m->d * m->u;
+        } else if (key == "g.linear2.bias") { src = &t->gb2; total = m->d; }
+        PF_CHECK(src != nullptr, PFANN_ERR_ARG, "pfann_model_get_grad: unknown parameter '%s'", name);
+        PF_CHECK(total == numel, PFANN_ERR_ARG, "pfann_model_get_grad: '%s' has %lld elements, caller expects %lld", name, total,
+                 (long long)numel);
+        if (mode < 0) {
+            PF_CUDA(cudaMemcpyAsync(out, src->p, (size_t)total * 4, cudaMemcpyDeviceToDevice, st));
+        } else {
+            grad_layout_kernel<<<cdiv(total, 256), 256, 0, st>>>(src->as<float>(), out, total, mode, g->Ci, g->Co, g->ntaps,
+                                                                 g->tap_k[0], g->tap_k[1], g->tap_k[2], g->Fo, g->To);
+            m->ctx->launches++;
+            PF_CUDA(cudaGetLastError());
+        }
+        return PFANN_OK;
+    }
+    if (conv_key) {
+        const std::string c(cn), p(pn);
+        const int which = (c == "conv2" || c == "ln2") ? 1 : 0, i = 2 * l + which;
+        const ConvGeom &g = m->conv[i].g;
+        if ((c == "conv1" || c == "conv2") && p == "weight") {
+            const int cin = g.depthwise ? 1 : g.Ci;
+            res.assign((size_t)g.Co * cin * 3, 0.f);   // dead taps only ever multiply padding: gradient 0
+            if (g.depthwise) {
+                PF_TRY(fetch(t->gW[i], (size_t)g.Co * g.ntaps, hbuf));
+                for (int o = 0; o < g.Co; o++)
+                    for (int j = 0; j < g.ntaps; j++) res[(size_t)o * 3 + g.tap_k[j]] = hbuf[(size_t)o * g.ntaps + j];
+            } else {
+                PF_TRY(fetch(t->gW[i], (size_t)g.K() * g.Co, hbuf));
+                for (int o = 0; o < g.Co; o++)
+                    for (int j = 0; j < g.ntaps; j++)
+                        for (int cc = 0; cc < g.Ci; cc++)
+                            res[((size_t)o * g.Ci + cc) * 3 + g.tap_k[j]] = hbuf[((size_t)j * g.Ci + cc) * g.Co + o];
+            }
+        } else if ((c == "conv1" || c == "conv2") && p == "bias") {
+            PF_TRY(fetch(t->gB[i], (size_t)g.Co, res));
+        } else if ((c == "ln1" || c == "ln2") && (p == "weight" || p == "bias")) {
+            PF_TRY(fetch(p == "weight" ? t->gG[i] : t->gBe[i], (size_t)g.out_per_sample(), hbuf));
+            res.resize(hbuf.size());
+            for (int o = 0; o < g.Co; o++)
+                for (int f = 0; f < g.Fo; f++)
+                    for (int tt = 0; tt < g.To; tt++)
+                        res[((size_t)o * g.Fo + f) * g.To + tt] = hbuf[((size_t)f * g.To + tt) * g.Co + o];
+        }
+    } else if (key == "g.linear1.weight") {
+        PF_TRY(fetch(t->gw1, (size_t)m->d * m->u * (m->h / m->d), res));
+    } else if (key == "g.linear1.bias") {
+        PF_TRY(fetch(t->gb1, (size_t)m->d * m->u, res));
+    } else if (key == "g.linear2.weight") {
+        PF_TRY(fetch(t->gw2, (size_t)m->d * m->u, res));
+    } else if (key == "g.linear2.bias") {
+        PF_TRY(fetch(t->gb2, (size_t)m->d, res));
+    }
+    PF_CHECK(!res.empty(), PFANN_ERR_ARG, "pfann_model_get_grad: unknown parameter '%s'", name);
+    PF_CHECK((int64_t)res.size() == numel, PFANN_ERR_ARG, "pfann_model_get_grad: '%s' has %zu elements, caller expects %lld", name,
+             res.size(), (long long)numel);
+    memcpy(out, res.data(), res.size() * 4);
+    return PFANN_OK;
+}
+
+}  // extern "C"

@@ -75,6 +75,44 @@ class MyG(Module):
         self.linear2 = Conv1d(d * u, d, kernel_size=(1,), groups=d)
 
 
+class _TrainStep(torch.autograd.Function):
+    """``y = model(x)`` with a backward: what torch autograd does for the reference in the training loop
+    (train.py:96-103).  Forward keeps the activations inside the native model (pfann_model_train_forward), backward
+    runs pfann_model_train_backward and reads one gradient per parameter in the reference's element order.  The input
+    (the log-mel, nothing learnable upstream of it) gets no gradient."""
+
+    @staticmethod
+    def forward(ctx, net, x, norm, *params):
+        d, h, u, F, T = net.dims
+        dev = _lib.device_index(x)
+        hnd = net.native_handle(dev, training=True)
+        _lib.use_torch_stream(dev)
+        xf = x.detach().reshape(-1, F, T).to(torch.float32).contiguous()
+        z = torch.empty((xf.shape[0], d), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().pfann_model_train_forward(hnd, _lib.ptr(xf), xf.shape[0], int(bool(norm)), _lib.ptr(z)),
+                   'pfann_model_train_forward')
+        ctx.net, ctx.dev, ctx.hnd, ctx.norm, ctx.keep = net, dev, hnd, int(bool(norm)), xf
+        ctx.names = [n for n, _ in net.named_parameters()]
+        ctx.shapes = [(tuple(p.shape), p.dtype) for p in params]
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        L = _lib.lib()
+        _lib.use_torch_stream(ctx.dev)
+        dz = dz.to(torch.float32).contiguous()
+        _lib.check(L.pfann_model_train_backward(ctx.hnd, _lib.ptr(dz), ctx.norm), 'pfann_model_train_backward')
+        grads = []
+        for name, (shape, dtype), need in zip(ctx.names, ctx.shapes, ctx.needs_input_grad[3:]):
+            if not need:
+                grads.append(None)
+                continue
+            g = torch.empty(shape, dtype=torch.float32, device=dz.device)
+            _lib.check(L.pfann_model_get_grad(ctx.hnd, name.encode(), _lib.ptr(g), g.numel()), 'pfann_model_get_grad')
+            grads.append(g.to(dtype))
+        return (None, None, None) + tuple(grads)
+
+
 class FpNetwork(Module):
     """model.py:132-153.  ``params`` is ``params['model']`` of the JSON config; the extra optional key
     ``b200_precision`` ('bf16' tensor-core path, default; 'fp32' CUDA-core validation path) picks the kernels.
@@ -98,12 +136,17 @@ class FpNetwork(Module):
         self._handles = {}     # device -> (handle, weights fingerprint)
 
     # -- native handle management ------------------------------------------------------------------
-    def _fingerprint(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters()) + (self.precision, self.chunk)
+    def _fingerprint(self, training=False):
+        # the training kernels are fp32: a separate native model, so that eval() between epochs (validation,
+        # train.py:112-140) keeps the tensor-core one
+        return tuple((p.data_ptr(), p._version) for p in self.parameters()) + (
+            _lib.PRECISION_FP32 if training else self.precision, self.chunk)
 
-    def native_handle(self, device):
+    def native_handle(self, device, training=False):
         """pfann_model* for `device`, (re)built when the parameters changed since the last call."""
-        fp = self._fingerprint()
+        fp = self._fingerprint(training)
+        precision = fp[-2]
+        device = (device, 'train') if training else device
         ent = self._handles.get(device)
         if ent is not None and ent[1] == fp:
             return ent[0]
@@ -112,7 +155,7 @@ class FpNetwork(Module):
             d, h, u, F, T = self.dims
             hnd = ctypes.c_void_p()
             st = (ctypes.c_int * 16)(*[v for pair in self.f.strides for v in pair])
-            _lib.check(L.pfann_model_create_ex(_lib.ctx(device), d, h, u, F, T, int(self.fuller),
+            _lib.check(L.pfann_model_create_ex(_lib.ctx(device[0] if training else device), d, h, u, F, T, int(self.fuller),
                                                {'ReLU': 0, 'ELU': 1}[self.activation], int(self.relu_after_bn), st,
                                                ctypes.byref(hnd)), 'pfann_model_create_ex')
         else:
@@ -122,7 +165,7 @@ class FpNetwork(Module):
             _lib.check(L.pfann_model_set_param(hnd, name.encode(), _lib.ptr(t), t.numel()), 'pfann_model_set_param')
         if t.is_cuda:
             torch.cuda.synchronize(t.device)
-        _lib.check(L.pfann_model_finalize(hnd, self.precision), 'pfann_model_finalize')
+        _lib.check(L.pfann_model_finalize(hnd, precision), 'pfann_model_finalize')
         if self.chunk > 0:
             _lib.check(L.pfann_model_set_chunk(hnd, self.chunk), 'pfann_model_set_chunk')
         self._handles[device] = (hnd, fp)
@@ -131,6 +174,10 @@ class FpNetwork(Module):
     def forward(self, x, norm=True):
         d, h, u, F, T = self.dims
         assert x.shape[-2:] == (F, T), 'expected [B, %d, %d], got %s' % (F, T, tuple(x.shape))
+        if self.training and torch.is_grad_enabled():
+            params = [p for _, p in self.named_parameters()]
+            if any(p.requires_grad for p in params):
+                return _TrainStep.apply(self, x, norm, *params)        # train.py:99-103
         dev = _lib.device_index(x)
         hnd = self.native_handle(dev)
         _lib.use_torch_stream(dev)

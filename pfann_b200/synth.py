@@ -146,3 +146,32 @@ def synth_queries(db, key, n_queries, q_len=19, noise=1.0, seed=7):
     q = db[idx] + rng.standard_normal((n_queries, q_len, d), dtype=np.float32) * np.float32(noise / np.sqrt(d))
     q /= np.linalg.norm(q, axis=2, keepdims=True)
     return q.astype(np.float32), songs.astype(np.int64), offs
+
+
+# NAF-style stride schedule for F = 256, T = 32 (tools/gen_golden.py MODEL_VARIANTS['strides'])
+NAF_STRIDES = [[[1, 2], [2, 1]], [[1, 2], [2, 1]], [[1, 2], [2, 1]], [[1, 2], [2, 1]],
+               [[1, 1], [2, 1]], [[1, 2], [2, 1]], [[1, 1], [2, 1]], [[1, 1], [2, 1]]]
+# training-step cases: name -> (config, model option overrides, batch, weight seed)
+TRAIN_CASES = {
+    'tiny': ('tiny', {}, 8, 31),
+    'tiny_dw': ('tiny', {'fuller': False}, 8, 32),
+    'tiny_strides': ('tiny', {'strides': NAF_STRIDES}, 6, 33),
+    'n640d64': ('n640d64', {}, 4, 34),
+}
+
+
+def train_case_input(name):
+    """Seeded stand-in for a batch of log-mel segments [B][256][32] (pairs 2i, 2i+1 correlated like a clip and its
+    augmentation); shared by tools/gen_golden.py and the tests."""
+    cfg, opt, B, seed = TRAIN_CASES[name]
+    rng = np.random.Generator(np.random.PCG64(1000 + seed))
+    x = rng.standard_normal((B, 256, 32)).astype(np.float32) * np.float32(0.5)
+    x[1::2] = x[0::2] + np.float32(0.3) * x[1::2]
+    return x
+
+
+def grad_sample_index(numel, seed):
+    """Which elements of a gradient the fixture keeps (all of a small one, 512 seeded positions of a large one)."""
+    if numel <= 512:
+        return np.arange(numel)
+    return np.sort(np.random.Generator(np.random.PCG64(seed)).choice(numel, 512, replace=False))

@@ -134,3 +134,81 @@ def test_gpu_ingest_resample_and_mix_vs_oracle(dev, tmp_path):
     rows = np.concatenate([musicdata.frame_float(m, 8000, 4000) for m in monos])
     zr = ex.extract_segments(rows)
     assert (1 - (z * zr).sum(1)).max() < 1e-5
+
+
+def _train_net(name, dev):
+    from pfann_b200.model import FpNetwork
+    cfg, opt, B, seed = synth.TRAIN_CASES[name]
+    base = synth.read_config(cfg)
+    params = dict(base, model=dict(base['model'], **opt))
+    d, h, u, F, T = synth.model_dims(params)
+    net = FpNetwork(d, h, u, F, T, params['model']).to(dev)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_state_dict(params, seed=seed).items()})
+    return net.train(), params, seed
+
+
+@pytest.mark.parametrize('name', list(synth.TRAIN_CASES))
+def test_training_step_gradients_vs_reference_autograd(dev, golden_dir, name):
+    """train.py:96-103: z = model(x); loss = similarity_loss(z, tau); loss.backward().  Every parameter's gradient
+    against the reference network under torch autograd (golden: l2 norm + a seeded sample of elements), driven by the
+    reference's own dL/dz so that this checks the encoder backward alone."""
+    g = np.load(os.path.join(golden_dir, 'train_step.npz'))
+    net, params, seed = _train_net(name, dev)
+    x = torch.from_numpy(synth.train_case_input(name)).to(dev)
+    z = net(x)
+    assert z.requires_grad
+    np.testing.assert_allclose(z.detach().cpu().numpy(), g[name + '/z'], rtol=0, atol=2e-5)
+    z.backward(torch.from_numpy(g[name + '/dz']).to(dev))
+    worst = 0.0
+    for i, (k, p) in enumerate(net.named_parameters()):
+        assert p.grad is not None and p.grad.shape == p.shape, k
+        got = p.grad.detach().cpu().numpy().reshape(-1)
+        ref_norm = float(g['%s/norm/%s' % (name, k)])
+        ref_vals = g['%s/vals/%s' % (name, k)]
+        vals = got[synth.grad_sample_index(got.size, seed * 100 + i)]
+        # fp32 sums in another order than torch's: 1e-4 of the gradient's scale (its rms) plus 1e-4 relative
+        scale = ref_norm / np.sqrt(got.size)
+        err = np.abs(vals - ref_vals) / (1e-4 * scale + 1e-4 * np.abs(ref_vals) + 1e-9)
+        worst = max(worst, float(err.max()))
+        assert err.max() <= 1.0, (k, float(err.max()), scale)
+        assert abs(np.sqrt((got.astype(np.float64) ** 2).sum()) - ref_norm) <= 1e-4 * ref_norm + 1e-9, k
+    print('%s: worst gradient error %.3f of the tolerance' % (name, worst))
+
+
+def test_training_step_end_to_end_loss_and_optimizer(dev, golden_dir):
+    """The loop body of train.py:96-108 through the drop-in modules: loss matches the reference's, an optimizer step
+    on the received gradients lowers it, and eval() returns to the inference kernels with the updated weights."""
+    from pfann_b200.train import similarity_loss
+    g = np.load(os.path.join(golden_dir, 'train_step.npz'))
+    net, params, seed = _train_net('tiny', dev)
+    x = torch.from_numpy(synth.train_case_input('tiny')).to(dev)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    losses = []
+    for step in range(4):
+        opt.zero_grad()
+        loss = similarity_loss(net(x), params['tau'])
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert abs(losses[0] - float(g['tiny/loss'])) < 1e-4
+    assert losses[-1] < losses[0]
+    net.eval()
+    with torch.no_grad():
+        z_eval = net(x)
+    net.train()
+    z_train = net(x).detach()
+    np.testing.assert_allclose(z_eval.cpu().numpy(), z_train.cpu().numpy(), rtol=0, atol=2e-2)   # bf16 vs fp32 kernels
+    # frozen parameters get no gradient, like torch's
+    for p in net.f.parameters():
+        p.requires_grad_(False)
+    opt.zero_grad(set_to_none=True)
+    similarity_loss(net(x), params['tau']).backward()
+    assert all(p.grad is None for p in net.f.parameters()) and all(p.grad is not None for p in net.g.parameters())
+
+
+def test_training_forward_rejects_unsupported_options(dev):
+    from pfann_b200 import _lib
+    from pfann_b200.model import FpNetwork
+    net = FpNetwork(8, 32, 4, 256, 32, {'fuller': True, 'conv_activation': 'ELU'}).to(dev).train()
+    with pytest.raises(_lib.PfannError, match='ReLU'):
+        net(torch.zeros(2, 256, 32, device=dev))

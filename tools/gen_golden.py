@@ -197,6 +197,35 @@ def golden_train():
     np.savez_compressed(os.path.join(OUT, 'train.npz'), **out)
 
 
+def golden_train_step():
+    """One training step of the reference network under torch autograd (train.py:96-103 without the optimizer):
+    z = model(x), loss = similarity_loss(z, tau), loss.backward().  Per parameter the fixture keeps the gradient's
+    l2 norm and a seeded sample of its elements."""
+    from model import FpNetwork
+    loss_fn = _reference_function('train.py', 'similarity_loss')
+    out = {}
+    for name, (cfg, opt, B, seed) in synth.TRAIN_CASES.items():
+        base = synth.read_config(cfg)
+        params = dict(base, model=dict(base['model'], **opt))
+        d, h, u, F, T = synth.model_dims(params)
+        sd = synth.make_state_dict(params, seed=seed)
+        net = FpNetwork(d, h, u, F, T, params['model']).train()
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        x = torch.from_numpy(synth.train_case_input(name))
+        z = net(x)
+        z.retain_grad()
+        loss = loss_fn(z, params['tau'])
+        loss.backward()
+        out[name + '/z'] = z.detach().numpy()
+        out[name + '/dz'] = z.grad.numpy()
+        out[name + '/loss'] = np.float64(loss.item())
+        for i, (k, p) in enumerate(net.named_parameters()):
+            g = p.grad.numpy().reshape(-1)
+            out['%s/norm/%s' % (name, k)] = np.float64(np.sqrt((g.astype(np.float64) ** 2).sum()))
+            out['%s/vals/%s' % (name, k)] = g[synth.grad_sample_index(g.size, seed * 100 + i)].astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, 'train_step.npz'), **out)
+
+
 def golden_encoder(name, params, mel, seed):
     from model import FpNetwork
     d, h, u, F, T = synth.model_dims(params)
@@ -308,6 +337,7 @@ def main():
     golden_mel_variants(default)
     golden_model_variants(mel)
     golden_train()
+    golden_train_step()
     golden_db(faiss)
     golden_musicdata(default)
     for f in sorted(os.listdir(OUT)):
