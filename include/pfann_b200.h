@@ -165,6 +165,13 @@ int pfann_specaug_apply(pfann_ctx *ctx, float *x, const int32_t *rects, int64_t 
 /* Replaces NoiseData.add_noises arithmetic (datautil/noise.py:96-109): out[b] = x[b] + ratio_b * noise[b],
  * ratio_b = rms(x[b]) / rms(noise[b]) * 10^(-snr_db[b] / 20), rms clamped at sqrt(1e-12). */
 int pfann_snr_mix(pfann_ctx *ctx, const float *x, const float *noise, const float *snr_db, int64_t B, int n, float *out);
+/* Replaces the impulse-response augmentation of MusicSegmentDataset.__getitem__ (datautil/dataset_v2.py:157-163:
+ * irfft(rfft(x, n) * H_room * H_mic, n)[pad_start:segment_size], n >= len(x) + len(h), i.e. a causal LINEAR convolution)
+ * by the direct form: out[b][i] = sum_{k<L} h[b][k] x[b][out_start + i - k], x = 0 outside [0, n).  x [B][n], h [B][L]
+ * (the room and microphone responses of row b, already convolved with each other or applied in two calls),
+ * out [B][out_len].  fp32; differs from the fp32 FFT route by rounding only (test tolerance 2e-5 of the row's peak). */
+int pfann_ir_conv(pfann_ctx *ctx, const float *x, int64_t B, int n, const float *h, int L, float *out, int out_start,
+                  int out_len);
 
 /* Replaces the forward/backward of `y = model(mel(x))` ... `loss.backward()` in the training loop (train.py:96-103,
  * FpNetwork.forward model.py:148-153 under torch autograd), fp32.  train_forward computes z[B][d] from mel[B][F][T]
@@ -176,6 +183,10 @@ int pfann_snr_mix(pfann_ctx *ctx, const float *x, const float *noise, const floa
 int pfann_model_train_forward(pfann_model *m, const float *mel, int64_t B, int norm, float *z);
 int pfann_model_train_backward(pfann_model *m, const float *dz, int norm);
 int pfann_model_get_grad(pfann_model *m, const char *name, float *out, int64_t numel);
+/* optimizer.step() (train.py:103) changed the parameters: refresh one of them from DEVICE memory (the reference's
+ * element order) without the host round trip of pfann_model_set_param + pfann_model_finalize.  The model must have
+ * been finalized with PFANN_PRECISION_FP32 once; it then serves the training entry points and the fp32 forward. */
+int pfann_model_train_load_param(pfann_model *m, const char *name, const float *data, int64_t numel);
 
 /* ---- stage 3: database search + sequence score ------------------------------------------------- */
 

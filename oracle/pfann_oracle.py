@@ -339,3 +339,18 @@ def mix_mono(wav):
         if pow1 > pow2 * 1000:
             wav[1] *= -1
     return wav.mean(axis=0, dtype=np.float32)
+
+
+def apply_ir(x, responses, pad_start=0, segment_size=None):
+    """datautil/dataset_v2.py:157-163 in float64, direct form: rows of x convolved with their impulse responses one after
+    the other (the reference multiplies spectra of an FFT long enough that nothing wraps: a causal linear convolution),
+    samples [pad_start, segment_size) kept."""
+    x = np.asarray(x, np.float64)
+    end = x.shape[1] if segment_size is None else int(segment_size)
+    out = np.empty((x.shape[0], end - pad_start))
+    for b in range(x.shape[0]):
+        y = x[b]
+        for h in responses:
+            y = np.convolve(y, np.asarray(h[b], np.float64))[:end]
+        out[b] = y[pad_start:end]
+    return out

@@ -74,3 +74,37 @@ class TorchPort:
         for b in torch.split(rows, batch):
             out.append(self.encoder(self.mel(b)))
         return torch.cat(out)
+
+
+def similarity_loss(y, tau):
+    """train.py:41-52 with library ops (masked log-softmax instead of the per-row python loop; same numbers)."""
+    n = y.shape[0]
+    a = torch.matmul(y, y.T) / tau
+    a = a.masked_fill(torch.eye(n, dtype=torch.bool, device=y.device), float('-inf'))   # the row's own entry is left out
+    ls = F.log_softmax(a, dim=1)
+    idx = torch.arange(n, device=y.device)
+    return ls[idx, idx ^ 1].sum() / -n
+
+
+def train_step_cpu(port, b, tau, lr=1e-4):
+    """CPU baseline of one training step with the reference's library calls: dataset_v2.py:152-169 on the batch
+    b = {orig, aug, noise, snr, air, mic} (SNR mix noise.py:96-109, rfft * H * H -> irfft, interleave) -> mel -> encoder
+    under autograd -> NT-Xent -> backward -> Adam (train.py:78-104 without SpecAugment's draws).  Returns the loss."""
+    params = [p.requires_grad_(True) for p in port.sd.values()]
+    opt = torch.optim.Adam(params, lr=lr)
+    with torch.no_grad():
+        x, noise = b['aug'], b['noise']
+        vx = x.pow(2).mean(dim=1).clamp_min(1e-12).sqrt()
+        vn = noise.pow(2).mean(dim=1).clamp_min(1e-12).sqrt()
+        x = x + (vx / vn * torch.pow(10.0, -b['snr'] / 20.0))[:, None] * noise
+        n = 1024
+        while n < x.shape[1] + b['air'].shape[1] + b['mic'].shape[1]:
+            n *= 2
+        spec = torch.fft.rfft(x, n) * torch.fft.rfft(b['air'], n) * torch.fft.rfft(b['mic'], n)
+        x = torch.fft.irfft(spec, n)[..., :x.shape[1]]
+        g = port.mel(torch.stack([b['orig'], x], dim=1).flatten(0, 1))
+    opt.zero_grad()
+    loss = similarity_loss(port.encoder(g), tau)
+    loss.backward()
+    opt.step()
+    return float(loss.detach())

@@ -68,9 +68,11 @@ def _declare(L):
     L.pfann_resample_frac.argtypes = [vp, vp, c_int, c_int64, c_int, c_int, vp]
     L.pfann_mix_mono.argtypes = [vp, vp, c_int, c_int64, vp]
     L.pfann_ntxent.argtypes = [vp, vp, c_int, c_int, c_float, vp, vp]
+    L.pfann_ir_conv.argtypes = [vp, vp, c_int64, c_int, vp, c_int, vp, c_int, c_int]
     L.pfann_model_train_forward.argtypes = [vp, vp, c_int64, c_int, vp]
     L.pfann_model_train_backward.argtypes = [vp, vp, c_int]
     L.pfann_model_get_grad.argtypes = [vp, c_char_p, vp, c_int64]
+    L.pfann_model_train_load_param.argtypes = [vp, c_char_p, vp, c_int64]
     L.pfann_specaug_apply.argtypes = [vp, vp, vp, c_int64, c_int, c_int]
     L.pfann_snr_mix.argtypes = [vp, vp, vp, vp, c_int64, c_int, vp]
     L.pfann_count_segments.argtypes = [POINTER(c_int64), c_int, c_int, c_int]

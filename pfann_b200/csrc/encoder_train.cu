@@ -39,6 +39,7 @@ struct TrainState {
     DevBuf hp, hr, hdr;                    // head: pre-ELU [B][d u], pre-normalisation output [B][d], its gradient
     DevBuf gW[16], gB[16], gG[16], gBe[16], gw1, gb1, gw2, gb2;   // parameter gradients (kernel layouts)
     float *wt[16] = {};                    // transposed weights [(tap, o)][c] for the data gradient
+    bool wt_valid[16] = {};
     const float *mel = nullptr;
     bool have_grads = false;
 };
@@ -107,7 +108,8 @@ __global__ void normalize_bwd_kernel(const float *dz, const float *r, float *dr,
     if (g < d) dr[b * d + g] = (gv - rv * (t2 / (nrm * nrm))) / nrm;
 }
 
-// one CTA per output dimension g, one thread per hidden unit j: sums over the batch in registers (no atomics);
+// CTA = (output dimension g, slice of the batch), one thread per hidden unit j: sums over the slice in registers, then
+// one atomic per parameter element and CTA;
 // dx[b][g v + i] = sum_j dp[b][g][j] w1[g][j][i] via a warp reduction
 __global__ void head_bwd_kernel(const float *x, const float *p, const float *dr, const float *w1, const float *w2, int B, int d,
                                 int h, int u, float *gw1, float *gb1, float *gw2, float *gb2, float *dx) {
@@ -119,7 +121,9 @@ __global__ void head_bwd_kernel(const float *x, const float *p, const float *dr,
         w1r[i] = (j < u && i < v) ? w1[(size_t)(g * u + j) * v + i] : 0.f;
     }
     const float w2v = j < u ? w2[g * u + j] : 0.f;
-    for (int b = 0; b < B; b++) {
+    const int per = (B + gridDim.y - 1) / gridDim.y;
+    const int bb0 = blockIdx.y * per, bb1 = (bb0 + per) < B ? (bb0 + per) : B;
+    for (int b = bb0; b < bb1; b++) {
         const float drv = dr[(size_t)b * d + g];
         const float pv = j < u ? p[((size_t)b * d + g) * u + j] : 0.f;
         const float e = pv > 0.f ? pv : expm1f(pv);
@@ -140,11 +144,11 @@ __global__ void head_bwd_kernel(const float *x, const float *p, const float *dr,
         }
     }
     if (j < u) {
-        for (int i = 0; i < v && i < 16; i++) gw1[(size_t)(g * u + j) * v + i] = aw1[i];
-        gb1[g * u + j] = ab1;
-        gw2[g * u + j] = aw2;
+        for (int i = 0; i < v && i < 16; i++) atomicAdd(gw1 + (size_t)(g * u + j) * v + i, aw1[i]);
+        atomicAdd(gb1 + g * u + j, ab1);
+        atomicAdd(gw2 + g * u + j, aw2);
     }
-    if (j == 0) gb2[g] = ab2;
+    if (j == 0) atomicAdd(gb2 + g, ab2);
 }
 
 // ---- LayerNorm + ReLU backward ----
@@ -301,30 +305,47 @@ __global__ void dw_bwd_data_kernel(const float *dY, const float *W /*[C][ntaps]*
     dX[i] = acc;
 }
 
-// thread = (channel c, slice of positions): partial sums over its slice, then atomics (C * ntaps addresses)
-__global__ void dw_bwd_w_kernel(const float *X, const float *dY, long long rows /*nb*Fo*To*/, int C, int Fi, int Ti, int Fo,
-                                int To, int ntaps, int off0, int off1, int off2, int stride, float *gW, float *gB) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+// CTA = (256 / CW row lanes) x (CW channels) over a slice of output positions: coalesced along the channels, partial
+// sums in registers, row lanes folded through shared memory, then C * ntaps atomics per CTA
+__global__ void __launch_bounds__(256) dw_bwd_w_kernel(const float *X, const float *dY, long long rows /*nb*Fo*To*/, int C, int CW,
+                                                       int Fi, int Ti, int Fo, int To, int ntaps, int off0, int off1, int off2,
+                                                       int stride, float *gW, float *gB) {
+    __shared__ float sh[4][256];
+    const int lane_c = threadIdx.x % CW, lane_r = threadIdx.x / CW, RL = 256 / CW;
+    const int c = blockIdx.x * CW + lane_c;
     const int offs[3] = {off0, off1, off2};
     const long long per = (rows + gridDim.y - 1) / gridDim.y;
     const long long r0 = (long long)blockIdx.y * per, r1 = (r0 + per) < rows ? (r0 + per) : rows;
     float aw[3] = {0.f, 0.f, 0.f}, ab = 0.f;
-    for (long long m = r0; m < r1; m++) {
-        const int to = (int)(m % To);
-        const long long r = m / To;
-        const int fo = (int)(r % Fo);
-        const long long b = r / Fo;
-        const float g = dY[m * C + c];
-        ab += g;
-        for (int j = 0; j < ntaps; j++) {
-            const int fi = stride * fo + offs[j];
-            if (fi >= 0 && fi < Fi) aw[j] = fmaf(g, X[((b * Fi + fi) * Ti + to) * (long long)C + c], aw[j]);
+    if (c < C) {
+        for (long long m = r0 + lane_r; m < r1; m += RL) {
+            const int to = (int)(m % To);
+            const long long r = m / To;
+            const int fo = (int)(r % Fo);
+            const long long b = r / Fo;
+            const float g = __ldg(dY + m * C + c);
+            ab += g;
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                if (j < ntaps) {
+                    const int fi = stride * fo + offs[j];
+                    if (fi >= 0 && fi < Fi) aw[j] = fmaf(g, __ldg(X + ((b * Fi + fi) * Ti + to) * (long long)C + c), aw[j]);
+                }
+            }
         }
     }
-    for (int j = 0; j < ntaps; j++) atomicAdd(gW + c * ntaps + j, aw[j]);
-    atomicAdd(gB + c, ab);
+    sh[0][threadIdx.x] = aw[0]; sh[1][threadIdx.x] = aw[1]; sh[2][threadIdx.x] = aw[2]; sh[3][threadIdx.x] = ab;
+    __syncthreads();
+    if (lane_r == 0 && c < C) {
+        float t[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int q = 0; q < RL; q++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) t[e] += sh[e][q * CW + lane_c];
+        for (int jj = 0; jj < ntaps; jj++) atomicAdd(gW + c * ntaps + jj, t[jj]);
+        atomicAdd(gB + c, t[3]);
+    }
 }
+
 
 // kernel layouts -> the reference's (PyTorch) element order, for device-side readers of the gradients
 // mode 0: dense conv [(j, c)][o] -> [o][c][3];  1: depthwise [o][ntaps] -> [o][1][3];  2: LayerNorm [f][t][o] -> [o][f][t]
@@ -356,6 +377,37 @@ __global__ void grad_layout_kernel(const float *src, float *dst, long long total
     dst[i] = v;
 }
 
+// the reference's element order -> kernel layouts (inverse of grad_layout_kernel), for parameters that live on the device
+__global__ void param_layout_kernel(const float *src, float *dst, long long total, int mode, int Ci, int Co, int ntaps, int k0,
+                                    int k1, int k2, int Fo, int To) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over dst
+    if (i >= total) return;
+    const int tk[3] = {k0, k1, k2};
+    if (mode == 2) {            // [f][t][o] <- [o][f][t]
+        const int o = (int)(i % Co);
+        const long long r = i / Co;
+        dst[i] = src[(long long)o * Fo * To + r];
+    } else if (mode == 1) {     // [o][ntaps] <- [o][1][3]
+        const int j = (int)(i % ntaps);
+        dst[i] = src[(i / ntaps) * 3 + tk[j]];
+    } else {                    // [(j, c)][o] <- [o][c][3]
+        const int o = (int)(i % Co);
+        const long long r = i / Co;
+        const int c = (int)(r % Ci), j = (int)(r / Ci);
+        dst[i] = src[((long long)o * Ci + c) * 3 + tk[j]];
+    }
+}
+
+// wt[(j, o)][c] <- w_kn[(j, c)][o]
+__global__ void wt_kernel(const float *w_kn, float *wt, long long total, int Ci, int Co) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over wt
+    if (i >= total) return;
+    const int c = (int)(i % Ci);
+    const long long r = i / Ci;
+    const int o = (int)(r % Co), j = (int)(r / Co);
+    wt[i] = w_kn[((long long)j * Ci + c) * Co + o];
+}
+
 TrainState *state(Model *m) {
     if (m->train_state == nullptr) m->train_state = new TrainState();
     return reinterpret_cast<TrainState *>(m->train_state);
@@ -373,10 +425,7 @@ namespace pfann {
 void train_invalidate(Model *m) {
     TrainState *t = reinterpret_cast<TrainState *>(m->train_state);
     if (!t) return;
-    for (int i = 0; i < 16; i++) {
-        cudaFree(t->wt[i]);
-        t->wt[i] = nullptr;
-    }
+    for (int i = 0; i < 16; i++) t->wt_valid[i] = false;
     t->B = 0;
     t->have_grads = false;
 }
@@ -447,10 +496,10 @@ int pfann_model_train_backward(pfann_model *hm, const float *dz, int norm) {
     const int B = t->B, d = m->d, h = m->h, u = m->u, v = h / d;
     // ---- head ----
     PF_TRY(t->hdr.ensure((size_t)B * d * 4));
-    PF_TRY(t->gw1.ensure((size_t)d * u * v * 4));
-    PF_TRY(t->gb1.ensure((size_t)d * u * 4));
-    PF_TRY(t->gw2.ensure((size_t)d * u * 4));
-    PF_TRY(t->gb2.ensure((size_t)d * 4));
+    PF_TRY(zero(ctx, t->gw1, (size_t)d * u * v * 4));
+    PF_TRY(zero(ctx, t->gb1, (size_t)d * u * 4));
+    PF_TRY(zero(ctx, t->gw2, (size_t)d * u * 4));
+    PF_TRY(zero(ctx, t->gb2, (size_t)d * 4));
     size_t max_act = 0;
     for (int i = 0; i < 16; i++)
         if ((size_t)m->conv[i].g.out_per_sample() > max_act) max_act = (size_t)m->conv[i].g.out_per_sample();
@@ -460,7 +509,9 @@ int pfann_model_train_backward(pfann_model *hm, const float *dz, int norm) {
     {
         ProfScope ps(ctx, K_HEAD, 33);
         normalize_bwd_kernel<<<B, threads, 64 * sizeof(float), st>>>(dz, t->hr.as<float>(), t->hdr.as<float>(), d, norm);
-        head_bwd_kernel<<<d, 32, 0, st>>>(t->X[15].as<float>(), t->hp.as<float>(), t->hdr.as<float>(), m->w1, m->w2, B, d, h, u,
+        int hb = (4 * ctx->sm_count + d - 1) / d;
+        if (hb > B) hb = B;
+        head_bwd_kernel<<<dim3(d, hb), 32, 0, st>>>(t->X[15].as<float>(), t->hp.as<float>(), t->hdr.as<float>(), m->w1, m->w2, B, d, h, u,
                                           t->gw1.as<float>(), t->gb1.as<float>(), t->gw2.as<float>(), t->gb2.as<float>(),
                                           t->dA.as<float>());
         ctx->launches += 2;
@@ -495,9 +546,15 @@ int pfann_model_train_backward(pfann_model *hm, const float *dz, int norm) {
         const long long rows = (long long)B * g.rows_per_sample();
         ProfScope ps(ctx, K_CONV_CC, i);
         if (g.depthwise) {
-            dim3 gw(cdiv(g.Co, 128), 64);
-            dw_bwd_w_kernel<<<gw, 128, 0, st>>>(xin, dcur, rows, g.Co, g.Fi, g.Ti, g.Fo, g.To, g.ntaps, g.tap_off[0], g.tap_off[1],
-                                                g.tap_off[2], g.stride, t->gW[i].as<float>(), t->gB[i].as<float>());
+            int CW = 32;
+            while (CW < 256 && CW < g.Co) CW <<= 1;
+            const int cx = (int)cdiv(g.Co, CW);
+            long long ys = (8LL * ctx->sm_count + cx - 1) / cx;
+            if (ys > (long long)cdiv(rows, 256 / CW)) ys = cdiv(rows, 256 / CW);
+            if (ys > 65535) ys = 65535;
+            dw_bwd_w_kernel<<<dim3(cx, (unsigned)ys), 256, 0, st>>>(xin, dcur, rows, g.Co, CW, g.Fi, g.Ti, g.Fo, g.To, g.ntaps,
+                                                                   g.tap_off[0], g.tap_off[1], g.tap_off[2], g.stride,
+                                                                   t->gW[i].as<float>(), t->gB[i].as<float>());
             const long long total = (long long)B * g.Fi * g.Ti * g.Ci;
             dw_bwd_data_kernel<<<cdiv(total, 256), 256, 0, st>>>(dcur, cw.w_kn, dnext, total, g.Co, g.Fi, g.Ti, g.Fo, g.ntaps,
                                                                  g.tap_off[0], g.tap_off[1], g.tap_off[2], g.stride);
@@ -518,17 +575,12 @@ int pfann_model_train_backward(pfann_model *hm, const float *dz, int norm) {
             conv_bwd_w_kernel<<<dim3(kt, nt, splits), 256, 0, st>>>(a);
             ctx->launches++;
             if (i > 0) {
-                if (t->wt[i] == nullptr) {   // [(tap, o)][c] from w_kn [(tap, c)][o], once per finalize
-                    std::vector<float> hw((size_t)g.K() * g.Co), ht((size_t)g.ntaps * g.Co * g.Ci);
-                    PF_CUDA(cudaMemcpyAsync(hw.data(), cw.w_kn, hw.size() * 4, cudaMemcpyDeviceToHost, st));
-                    PF_CUDA(cudaStreamSynchronize(st));
-                    for (int j = 0; j < g.ntaps; j++)
-                        for (int c = 0; c < g.Ci; c++)
-                            for (int o = 0; o < g.Co; o++)
-                                ht[((size_t)j * g.Co + o) * g.Ci + c] = hw[((size_t)j * g.Ci + c) * g.Co + o];
-                    PF_CUDA(cudaMalloc(&t->wt[i], ht.size() * 4));
-                    PF_CUDA(cudaMemcpyAsync(t->wt[i], ht.data(), ht.size() * 4, cudaMemcpyHostToDevice, st));
-                    PF_CUDA(cudaStreamSynchronize(st));
+                if (!t->wt_valid[i]) {   // [(tap, o)][c] from w_kn [(tap, c)][o], once per parameter update
+                    const long long total = (long long)g.K() * g.Co;
+                    if (t->wt[i] == nullptr) PF_CUDA(cudaMalloc(&t->wt[i], (size_t)total * 4));
+                    wt_kernel<<<cdiv(total, 256), 256, 0, st>>>(cw.w_kn, t->wt[i], total, g.Ci, g.Co);
+                    ctx->launches++;
+                    t->wt_valid[i] = true;
                 }
                 PF_TRY(enc_conv_bwd_data_f32(m, g, dcur, t->wt[i], dnext, B));
             }
@@ -537,6 +589,58 @@ int pfann_model_train_backward(pfann_model *hm, const float *dz, int norm) {
         float *tmp = dcur; dcur = dnext; dnext = tmp;
     }
     t->have_grads = true;
+    return PFANN_OK;
+}
+
+// Parameter refresh for the training loop: `data` (DEVICE, the reference's element order) goes straight into the
+// kernel layouts of a finalized fp32 model -- one small kernel per parameter on the context's stream, no host copies.
+int pfann_model_train_load_param(pfann_model *hm, const char *name, const float *data, int64_t numel) {
+    PF_CHECK(hm && name && data, PFANN_ERR_ARG, "pfann_model_train_load_param: bad argument");
+    Model *m = reinterpret_cast<Model *>(hm);
+    PF_CHECK(m->precision == PFANN_PRECISION_FP32, PFANN_ERR_STATE,
+             "pfann_model_train_load_param: the model must be finalized with PFANN_PRECISION_FP32 first");
+    PF_CHECK(is_device_ptr(data), PFANN_ERR_ARG, "pfann_model_train_load_param: device pointers only");
+    PF_CUDA(cudaSetDevice(m->ctx->device));
+    cudaStream_t st = m->ctx->stream;
+    TrainState *t = state(m);
+    const std::string key(name);
+    int l = -1;
+    char cn[16] = {0}, pn[16] = {0};
+    float *dst = nullptr;
+    long long total = 0, expect = 0;
+    int mode = -1;
+    const ConvGeom *g = nullptr;
+    if (sscanf(name, "f.convs.%d.%15[a-z0-9].%15s", &l, cn, pn) == 3 && l >= 0 && l < 8) {
+        const std::string c(cn), p(pn);
+        const int i = 2 * l + ((c == "conv2" || c == "ln2") ? 1 : 0);
+        ConvWeights &cw = m->conv[i];
+        g = &cw.g;
+        if ((c == "conv1" || c == "conv2") && p == "weight") {
+            dst = cw.w_kn; mode = g->depthwise ? 1 : 0;
+            total = g->depthwise ? (long long)g->Co * g->ntaps : (long long)g->K() * g->Co;
+            expect = (long long)g->Co * (g->depthwise ? 1 : g->Ci) * 3;
+            t->wt_valid[i] = false;
+        } else if ((c == "conv1" || c == "conv2") && p == "bias") {
+            dst = cw.bias; total = expect = g->Co;
+        } else if ((c == "ln1" || c == "ln2") && (p == "weight" || p == "bias")) {
+            dst = p == "weight" ? cw.gamma : cw.beta; mode = 2; total = expect = g->out_per_sample();
+        }
+    } else if (key == "g.linear1.weight") { dst = m->w1; total = expect = (long long)m->d * m->u * (m->h / m->d);
+    } else if (key == "g.linear1.bias") { dst = m->b1; total = expect = (long long)m->d * m->u;
+    } else if (key == "g.linear2.weight") { dst = m->w2; total = expect = (long long)m->d * m->u;
+    } else if (key == "g.linear2.bias") { dst = m->b2; total = expect = m->d; }
+    PF_CHECK(dst != nullptr, PFANN_ERR_ARG, "pfann_model_train_load_param: unknown parameter '%s'", name);
+    PF_CHECK(expect == numel, PFANN_ERR_ARG, "pfann_model_train_load_param: '%s' has %lld elements, got %lld", name, expect,
+             (long long)numel);
+    if (mode < 0) {
+        PF_CUDA(cudaMemcpyAsync(dst, data, (size_t)total * 4, cudaMemcpyDeviceToDevice, st));
+    } else {
+        param_layout_kernel<<<cdiv(total, 256), 256, 0, st>>>(data, dst, total, mode, g->Ci, g->Co, g->ntaps, g->tap_k[0],
+                                                              g->tap_k[1], g->tap_k[2], g->Fo, g->To);
+        m->ctx->launches++;
+        PF_CUDA(cudaGetLastError());
+    }
+    t->have_grads = false;
     return PFANN_OK;
 }
 

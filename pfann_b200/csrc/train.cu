@@ -165,6 +165,63 @@ __global__ void __launch_bounds__(256) snr_mix_kernel(const float *x, const floa
     for (int i = threadIdx.x; i < n; i += 256) out[b * n + i] = fmaf(ratio, nb[i], xb[i]);
 }
 
+
+// ---- impulse-response convolution (datautil/dataset_v2.py:157-163) ----
+// The reference multiplies rfft(x, n) by the spectra of a room and a microphone response and keeps samples
+// [pad_start, segment_size) of the inverse transform; n is chosen >= len(x) + len(h1) + len(h2) (dataset_v2.py:51-58), so
+// the circular product IS the causal linear convolution.  Here: the direct form, register-tiled FIR --
+//     out[b][i] = sum_{k < L} h[b][k] * x[b][out_start + i - k]        (x = 0 outside [0, n))
+// CTA = 1024 outputs of one row, thread = 8 consecutive outputs; per chunk of 256 taps the CTA stages the taps and the
+// 1280-sample window they touch; per 8 taps a thread reads 16 window samples (4 LDS.128) + 8 taps for 64 FMAs.
+constexpr int IR_OUT = 1024, IR_TK = 256;
+__global__ void __launch_bounds__(128) ir_conv_kernel(const float *x, int n, const float *h, int L, float *out, int out_start,
+                                                      int out_len) {
+    __shared__ __align__(16) float h_s[IR_TK];
+    __shared__ __align__(16) float x_s[IR_OUT + IR_TK];
+    const int b = blockIdx.y, base = blockIdx.x * IR_OUT, tid = threadIdx.x;
+    const float *xb = x + (long long)b * n, *hb = h + (long long)b * L;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = 0.f;
+    const int g_last = out_start + min(base + IR_OUT, out_len) - 1;   // last output this CTA owns
+    const int k_end = min(L, g_last + 1);                             // taps beyond it only see x[< 0]
+    for (int k0 = 0; k0 < k_end; k0 += IR_TK) {
+        const int ws = out_start + base - k0 - IR_TK;
+        __syncthreads();
+        for (int j = tid; j < IR_TK; j += 128) h_s[j] = (k0 + j < L) ? __ldg(hb + k0 + j) : 0.f;
+        for (int j = tid; j < IR_OUT + IR_TK; j += 128) {
+            const int gi = ws + j;
+            x_s[j] = (gi >= 0 && gi < n) ? __ldg(xb + gi) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int kk8 = 0; kk8 < IR_TK; kk8 += 8) {
+            float xs[16], hs[8];
+            const float4 *xp = reinterpret_cast<const float4 *>(x_s + 8 * tid - kk8 + IR_TK - 8);
+            const float4 *hp = reinterpret_cast<const float4 *>(h_s + kk8);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const float4 v = xp[q];
+                xs[4 * q] = v.x; xs[4 * q + 1] = v.y; xs[4 * q + 2] = v.z; xs[4 * q + 3] = v.w;
+            }
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const float4 v = hp[q];
+                hs[4 * q] = v.x; hs[4 * q + 1] = v.y; hs[4 * q + 2] = v.z; hs[4 * q + 3] = v.w;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; e++)
+#pragma unroll
+                for (int i = 0; i < 8; i++) acc[i] = fmaf(hs[e], xs[i - e + 8], acc[i]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int o = base + 8 * tid + i;
+        if (o < out_len) out[(long long)b * out_len + o] = acc[i];
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -214,6 +271,21 @@ int pfann_snr_mix(pfann_ctx *hctx, const float *x, const float *noise, const flo
     PF_CUDA(cudaSetDevice(ctx->device));
     ProfScope ps(ctx, K_MISC);
     snr_mix_kernel<<<(unsigned)B, 256, 0, ctx->stream>>>(x, noise, snr_db, out, n);
+    ctx->launches++;
+    PF_CUDA(cudaGetLastError());
+    return PFANN_OK;
+}
+
+int pfann_ir_conv(pfann_ctx *hctx, const float *x, int64_t B, int n, const float *h, int L, float *out, int out_start,
+                  int out_len) {
+    PF_CHECK(hctx && B >= 0 && B <= 65535 && n > 0 && L > 0 && out_start >= 0 && out_len > 0 && (B == 0 || (x && h && out)),
+             PFANN_ERR_ARG, "pfann_ir_conv: bad argument");
+    if (B == 0) return PFANN_OK;
+    PF_CHECK(is_device_ptr(x) && is_device_ptr(h) && is_device_ptr(out), PFANN_ERR_ARG, "pfann_ir_conv: device pointers only");
+    Ctx *ctx = reinterpret_cast<Ctx *>(hctx);
+    PF_CUDA(cudaSetDevice(ctx->device));
+    ProfScope ps(ctx, K_MISC);
+    ir_conv_kernel<<<dim3(cdiv(out_len, IR_OUT), (unsigned)B), 128, 0, ctx->stream>>>(x, n, h, L, out, out_start, out_len);
     ctx->launches++;
     PF_CUDA(cudaGetLastError());
     return PFANN_OK;

@@ -85,8 +85,8 @@ class _TrainStep(torch.autograd.Function):
     def forward(ctx, net, x, norm, *params):
         d, h, u, F, T = net.dims
         dev = _lib.device_index(x)
+        _lib.use_torch_stream(dev)          # before the handle: a parameter refresh is ordered after optimizer.step()
         hnd = net.native_handle(dev, training=True)
-        _lib.use_torch_stream(dev)
         xf = x.detach().reshape(-1, F, T).to(torch.float32).contiguous()
         z = torch.empty((xf.shape[0], d), dtype=torch.float32, device=x.device)
         _lib.check(_lib.lib().pfann_model_train_forward(hnd, _lib.ptr(xf), xf.shape[0], int(bool(norm)), _lib.ptr(z)),
@@ -160,6 +160,14 @@ class FpNetwork(Module):
                                                ctypes.byref(hnd)), 'pfann_model_create_ex')
         else:
             hnd = ent[0]
+            if training and all(p.is_cuda for p in self.parameters()):
+                # optimizer.step() moved the weights: refresh the kernel layouts on the device, no host round trip
+                for name, p in self.named_parameters():
+                    t = p.detach().to(torch.float32).contiguous()
+                    _lib.check(L.pfann_model_train_load_param(hnd, name.encode(), _lib.ptr(t), t.numel()),
+                               'pfann_model_train_load_param')
+                self._handles[device] = (hnd, fp)
+                return hnd
         for name, p in self.state_dict().items():
             t = p.detach().to(torch.float32).contiguous()
             _lib.check(L.pfann_model_set_param(hnd, name.encode(), _lib.ptr(t), t.numel()), 'pfann_model_set_param')

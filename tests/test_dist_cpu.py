@@ -152,3 +152,40 @@ def test_key_packing_orders_like_score_desc_id_asc():
     d2, i2 = unpack_keys(srt)
     assert list(i2[0][:2]) == [3, 9] and i2[0][-1] == -1 and d2[0][0] == np.float32(0.5)
     assert np.array_equal(unpack_keys(keys)[0][0][:5].view(np.uint32), D[0][:5].view(np.uint32))   # bit-exact scores
+
+
+def _grad_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    import torch
+    from pfann_b200.train import allreduce_gradients
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Tanh(), torch.nn.Linear(7, 3))
+    x = torch.arange(8 * 5, dtype=torch.float32).reshape(8, 5) / 40
+    net(x[rank * 4:(rank + 1) * 4]).pow(2).sum().backward()          # each rank: its rows of a sum-type loss
+    net[2].bias.grad = None                                          # parameters without a gradient are skipped
+    allreduce_gradients(list(net.parameters()))
+    if rank == 0:
+        ret['grads'] = [None if p.grad is None else p.grad.numpy().copy() for p in net.parameters()]
+    dist.destroy_process_group()
+
+
+def test_gradient_sum_over_ranks_equals_the_whole_batch():
+    """train step at world 2 (BASELINE configs[4]): one flat all-reduce(SUM) of the per-rank gradients of a loss that
+    is a sum over rows gives the single-process gradient on all rows."""
+    import torch
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_grad_worker, args=(2, port, ret), nprocs=2, join=True)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Tanh(), torch.nn.Linear(7, 3))
+    x = torch.arange(8 * 5, dtype=torch.float32).reshape(8, 5) / 40
+    net(x).pow(2).sum().backward()
+    got = ret['grads']
+    assert got[3] is None
+    for g, p in zip(got[:3], list(net.parameters())[:3]):
+        np.testing.assert_allclose(g, p.grad.numpy(), rtol=1e-5, atol=1e-6)

@@ -214,3 +214,16 @@ def test_mix_mono_fake_stereo_rule():
     assert np.array_equal(orc.mix_mono(np.stack([a, -a])), a)                 # opposite phase: channel 1 is flipped
     b = rng.standard_normal(1000).astype(np.float32)
     assert np.array_equal(orc.mix_mono(np.stack([a, b])), ((a + b) / 2).astype(np.float32))
+
+
+def test_impulse_response_convolution_vs_reference_fft(golden_dir):
+    """oracle.apply_ir (float64 direct form) against the reference's rfft * H_air * H_mic -> irfft -> crop
+    (dataset_v2.py:157-163 executed by tools/gen_golden.py): the FFT is long enough that nothing wraps."""
+    g = np.load(os.path.join(golden_dir, 'train.npz'))
+    x = synth.synth_segments(3, seed=8, seg=8100)
+    got = orc.apply_ir(x, [g['ir_air'], g['ir_mic']], 100, 8100)
+    assert got.shape == g['ir_out'].shape == (3, 8000)
+    assert np.abs(got - g['ir_out']).max() <= 1e-6 * np.abs(g['ir_out']).max()
+    # one response, no crop: plain causal convolution truncated to the input length
+    one = orc.apply_ir(x[:1, :50], [g['ir_mic'][:1, :7]])
+    np.testing.assert_allclose(one[0], np.convolve(x[0, :50].astype(np.float64), g['ir_mic'][0, :7])[:50], atol=1e-12)

@@ -194,6 +194,21 @@ def golden_train():
     torch.manual_seed(77)
     x = torch.arange(2 * 256 * 32, dtype=torch.float32).reshape(2, 256, 32) + 1
     out['specaug_x'] = sa.augment(x).numpy()
+    # impulse responses: the statements of datautil/dataset_v2.py:51-58,157-163 and ir.py:37-38,72-73 executed as
+    # written (the classes around them need the AIR / microphone data sets, which are not available offline)
+    rng = np.random.Generator(np.random.PCG64(41))
+    pad_start, segment_size_total = 100, 8100                       # pad_start + segment_size (dataset_v2.py:133)
+    x_aug = torch.from_numpy(synth.synth_segments(3, seed=8, seg=segment_size_total))
+    air = (rng.standard_normal((3, 8000)) * np.exp(-np.arange(8000) / 900.0)).astype(np.float32)
+    mic = (rng.standard_normal((3, 4000)) * np.exp(-np.arange(4000) / 60.0)).astype(np.float32)
+    fftconv_n = 1024
+    while fftconv_n < segment_size_total + 8000 + 4000:
+        fftconv_n *= 2
+    spec = torch.fft.rfft(x_aug, fftconv_n)
+    spec *= torch.fft.rfft(torch.from_numpy(air), fftconv_n)
+    spec *= torch.fft.rfft(torch.from_numpy(mic), fftconv_n)
+    y = torch.fft.irfft(spec, fftconv_n)[..., pad_start:segment_size_total]
+    out['ir_air'], out['ir_mic'], out['ir_out'] = air, mic, y.numpy().astype(np.float32)
     np.savez_compressed(os.path.join(OUT, 'train.npz'), **out)
 
 
