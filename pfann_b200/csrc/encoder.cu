@@ -480,10 +480,14 @@ __global__ void to_nchw_kernel(const InT *X, float *out, long long total, int C,
 // ------------------------------------------------------------------------------------------------
 // HG groups of dp threads per CTA; every group handles HS samples per iteration so that one shared-memory read of a
 // weight feeds HS FMAs, and the loads of the next iteration's inputs are independent of the current arithmetic.
-constexpr int HEAD_HG = 2, HEAD_HS = 4;
+constexpr int HEAD_HG = 4, HEAD_HS = 4;
+
+// ELU(alpha = 1) with exp through MUFU.EX2: absolute error ~1e-7 (expm1f costs ~20 instructions per call and was
+// two thirds of the head kernel's instruction stream; the head adds 32 such terms with |w2| < 1)
+__device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : exp2f(x * 1.4426950408889634f) - 1.f; }
 
 template <int V>
-__global__ void __launch_bounds__(256) head_kernel(const float *Y /*[nb][h]*/, const float2 *stats, const float *gamma,
+__global__ void __launch_bounds__(128 * HEAD_HG) head_kernel(const float *Y /*[nb][h]*/, const float2 *stats, const float *gamma,
                                                    const float *beta, const float *w1, const float *b1, const float *w2,
                                                    const float *b2, float *z, int nb, int d, int h, int u, int norm) {
     extern __shared__ float hsm[];
@@ -556,7 +560,7 @@ __global__ void __launch_bounds__(256) head_kernel(const float *Y /*[nb][h]*/, c
             }
 #pragma unroll
             for (int s = 0; s < HEAD_HS; s++) {
-                const float e = acc[s] > 0.f ? acc[s] : expm1f(acc[s]);  // ELU(alpha = 1)
+                const float e = elu_fast(acc[s]);
                 out[s] = fmaf(wj, e, out[s]);
             }
         }
@@ -954,7 +958,7 @@ int forward_chunk(Model *m, const float *mel, int nb, int norm, float *z) {
     const int v = m->h / m->d;
     const size_t smem_fast =
         ((size_t)m->u * v * threads + 2 * (size_t)m->u * threads + (size_t)HEAD_HG * HEAD_HS * (threads / 32)) * 4;
-    if (!m->variant && (v == 8 || v == 16) && threads * HEAD_HG <= 256 && smem_fast <= 200 * 1024) {
+    if (!m->variant && (v == 8 || v == 16) && threads <= 128 && smem_fast <= 200 * 1024) {
         // the opt-in is per device/context and per function: set it for the instantiation being launched
         if (v == 8)
             PF_CUDA(cudaFuncSetAttribute(head_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));

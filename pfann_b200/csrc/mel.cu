@@ -44,6 +44,12 @@ struct MelPlan {
     float *d_win = nullptr;   // periodic Hann, 1024
     int *d_fb_start = nullptr, *d_fb_cnt = nullptr;
     float *d_fb_w = nullptr;  // [n_mels][fb_stride]
+    // fast path (default options, <= 7 taps per filter): weights tap-major [FB_TAPS][n_mels] against a start index that
+    // is clamped so that start + FB_TAPS never leaves the spectrum
+    float *d_fb_wt = nullptr;
+    int *d_fb_start2 = nullptr;
+    bool fast = false;
+    size_t smem_fast = 0;
     DevBuf seg_start, seg_valid;
     size_t smem_bytes;
 };
@@ -62,6 +68,8 @@ struct MelArgs {
     const float *win;
     const int *fb_start, *fb_cnt;
     const float *fb_w;
+    const float *fb_wt;      // fast path tables (see MelPlan)
+    const int *fb_start2;
     // optional (fused extract path): 9 moments of the log-mel tile under the taps of layer-0 conv1, so that the
     // encoder needs no second pass over the tile for its first LayerNorm (see encoder.cu: l0_stats_kernel)
     double *moments;         // [B][9]: S0 S1 S2 R00 R01 R02 R11 R12 R22, or nullptr
@@ -359,6 +367,312 @@ __global__ void __launch_bounds__(NTHREADS, 2) mel_kernel(const MelArgs a) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Round-2 kernel for the default option set (power spectrum, natural log, L2 norm, n_mels = 256, <= 7 taps per mel
+// filter).  Same results as mel_kernel within rounding, about half the instructions per frame:
+//   * the 32-point cross-lane DFT is ONE shared-memory transpose + a second in-lane 16-point DFT + a single
+//     shfl_xor(1) butterfly (was five shuffle stages: 160 SHFL and 480 arithmetic instructions per frame);
+//   * the recombination forms bins k and 512-k from one (Z[k], Z[512-k]) pair and one twiddle;
+//   * the mel projection is a fixed 7-tap dot product against a tap-major weight table staged once per CTA in shared
+//     memory (was a divergent variable-length loop over global memory: a third of the frame's instructions);
+//   * the 1/|x| factor of melspec.py:36 is applied once per mel bin (the spectrum is quadratic in the signal);
+//   * the option branches are compiled out.
+// tools/fft_dataflow_check.py (warp_fft_1024_real_v2) is the numpy emulation of this dataflow.
+// ------------------------------------------------------------------------------------------------
+constexpr int FB_TAPS = 7;
+constexpr int FAST_MELS = 256;
+constexpr int ZB2 = 552;   // float2 per warp: Z[k] at k + (k >> 4) + (k >> 8) * 8 (k < 512); transpose tile 16 x 34
+
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }   // * (-i)
+
+// 16-point radix-2 DIF, a[i] = X[bitrev4(i)]; the trivial twiddles (1, -i, W_8, W_8^3) are spelled out
+__device__ __forceinline__ void fft16_fast(float2 (&a)[16]) {
+    const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, r2 = 0.70710678118654752f;
+    // stage 1: half = 8, twiddles W_16^j
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const float2 u = a[j], v = a[j + 8];
+        a[j] = cadd(u, v);
+        a[j + 8] = csub(u, v);
+    }
+    a[9] = cmul(a[9], make_float2(c1, -s1));
+    a[10] = make_float2((a[10].x + a[10].y) * r2, (a[10].y - a[10].x) * r2);
+    a[11] = cmul(a[11], make_float2(s1, -c1));
+    a[12] = mul_mi(a[12]);
+    a[13] = cmul(a[13], make_float2(-s1, -c1));
+    a[14] = make_float2((a[14].y - a[14].x) * r2, -(a[14].x + a[14].y) * r2);
+    a[15] = cmul(a[15], make_float2(-c1, -s1));
+    // stage 2: half = 4, twiddles W_8^j
+#pragma unroll
+    for (int base = 0; base < 16; base += 8) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float2 u = a[base + j], v = a[base + j + 4];
+            a[base + j] = cadd(u, v);
+            a[base + j + 4] = csub(u, v);
+        }
+        a[base + 5] = make_float2((a[base + 5].x + a[base + 5].y) * r2, (a[base + 5].y - a[base + 5].x) * r2);
+        a[base + 6] = mul_mi(a[base + 6]);
+        a[base + 7] = make_float2((a[base + 7].y - a[base + 7].x) * r2, -(a[base + 7].x + a[base + 7].y) * r2);
+    }
+    // stage 3: half = 2, twiddles 1, -i
+#pragma unroll
+    for (int base = 0; base < 16; base += 4) {
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const float2 u = a[base + j], v = a[base + j + 2];
+            a[base + j] = cadd(u, v);
+            a[base + j + 2] = csub(u, v);
+        }
+        a[base + 3] = mul_mi(a[base + 3]);
+    }
+    // stage 4: half = 1
+#pragma unroll
+    for (int base = 0; base < 16; base += 2) {
+        const float2 u = a[base], v = a[base + 1];
+        a[base] = cadd(u, v);
+        a[base + 1] = csub(u, v);
+    }
+}
+
+__host__ __device__ constexpr int zidx(int k) { return k + (k >> 4) + (k >> 8) * 8; }
+// W_32^q = exp(-2 pi i q / 32), q = 0..15
+__device__ constexpr float W32R[16] = {1.000000000e+00f, 9.807852804e-01f, 9.238795325e-01f, 8.314696123e-01f, 7.071067812e-01f, 5.555702330e-01f, 3.826834324e-01f, 1.950903220e-01f, 6.123233996e-17f, -1.950903220e-01f, -3.826834324e-01f, -5.555702330e-01f, -7.071067812e-01f, -8.314696123e-01f, -9.238795325e-01f, -9.807852804e-01f};
+__device__ constexpr float W32I[16] = {-0.000000000e+00f, -1.950903220e-01f, -3.826834324e-01f, -5.555702330e-01f, -7.071067812e-01f, -8.314696123e-01f, -9.238795325e-01f, -9.807852804e-01f, -1.000000000e+00f, -9.807852804e-01f, -9.238795325e-01f, -8.314696123e-01f, -7.071067812e-01f, -5.555702330e-01f, -3.826834324e-01f, -1.950903220e-01f};
+
+template <bool PCM>
+__global__ void __launch_bounds__(NTHREADS, 2) mel_fast_kernel(const MelArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int n = a.n, pad = NFFT / 2;
+    float *xs = reinterpret_cast<float *>(smem_raw);                        // [n + NFFT]
+    float2 *zbuf = reinterpret_cast<float2 *>(xs + ((n + NFFT + 3) & ~3));  // [NWARPS][ZB2]
+    float *tile = reinterpret_cast<float *>(zbuf + NWARPS * ZB2);           // [256][T+1] (also int16 stage)
+    float *fbw = tile + FAST_MELS * (a.T + 1);                              // [FB_TAPS][256]
+    __shared__ float red[NWARPS];
+    __shared__ __align__(8) uint64_t bar;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t b = blockIdx.x;
+    float *x = xs + pad;
+
+    if (tid == 0) {
+        ptx::mbar_init(&bar, 1);
+        ptx::fence_mbar_init();
+    }
+    __syncthreads();
+    for (int i = tid; i < FB_TAPS * FAST_MELS; i += NTHREADS) fbw[i] = __ldg(a.fb_wt + i);
+
+    // ---- load the segment (as mel_kernel) ----
+    if (!PCM) {
+        const float *src = a.x + b * (int64_t)n;
+        const bool bulk = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((n & 3) == 0);
+        if (bulk) {
+            if (tid == 0) {
+                ptx::mbar_expect_tx(&bar, (uint32_t)n * 4u);
+                ptx::bulk_g2s(x, src, (uint32_t)n * 4u, &bar);
+            }
+            ptx::mbar_wait(&bar, 0);
+        } else {
+            for (int i = tid; i < n; i += NTHREADS) x[i] = __ldg(src + i);
+            __syncthreads();
+        }
+    } else {
+        const int64_t start = a.seg_start[b];
+        const int valid = a.seg_valid[b];
+        float part = 0.f;
+        if (a.wavf != nullptr) {
+            const float *src = a.wavf + start;
+            for (int i = tid; i < n; i += NTHREADS) {
+                const float v = i < valid ? __ldg(src + i) : 0.f;
+                x[i] = v;
+                part += v;
+            }
+        } else {
+            const int16_t *src = a.pcm + start;
+            int16_t *stg = reinterpret_cast<int16_t *>(tile);
+            const bool bulk = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((valid & 7) == 0) && valid > 0;
+            if (bulk) {
+                if (tid == 0) {
+                    ptx::mbar_expect_tx(&bar, (uint32_t)valid * 2u);
+                    ptx::bulk_g2s(stg, src, (uint32_t)valid * 2u, &bar);
+                }
+                ptx::mbar_wait(&bar, 0);
+            } else {
+                for (int i = tid; i < valid; i += NTHREADS) stg[i] = src[i];
+                __syncthreads();
+            }
+            for (int i = tid; i < n; i += NTHREADS) {
+                float v = i < valid ? (float)stg[i] * (1.0f / 32768.0f) : 0.f;
+                x[i] = v;
+                part += v;
+            }
+        }
+        const float mean = block_sum(part, red) / (float)n;
+        for (int i = tid; i < n; i += NTHREADS) x[i] -= mean;
+        __syncthreads();
+    }
+    float sc2;   // (1 / max(|x|_2, 1e-12))^2, applied to the mel energies
+    {
+        float part = 0.f;
+        for (int i = tid; i < n; i += NTHREADS) part = fmaf(x[i], x[i], part);
+        const float ss = block_sum(part, red);
+        const float scale = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+        sc2 = scale * scale;
+    }
+    for (int i = tid; i < pad; i += NTHREADS) {
+        xs[i] = xs[2 * pad - i];
+        xs[pad + n + i] = xs[pad + n - 2 - i];
+    }
+    __syncthreads();
+
+    // ---- per-lane constants ----
+    float2 twl[16];   // W_512^(lane * k1), k1 = bitrev4(i)
+#pragma unroll
+    for (int i = 0; i < 16; i++) twl[i] = __ldg(a.tw + ((2 * lane * bitrev4(i)) & (NFFT - 1)));
+    int s0[FAST_MELS / 32];
+#pragma unroll
+    for (int i = 0; i < FAST_MELS / 32; i++) s0[i] = __ldg(a.fb_start2 + lane + 32 * i);
+    const bool odd = (lane & 1) != 0;
+    const float sgn = odd ? -1.f : 1.f;
+    float2 *zw = zbuf + warp * ZB2;
+    float *pw = reinterpret_cast<float *>(zw);
+    const int Tp = a.T + 1;
+    const float2 *tr_rd = zw + (lane >> 1) * 34 + (lane & 1);
+    const int kz = (lane >> 1) + (odd ? 256 : 0);   // Z index of this lane's results: kz + 16 q
+
+    for (int t = warp; t < a.T; t += NWARPS) {
+        float2 v[16];
+        const float *fr = xs + t * a.hop;
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            const int j = 64 * r + 2 * lane;
+            const float2 xv = *reinterpret_cast<const float2 *>(fr + j);
+            const float2 wv = __ldg(reinterpret_cast<const float2 *>(a.win + j));
+            v[r] = make_float2(xv.x * wv.x, xv.y * wv.y);
+        }
+        fft16_fast(v);
+#pragma unroll
+        for (int i = 1; i < 16; i++) v[i] = cmul(v[i], twl[i]);
+        // transpose: Y[k1][n2 = lane] -> lane L holds k1 = L >> 1, n2 = (L & 1) + 2 j
+#pragma unroll
+        for (int i = 0; i < 16; i++) zw[bitrev4(i) * 34 + lane] = v[i];
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[j] = tr_rd[2 * j];
+        __syncwarp();
+        fft16_fast(v);   // v[i] = E[q] (even lanes) / O[q] (odd lanes), q = bitrev4(i)
+        // last butterfly of the 32-point DFT between lanes L and L ^ 1: X[q] = E + W_32^q O, X[q + 16] = E - W_32^q O
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const int q = bitrev4(i);
+            const float wr = W32R[q], wi = W32I[q];   // compile-time after unrolling
+            float2 w = v[i];
+            if (q != 0) {
+                const float2 m = cmul(v[i], make_float2(wr, wi));
+                w.x = odd ? m.x : v[i].x;
+                w.y = odd ? m.y : v[i].y;
+            }
+            float2 p;
+            p.x = __shfl_xor_sync(0xffffffffu, w.x, 1);
+            p.y = __shfl_xor_sync(0xffffffffu, w.y, 1);
+            // even lane: w + p; odd lane: p - w
+            zw[zidx(kz + 16 * q) - 0] = make_float2(fmaf(sgn, w.x, p.x), fmaf(sgn, w.y, p.y));
+        }
+        __syncwarp();
+        // recombination, bins k and 512 - k from one pair
+        float P1[8], P2[8], Pm = 0.f;
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+            const int k = lane + 32 * it, kb = (512 - k) & 511;
+            const float2 A = zw[zidx(k)];
+            float2 Bc = zw[zidx(kb)];
+            Bc.y = -Bc.y;
+            const float2 E = make_float2(0.5f * (A.x + Bc.x), 0.5f * (A.y + Bc.y));
+            const float2 D = csub(A, Bc);
+            const float2 O = make_float2(0.5f * D.y, -0.5f * D.x);
+            const float2 T = cmul(__ldg(a.tw + k), O);
+            const float2 X1 = cadd(E, T), X2 = csub(E, T);
+            P1[it] = X1.x * X1.x + X1.y * X1.y;
+            P2[it] = X2.x * X2.x + X2.y * X2.y;
+        }
+        if (lane == 0) {   // k = 256 pairs with itself: W_1024^256 = -i
+            const float2 A = zw[zidx(256)];
+            // E = (Re A, 0), O = (Im A, 0), X = E - i O
+            Pm = A.x * A.x + A.y * A.y;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+            const int k = lane + 32 * it;
+            pw[k] = P1[it];
+            pw[512 - k] = P2[it];
+        }
+        if (lane == 0) pw[256] = Pm;
+        __syncwarp();
+        // mel projection (7 taps from shared memory) + log
+#pragma unroll
+        for (int i = 0; i < FAST_MELS / 32; i++) {
+            const int m = lane + 32 * i;
+            const float *pp = pw + s0[i];
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < FB_TAPS; j++) acc = fmaf(fbw[j * FAST_MELS + m], pp[j], acc);
+            tile[m * Tp + t] = __logf(fmaf(acc, sc2, 1e-8f));
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (a.moments != nullptr) {
+        const int To = (a.T + 1) / 2, P = FAST_MELS * To;
+        float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int p = tid; p < P; p += NTHREADS) {
+            const int f = p / To, to = p - f * To;
+            float v[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const int t = 2 * to + a.m_off[j];
+                if (j < a.m_ntaps && t >= 0 && t < a.T) v[j] = tile[f * Tp + t];
+            }
+            acc[0] += v[0]; acc[1] += v[1]; acc[2] += v[2];
+            acc[3] = fmaf(v[0], v[0], acc[3]); acc[4] = fmaf(v[0], v[1], acc[4]); acc[5] = fmaf(v[0], v[2], acc[5]);
+            acc[6] = fmaf(v[1], v[1], acc[6]); acc[7] = fmaf(v[1], v[2], acc[7]); acc[8] = fmaf(v[2], v[2], acc[8]);
+        }
+        double *wred = reinterpret_cast<double *>(zbuf);
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 9; i++) wred[warp * 9 + i] = (double)acc[i];
+        }
+        __syncthreads();
+        if (tid < 9) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < NWARPS; w++) t += wred[w * 9 + tid];
+            a.moments[b * 9 + tid] = t;
+        }
+    }
+    float *o = a.out + b * (int64_t)FAST_MELS * a.T;
+    const int tot = FAST_MELS * a.T;
+    for (int i = tid; i < tot; i += NTHREADS) {
+        const int m = i / a.T, t = i - m * a.T;
+        o[i] = tile[m * Tp + t];
+    }
+}
+
+size_t mel_smem_bytes_fast(int n, int T) {
+    size_t xs = (size_t)((n + NFFT + 3) & ~3) * 4;
+    size_t z = (size_t)NWARPS * ZB2 * 8;
+    size_t tile = (size_t)FAST_MELS * (T + 1) * 4;
+    // int16 staging aliases tile + weight table (the table is written before the staging copy completes only when the
+    // staging fits in the tile alone, which is checked at plan time)
+    return xs + z + tile + (size_t)FB_TAPS * FAST_MELS * 4;
+}
+
 size_t mel_smem_bytes(int n, int n_mels, int T) {
     size_t xs = (size_t)((n + NFFT + 3) & ~3) * 4;
     size_t z = (size_t)NWARPS * ZBUF_F2 * 8;
@@ -376,7 +690,15 @@ int launch_mel(MelPlan *p, const MelArgs &a, int64_t B, bool pcm) {
     else
         PF_CUDA(cudaFuncSetAttribute(mel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
     ProfScope ps(p->ctx, K_MEL, 32);
-    if (pcm)
+    if (p->fast && getenv("PFANN_B200_MEL_V1") == nullptr) {   // read per call: tests compare the two kernels
+        if (pcm) {
+            PF_CUDA(cudaFuncSetAttribute(mel_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_fast));
+            mel_fast_kernel<true><<<(unsigned)B, NTHREADS, p->smem_fast, p->ctx->stream>>>(a);
+        } else {
+            PF_CUDA(cudaFuncSetAttribute(mel_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_fast));
+            mel_fast_kernel<false><<<(unsigned)B, NTHREADS, p->smem_fast, p->ctx->stream>>>(a);
+        }
+    } else if (pcm)
         mel_kernel<true><<<(unsigned)B, NTHREADS, p->smem_bytes, p->ctx->stream>>>(a);
     else
         mel_kernel<false><<<(unsigned)B, NTHREADS, p->smem_bytes, p->ctx->stream>>>(a);
@@ -399,6 +721,8 @@ MelArgs base_args(MelPlan *p) {
     a.fb_start = p->d_fb_start;
     a.fb_cnt = p->d_fb_cnt;
     a.fb_w = p->d_fb_w;
+    a.fb_wt = p->d_fb_wt;
+    a.fb_start2 = p->d_fb_start2;
     return a;
 }
 
@@ -545,6 +869,22 @@ int pfann_mel_create_ex(pfann_ctx *hctx, int sample_rate, int n_fft, int hop, do
     PF_CUDA(cudaMemcpy(p->d_fb_start, start.data(), sizeof(int) * n_mels, cudaMemcpyHostToDevice));
     PF_CUDA(cudaMemcpy(p->d_fb_cnt, cnt.data(), sizeof(int) * n_mels, cudaMemcpyHostToDevice));
     PF_CUDA(cudaMemcpy(p->d_fb_w, fbw.data(), sizeof(float) * fbw.size(), cudaMemcpyHostToDevice));
+    // fast path tables
+    p->smem_fast = mel_smem_bytes_fast(seg_len, p->T);
+    p->fast = !p->naf_mode && p->mel_log == PFANN_MEL_LOG_E && !p->norm_max && n_mels == FAST_MELS && stride <= FB_TAPS &&
+              p->smem_fast <= 227 * 1024 && (size_t)seg_len * 2 + 16 <= (size_t)FAST_MELS * (p->T + 1) * 4;
+    if (p->fast) {
+        std::vector<float> wt((size_t)FB_TAPS * n_mels, 0.f);
+        std::vector<int> st2(n_mels);
+        for (int m = 0; m < n_mels; m++) {
+            st2[m] = start[m] < n_freqs - FB_TAPS ? start[m] : n_freqs - FB_TAPS;
+            for (int j = 0; j < cnt[m]; j++) wt[(size_t)(start[m] - st2[m] + j) * n_mels + m] = rows[m][j];
+        }
+        PF_CUDA(cudaMalloc(&p->d_fb_wt, sizeof(float) * wt.size()));
+        PF_CUDA(cudaMalloc(&p->d_fb_start2, sizeof(int) * n_mels));
+        PF_CUDA(cudaMemcpy(p->d_fb_wt, wt.data(), sizeof(float) * wt.size(), cudaMemcpyHostToDevice));
+        PF_CUDA(cudaMemcpy(p->d_fb_start2, st2.data(), sizeof(int) * n_mels, cudaMemcpyHostToDevice));
+    }
     *out = reinterpret_cast<pfann_mel *>(p);
     return PFANN_OK;
 }
@@ -558,6 +898,8 @@ void pfann_mel_destroy(pfann_mel *h) {
     cudaFree(p->d_fb_start);
     cudaFree(p->d_fb_cnt);
     cudaFree(p->d_fb_w);
+    cudaFree(p->d_fb_wt);
+    cudaFree(p->d_fb_start2);
     p->seg_start.release();
     p->seg_valid.release();
     delete p;

@@ -73,6 +73,28 @@ def test_mel_many_segments_vs_oracle(dev):
     _mel_check(y, orc.melspec(x, params))
 
 
+def test_mel_fast_kernel_equals_the_general_kernel(dev, monkeypatch):
+    """The default option set runs the round-2 kernel (transpose FFT, paired recombination, 7-tap projection from
+    shared memory); PFANN_B200_MEL_V1 selects the general kernel the variants use.  Same numbers within rounding,
+    same moments, other segment lengths included."""
+    from pfann_b200.datautil.melspec import build_mel_spec_layer
+    params = synth.read_config('default')
+    mel = build_mel_spec_layer(params).to(dev)
+    for n, count in ((8000, 64), (4000, 5), (12000, 3)):
+        x = torch.from_numpy(synth.synth_segments(count, seed=5, seg=n)).to(dev)
+        x[-1] = 0
+        monkeypatch.delenv('PFANN_B200_MEL_V1', raising=False)
+        fast = mel(x).cpu().numpy()
+        monkeypatch.setenv('PFANN_B200_MEL_V1', '1')
+        slow = mel(x).cpu().numpy()
+        monkeypatch.delenv('PFANN_B200_MEL_V1', raising=False)
+        ref = orc.melspec(x.cpu().numpy(), params)
+        _mel_check(fast[:-1], ref[:-1])
+        assert np.abs(fast - slow).mean() < 1e-5
+        np.testing.assert_allclose(fast[-1], np.log(np.float32(1e-8)), atol=1e-6)
+        assert np.array_equal(fast, mel(x).cpu().numpy())                      # bit-reproducible
+
+
 MEL_VARIANTS = {     # tools/gen_golden.py MEL_VARIANTS: option sets of melspec.py:27-49 beyond the default
     'naf': {'naf_mode': True, 'mel_log': 'log10', 'spec_norm': 'max'},
     'log10': {'mel_log': 'log10'},

@@ -75,3 +75,63 @@ if __name__ == '__main__':
     err = np.abs(ref - got).max()
     print('max err', err)
     assert err < 1e-10
+
+
+def warp_fft_1024_real_v2(x):
+    """Round-2 dataflow (mel_fast_kernel): the 32-point cross-lane part is ONE shared-memory transpose, a second
+    in-lane 16-point DFT and a single shfl_xor(1) butterfly; the recombination forms bins k and 512-k from one pair."""
+    z = x[0::2] + 1j * x[1::2]
+    lanes = np.arange(32)
+    a = np.empty((16, 32), complex)
+    for r in range(16):
+        a[r] = z[32 * r + lanes]
+    Y = fft16_dif_inplace(a)                   # Y[k1][n2 = lane]
+    for k1 in range(16):
+        Y[k1] *= np.exp(-2j * np.pi * lanes * k1 / 512)
+    # transpose through shared memory: buf[k1 * 34 + n2]; lane L reads k1 = L >> 1, n2 = (L & 1) + 2 j
+    buf = np.zeros(16 * 34, complex)
+    for k1 in range(16):
+        buf[k1 * 34 + lanes] = Y[k1]
+    u = np.empty((16, 32), complex)
+    for j in range(16):
+        u[j] = buf[(lanes >> 1) * 34 + (lanes & 1) + 2 * j]
+    F = fft16_dif_inplace(u)                   # F[q][lane]: E (even lanes) / O (odd lanes) of the 32-point DFT
+    b = lanes & 1
+    Zbuf = np.zeros(552, complex)
+    idx = lambda k: k + (k >> 4) + (k >> 8) * 8
+    for q in range(16):
+        w = np.where(b == 1, F[q] * np.exp(-2j * np.pi * q / 32), F[q])
+        p = w[lanes ^ 1]
+        res = np.where(b == 1, p - w, w + p)
+        k = (lanes >> 1) + 16 * (q + 16 * b)
+        Zbuf[idx(k)] = res
+    P = np.zeros(513)
+    for it in range(8):
+        k = lanes + 32 * it
+        A = Zbuf[idx(k)]
+        B = np.conj(Zbuf[idx((512 - k) & 511)])
+        E = 0.5 * (A + B)
+        O = -0.5j * (A - B)
+        T = np.exp(-2j * np.pi * k / 1024) * O
+        P[k] = np.abs(E + T) ** 2
+        P[512 - k] = np.abs(E - T) ** 2
+    A = Zbuf[idx(256)]
+    B = np.conj(A)
+    P[256] = np.abs(0.5 * (A + B) + np.exp(-2j * np.pi * 256 / 1024) * (-0.5j) * (A - B)) ** 2
+    return P
+
+
+if __name__ == '__main__':
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(1024)
+    ref = np.abs(np.fft.rfft(x)) ** 2
+    got = warp_fft_1024_real_v2(x)
+    err = np.abs(ref - got).max() / ref.max()
+    print('v2 max rel err', err)
+    assert err < 1e-12
+    # bank check of the transpose reads (64-bit accesses are served per half-warp): 16 lanes -> 32 distinct banks
+    for half in (0, 16):
+        L = np.arange(half, half + 16)
+        words = 2 * ((L >> 1) * 34 + (L & 1))
+        banks = np.concatenate([words % 32, (words + 1) % 32])
+        assert len(set(banks.tolist())) == 32
