@@ -11,6 +11,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "encoder.cuh"
 #include "pfann_b200.h"
 
@@ -271,6 +273,51 @@ __global__ void __launch_bounds__(256) ln_apply_kernel(const YT *Y, const float2
             for (int i = 0; i < 4 && e0 + i < E; i++)
                 store_out(X + (long long)b * E + e0 + i,
                           ln_act(ld_y1(Y + (long long)b * E + e0 + i), st, __ldg(gamma + e0 + i), __ldg(beta + e0 + i), mode));
+        }
+    }
+}
+
+// bf16 -> bf16 form of ln_apply_kernel for the default option set (the tail of the tensor-core path): 8 elements
+// (16 bytes) per thread and four samples in flight per thread, so that the loads of a group do not serialise
+__global__ void __launch_bounds__(256) ln_apply_bf16x8_kernel(const __nv_bfloat16 *Y, const float2 *stats, const float *gamma,
+                                                              const float *beta, __nv_bfloat16 *X, long long E, int nb,
+                                                              int group) {
+    const long long e0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (e0 >= E) return;
+    const int b0 = blockIdx.y * group;
+    const int b1 = (b0 + group) < nb ? (b0 + group) : nb;
+    float g[8], be[8];
+    {
+        const float4 g0 = __ldg(reinterpret_cast<const float4 *>(gamma + e0)), g1 = __ldg(reinterpret_cast<const float4 *>(gamma + e0 + 4));
+        const float4 c0 = __ldg(reinterpret_cast<const float4 *>(beta + e0)), c1 = __ldg(reinterpret_cast<const float4 *>(beta + e0 + 4));
+        g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+        be[0] = c0.x; be[1] = c0.y; be[2] = c0.z; be[3] = c0.w; be[4] = c1.x; be[5] = c1.y; be[6] = c1.z; be[7] = c1.w;
+    }
+    for (int b = b0; b < b1; b += 4) {
+        uint4 v[4];
+        float2 st[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int bb = b + q < b1 ? b + q : b1 - 1;
+            st[q] = __ldg(stats + bb);
+            v[q] = *reinterpret_cast<const uint4 *>(Y + (long long)bb * E + e0);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (b + q >= b1) break;
+            const uint32_t w[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+            uint32_t o[4];
+            const float a = st[q].y, c = -st[q].x * st[q].y;   // (y - mean) * rstd = y * a + c
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&w[i]));
+                const float o0 = fmaxf(fmaf((f.x - st[q].x) * a, g[2 * i], be[2 * i]), 0.f);
+                const float o1 = fmaxf(fmaf((f.y - st[q].x) * a, g[2 * i + 1], be[2 * i + 1]), 0.f);
+                const __nv_bfloat162 pk = __floats2bfloat162_rn(o0, o1);
+                o[i] = *reinterpret_cast<const uint32_t *>(&pk);
+            }
+            (void)c;
+            *reinterpret_cast<uint4 *>(X + (long long)(b + q) * E + e0) = make_uint4(o[0], o[1], o[2], o[3]);
         }
     }
 }
@@ -796,6 +843,15 @@ int launch_ln_apply(Model *m, const ConvWeights &cw, const YT *Y, OutT *X, int n
     while (group > 1 && (long long)cdiv(E, 1024) * cdiv(nb, group) < 2LL * m->ctx->sm_count) group >>= 1;
     dim3 grid(cdiv(E, 1024), cdiv(nb, group));
     ProfScope ps(m->ctx, K_LN, 16 + m->prof_idx);
+    if (std::is_same<YT, __nv_bfloat16>::value && std::is_same<OutT, __nv_bfloat16>::value && m->act == 0 && !m->act_first &&
+        (E & 7) == 0) {
+        const int threads = E / 8 < 256 ? (int)((E / 8 + 31) / 32 * 32) : 256;
+        int grp = 16;
+        while (grp > 4 && (long long)cdiv(E, 8 * threads) * cdiv(nb, grp) < 4LL * m->ctx->sm_count) grp >>= 1;
+        ln_apply_bf16x8_kernel<<<dim3(cdiv(E, 8 * threads), cdiv(nb, grp)), threads, 0, m->ctx->stream>>>(
+            reinterpret_cast<const __nv_bfloat16 *>(Y), m->cur_stats, cw.gamma, cw.beta, reinterpret_cast<__nv_bfloat16 *>(X), E,
+            nb, grp);
+    } else
     ln_apply_kernel<YT, OutT><<<grid, 256, 0, m->ctx->stream>>>(Y, m->cur_stats, cw.gamma, cw.beta, X, E, nb,
                                                                 group, m->act | (m->act_first ? 4 : 0));
     m->ctx->launches++;
