@@ -48,6 +48,7 @@ struct MelPlan {
     // is clamped so that start + FB_TAPS never leaves the spectrum
     float *d_fb_wt = nullptr;
     int *d_fb_start2 = nullptr;
+    int fb_blk_taps[8] = {};
     bool fast = false;
     size_t smem_fast = 0;
     DevBuf seg_start, seg_valid;
@@ -70,6 +71,7 @@ struct MelArgs {
     const float *fb_w;
     const float *fb_wt;      // fast path tables (see MelPlan)
     const int *fb_start2;
+    int fb_blk_taps[8];      // taps actually used by mel bins [32 i, 32 i + 32): the projection stops there
     // optional (fused extract path): 9 moments of the log-mel tile under the taps of layer-0 conv1, so that the
     // encoder needs no second pass over the tile for its first LayerNorm (see encoder.cu: l0_stats_kernel)
     double *moments;         // [B][9]: S0 S1 S2 R00 R01 R02 R11 R12 R22, or nullptr
@@ -616,8 +618,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) mel_fast_kernel(const MelArgs a) 
             const int m = lane + 32 * i;
             const float *pp = pw + s0[i];
             float acc = 0.f;
+            const int nt = a.fb_blk_taps[i];   // warp-uniform: low mel filters are narrower than one FFT bin
 #pragma unroll
-            for (int j = 0; j < FB_TAPS; j++) acc = fmaf(fbw[j * FAST_MELS + m], pp[j], acc);
+            for (int j = 0; j < FB_TAPS; j++)
+                if (j < nt) acc = fmaf(fbw[j * FAST_MELS + m], pp[j], acc);
             tile[m * Tp + t] = __logf(fmaf(acc, sc2, 1e-8f));
         }
         __syncwarp();
@@ -723,6 +727,7 @@ MelArgs base_args(MelPlan *p) {
     a.fb_w = p->d_fb_w;
     a.fb_wt = p->d_fb_wt;
     a.fb_start2 = p->d_fb_start2;
+    for (int i = 0; i < 8; i++) a.fb_blk_taps[i] = p->fb_blk_taps[i];
     return a;
 }
 
@@ -879,6 +884,8 @@ int pfann_mel_create_ex(pfann_ctx *hctx, int sample_rate, int n_fft, int hop, do
         for (int m = 0; m < n_mels; m++) {
             st2[m] = start[m] < n_freqs - FB_TAPS ? start[m] : n_freqs - FB_TAPS;
             for (int j = 0; j < cnt[m]; j++) wt[(size_t)(start[m] - st2[m] + j) * n_mels + m] = rows[m][j];
+            const int used = start[m] - st2[m] + cnt[m];
+            if (used > p->fb_blk_taps[m / 32]) p->fb_blk_taps[m / 32] = used;
         }
         PF_CUDA(cudaMalloc(&p->d_fb_wt, sizeof(float) * wt.size()));
         PF_CUDA(cudaMalloc(&p->d_fb_start2, sizeof(int) * n_mels));
