@@ -235,6 +235,14 @@ int pfann_db_rerank(pfann_db *db, const float *queries, const int64_t *query_ind
                     const int64_t *labels, int top_k, int frame_shift_mul, float score_alpha,
                     float *best_score, int32_t *best_song, float *best_time);
 
+/* Sharded search, tighter variant of the threshold phase: besides this shard's own threshold, the k best SAMPLED scan
+ * scores per query as sortable 32-bit keys (0 = none), topk [Q][k].  The ranks all-gather these lists (Q * k * 4 bytes
+ * each) and call pfann_db_thresholds_from_topk on the gathered [world][Q][k] array: thr[q] = the k-th best of the UNION
+ * of the samples minus the scan's error bound -- a lower bound of the global k-th best score that is several times
+ * tighter than the maximum of the per-shard k-th bests, so fewer rows survive the filtered scan. */
+int pfann_db_search_sample_topk(pfann_db *db, const float *q, int64_t Q, int k, float *thr, uint32_t *topk);
+int pfann_db_thresholds_from_topk(pfann_db *db, const uint32_t *gathered, int world, const float *q, int64_t Q, int k,
+                                  float *thr);
 /* The same exchange for many GPUs without a host round trip per batch (pfann_b200/dist.py).  All data pointers
  * are DEVICE pointers and every call is stream-ordered; nothing is read back.
  *   1. pfann_db_search_thresholds: thr[Q] = a lower bound of this shard's k-th best score per query (sample

@@ -91,6 +91,8 @@ def _declare(L):
     L.pfann_topk_merge.argtypes = [vp, vp, vp, c_int, c_int64, c_int, vp, vp]
     L.pfann_db_rerank.argtypes = [vp, vp, vp, c_int, vp, c_int, c_int, c_float, vp, vp, vp]
     L.pfann_db_search_thresholds.argtypes = [vp, vp, c_int64, c_int, vp]
+    L.pfann_db_search_sample_topk.argtypes = [vp, vp, c_int64, c_int, vp, vp]
+    L.pfann_db_thresholds_from_topk.argtypes = [vp, vp, c_int, vp, c_int64, c_int, vp]
     L.pfann_db_search_filtered.argtypes = [vp, vp, c_int64, c_int, vp, vp, c_int]
     L.pfann_db_take_overflow.argtypes = [vp]
     L.pfann_topk_merge_keys.argtypes = [vp, vp, c_int, c_int64, c_int, vp, vp]

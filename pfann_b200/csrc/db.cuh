@@ -97,7 +97,7 @@ __device__ void bitonic_sort(K *keys, int n) {
 // knn.cu: device-pointer search (q, dist, labels all on the device, stream-ordered except for the
 // overflow check which synchronises once per query group)
 int db_search_dev(Db *db, const float *q, int64_t Q, int k, float *dist, int64_t *labels);
-int db_search_thresholds_dev(Db *db, const float *q, int64_t Q, int k, float *thr);
+int db_search_thresholds_dev(Db *db, const float *q, int64_t Q, int k, float *thr, uint32_t *topk_out = nullptr);
 int db_search_filtered_dev(Db *db, const float *q, int64_t Q, int k, float *thr, unsigned long long *keys, bool defer);
 // knn_tc.cu
 int knn_tc_prepare(Db *db);

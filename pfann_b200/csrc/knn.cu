@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) knn_kth_chunk_kernel(const float *sample,
 
 __global__ void __launch_bounds__(256) knn_kth_merge_kernel(const uint32_t *part, int nkeys, int P, int S,
                                                             const float *q, int d, int k, float eps_rel,
-                                                            float max_norm, float *thr, float *qnorm) {
+                                                            float max_norm, float *thr, float *qnorm, uint32_t *topk_out) {
     extern __shared__ uint32_t keys[];  // [P]
     __shared__ float red[8];
     const int qi = blockIdx.x;
@@ -138,6 +138,32 @@ __global__ void __launch_bounds__(256) knn_kth_merge_kernel(const uint32_t *part
         qnorm[qi] = qn;
         thr[qi] = (S >= k) ? unflipf(keys[k - 1]) - 2.f * eps_rel * qn * max_norm : -INFINITY;
     }
+    // sharded search: the k best sampled scan scores themselves (sortable keys, 0 = none), so that the ranks can take
+    // the k-th best of the UNION of their samples instead of the maximum of their k-th bests
+    if (topk_out != nullptr)
+        for (int i = threadIdx.x; i < k; i += blockDim.x) topk_out[(int64_t)qi * k + i] = (i < nkeys && i < S) ? keys[i] : 0u;
+}
+
+// thr[q] = k-th best of the gathered per-shard sample top-k lists [world][Q][k] minus the scan's error bound
+__global__ void __launch_bounds__(256) thr_union_kernel(const uint32_t *gathered, int world, int64_t Q, int P, const float *q,
+                                                        int d, int k, float eps_rel, float max_norm, float *thr) {
+    extern __shared__ uint32_t keys[];  // [P]
+    __shared__ float red[8];
+    const int64_t qi = blockIdx.x;
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) ss = fmaf(q[qi * d + i], q[qi * d + i], ss);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const int w = i / k, j = i - w * k;
+        keys[i] = w < world ? gathered[((int64_t)w * Q + qi) * k + j] : 0u;
+    }
+    __syncthreads();
+    float tot = 0.f;
+    for (int i = 0; i < 8; i++) tot += red[i];
+    bitonic_sort<uint32_t, true>(keys, P);
+    if (threadIdx.x == 0) thr[qi] = keys[k - 1] != 0u ? unflipf(keys[k - 1]) - 2.f * eps_rel * sqrtf(tot) * max_norm : -INFINITY;
 }
 
 // ---- select: rank by scan score, exact rescoring of the few that can matter, sort, emit ------------------------
@@ -531,7 +557,7 @@ int plan_search(Db *db, int64_t Q, int k, SearchPlan *p) {
 
 // 1. threshold pre-pass on the first S rows for Qs <= sgroup queries: thr[q] = a lower bound of the k-th best scan
 // score of this shard (minus the scan's error bound), qnorm[q] = |q|
-int prepass(Db *db, const SearchPlan &p, const float *qs, int Qs, int k, float *thr, float *qnorm) {
+int prepass(Db *db, const SearchPlan &p, const float *qs, int Qs, int k, float *thr, float *qnorm, uint32_t *topk_out = nullptr) {
     cudaStream_t st = db->ctx->stream;
     const int d = db->d;
     const int ng = (Qs + p.group - 1) / p.group;
@@ -549,7 +575,7 @@ int prepass(Db *db, const SearchPlan &p, const float *qs, int Qs, int k, float *
     knn_kth_chunk_kernel<<<dim3(Qs, nchunks), 256, (size_t)(cpad > 256 ? cpad : 256) * 4, st>>>(
         db->sample.as<float>(), S_keys, S_keys, p.chunk, cpad, k, db->rr_keys.as<uint32_t>());
     knn_kth_merge_kernel<<<Qs, 256, (size_t)P2 * 4, st>>>(db->rr_keys.as<uint32_t>(), nchunks * k, P2, S_keys, qs, d, k,
-                                                         p.eps_rel, db->max_norm, thr, qnorm);
+                                                         p.eps_rel, db->max_norm, thr, qnorm, topk_out);
     db->ctx->launches += 2;
     PF_CUDA(cudaGetLastError());
     return PFANN_OK;
@@ -643,11 +669,12 @@ int db_search_dev(Db *db, const float *q, int64_t Q, int k, float *dist, int64_t
 // Sharded search, phase 1 (device pointers): per-query thresholds of THIS shard for all Q queries.  A caller that
 // searches several shards takes the element-wise maximum over the shards (each is a lower bound of the GLOBAL k-th
 // best score, provided every shard uses the same error bound: pfann_db_set_max_norm) and hands it to phase 2.
-int db_search_thresholds_dev(Db *db, const float *q, int64_t Q, int k, float *thr) {
+int db_search_thresholds_dev(Db *db, const float *q, int64_t Q, int k, float *thr, uint32_t *topk_out) {
     if (Q == 0) return PFANN_OK;
     SearchPlan p;
     PF_TRY(plan_search(db, Q, k, &p));
     if (db->n == 0) {
+        if (topk_out) PF_CUDA(cudaMemsetAsync(topk_out, 0, sizeof(uint32_t) * (size_t)Q * k, db->ctx->stream));
         fill_f32_kernel<<<cdiv(Q, 256), 256, 0, db->ctx->stream>>>(thr, -INFINITY, Q);   // an empty shard bounds nothing
         db->ctx->launches++;
         PF_CUDA(cudaGetLastError());
@@ -656,7 +683,7 @@ int db_search_thresholds_dev(Db *db, const float *q, int64_t Q, int k, float *th
     for (int64_t g = 0; g < p.ngroups; g++) {
         const int64_t q0 = g * p.sgroup;
         const int Qs = (int)((Q - q0) < p.sgroup ? (Q - q0) : p.sgroup);
-        PF_TRY(prepass(db, p, q + q0 * db->d, Qs, k, thr + q0, db->qnorm.as<float>() + q0));
+        PF_TRY(prepass(db, p, q + q0 * db->d, Qs, k, thr + q0, db->qnorm.as<float>() + q0, topk_out ? topk_out + q0 * k : nullptr));
     }
     return PFANN_OK;
 }
@@ -859,6 +886,39 @@ int pfann_db_search_thresholds(pfann_db *h, const float *q, int64_t Q, int k, fl
              "pfann_db_search_thresholds: q and thr must be device pointers");
     PF_CUDA(cudaSetDevice(db->ctx->device));
     return db_search_thresholds_dev(db, q, Q, k, thr);
+}
+
+int pfann_db_search_sample_topk(pfann_db *h, const float *q, int64_t Q, int k, float *thr, uint32_t *topk) {
+    PF_CHECK(h && Q >= 0 && k > 0 && (Q == 0 || (q && thr && topk)), PFANN_ERR_ARG, "pfann_db_search_sample_topk: bad argument");
+    Db *db = reinterpret_cast<Db *>(h);
+    PF_CHECK(Q == 0 || (is_device_ptr(q) && is_device_ptr(thr) && is_device_ptr(topk)), PFANN_ERR_ARG,
+             "pfann_db_search_sample_topk: q, thr and topk must be device pointers");
+    PF_CUDA(cudaSetDevice(db->ctx->device));
+    return db_search_thresholds_dev(db, q, Q, k, thr, topk);
+}
+
+int pfann_db_thresholds_from_topk(pfann_db *h, const uint32_t *gathered, int world, const float *q, int64_t Q, int k, float *thr) {
+    PF_CHECK(h && world > 0 && Q >= 0 && k > 0 && (Q == 0 || (gathered && q && thr)), PFANN_ERR_ARG,
+             "pfann_db_thresholds_from_topk: bad argument");
+    if (Q == 0) return PFANN_OK;
+    Db *db = reinterpret_cast<Db *>(h);
+    PF_CHECK(is_device_ptr(gathered) && is_device_ptr(q) && is_device_ptr(thr), PFANN_ERR_ARG,
+             "pfann_db_thresholds_from_topk: device pointers only");
+    PF_CUDA(cudaSetDevice(db->ctx->device));
+    SearchPlan p;
+    PF_TRY(plan_search(db, Q, k, &p));
+    int P2 = 1;
+    while (P2 < world * k) P2 <<= 1;
+    PF_CHECK((size_t)P2 * 4 <= 160 * 1024, PFANN_ERR_UNSUPPORTED, "pfann_db_thresholds_from_topk: world * k = %d too large", world * k);
+    PF_CUDA(cudaFuncSetAttribute(thr_union_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2 * 4));
+    ProfScope ps(db->ctx, K_KNN_SELECT, 37);
+    // the gathered scores may come from another shard's bf16 scan whatever this shard runs: always the larger bound
+    const float eps_union = 4.0e-3f + fmaxf(1.0e-5f, 1.2e-7f * (float)db->d);
+    thr_union_kernel<<<(unsigned)Q, 256, (size_t)P2 * 4, db->ctx->stream>>>(gathered, world, Q, P2, q, db->d, k, eps_union,
+                                                                           db->max_norm, thr);
+    db->ctx->launches++;
+    PF_CUDA(cudaGetLastError());
+    return PFANN_OK;
 }
 
 int pfann_db_search_filtered(pfann_db *h, const float *q, int64_t Q, int k, float *thr, uint64_t *keys, int defer_overflow_check) {

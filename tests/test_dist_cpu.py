@@ -43,6 +43,18 @@ class OracleShard:
         thr = sc[:, k - 1] if rows.shape[0] >= k else np.full(q.shape[0], -np.inf, np.float32)
         return torch.from_numpy(np.ascontiguousarray(thr, dtype=np.float32))
 
+    def sample_topk(self, q, k):
+        # the k best SAMPLED scores per query as opaque sortable keys (here: the fp32 bits of non-negative shifted scores)
+        rows = self.db[self.r0:self.r1][::3]
+        sc = np.sort(q.numpy() @ rows.T, axis=1)[:, ::-1][:, :k].astype(np.float32)
+        out = np.full((q.shape[0], k), -np.inf, np.float32)
+        out[:, :sc.shape[1]] = sc
+        return torch.from_numpy(out.view(np.int32).copy())
+
+    def thresholds_from_topk(self, top_g, q, k):
+        sc = np.concatenate(list(top_g.numpy().view(np.float32)), axis=1)      # [Q, G * k]
+        return torch.from_numpy(np.ascontiguousarray(np.sort(sc, axis=1)[:, ::-1][:, k - 1]))
+
     def take_overflow(self):
         return 0
 
@@ -92,6 +104,14 @@ def _worker(rank, world, port, ret):
     qi = np.stack([np.arange(6) * 19, np.full(6, 19)], 1).astype(np.int64)
     shard = OracleShard(db, pos, shard_songs(pos, world)[rank])
     sdb = ShardedDatabase(shard, 10, 1, 0.5)
+    # the union-of-samples threshold is a lower bound of the global k-th best score and at least as tight as the
+    # maximum of the per-shard thresholds (the older exchange, still used by backends without sample_topk)
+    qt = shard.to_device(q)
+    thr_union = shard.thresholds_from_topk(sdb._all_gather(shard.sample_topk(qt, 10)), qt, 10)
+    thr_max = shard.thresholds(qt, 10)
+    dist.all_reduce(thr_max, op=dist.ReduceOp.MAX)
+    kth = np.sort(q @ db.T, axis=1)[:, ::-1][:, 9]
+    assert (thr_union.numpy() <= kth + 1e-6).all() and (thr_union.numpy() >= thr_max.numpy() - 1e-6).all()
     score, song, tim = sdb.query_batch(q, qi)
     s2, g2, t2 = sdb.query_batches(q, qi, 4)                      # two batches, one read-back: same answers
     assert np.array_equal(score, s2) and np.array_equal(song, g2) and np.array_equal(tim, t2)

@@ -616,8 +616,16 @@ def test_sharded_search_phases_three_shards_one_gpu(dev):
     for s in shards:
         s.set_max_norm(m)
     q = shards[0].to_device(q_flat)
-    thr = torch.stack([s.thresholds(q, k) for s in shards]).amax(dim=0)
+    thr_max = torch.stack([s.thresholds(q, k) for s in shards]).amax(dim=0)
     assert torch.isinf(shards[2].thresholds(q, k)).all()            # an empty shard bounds nothing
+    # thresholds from the union of the shards' samples (the exchange dist.py uses): still a lower bound of the global
+    # k-th best score, at least as tight as the maximum of the per-shard bounds, identical on every shard
+    top = torch.stack([s.sample_topk(q, k) for s in shards])
+    assert (top[2] == 0).all()
+    thr = shards[0].thresholds_from_topk(top, q, k)
+    assert torch.equal(thr, shards[2].thresholds_from_topk(top, q, k))
+    kth = torch.from_numpy(np.sort(q_flat @ db.T, axis=1)[:, ::-1][:, k - 1].copy()).to(thr.device)
+    assert (thr <= kth).all() and (thr >= thr_max - 1e-6).all() and (thr > thr_max).any()
     keys = torch.stack([s.filtered_keys(q, k, thr.clone(), True) for s in shards])
     assert (keys[2] == 0).all() and (keys[:2] == 0).any()           # empty shard; some lists shorter than k
     D, I = shards[0].merge_keys(keys, k, want_dist=True)
