@@ -342,6 +342,11 @@ def main():
     mel_ms, _ = prof['mel']
     if mel_ms > 0:
         roofline['mel_hbm_frac'] = (SEG_BYTES_MEL * n_seg * args.steps / (mel_ms / 1000.0) / 1e9) / pk['hbm_gbs']
+        if os.environ.get('PFANN_B200_NO_OVERLAP') is None:
+            # the mel kernel of chunk k + 1 runs on a low-priority stream next to the encoder of chunk k: its event
+            # pairs span the time it waits for SMs, not its work (serial run, PFANN_B200_NO_OVERLAP=1: ~52 ms per step)
+            roofline['mel_note'] = ('mel runs concurrently with the encoder at low priority: its event time is elapsed '
+                                    'time, not work (52 ms per 590000 segments when run alone)')
 
     out = {
         'metric': METRIC, 'value': value,
