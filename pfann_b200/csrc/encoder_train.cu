@@ -159,12 +159,25 @@ __global__ void __launch_bounds__(512) ln_bwd_reduce_kernel(const float *dA, con
     const long long b = blockIdx.x;
     const float2 st = stats[b];
     double s1 = 0.0, s2 = 0.0;
-    for (long long e = threadIdx.x; e < E; e += blockDim.x) {
-        const float a = A[b * E + e];
-        if (a > 0.f) {
-            const float g = dA[b * E + e] * gamma[e];
-            s1 += (double)g;
-            s2 += (double)g * (double)((Y[b * E + e] - st.x) * st.y);
+    if ((E & 3) == 0) {   // 16-byte loads, fp32 within a group of four, double across groups
+        const float4 *a4 = reinterpret_cast<const float4 *>(A + b * E), *d4 = reinterpret_cast<const float4 *>(dA + b * E);
+        const float4 *y4 = reinterpret_cast<const float4 *>(Y + b * E), *g4 = reinterpret_cast<const float4 *>(gamma);
+        for (long long e = threadIdx.x; e < E / 4; e += blockDim.x) {
+            const float4 a = a4[e], d = d4[e], y = y4[e], gm = __ldg(g4 + e);
+            const float g0 = a.x > 0.f ? d.x * gm.x : 0.f, g1 = a.y > 0.f ? d.y * gm.y : 0.f;
+            const float g2 = a.z > 0.f ? d.z * gm.z : 0.f, g3 = a.w > 0.f ? d.w * gm.w : 0.f;
+            s1 += (double)((g0 + g1) + (g2 + g3));
+            s2 += (double)(fmaf(g0, (y.x - st.x) * st.y, g1 * ((y.y - st.x) * st.y)) +
+                           fmaf(g2, (y.z - st.x) * st.y, g3 * ((y.w - st.x) * st.y)));
+        }
+    } else {
+        for (long long e = threadIdx.x; e < E; e += blockDim.x) {
+            const float a = A[b * E + e];
+            if (a > 0.f) {
+                const float g = dA[b * E + e] * gamma[e];
+                s1 += (double)g;
+                s2 += (double)g * (double)((Y[b * E + e] - st.x) * st.y);
+            }
         }
     }
     const double t1 = block_sum_d(s1, sh), t2 = block_sum_d(s2, sh);
@@ -181,6 +194,25 @@ __global__ void __launch_bounds__(256) ln_bwd_apply_kernel(float *dA, const floa
     const int n = (int)((E - e0) < 4 ? (E - e0) : 4);
     float gam[4], ag[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f};
     for (int i = 0; i < n; i++) gam[i] = gamma[e0 + i];
+    if ((E & 3) == 0) {   // n == 4 and 16-byte aligned rows
+        for (int b = b0; b < b1; b++) {
+            const float2 st = __ldg(stats + b), rd = __ldg(red + b);
+            const long long idx = (long long)b * E + e0;
+            const float4 a = *reinterpret_cast<const float4 *>(A + idx), y = *reinterpret_cast<const float4 *>(Y + idx);
+            float4 d = *reinterpret_cast<const float4 *>(dA + idx);
+            const float av[4] = {a.x, a.y, a.z, a.w}, yv[4] = {y.x, y.y, y.z, y.w};
+            float dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const float dn = av[i] > 0.f ? dv[i] : 0.f;
+                const float xh = (yv[i] - st.x) * st.y;
+                ag[i] = fmaf(dn, xh, ag[i]);
+                ab[i] += dn;
+                dv[i] = st.y * (dn * gam[i] - rd.x - xh * rd.y);
+            }
+            *reinterpret_cast<float4 *>(dA + idx) = make_float4(dv[0], dv[1], dv[2], dv[3]);
+        }
+    } else
     for (int b = b0; b < b1; b++) {
         const float2 st = stats[b], rd = red[b];
         for (int i = 0; i < n; i++) {
@@ -285,7 +317,9 @@ __global__ void __launch_bounds__(256) conv_bwd_w_kernel(const BwdWArgs a) {
 // ---- depthwise conv2 (fuller == false): data and weight gradients ----
 __global__ void dw_bwd_data_kernel(const float *dY, const float *W /*[C][ntaps]*/, float *dX, long long total, int C, int Fi,
                                    int Ti, int Fo, int ntaps, int off0, int off1, int off2, int stride) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over dX [nb][Fi][Ti][C]
+    // thread = VEC consecutive channels of one input position; total = elements of dX [nb][Fi][Ti][C]
+    const int VEC = (C & 3) == 0 ? 4 : 1;
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     if (i >= total) return;
     const int c = (int)(i % C);
     long long r = i / C;
@@ -294,15 +328,25 @@ __global__ void dw_bwd_data_kernel(const float *dY, const float *W /*[C][ntaps]*
     const int fi = (int)(r % Fi);
     const long long b = r / Fi;
     const int offs[3] = {off0, off1, off2};
-    float acc = 0.f;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int j = 0; j < ntaps; j++) {
         const int num = fi - offs[j];
         if (num < 0 || num % stride) continue;
         const int fo = num / stride;
         if (fo >= Fo) continue;
-        acc = fmaf(W[c * ntaps + j], dY[((b * Fo + fo) * Ti + t) * (long long)C + c], acc);
+        const float *g = dY + ((b * Fo + fo) * Ti + t) * (long long)C + c;
+        if (VEC == 4) {
+            const float4 gv = *reinterpret_cast<const float4 *>(g);
+            acc[0] = fmaf(__ldg(W + c * ntaps + j), gv.x, acc[0]);
+            acc[1] = fmaf(__ldg(W + (c + 1) * ntaps + j), gv.y, acc[1]);
+            acc[2] = fmaf(__ldg(W + (c + 2) * ntaps + j), gv.z, acc[2]);
+            acc[3] = fmaf(__ldg(W + (c + 3) * ntaps + j), gv.w, acc[3]);
+        } else {
+            acc[0] = fmaf(__ldg(W + c * ntaps + j), *g, acc[0]);
+        }
     }
-    dX[i] = acc;
+    if (VEC == 4) *reinterpret_cast<float4 *>(dX + i) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    else dX[i] = acc[0];
 }
 
 // CTA = (256 / CW row lanes) x (CW channels) over a slice of output positions: coalesced along the channels, partial
@@ -533,8 +577,8 @@ int pfann_model_train_backward(pfann_model *hm, const float *dz, int norm) {
             ProfScope ps(ctx, K_LN, 16 + i);
             ln_bwd_reduce_kernel<<<B, 512, 0, st>>>(dcur, t->X[i].as<float>(), t->Y[i].as<float>(), t->stats[i].as<float2>(),
                                                     cw.gamma, E, t->lnred.as<float2>());
-            int group = 16;
-            while (group > 1 && (long long)cdiv(E, 1024) * cdiv(B, group) < 2LL * ctx->sm_count) group >>= 1;
+            int group = 64;   // samples per thread before its 8 atomics
+            while (group > 1 && (long long)cdiv(E, 1024) * cdiv(B, group) < 4LL * ctx->sm_count) group >>= 1;
             dim3 grid(cdiv(E, 1024), cdiv(B, group));
             ln_bwd_apply_kernel<<<grid, 256, 0, st>>>(dcur, t->X[i].as<float>(), t->Y[i].as<float>(), t->stats[i].as<float2>(),
                                                       t->lnred.as<float2>(), cw.gamma, E, B, group, t->gG[i].as<float>(),
@@ -556,7 +600,7 @@ int pfann_model_train_backward(pfann_model *hm, const float *dz, int norm) {
                                                                    g.tap_off[0], g.tap_off[1], g.tap_off[2], g.stride,
                                                                    t->gW[i].as<float>(), t->gB[i].as<float>());
             const long long total = (long long)B * g.Fi * g.Ti * g.Ci;
-            dw_bwd_data_kernel<<<cdiv(total, 256), 256, 0, st>>>(dcur, cw.w_kn, dnext, total, g.Co, g.Fi, g.Ti, g.Fo, g.ntaps,
+            dw_bwd_data_kernel<<<cdiv(total, 256 * ((g.Co & 3) == 0 ? 4 : 1)), 256, 0, st>>>(dcur, cw.w_kn, dnext, total, g.Co, g.Fi, g.Ti, g.Fo, g.ntaps,
                                                                  g.tap_off[0], g.tap_off[1], g.tap_off[2], g.stride);
             ctx->launches += 2;
         } else {
