@@ -24,7 +24,7 @@ struct Db {
     float sample_scale = 1.f;        // multiplier of the k * n / 256 target (sharded search: thresholds are max-reduced)
     int use_tc = 1;                  // tensor-core bf16 scan when available, else fp32 CUDA-core scan
     // scratch
-    DevBuf qbuf, qnorm, thr, cnt, cand, cand_v, sample, flags, dist, labels, rr_keys, rr_scores, rr_out, lab_stage;
+    DevBuf qbuf, qnorm, thr, cnt, cand, cand_v, sample, flags, dist, labels, rr_keys, rr_scores, rr_out, lab_stage, rr_xscores, rr_done;
     void *tc_state = nullptr;
     int *ovf_host = nullptr, *ovf_dev = nullptr;  // deferred overflow count of the sharded search (pinned, mapped)
 };

@@ -814,7 +814,7 @@ void pfann_db_close(pfann_db *h) {
     cudaFree(db->emb16);
     cudaFree(db->song_pos);
     DevBuf *bufs[] = {&db->qbuf, &db->qnorm, &db->thr, &db->cnt, &db->cand, &db->cand_v, &db->sample, &db->flags, &db->dist,
-                      &db->labels, &db->rr_keys, &db->rr_scores, &db->rr_out, &db->lab_stage};
+                      &db->labels, &db->rr_keys, &db->rr_scores, &db->rr_out, &db->lab_stage, &db->rr_xscores, &db->rr_done};
     for (DevBuf *b : bufs) b->release();
     if (db->ovf_host) cudaFreeHost(db->ovf_host);
     delete db;

@@ -57,6 +57,10 @@ struct RerankArgs {
     unsigned long long *gkeys;   // [nq][capK] or nullptr when shared memory is used
     float *gscores;              // [nq][capK] or nullptr
     unsigned stage_off;          // byte offset of the row staging tiles in dynamic shared memory, 0 = none
+    // few query files per launch (matcher.py:136 calls once per file): gridDim.y CTAs share one file's candidates, the
+    // last one to finish gathers the scores and runs the per-song reduction
+    float *xscores;              // [nq][capK] exchange of candidate scores, or nullptr (one CTA per file)
+    unsigned *done_cnt;          // [nq] CTAs finished, zero on entry
     // outputs
     float *best_score;           // [nq] raw best candidate score (-inf if none)
     int *best_song;              // [nq] global song id or -1
@@ -67,7 +71,7 @@ struct RerankArgs {
 
 __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(const RerankArgs a) {
     extern __shared__ __align__(16) unsigned char smraw[];
-    __shared__ int n_valid_s;
+    __shared__ int n_valid_s, last_s;
     __shared__ float red_s[RR_THREADS / 32];
     __shared__ int red_song[RR_THREADS / 32];
     __shared__ float red_t[RR_THREADS / 32];
@@ -119,11 +123,16 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(const RerankArgs a) 
     bitonic_sort<unsigned long long, false>(keys, P);
     const int n_valid = n_valid_s;
     // (3) score every unique candidate: one warp per candidate, one lane per sub-query row
-    for (int i = warp; i < n_valid; i += RR_THREADS / 32) {
+    const int nsplit = (int)gridDim.y, split = (int)blockIdx.y;
+    float *xs = a.xscores ? a.xscores + (int64_t)qi * a.capK : nullptr;
+    for (int i = warp + (RR_THREADS / 32) * split; i < n_valid; i += (RR_THREADS / 32) * nsplit) {
         const unsigned long long key = keys[i];
         const bool head = (i == 0) || (keys[i - 1] != key);
         if (!head) {
-            if (lane == 0) scores[i] = -INFINITY;
+            if (lane == 0) {
+                scores[i] = -INFINITY;
+                if (xs) xs[i] = -INFINITY;
+            }
             continue;
         }
         const int song = key_song(key) - (int)a.song_base, off = key_off(key), shift = key_shift(key);
@@ -194,9 +203,26 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(const RerankArgs a) 
             }
         }
         sco = __fdiv_rn(sco, (float)(my_len > 1 ? my_len : 1));
-        if (lane == 0) scores[i] = sco;
+        if (lane == 0) {
+            scores[i] = sco;
+            if (xs) xs[i] = sco;
+        }
     }
     __syncthreads();
+    if (xs != nullptr) {
+        // the last of this file's CTAs to arrive continues with everybody's scores; the others are done
+        if (tid == 0) {
+            __threadfence();
+            const unsigned prev = atomicAdd(a.done_cnt + qi, 1u);
+            last_s = (prev == (unsigned)nsplit - 1u);
+            if (last_s) a.done_cnt[qi] = 0u;   // ready for the next launch
+        }
+        __syncthreads();
+        if (!last_s) return;
+        __threadfence();
+        for (int i = tid; i < n_valid; i += RR_THREADS) scores[i] = __ldcg(xs + i);
+        __syncthreads();
+    }
     // (4) per-song first strict maximum, then the best song (ties -> lower song id)
     float my_best = -INFINITY, my_t = 0.f;
     int my_song = -1;
@@ -290,8 +316,19 @@ int rerank_dev(Db *db, const float *queries, const int64_t *query_index, int nq,
     }
     PF_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(SMEM_CAND_MAX * 12 + 16 + stage_bytes)));
+    int nsplit = 1;
+    if (a.gkeys == nullptr && nq * 4 <= db->ctx->sm_count) {   // a handful of files: spread each over several CTAs
+        nsplit = db->ctx->sm_count / nq;
+        if (nsplit > 16) nsplit = 16;
+        const bool fresh = db->rr_done.cap < (size_t)nq * 4;
+        PF_TRY(db->rr_xscores.ensure((size_t)nq * capK * 4));
+        PF_TRY(db->rr_done.ensure((size_t)nq * 4 < 1024 ? 1024 : (size_t)nq * 4));
+        if (fresh) PF_CUDA(cudaMemsetAsync(db->rr_done.p, 0, db->rr_done.cap, db->ctx->stream));   // self-resetting afterwards
+        a.xscores = db->rr_xscores.as<float>();
+        a.done_cnt = db->rr_done.as<unsigned>();
+    }
     ProfScope ps(db->ctx, K_RERANK, 39);
-    rerank_kernel<<<nq, RR_THREADS, smem, db->ctx->stream>>>(a);
+    rerank_kernel<<<dim3(nq, nsplit), RR_THREADS, smem, db->ctx->stream>>>(a);
     db->ctx->launches++;
     PF_CUDA(cudaGetLastError());
     return PFANN_OK;
