@@ -529,9 +529,14 @@ int plan_search(Db *db, int64_t Q, int k, SearchPlan *p) {
     // sample size: aim at ~256 rows above the threshold (k * n / S ~ 256), within [sample_rows, 256 Ki].  Every
     // survivor costs ~100 instructions on the filter's hit path (measured: 360 k survivors per 256-query pass doubled
     // the scan time of a 1.25 M-row shard), a sampled row costs one more tile of the cheap pre-pass.
-    int64_t want = (int64_t)((double)k * db->n / 256 * db->sample_scale);
+    // Measured on 10 M rows, 190 k queries: 262 k sampled rows -> pre-pass 26 ms + filtered scan 470 ms; 524 k -> 50 + 418;
+    // 781 k -> 73 + 393 (the pre-pass costs twice the filtered scan per row: it keeps maxima instead of testing signs).
+    int64_t cap_rows = 524288;
+    if (const char *e = getenv("PFANN_B200_SAMPLE_ROWS_MAX")) cap_rows = atoll(e);   // experiment knob
+    int64_t want = (int64_t)((double)k * db->n / 256);
+    if (want > cap_rows) want = cap_rows;
+    want = (int64_t)((double)want * db->sample_scale);   // sharded search: the threshold comes from all shards' samples
     if (want < db->sample_rows) want = db->sample_rows;
-    if (want > 262144) want = 262144;
     p->chunk = 8192;  // one kth-select CTA sorts this many sample scores in shared memory
     int64_t max_chunks = 8192 / k;  // stage 2 sorts nchunks * k keys in shared memory
     if (want > max_chunks * p->chunk) want = max_chunks * p->chunk;
