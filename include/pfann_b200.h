@@ -179,7 +179,7 @@ int pfann_ir_conv(pfann_ctx *ctx, const float *x, int64_t B, int n, const float 
  * LayerNorm statistics and activations; train_backward takes dz = dL/dz [B][d] of the same batch and leaves the
  * parameter gradients in the model; get_grad copies the gradient of the parameter with state_dict key `name`, in the
  * reference's element order (host or device `out`).  Gradients are sums over the batch like torch's; they are
- * overwritten, not accumulated, by the next backward.  ReLU + relu_after_bn only (PFANN_ERR_UNSUPPORTED otherwise). */
+ * overwritten, not accumulated, by the next backward.  Every option set of pfann_model_create_ex is supported. */
 int pfann_model_train_forward(pfann_model *m, const float *mel, int64_t B, int norm, float *z);
 int pfann_model_train_backward(pfann_model *m, const float *dz, int norm);
 int pfann_model_get_grad(pfann_model *m, const char *name, float *out, int64_t numel);

@@ -2,7 +2,7 @@
 // with the activations kept (model.py:148-153) and its backward, i.e. what torch autograd does for the reference in
 // train.py:99-103.  fp32 CUDA-core kernels throughout (the reference trains in fp32 / AMP; gradients feed an optimizer, a
 // bf16 tensor-core backward is future work -- DESIGN.md section 8); activations are channels-last like the inference
-// path.  Supported option set: ReLU, relu_after_bn = True, any strides, dense or depthwise conv2.
+// path.  Every option set of FpNetwork: ReLU / ELU, relu_after_bn True / False, any strides, dense or depthwise conv2.
 //
 // Per convolution i (conv -> LayerNorm over (C,F,T) with per-element affine -> ReLU), given dA = dL/d(output):
 //     dn   = dA * [A > 0]                                   ReLU'
@@ -151,10 +151,29 @@ __global__ void head_bwd_kernel(const float *x, const float *p, const float *dr,
     if (j == 0) atomicAdd(gb2 + g, ab2);
 }
 
-// ---- LayerNorm + ReLU backward ----
-// red[b] = (mean_e g, mean_e g xhat), g = dA [A > 0] gamma
+// ---- LayerNorm + activation backward, all option sets of model.py:58-72 ----
+// mode bits 0-1: 0 ReLU, 1 ELU; bit 2: activation BEFORE the LayerNorm (relu_after_bn == False).
+//   after  (default): A = act(n), n = xhat gamma + beta, xhat = (Y - mean) rstd:  dn = dA act'(n), dY = LNbwd(dn gamma)
+//   before          : A = zhat gamma + beta, zhat = (act(Y) - mean) rstd:          dn = dA, dY = LNbwd(dn gamma) act'(Y)
+// act' from the stored output: ReLU' = [out > 0]; ELU' = out > 0 ? 1 : out + 1 (= exp(in) for in <= 0).
+__device__ __forceinline__ float act_val(float y, int act) { return act == 1 ? (y > 0.f ? y : expm1f(y)) : fmaxf(y, 0.f); }
+__device__ __forceinline__ float act_grad_from_out(float out, int act) {
+    return act == 1 ? (out > 0.f ? 1.f : out + 1.f) : (out > 0.f ? 1.f : 0.f);
+}
+// (dn, normalised input of the LayerNorm) for one element
+__device__ __forceinline__ void ln_bwd_terms(float dA, float A, float Y, float2 st, int mode, float &dn, float &xh) {
+    if (mode & 4) {
+        dn = dA;
+        xh = (act_val(Y, mode & 3) - st.x) * st.y;
+    } else {
+        dn = dA * act_grad_from_out(A, mode & 3);
+        xh = (Y - st.x) * st.y;
+    }
+}
+
+// red[b] = (mean_e g, mean_e g xhat), g = dn gamma
 __global__ void __launch_bounds__(512) ln_bwd_reduce_kernel(const float *dA, const float *A, const float *Y, const float2 *stats,
-                                                            const float *gamma, long long E, float2 *red) {
+                                                            const float *gamma, long long E, float2 *red, int mode) {
     __shared__ double sh[16];
     const long long b = blockIdx.x;
     const float2 st = stats[b];
@@ -164,20 +183,22 @@ __global__ void __launch_bounds__(512) ln_bwd_reduce_kernel(const float *dA, con
         const float4 *y4 = reinterpret_cast<const float4 *>(Y + b * E), *g4 = reinterpret_cast<const float4 *>(gamma);
         for (long long e = threadIdx.x; e < E / 4; e += blockDim.x) {
             const float4 a = a4[e], d = d4[e], y = y4[e], gm = __ldg(g4 + e);
-            const float g0 = a.x > 0.f ? d.x * gm.x : 0.f, g1 = a.y > 0.f ? d.y * gm.y : 0.f;
-            const float g2 = a.z > 0.f ? d.z * gm.z : 0.f, g3 = a.w > 0.f ? d.w * gm.w : 0.f;
+            float dn[4], xh[4];
+            ln_bwd_terms(d.x, a.x, y.x, st, mode, dn[0], xh[0]);
+            ln_bwd_terms(d.y, a.y, y.y, st, mode, dn[1], xh[1]);
+            ln_bwd_terms(d.z, a.z, y.z, st, mode, dn[2], xh[2]);
+            ln_bwd_terms(d.w, a.w, y.w, st, mode, dn[3], xh[3]);
+            const float g0 = dn[0] * gm.x, g1 = dn[1] * gm.y, g2 = dn[2] * gm.z, g3 = dn[3] * gm.w;
             s1 += (double)((g0 + g1) + (g2 + g3));
-            s2 += (double)(fmaf(g0, (y.x - st.x) * st.y, g1 * ((y.y - st.x) * st.y)) +
-                           fmaf(g2, (y.z - st.x) * st.y, g3 * ((y.w - st.x) * st.y)));
+            s2 += (double)(fmaf(g0, xh[0], g1 * xh[1]) + fmaf(g2, xh[2], g3 * xh[3]));
         }
     } else {
         for (long long e = threadIdx.x; e < E; e += blockDim.x) {
-            const float a = A[b * E + e];
-            if (a > 0.f) {
-                const float g = dA[b * E + e] * gamma[e];
-                s1 += (double)g;
-                s2 += (double)g * (double)((Y[b * E + e] - st.x) * st.y);
-            }
+            float dn, xh;
+            ln_bwd_terms(dA[b * E + e], A[b * E + e], Y[b * E + e], st, mode, dn, xh);
+            const float g = dn * gamma[e];
+            s1 += (double)g;
+            s2 += (double)g * (double)xh;
         }
     }
     const double t1 = block_sum_d(s1, sh), t2 = block_sum_d(s2, sh);
@@ -187,42 +208,42 @@ __global__ void __launch_bounds__(512) ln_bwd_reduce_kernel(const float *dA, con
 // dY (in place over dA) and the affine gradients; a thread owns 4 consecutive elements and walks `group` samples
 __global__ void __launch_bounds__(256) ln_bwd_apply_kernel(float *dA, const float *A, const float *Y, const float2 *stats,
                                                            const float2 *red, const float *gamma, long long E, int nb, int group,
-                                                           float *gG, float *gBe) {
+                                                           float *gG, float *gBe, int mode) {
     const long long e0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (e0 >= E) return;
     const int b0 = blockIdx.y * group, b1 = (b0 + group) < nb ? (b0 + group) : nb;
     const int n = (int)((E - e0) < 4 ? (E - e0) : 4);
     float gam[4], ag[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f};
     for (int i = 0; i < n; i++) gam[i] = gamma[e0 + i];
-    if ((E & 3) == 0) {   // n == 4 and 16-byte aligned rows
-        for (int b = b0; b < b1; b++) {
-            const float2 st = __ldg(stats + b), rd = __ldg(red + b);
-            const long long idx = (long long)b * E + e0;
+    const bool vec = (E & 3) == 0;   // n == 4 and 16-byte aligned rows
+    for (int b = b0; b < b1; b++) {
+        const float2 st = __ldg(stats + b), rd = __ldg(red + b);
+        const long long idx = (long long)b * E + e0;
+        float av[4], yv[4], dv[4];
+        if (vec) {
             const float4 a = *reinterpret_cast<const float4 *>(A + idx), y = *reinterpret_cast<const float4 *>(Y + idx);
-            float4 d = *reinterpret_cast<const float4 *>(dA + idx);
-            const float av[4] = {a.x, a.y, a.z, a.w}, yv[4] = {y.x, y.y, y.z, y.w};
-            float dv[4] = {d.x, d.y, d.z, d.w};
+            const float4 d = *reinterpret_cast<const float4 *>(dA + idx);
+            av[0] = a.x; av[1] = a.y; av[2] = a.z; av[3] = a.w;
+            yv[0] = y.x; yv[1] = y.y; yv[2] = y.z; yv[3] = y.w;
+            dv[0] = d.x; dv[1] = d.y; dv[2] = d.z; dv[3] = d.w;
+        } else {
+            for (int i = 0; i < n; i++) { av[i] = A[idx + i]; yv[i] = Y[idx + i]; dv[i] = dA[idx + i]; }
+        }
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const float dn = av[i] > 0.f ? dv[i] : 0.f;
-                const float xh = (yv[i] - st.x) * st.y;
+        for (int i = 0; i < 4; i++) {
+            if (i < n) {
+                float dn, xh;
+                ln_bwd_terms(dv[i], av[i], yv[i], st, mode, dn, xh);
                 ag[i] = fmaf(dn, xh, ag[i]);
                 ab[i] += dn;
-                dv[i] = st.y * (dn * gam[i] - rd.x - xh * rd.y);
+                float dz = st.y * (dn * gam[i] - rd.x - xh * rd.y);
+                // activation before the LayerNorm: its derivative at the conv output (ReLU: Y > 0; ELU: exp(Y) for Y <= 0)
+                if (mode & 4) dz *= (mode & 3) == 1 ? (yv[i] > 0.f ? 1.f : expf(yv[i])) : (yv[i] > 0.f ? 1.f : 0.f);
+                dv[i] = dz;
             }
-            *reinterpret_cast<float4 *>(dA + idx) = make_float4(dv[0], dv[1], dv[2], dv[3]);
         }
-    } else
-    for (int b = b0; b < b1; b++) {
-        const float2 st = stats[b], rd = red[b];
-        for (int i = 0; i < n; i++) {
-            const long long idx = (long long)b * E + e0 + i;
-            const float dn = A[idx] > 0.f ? dA[idx] : 0.f;
-            const float xh = (Y[idx] - st.x) * st.y;
-            ag[i] = fmaf(dn, xh, ag[i]);
-            ab[i] += dn;
-            dA[idx] = st.y * (dn * gam[i] - rd.x - xh * rd.y);
-        }
+        if (vec) *reinterpret_cast<float4 *>(dA + idx) = make_float4(dv[0], dv[1], dv[2], dv[3]);
+        else for (int i = 0; i < n; i++) dA[idx + i] = dv[i];
     }
     for (int i = 0; i < n; i++) {
         atomicAdd(gG + e0 + i, ag[i]);
@@ -494,8 +515,6 @@ int pfann_model_train_forward(pfann_model *hm, const float *mel, int64_t B, int 
     PF_CHECK(hm && mel && z && B > 0 && B <= 65535, PFANN_ERR_ARG, "pfann_model_train_forward: bad argument");
     Model *m = reinterpret_cast<Model *>(hm);
     PF_CHECK(m->precision >= 0, PFANN_ERR_STATE, "pfann_model_train_forward: call pfann_model_finalize first");
-    PF_CHECK(m->act == PFANN_ACT_RELU && !m->act_first, PFANN_ERR_UNSUPPORTED,
-             "pfann_model_train_forward: only ReLU with relu_after_bn = True has a backward");
     PF_CHECK(is_device_ptr(mel) && is_device_ptr(z), PFANN_ERR_ARG, "pfann_model_train_forward: device pointers only");
     PF_CHECK(m->h / m->d <= 16 && m->u <= 32 && m->d <= 1024, PFANN_ERR_UNSUPPORTED,
              "pfann_model_train_forward: head needs h/d <= 16 and u <= 32");
@@ -562,6 +581,7 @@ int pfann_model_train_backward(pfann_model *hm, const float *dz, int norm) {
         PF_CUDA(cudaGetLastError());
     }
     float *dcur = t->dA.as<float>(), *dnext = t->dB.as<float>();   // dcur = gradient w.r.t. X[i]
+    const int lnmode = m->act | (m->act_first ? 4 : 0);
     PF_TRY(t->lnred.ensure((size_t)B * sizeof(float2)));
     for (int i = 15; i >= 0; i--) {
         const ConvWeights &cw = m->conv[i];
@@ -576,13 +596,13 @@ int pfann_model_train_backward(pfann_model *hm, const float *dz, int norm) {
         {   // LayerNorm + ReLU backward: dcur becomes dY in place
             ProfScope ps(ctx, K_LN, 16 + i);
             ln_bwd_reduce_kernel<<<B, 512, 0, st>>>(dcur, t->X[i].as<float>(), t->Y[i].as<float>(), t->stats[i].as<float2>(),
-                                                    cw.gamma, E, t->lnred.as<float2>());
+                                                    cw.gamma, E, t->lnred.as<float2>(), lnmode);
             int group = 64;   // samples per thread before its 8 atomics
             while (group > 1 && (long long)cdiv(E, 1024) * cdiv(B, group) < 4LL * ctx->sm_count) group >>= 1;
             dim3 grid(cdiv(E, 1024), cdiv(B, group));
             ln_bwd_apply_kernel<<<grid, 256, 0, st>>>(dcur, t->X[i].as<float>(), t->Y[i].as<float>(), t->stats[i].as<float2>(),
                                                       t->lnred.as<float2>(), cw.gamma, E, B, group, t->gG[i].as<float>(),
-                                                      t->gBe[i].as<float>());
+                                                      t->gBe[i].as<float>(), lnmode);
             ctx->launches += 2;
             PF_CUDA(cudaGetLastError());
         }

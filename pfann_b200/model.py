@@ -117,7 +117,8 @@ class FpNetwork(Module):
     """model.py:132-153.  ``params`` is ``params['model']`` of the JSON config; the extra optional key
     ``b200_precision`` ('bf16' tensor-core path, default; 'fp32' CUDA-core validation path) picks the kernels.
     The option variants (conv_activation='ELU', relu_after_bn=False, custom strides -- NAF-converted models) run on
-    the CUDA-core kernels whatever precision is asked for: the tcgen05 path serves the default option set."""
+    the CUDA-core kernels whatever precision is asked for: the tcgen05 path serves the default option set.
+    In train() mode with gradients enabled the forward is differentiable (fp32 kernels, every option set)."""
 
     def __init__(self, d, h, u, F, T, params):
         super(FpNetwork, self).__init__()

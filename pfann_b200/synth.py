@@ -157,6 +157,9 @@ TRAIN_CASES = {
     'tiny_dw': ('tiny', {'fuller': False}, 8, 32),
     'tiny_strides': ('tiny', {'strides': NAF_STRIDES}, 6, 33),
     'n640d64': ('n640d64', {}, 4, 34),
+    'tiny_elu': ('tiny', {'conv_activation': 'ELU'}, 6, 35),
+    'tiny_act_first': ('tiny', {'relu_after_bn': False}, 6, 36),
+    'tiny_elu_act_first': ('tiny', {'conv_activation': 'ELU', 'relu_after_bn': False, 'fuller': False}, 6, 37),
 }
 
 

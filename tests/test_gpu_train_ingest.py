@@ -151,7 +151,8 @@ def _train_net(name, dev):
 def test_training_step_gradients_vs_reference_autograd(dev, golden_dir, name):
     """train.py:96-103: z = model(x); loss = similarity_loss(z, tau); loss.backward().  Every parameter's gradient
     against the reference network under torch autograd (golden: l2 norm + a seeded sample of elements), driven by the
-    reference's own dL/dz so that this checks the encoder backward alone."""
+    reference's own dL/dz so that this checks the encoder backward alone.  Cases: dense and depthwise conv2, a custom
+    stride schedule, n640d64, and the option variants ELU / activation before the LayerNorm / both (model.py:58-72)."""
     g = np.load(os.path.join(golden_dir, 'train_step.npz'))
     net, params, seed = _train_net(name, dev)
     x = torch.from_numpy(synth.train_case_input(name)).to(dev)
@@ -204,39 +205,3 @@ def test_training_step_end_to_end_loss_and_optimizer(dev, golden_dir):
     opt.zero_grad(set_to_none=True)
     similarity_loss(net(x), params['tau']).backward()
     assert all(p.grad is None for p in net.f.parameters()) and all(p.grad is not None for p in net.g.parameters())
-
-
-def test_training_forward_rejects_unsupported_options(dev):
-    from pfann_b200 import _lib
-    from pfann_b200.model import FpNetwork
-    net = FpNetwork(8, 32, 4, 256, 32, {'fuller': True, 'conv_activation': 'ELU'}).to(dev).train()
-    with pytest.raises(_lib.PfannError, match='ReLU'):
-        net(torch.zeros(2, 256, 32, device=dev))
-
-
-def test_impulse_response_convolution_vs_reference_fft(dev, golden_dir):
-    """dataset_v2.py:157-163: room + microphone responses.  The direct-form kernel against the reference's FFT route
-    (golden) and the float64 oracle, 2e-5 of the peak; plus ragged sizes (taps and outputs that do not fill a tile)."""
-    from pfann_b200.train import ImpulseResponses, apply_ir
-    g = np.load(os.path.join(golden_dir, 'train.npz'))
-    x = synth.synth_segments(3, seed=8, seg=8100)
-    air, mic = torch.from_numpy(g['ir_air']).to(dev), torch.from_numpy(g['ir_mic']).to(dev)
-    got = apply_ir(torch.from_numpy(x).to(dev), [air, mic], pad_start=100, segment_size=8100).cpu().numpy()
-    peak = np.abs(g['ir_out']).max()
-    assert got.shape == (3, 8000)
-    assert np.abs(got - g['ir_out']).max() <= 2e-5 * peak
-    assert np.abs(got - orc.apply_ir(x, [g['ir_air'], g['ir_mic']], 100, 8100)).max() <= 2e-5 * peak
-    rng = np.random.Generator(np.random.PCG64(3))
-    for n, L, start, end in [(1500, 301, 7, 1400), (50, 7, 0, 50), (3000, 1, 0, 2999), (1030, 2000, 3, 1030)]:
-        xs = rng.standard_normal((2, n)).astype(np.float32)
-        hs = rng.standard_normal((2, L)).astype(np.float32)
-        out = apply_ir(torch.from_numpy(xs).to(dev), [torch.from_numpy(hs).to(dev)], start, end).cpu().numpy()
-        ref = orc.apply_ir(xs, [hs], start, end)
-        assert out.shape == ref.shape and np.abs(out - ref).max() <= 2e-5 * np.abs(ref).max(), (n, L)
-    # the bank draws like ir.py:42-44
-    bank = ImpulseResponses([g['ir_mic'][0], g['ir_mic'][1][:100], g['ir_mic'][2]], dev)
-    torch.manual_seed(5)
-    rows = bank.random_choose(4)
-    torch.manual_seed(5)
-    idx = torch.randint(0, 3, size=(4,), dtype=torch.long)
-    assert torch.equal(rows.cpu(), bank.data.cpu()[idx])
