@@ -188,8 +188,10 @@ class FpNetwork(Module):
             if any(p.requires_grad for p in params):
                 return _TrainStep.apply(self, x, norm, *params)        # train.py:99-103
         dev = _lib.device_index(x)
-        hnd = self.native_handle(dev)
         _lib.use_torch_stream(dev)
+        # train() without a graph (the first pass of train.py:83-89): the fp32 kernels of the training model, so that
+        # the fingerprints agree with what the second, differentiated pass computes; eval(): the tensor-core model
+        hnd = self.native_handle(dev, training=self.training and x.is_cuda)
         xf = x.reshape(-1, F, T).to(torch.float32).contiguous()
         z = torch.empty((xf.shape[0], d), dtype=torch.float32, device=x.device)
         _lib.check(_lib.lib().pfann_model_forward(hnd, _lib.ptr(xf), xf.shape[0], int(bool(norm)), _lib.ptr(z)),
@@ -200,12 +202,13 @@ class FpNetwork(Module):
         """Parity tap: output of ``self.f.convs[layer]`` as the reference module would return it (NCHW)."""
         d, h, u, F, T = self.dims
         dev = _lib.device_index(x)
-        hnd = self.native_handle(dev)
+        hnd = self.native_handle(dev, training=self.training and x.is_cuda)    # the handle forward() will use
         _lib.use_torch_stream(dev)
         L = _lib.lib()
         _lib.check(L.pfann_model_set_tap(hnd, layer), 'pfann_model_set_tap')
         try:
-            self.forward(x)
+            with torch.no_grad():
+                self.forward(x)
             conv = self.f.convs[layer]
             shape = (x.shape[0],) + tuple(conv.ln2.normalized_shape)
             out = torch.empty(shape, dtype=torch.float32)

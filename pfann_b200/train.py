@@ -201,10 +201,7 @@ def train_step(model, optimizer, x, tau, specaug=None, minibatch=None, group=Non
     n = x.shape[0]
     if minibatch is not None and minibatch < n:
         with torch.no_grad():
-            was_training = model.training
-            model.eval()
-            ys = [model(xx) for xx in torch.split(x, minibatch)]
-            model.train(was_training)
+            ys = [model(xx) for xx in torch.split(x, minibatch)]                   # train.py:85-89
         y = torch.cat(ys).requires_grad_(True)
         loss = similarity_loss_gathered(y, tau, group)
         loss.backward()

@@ -205,3 +205,31 @@ def test_training_step_end_to_end_loss_and_optimizer(dev, golden_dir):
     opt.zero_grad(set_to_none=True)
     similarity_loss(net(x), params['tau']).backward()
     assert all(p.grad is None for p in net.f.parameters()) and all(p.grad is not None for p in net.g.parameters())
+
+
+def test_train_step_minibatch_route_equals_the_full_batch(dev):
+    """train.py:83-97: fingerprints without a graph, the loss gradient, then one backward per minibatch -- the same
+    parameter gradients as the single differentiated pass (train.py:99-101)."""
+    from pfann_b200.train import train_step
+
+    class NoStep:
+        def __init__(self, params):
+            self.params = list(params)
+
+        def zero_grad(self):
+            for p in self.params:
+                p.grad = None
+
+        def step(self):
+            pass
+
+    x = torch.from_numpy(synth.train_case_input('tiny')).to(dev)
+    grads = []
+    for mb in (None, 2, 3):
+        net, params, _ = _train_net('tiny', dev)
+        loss = train_step(net, NoStep(net.parameters()), x, params['tau'], minibatch=mb)
+        grads.append((loss.item(), [p.grad.detach().clone() for p in net.parameters()]))
+    for loss, g in grads[1:]:
+        assert abs(loss - grads[0][0]) < 1e-5
+        for a, b in zip(g, grads[0][1]):
+            assert float((a - b).norm()) <= 1e-4 * float(b.norm()) + 1e-7
