@@ -227,3 +227,22 @@ def test_impulse_response_convolution_vs_reference_fft(golden_dir):
     # one response, no crop: plain causal convolution truncated to the input length
     one = orc.apply_ir(x[:1, :50], [g['ir_mic'][:1, :7]])
     np.testing.assert_allclose(one[0], np.convolve(x[0, :50].astype(np.float64), g['ir_mic'][0, :7])[:50], atol=1e-12)
+
+
+def test_mel_kernel_fft_dataflows_reproduce_numpy_rfft():
+    """tools/fft_dataflow_check.py emulates, lane by lane, the index algebra of the two mel kernels (mel.cu): the
+    five-stage shuffle FFT of the general kernel and the transpose + second in-lane FFT + one butterfly of the fast
+    kernel, both with the real-FFT recombination.  Checked against numpy's rfft on the CPU, so a wrong twiddle or
+    bit-reversal shows up without a GPU."""
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tools', 'fft_dataflow_check.py')
+    spec = importlib.util.spec_from_file_location('fft_dataflow_check', path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(7)
+    for _ in range(3):
+        x = rng.standard_normal(1024)
+        ref = np.fft.rfft(x)
+        assert np.abs(ref - mod.warp_fft_1024_real(x)).max() < 1e-10
+        assert np.abs(np.abs(ref) ** 2 - mod.warp_fft_1024_real_v2(x)).max() < 1e-12 * (np.abs(ref) ** 2).max()
+    assert all(len(b) == 32 for b in mod.transpose_read_banks())      # the transpose reads are bank-conflict free

@@ -67,16 +67,6 @@ def warp_fft_1024_real(x):
     return X
 
 
-if __name__ == '__main__':
-    rng = np.random.default_rng(0)
-    x = rng.standard_normal(1024)
-    ref = np.fft.rfft(x)
-    got = warp_fft_1024_real(x)
-    err = np.abs(ref - got).max()
-    print('max err', err)
-    assert err < 1e-10
-
-
 def warp_fft_1024_real_v2(x):
     """Round-2 dataflow (mel_fast_kernel): the 32-point cross-lane part is ONE shared-memory transpose, a second
     in-lane 16-point DFT and a single shfl_xor(1) butterfly; the recombination forms bins k and 512-k from one pair."""
@@ -121,17 +111,24 @@ def warp_fft_1024_real_v2(x):
     return P
 
 
-if __name__ == '__main__':
-    rng = np.random.default_rng(1)
-    x = rng.standard_normal(1024)
-    ref = np.abs(np.fft.rfft(x)) ** 2
-    got = warp_fft_1024_real_v2(x)
-    err = np.abs(ref - got).max() / ref.max()
-    print('v2 max rel err', err)
-    assert err < 1e-12
-    # bank check of the transpose reads (64-bit accesses are served per half-warp): 16 lanes -> 32 distinct banks
+def transpose_read_banks():
+    """Banks touched by the transpose reads of one half-warp (64-bit accesses are served per half-warp)."""
+    out = []
     for half in (0, 16):
         L = np.arange(half, half + 16)
         words = 2 * ((L >> 1) * 34 + (L & 1))
-        banks = np.concatenate([words % 32, (words + 1) % 32])
-        assert len(set(banks.tolist())) == 32
+        out.append(sorted(set(np.concatenate([words % 32, (words + 1) % 32]).tolist())))
+    return out
+
+
+if __name__ == '__main__':
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(1024)
+    err = np.abs(np.fft.rfft(x) - warp_fft_1024_real(x)).max()
+    print('v1 max err', err)
+    assert err < 1e-10
+    ref = np.abs(np.fft.rfft(x)) ** 2
+    err = np.abs(ref - warp_fft_1024_real_v2(x)).max() / ref.max()
+    print('v2 max rel err', err)
+    assert err < 1e-12
+    assert all(len(b) == 32 for b in transpose_read_banks())
