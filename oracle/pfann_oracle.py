@@ -354,3 +354,30 @@ def apply_ir(x, responses, pad_start=0, segment_size=None):
             y = np.convolve(y, np.asarray(h[b], np.float64))[:end]
         out[b] = y[pad_start:end]
     return out
+
+
+def ln_act_backward(dA, Y, gamma, beta, act='ReLU', act_first=False, eps=1e-5):
+    """Backward of one `LayerNorm over (C,F,T) + activation` block of SeparableConv2d (model.py:58-72) in float64, the
+    formulas pfann_b200/csrc/encoder_train.cu implements: given dL/d(output) for Y[B, ...] (raw convolution output),
+    returns (dL/dY, dL/dgamma, dL/dbeta).  act_first = relu_after_bn False: out = LN(act(Y)); else out = act(LN(Y))."""
+    Y = np.asarray(Y, np.float64)
+    dA = np.asarray(dA, np.float64)
+    B = Y.shape[0]
+    red = tuple(range(1, Y.ndim))
+
+    def act_f(v):
+        return np.where(v > 0, v, np.expm1(np.minimum(v, 0))) if act == 'ELU' else np.maximum(v, 0)
+
+    def act_d(v):
+        return np.where(v > 0, 1.0, np.exp(np.minimum(v, 0))) if act == 'ELU' else (v > 0).astype(np.float64)
+
+    z = act_f(Y) if act_first else Y
+    mean = z.mean(axis=red, keepdims=True)
+    rstd = 1.0 / np.sqrt(z.var(axis=red, keepdims=True) + eps)
+    xh = (z - mean) * rstd
+    n = xh * gamma + beta
+    dn = dA if act_first else dA * act_d(n)
+    g = dn * gamma
+    dz = rstd * (g - g.mean(axis=red, keepdims=True) - xh * (g * xh).mean(axis=red, keepdims=True))
+    dY = dz * act_d(Y) if act_first else dz
+    return dY, (dn * xh).sum(axis=0), dn.sum(axis=0)

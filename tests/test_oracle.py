@@ -246,3 +246,26 @@ def test_mel_kernel_fft_dataflows_reproduce_numpy_rfft():
         assert np.abs(ref - mod.warp_fft_1024_real(x)).max() < 1e-10
         assert np.abs(np.abs(ref) ** 2 - mod.warp_fft_1024_real_v2(x)).max() < 1e-12 * (np.abs(ref) ** 2).max()
     assert all(len(b) == 32 for b in mod.transpose_read_banks())      # the transpose reads are bank-conflict free
+
+
+@pytest.mark.parametrize('act', ['ReLU', 'ELU'])
+@pytest.mark.parametrize('act_first', [False, True])
+def test_layernorm_activation_backward_vs_torch_autograd(act, act_first):
+    """The closed-form backward the training kernels implement (oracle.ln_act_backward: activation derivative from the
+    stored output, LayerNorm backward from two per-sample means) against torch autograd on the reference's own layer
+    sequence (model.py:58-72), all four option sets."""
+    torch = pytest.importorskip('torch')
+    rng = np.random.default_rng(11)
+    Y = rng.standard_normal((3, 4, 6, 5))
+    gamma, beta = 1 + 0.2 * rng.standard_normal((4, 6, 5)), 0.1 * rng.standard_normal((4, 6, 5))
+    dA = rng.standard_normal(Y.shape)
+    yt = torch.tensor(Y, requires_grad=True)
+    gt, bt = torch.tensor(gamma, requires_grad=True), torch.tensor(beta, requires_grad=True)
+    f = torch.nn.functional
+    a = f.elu if act == 'ELU' else f.relu
+    out = f.layer_norm(a(yt), gamma.shape, gt, bt, 1e-5) if act_first else a(f.layer_norm(yt, gamma.shape, gt, bt, 1e-5))
+    out.backward(torch.tensor(dA))
+    dY, dg, db = orc.ln_act_backward(dA, Y, gamma, beta, act, act_first)
+    np.testing.assert_allclose(dY, yt.grad.numpy(), rtol=0, atol=1e-10)
+    np.testing.assert_allclose(dg, gt.grad.numpy(), rtol=0, atol=1e-10)
+    np.testing.assert_allclose(db, bt.grad.numpy(), rtol=0, atol=1e-10)
